@@ -174,6 +174,16 @@ static void pass2(const struct shim_pass *ps,
     }
 }
 
+#ifdef SHIM_DIF
+/* Variant used only to prove the restatement's non-FFT arithmetic: route the reference's
+ * FFT calls through oracle/ir_oracle.c's radix-2 DIF so that reference+DIF must equal the
+ * restatement bit for bit (tests/test_oracle_ref.py::test_port_bit_exact_with_shared_fft). */
+#include "../ir_oracle.h"
+void fftwf_execute(const fftwf_plan p) {
+    memcpy(p->out, p->in, sizeof(fftwf_complex) * (size_t)p->n);
+    orc_fft((orc_cf32 *)p->out, p->n, p->sign > 0);
+}
+#else
 void fftwf_execute(const fftwf_plan p) {
     const int n = p->n;
     const float *src = (const float *)p->in;
@@ -198,3 +208,4 @@ void fftwf_execute(const fftwf_plan p) {
         dst[2 * i + 1] = (float)xi[i];
     }
 }
+#endif
