@@ -1,0 +1,164 @@
+/*
+ * iridium_b200.h -- C ABI of libiridium_b200.so: the B200-native Iridium
+ * burst-detect -> downmix -> DQPSK-demod path.
+ *
+ * Plain C, plain pointers and sizes, no torch / CUDA types in any signature.
+ * Every entry point names the reference interface it replaces (file:line relative
+ * to alphafox02/iridium-sniffer @ 99453295).  INTEGRATION.md shows the bindings a
+ * maintainer of the reference would add.
+ *
+ * Three layers are exported:
+ *   1. ir_pipeline_*      batched whole-path API (what bench.py and the tests drive);
+ *                         replaces the detector/downmix/demod thread trio of
+ *                         main.c:667-685 for file or block input.
+ *   2. ir_ref_*.h-shaped  the reference's own per-item functions with identical
+ *                         signatures and struct layouts (include/ir_ref_api.h).
+ *   3. gpu_burst_fft_*    the reference's existing accelerator plug-in ABI
+ *                         (opencl/burst_fft.h:35-47), see include/burst_fft.h.
+ *
+ * There is no CPU fallback anywhere: if no CUDA device / kernel image is usable the
+ * create calls return NULL and ir_last_error() says why.
+ */
+#ifndef IRIDIUM_B200_H
+#define IRIDIUM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IR_ABI_VERSION 1
+
+/* Sample formats of the input stream (options.c:326-337, main.c:236-262). */
+enum { IR_FMT_CF32 = 0, IR_FMT_CI16 = 1, IR_FMT_CI8 = 2 };
+
+/* Direction, same values as ir_direction_t (burst_downmix.h:32-36). */
+enum { IR_DIR_UNDEF = 0, IR_DIR_DOWNLINK = 1, IR_DIR_UPLINK = 2 };
+
+typedef struct ir_pipeline ir_pipeline_t;
+
+/* Configuration: the union of burst_config_t (burst_detect.h:51-63), downmix_config_t
+ * (burst_downmix.h:57-61) and the globals qpsk_demod reads (qpsk_demod.c:34-35).
+ * Zero means "reference default" exactly as in burst_detector_create (burst_detect.c:180-226). */
+typedef struct {
+    uint32_t abi_version;       /* IR_ABI_VERSION */
+    int32_t device;             /* CUDA device ordinal */
+    double center_frequency;    /* Hz (main.c:645) */
+    int32_t sample_rate;        /* Hz (main.c:646) */
+    int32_t fft_size;           /* 0 = auto (~1 ms, power of two) */
+    int32_t burst_width_hz;     /* 0 = 40000 */
+    float threshold_db;         /* 0 = 16.0 */
+    int32_t use_gardner;        /* main.c:143 default 1 */
+    int32_t feed_block;         /* samples per emulated burst_detector_feed call; 0 = 32768
+                                   (main.c:225).  Decides the emit cadence and therefore the
+                                   stale-tail samples of SURVEY.md D10. */
+    uint64_t start_time_ns;     /* timestamp of sample 0; 0 = CLOCK_REALTIME at first feed
+                                   (burst_detect.c:755-759) */
+    uint64_t max_samples;       /* capacity of the resident IQ buffer; 0 = size of first feed */
+    int32_t h2d_chunk;          /* samples per pinned->device copy in ir_pipeline_run_host;
+                                   0 = 16 Mi */
+    int32_t reserved[7];
+} ir_config_t;
+
+/* One demodulated frame == demod_frame_t (qpsk_demod.h:24-38) without the pointers. */
+typedef struct {
+    uint64_t id;
+    uint64_t timestamp;         /* ns */
+    double center_frequency;    /* Hz */
+    int32_t direction;
+    float magnitude;            /* dB */
+    float noise;                /* dBFS/Hz */
+    int32_t confidence;         /* 0..100 */
+    float level;
+    int32_t n_symbols;
+    int32_t n_payload_symbols;
+    int32_t n_bits;
+    uint32_t bits_offset;       /* into the bits / llr arrays of the result set */
+} ir_frame_t;
+
+/* Detected burst == burst_info_t + the fields of burst_data_t (burst_detect.h:29-48). */
+typedef struct {
+    uint64_t id;
+    uint64_t start;
+    uint64_t stop;
+    uint64_t last_active;
+    int32_t center_bin;
+    float magnitude;
+    float noise;
+    uint64_t num_samples;
+    uint64_t emit_count;        /* detector sample_count when the burst was emitted */
+    int32_t downmix_status;     /* 0 = frame produced, else stage that dropped it */
+    int32_t demod_ok;
+    float center_offset;        /* fine CFO, cycles/sample at 250 kHz */
+    int32_t dm_start;           /* find_burst_start result */
+    int32_t uw_start;           /* sample index of the unique word in the frame */
+    int32_t frame_len;          /* extracted samples */
+    float uw_start_frac;        /* sub-sample correction (downmix_frame_t.uw_start) */
+    int32_t dm_direction;
+    int32_t dec_len;
+} ir_burst_t;
+
+typedef struct {
+    size_t n_bursts;
+    const ir_burst_t *bursts;
+    size_t n_frames;
+    const ir_frame_t *frames;
+    const uint8_t *bits;        /* one byte per bit (0/1), like demod_frame_t.bits */
+    const float *llr;
+    size_t n_bits_total;
+    /* device time of the last run, from CUDA events on the launching streams (ms) */
+    float ms_total;             /* first kernel start .. last result ready */
+    float ms_detect_fft, ms_detect_scan, ms_downmix_fir, ms_downmix_chain, ms_demod;
+    uint64_t kernel_launches;   /* launches of this library's kernels in the last run */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t alg_bytes;         /* algorithmic bytes of the run (SURVEY.md 8d formula) */
+} ir_results_t;
+
+const char *ir_last_error(void);
+int ir_device_count(void);
+
+/* Replaces burst_detector_create + burst_downmix_create x4 (main.c:644-664). */
+ir_pipeline_t *ir_pipeline_create(const ir_config_t *cfg);
+void ir_pipeline_destroy(ir_pipeline_t *p);
+
+/* Forget all stream state (fresh detector, empty buffer). */
+int ir_pipeline_reset(ir_pipeline_t *p);
+
+/* Whole path over a block of IQ in HOST memory (pinned or pageable): chunked H2D copies
+ * overlapped with detection, then downmix + demod of every emitted burst, results copied
+ * back.  The block is treated like a file handed to the reference (fresh detector).
+ * Replaces spewer_thread -> burst_detector_thread -> burst_downmix_thread ->
+ * frame_consumer_thread (main.c:223-385) up to, not including, frame_output_print.
+ * Returns 0 on success. */
+int ir_pipeline_run_host(ir_pipeline_t *p, const void *iq, size_t n_samples, int fmt);
+
+/* Same, IQ already resident in DEVICE memory (device pointer of this pipeline's device). */
+int ir_pipeline_run_device(ir_pipeline_t *p, const void *iq_dev, size_t n_samples, int fmt);
+
+/* Results of the last run; pointers stay valid until the next run/reset/destroy. */
+int ir_pipeline_results(ir_pipeline_t *p, ir_results_t *out);
+
+/* Debug / parity taps on the last run (host copies; caller provides the buffers). */
+int ir_pipeline_copy_mag(ir_pipeline_t *p, size_t frame0, size_t n_frames, float *dst);
+int ir_pipeline_copy_frame_samples(ir_pipeline_t *p, size_t burst_index, float *dst_cf32,
+                                   size_t cap_samples);
+int ir_pipeline_copy_decimated(ir_pipeline_t *p, size_t burst_index, float *dst_cf32,
+                               size_t cap_samples);
+int ir_pipeline_copy_burst_samples(ir_pipeline_t *p, size_t burst_index, float *dst_cf32,
+                                   size_t cap_samples);
+
+/* frame_output_print's line (frame_output.c:160-199) into dst; t0 per ensure_initialized
+ * (frame_output.c:144-158).  Returns the length, or -1. */
+int ir_format_raw(char *dst, size_t cap, const char *file_info, uint64_t t0,
+                  const ir_frame_t *frame, const uint8_t *bits);
+
+/* Pinned host allocations for callers that want full-rate H2D. */
+void *ir_host_alloc(size_t bytes);
+void ir_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,148 @@
+// ir_internal.h -- structures and launcher prototypes shared between the kernels
+// (k_*.cu), the host tables (host_tables.cpp) and the pipeline (pipeline.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#define IR_MAX_ACTIVE 1024      // device-side cap on simultaneously tracked bursts
+#define IR_SCAN_THREADS 1024
+#define IR_ROT_G 16             // samples between NCO phase checkpoints
+#define IR_FIR_TILE 256         // decimated outputs per FIR CTA
+#define IR_FIR_R 8              // outputs per lane
+#define IR_INPUT_NTAPS 801      // burst_downmix.c:252-259 (always designed for 10 MHz)
+#define IR_DM_WORK (2 * 1024 * 1024)   // burst_downmix.c:366
+#define IR_OUT_RATE 250000
+#define IR_MAX_FRAME 4440       // 444 symbols * 10 (iridium.h:27)
+#define IR_MAX_SYMS 480
+#define IR_CFO_N 256
+#define IR_CFO_TOTAL 4096
+#define IR_CORR_N 2048
+#define IR_SYNC_SEARCH 840
+#define IR_SYNC_LEN 271
+
+namespace ir {
+
+// ------------------------------------------------------------------ detector
+struct DetConfig {                 // derived as burst_detector_create does (burst_detect.c:174-226)
+    int L, N;
+    int hist_size;
+    int half_bw;                   // burst_width / 2 (bins)
+    int burst_width;
+    int max_bursts;
+    int pre_len, post_len, max_burst_len;
+    float thr;                     // linear threshold
+    int sample_rate;
+    uint64_t ringbuf_size;
+};
+
+struct ActBurst {
+    uint64_t id, start, last_active;
+    int center_bin;
+    float peak_rel;
+    float base_at_create;
+    int pad;
+};
+
+struct GoneBurst {
+    uint64_t id, start, stop, last_active;
+    int center_bin;
+    float peak_rel;
+    float base_at_create;
+    int pad;
+};
+
+struct DetState {
+    int hist_idx, primed, n_act, squelch_count;
+    uint64_t next_id;
+    uint64_t index;                // absolute sample index of the next frame
+    uint32_t n_gone;               // entries written to the gone list so far
+    uint32_t n_squelch;
+    uint32_t overflow;             // IR_MAX_ACTIVE or gone list exceeded
+    uint32_t pad;
+    ActBurst act[IR_MAX_ACTIVE];
+};
+
+// ------------------------------------------------------------------ downmix
+struct BurstParam {                // one per emitted burst, built on the host
+    int64_t start;                 // first sample of the extract (after ring clamp)
+    int64_t emit_count;            // samples the detector had seen at emission
+    int32_t n;                     // samples in the extract (<= IR_DM_WORK)
+    int32_t dec_len;               // decimated length
+    int64_t dec_off;               // offset into the per-run decimated / scratch arrays
+    float2 incr_coarse;            // cexpf(-j*2*pi*rel) from the host libm (burst_downmix.c:668-669)
+    const float2 *rot_table;       // phase checkpoints every IR_ROT_G samples for this bin
+    int32_t tile0;                 // first FIR tile of this burst
+    int32_t simplex;               // extraction limits of burst_downmix.c:764-770 decided later
+    double cfreq_coarse;           // center_frequency after the coarse shift
+};
+
+struct ChainOut {                  // what the 250 kHz chain reports per burst
+    int32_t status;                // 0 ok, else failing stage (2,3,7,9)
+    int32_t start;                 // find_burst_start
+    float center_offset;
+    int32_t cfo_peak_bin;
+    int32_t direction;
+    int32_t corr_offset;
+    int32_t uw_start;
+    float uw_corr;                 // sub-sample correction
+    float corr_re, corr_im;
+    int32_t frame_len;
+    float2 incr_fine;
+};
+
+struct DemodOut {
+    int32_t ok;
+    int32_t direction;
+    int32_t confidence;
+    float level;
+    int32_t n_symbols;
+    int32_t n_raw_symbols;
+    float total_phase;
+    int32_t pad;
+};
+
+// Filters / windows / templates exactly as the reference designs them (host, float math).
+struct HostTables {
+    std::vector<float> det_window;        // blackman/0.42 (burst_detect.c:247-250)
+    std::vector<float> h_input;           // 801 taps (burst_downmix.c:252-259)
+    std::vector<float> h_noise;           // 25 taps  (:264-277)
+    std::vector<float> h_box;             // 20 taps  (:281-287)
+    std::vector<float> h_rrc;             // 51 taps  (:290-296)
+    std::vector<float> h_rc;              // 51 taps  (:299-305)
+    std::vector<float> cfo_window;        // blackman(256) (:320-321)
+    std::vector<float2> sync_dl_fft;      // 2048 (:358-363)
+    std::vector<float2> sync_ul_fft;
+};
+void build_host_tables(HostTables &t, int det_fft_size);
+void derive_det_config(DetConfig &c, int sample_rate, int fft_size, int burst_width_hz, float threshold_db);
+std::vector<float2> build_twiddle_image(int L);      // layout of ir_device.cuh
+void host_fft(std::vector<float2> &x, bool inverse);   // same radix-2 DIF, for the templates
+
+// ------------------------------------------------------------------ launchers
+// k_detect.cu
+cudaError_t launch_detect_fft(int L, int fmt, const void *iq, int64_t first_sample, const float *window,
+                              const float2 *tw, float *mag, int64_t n_frames, int sm_count,
+                              cudaStream_t st);
+cudaError_t launch_detect_scan(const DetConfig &c, DetState *state, float *base, float *hist,
+                               const float *mag, int64_t n_frames, GoneBurst *gone,
+                               uint32_t gone_cap, cudaStream_t st);
+// k_downmix.cu
+cudaError_t upload_input_taps(const float *taps, int ntaps);
+cudaError_t upload_chain_tables(const HostTables &t);
+cudaError_t launch_rot_tables(const float2 *incr, float2 *const *tables, const int *lens, int n,
+                              cudaStream_t st);
+cudaError_t launch_fir(int fmt, int dec, const void *iq, int64_t n_total, uint64_t ring,
+                       const BurstParam *bp, const int *tile_start, int n_bursts, int n_tiles,
+                       float2 *dec_out, cudaStream_t st);
+cudaError_t launch_chain(const BurstParam *bp, int n_bursts, const float2 *dec, float2 *scrA,
+                         float2 *scrB, const float2 *tw4096, const float2 *tw2048,
+                         const float2 *sync_dl, const float2 *sync_ul, ChainOut *out,
+                         float2 *frames, cudaStream_t st);
+// k_demod.cu
+cudaError_t launch_demod(const ChainOut *co, int n_bursts, const float2 *frames, int use_gardner,
+                         DemodOut *out, uint8_t *bits, float *llr, cudaStream_t st);
+
+}  // namespace ir

@@ -1,0 +1,377 @@
+// k_detect.cu -- burst detector on the device.
+//
+//  k_detect_fft : window -> N-point FFT -> fftshift -> |X|^2, one CTA per frame (persistent
+//                 over frames), replaces process_fft_frame's arithmetic (burst_detect.c:679-687,
+//                 simd_avx2.c:145-218) and the OpenCL window/VkFFT/fftshift_magnitude trio
+//                 (opencl/burst_fft.c:53-80,333-370).
+//  k_detect_scan: the burst state machine over the magnitude frames, strictly in frame order
+//                 (burst_detect.c:426-632), one persistent CTA with the noise baseline in
+//                 registers.  Emits burst descriptors; IQ never moves.
+#include "ir_device.cuh"
+#include "ir_internal.h"
+
+namespace ir {
+
+// =========================================================================== FFT + |X|^2
+template <int L, int FMT>
+__global__ void __launch_bounds__(fft_threads<L>())
+k_detect_fft(const void *__restrict__ iq, int64_t first_sample, const float *__restrict__ window,
+             const float2 *__restrict__ tw_g, float *__restrict__ mag, int64_t n_frames) {
+    constexpr int N = 1 << L;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *data = reinterpret_cast<float2 *>(smem_raw);
+    float2 *tw = data + fft_data_elems<L>();
+    fft_load_twiddles<L>(tw, tw_g);
+    __syncthreads();
+    for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        const int64_t s0 = first_sample + f * N;
+        float *out = mag + f * N;
+        fft_smem<L, false, true>(
+            data, tw,
+            [&](int p) {
+                float2 v = load_sample<FMT>(iq, s0 + p);
+                float w = __ldg(window + p);
+                return make_float2(v.x * w, v.y * w);          // simd_avx2.c:145-160
+            },
+            [&](int k, float2 v) { out[k ^ (N >> 1)] = mag2_fma(v); });   // :177-218
+    }
+}
+
+template <int L>
+static cudaError_t launch_fft_L(int fmt, const void *iq, int64_t first_sample, const float *window,
+                                const float2 *tw, float *mag, int64_t n_frames, int sm_count,
+                                cudaStream_t st) {
+    const size_t smem = sizeof(float2) * (fft_data_elems<L>() + fft_tw_elems<L>());
+    const int threads = fft_threads<L>();
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    int64_t grid = (int64_t)sm_count * per_sm;
+    if (grid > n_frames) grid = n_frames;
+    if (grid < 1) return cudaSuccess;
+#define IR_LAUNCH_FFT(F)                                                                          \
+    do {                                                                                          \
+        cudaError_t e = cudaFuncSetAttribute(k_detect_fft<L, F>,                                  \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                           \
+        k_detect_fft<L, F><<<(unsigned)grid, threads, smem, st>>>(iq, first_sample, window, tw,   \
+                                                                  mag, n_frames);                 \
+    } while (0)
+    if (fmt == IR_FMT_CF32) IR_LAUNCH_FFT(IR_FMT_CF32);
+    else if (fmt == IR_FMT_CI16) IR_LAUNCH_FFT(IR_FMT_CI16);
+    else IR_LAUNCH_FFT(IR_FMT_CI8);
+#undef IR_LAUNCH_FFT
+    return cudaGetLastError();
+}
+
+cudaError_t launch_detect_fft(int L, int fmt, const void *iq, int64_t first_sample, const float *window,
+                              const float2 *tw, float *mag, int64_t n_frames, int sm_count,
+                              cudaStream_t st) {
+    switch (L) {
+    case 10: return launch_fft_L<10>(fmt, iq, first_sample, window, tw, mag, n_frames, sm_count, st);
+    case 11: return launch_fft_L<11>(fmt, iq, first_sample, window, tw, mag, n_frames, sm_count, st);
+    case 12: return launch_fft_L<12>(fmt, iq, first_sample, window, tw, mag, n_frames, sm_count, st);
+    case 13: return launch_fft_L<13>(fmt, iq, first_sample, window, tw, mag, n_frames, sm_count, st);
+    case 14: return launch_fft_L<14>(fmt, iq, first_sample, window, tw, mag, n_frames, sm_count, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+// =========================================================================== state machine
+// Thread t owns bins t + 1024*u (u < BPT): one ballot per u yields 32 consecutive bins of the
+// "above threshold" bitmap.  The running noise baseline of the owned bins lives in registers
+// for the whole launch; the 512-frame history stays in HBM/L2 and is touched only on quiet
+// frames (burst_detect.c:438-454).
+
+struct ScanShared {
+    uint32_t above[512];
+    uint32_t free_mask[512];      // 1 = no active burst covers the bin (burst_mask != 0)
+    uint32_t valid[512];          // peak search range minus the DC notch (burst_detect.c:537-542)
+    ArgMax red[32];
+    int n_act;
+    int flags;
+    int squelch_count;
+    unsigned long long next_id;
+    uint32_t n_gone, n_squelch, overflow;
+    ActBurst act[IR_MAX_ACTIVE];
+};
+
+__device__ __forceinline__ bool bit_at(const uint32_t *bm, int bin) { return (bm[bin >> 5] >> (bin & 31)) & 1u; }
+
+__device__ __forceinline__ void clear_range(uint32_t *bm, int lo, int hi) {   // inclusive, single thread
+    for (int w = lo >> 5; w <= (hi >> 5); w++) {
+        int a = max(lo, w << 5) & 31, b = min(hi, (w << 5) + 31) & 31;
+        uint32_t m = (b == 31 ? 0xffffffffu : ((1u << (b + 1)) - 1u)) & ~((1u << a) - 1u);
+        atomicAnd(&bm[w], ~m);
+    }
+}
+
+template <int BPT>
+__global__ void __launch_bounds__(IR_SCAN_THREADS, 1)
+k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g,
+              float *__restrict__ hist, const float *__restrict__ mag, int64_t n_frames,
+              GoneBurst *__restrict__ gone, uint32_t gone_cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ScanShared &S = *reinterpret_cast<ScanShared *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = c.N, W = N >> 5;
+    const float thr = c.thr;
+
+    // ---- load state
+    float base[BPT];
+#pragma unroll
+    for (int u = 0; u < BPT; u++) base[u] = base_g[u * IR_SCAN_THREADS + tid];
+    int hist_idx = gs->hist_idx, primed = gs->primed;
+    uint64_t index = gs->index;
+    if (tid == 0) {
+        S.n_act = gs->n_act;
+        S.squelch_count = gs->squelch_count;
+        S.next_id = gs->next_id;
+        S.n_gone = gs->n_gone;
+        S.n_squelch = gs->n_squelch;
+        S.overflow = gs->overflow;
+        S.flags = 0;
+    }
+    for (int i = tid; i < IR_MAX_ACTIVE; i += blockDim.x)
+        if (i < gs->n_act) S.act[i] = gs->act[i];
+    for (int w = tid; w < W; w += blockDim.x) {
+        uint32_t v = 0;
+        for (int b = 0; b < 32; b++) {
+            int bin = (w << 5) + b;
+            bool ok = bin >= c.half_bw && bin < N - c.half_bw && !(bin >= N / 2 - 3 && bin <= N / 2 + 3);
+            v |= ok ? (1u << b) : 0u;
+        }
+        S.valid[w] = v;
+        S.free_mask[w] = 0xffffffffu;
+        S.above[w] = 0;
+    }
+    __syncthreads();
+    if (tid < S.n_act) clear_range(S.free_mask, max(S.act[tid].center_bin - c.half_bw, 0),
+                                   min(S.act[tid].center_bin + c.half_bw, N - 1));
+    __syncthreads();
+
+    auto baseline_push = [&](const float *m) {          // burst_detect.c:438-454, simd_avx2.c:221-236
+        float *h = hist + (size_t)hist_idx * N;
+#pragma unroll
+        for (int u = 0; u < BPT; u++) {
+            const int bin = u * IR_SCAN_THREADS + tid;
+            float old = primed ? h[bin] : 0.0f;          // untouched history is zero (calloc / reset)
+            float v = base[u] - old;
+            base[u] = v + m[u];
+            h[bin] = m[u];
+        }
+        if (++hist_idx == c.hist_size) { primed = 1; hist_idx = 0; }
+    };
+
+    for (int64_t f = 0; f < n_frames; f++, index += (uint64_t)N) {
+        float m[BPT];
+#pragma unroll
+        for (int u = 0; u < BPT; u++) m[u] = mag[f * N + u * IR_SCAN_THREADS + tid];
+
+        if (primed) {
+            float rel[BPT];
+            bool ab[BPT];
+            uint32_t any = 0;
+#pragma unroll
+            for (int u = 0; u < BPT; u++) {
+                rel[u] = base[u] > 0.0f ? m[u] / base[u] : 0.0f;      // simd_avx2.c:239-257
+                ab[u] = rel[u] > thr;
+                uint32_t bal = __ballot_sync(0xffffffffu, ab[u]);
+                if (lane == 0) S.above[u * 32 + warp] = bal;
+                any |= bal;
+            }
+            if (tid == 0) S.flags = 0;
+            const int any_above = __syncthreads_or(any != 0);
+            int n_act = S.n_act;
+            if (any_above || n_act > 0) {
+                int fl = 0;
+                // update_bursts (:458-469)
+                if (tid < n_act) {
+                    ActBurst &b = S.act[tid];
+                    const int cb = b.center_bin;
+                    bool hit = (cb > 0 && bit_at(S.above, cb - 1)) || bit_at(S.above, cb) ||
+                               (cb < N - 1 && bit_at(S.above, cb + 1));
+                    if (hit) b.last_active = index;
+                    bool too_long = c.max_burst_len > 0 &&
+                                    b.last_active - b.start > (uint64_t)c.max_burst_len;
+                    bool done = (b.last_active + (uint64_t)c.post_len <= index) || too_long;
+                    if (done) fl |= 2;
+                    if (too_long) fl |= 4;
+                }
+                // peaks after masking with the mask left by the previous frame (:522-548)
+                bool cand[BPT];
+#pragma unroll
+                for (int u = 0; u < BPT; u++) {
+                    const int bin = u * IR_SCAN_THREADS + tid;
+                    cand[u] = ab[u] && bit_at(S.free_mask, bin) && bit_at(S.valid, bin);
+                    if (cand[u]) fl |= 1;
+                }
+                if (fl) atomicOr(&S.flags, fl);
+                __syncthreads();
+                const int flags = S.flags;
+                if (flags & 2) {
+                    // delete_gone_bursts (:490-518): order-preserving, one thread
+                    if (tid == 0) {
+                        int k = 0;
+                        for (int i = 0; i < n_act; i++) {
+                            ActBurst b = S.act[i];
+                            bool too_long = c.max_burst_len > 0 &&
+                                            b.last_active - b.start > (uint64_t)c.max_burst_len;
+                            if ((b.last_active + (uint64_t)c.post_len <= index) || too_long) {
+                                if (S.n_gone < gone_cap) {
+                                    GoneBurst g;
+                                    g.id = b.id; g.start = b.start; g.stop = index;
+                                    g.last_active = b.last_active; g.center_bin = b.center_bin;
+                                    g.peak_rel = b.peak_rel; g.base_at_create = b.base_at_create;
+                                    g.pad = 0;
+                                    gone[S.n_gone] = g;
+                                } else {
+                                    S.overflow = 1;
+                                }
+                                S.n_gone++;
+                            } else {
+                                S.act[k++] = b;
+                            }
+                        }
+                        S.n_act = k;
+                    }
+                    __syncthreads();
+                    n_act = S.n_act;
+                    if (flags & 4) baseline_push(m);                    // update_filters_post(d, 1)
+                    // update_burst_mask (:482-486)
+                    for (int w = tid; w < W; w += blockDim.x) S.free_mask[w] = 0xffffffffu;
+                    __syncthreads();
+                    if (tid < n_act)
+                        clear_range(S.free_mask, max(S.act[tid].center_bin - c.half_bw, 0),
+                                    min(S.act[tid].center_bin + c.half_bw, N - 1));
+                    __syncthreads();
+                }
+                if (flags & 1) {
+                    // create_new_bursts (:556-591): strongest remaining peak first
+                    for (;;) {
+                        ArgMax best{-1.0f, 0x7fffffff};
+#pragma unroll
+                        for (int u = 0; u < BPT; u++)
+                            if (cand[u]) best = argmax_pick(best, ArgMax{rel[u], u * IR_SCAN_THREADS + tid});
+                        best = block_argmax(best, S.red);
+                        if (best.v < 0.0f) break;
+                        const int bin = best.i;
+                        const int slot = S.n_act;
+                        if (slot < IR_MAX_ACTIVE) {
+                            if (tid == (bin & (IR_SCAN_THREADS - 1))) {
+                                ActBurst nb;
+                                nb.id = S.next_id;
+                                nb.start = index - (uint64_t)c.pre_len;
+                                nb.last_active = nb.start;
+                                nb.center_bin = bin;
+                                nb.peak_rel = best.v;
+                                float bs = 0.0f;
+#pragma unroll
+                                for (int u = 0; u < BPT; u++) if (u == bin / IR_SCAN_THREADS) bs = base[u];
+                                nb.base_at_create = bs;
+                                nb.pad = 0;
+                                S.act[slot] = nb;
+                                clear_range(S.free_mask, max(bin - c.half_bw, 0), min(bin + c.half_bw, N - 1));
+                            }
+                        }
+                        const int lo = bin - c.half_bw, hi = bin + c.half_bw;
+#pragma unroll
+                        for (int u = 0; u < BPT; u++) {
+                            const int b = u * IR_SCAN_THREADS + tid;
+                            if (b >= lo && b <= hi) cand[u] = false;
+                        }
+                        __syncthreads();
+                        if (tid == 0) {
+                            if (slot < IR_MAX_ACTIVE) { S.n_act = slot + 1; S.next_id += 10; }
+                            else { S.overflow = 1; S.next_id += 10; }
+                        }
+                        __syncthreads();
+                    }
+                }
+                // squelch (:593-631)
+                n_act = S.n_act;
+                bool reset_noise = false;
+                if (c.max_bursts > 0 && n_act > c.max_bursts) {
+                    if (tid == 0) {
+                        for (int i = 0; i < n_act; i++) {
+                            const ActBurst &b = S.act[i];
+                            if (b.start != index - (uint64_t)c.pre_len) {
+                                if (S.n_gone < gone_cap) {
+                                    GoneBurst g;
+                                    g.id = b.id; g.start = b.start; g.stop = index;
+                                    g.last_active = b.last_active; g.center_bin = b.center_bin;
+                                    g.peak_rel = b.peak_rel; g.base_at_create = b.base_at_create;
+                                    g.pad = 0;
+                                    gone[S.n_gone] = g;
+                                } else {
+                                    S.overflow = 1;
+                                }
+                                S.n_gone++;
+                            }
+                        }
+                        S.n_act = 0;
+                        S.n_squelch++;
+                        S.squelch_count += 3;
+                    }
+                    for (int w = tid; w < W; w += blockDim.x) S.free_mask[w] = 0xffffffffu;
+                    __syncthreads();
+                    if (S.squelch_count >= 10) reset_noise = true;
+                    __syncthreads();
+                    if (reset_noise) {
+                        hist_idx = 0; primed = 0;
+#pragma unroll
+                        for (int u = 0; u < BPT; u++) base[u] = 0.0f;
+                        if (tid == 0) S.squelch_count = 0;
+                    }
+                } else if (tid == 0 && S.squelch_count > 0) {
+                    S.squelch_count--;
+                }
+                __syncthreads();
+            } else if (tid == 0 && S.squelch_count > 0) {
+                S.squelch_count--;
+            }
+        }
+        // update_filters_post(d, 0) (:438-454)
+        if (S.n_act == 0) baseline_push(m);
+        // S.n_act is only written inside barrier-separated sections above; the next frame's
+        // first barrier (__syncthreads_or) orders this read against later writes.
+    }
+
+    // ---- store state
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < BPT; u++) base_g[u * IR_SCAN_THREADS + tid] = base[u];
+    for (int i = tid; i < S.n_act; i += blockDim.x) gs->act[i] = S.act[i];
+    if (tid == 0) {
+        gs->hist_idx = hist_idx; gs->primed = primed; gs->n_act = S.n_act;
+        gs->squelch_count = S.squelch_count; gs->next_id = S.next_id; gs->index = index;
+        gs->n_gone = S.n_gone; gs->n_squelch = S.n_squelch; gs->overflow = S.overflow;
+    }
+}
+
+cudaError_t launch_detect_scan(const DetConfig &c, DetState *state, float *base, float *hist,
+                               const float *mag, int64_t n_frames, GoneBurst *gone,
+                               uint32_t gone_cap, cudaStream_t st) {
+    if (n_frames <= 0) return cudaSuccess;
+    const size_t smem = sizeof(ScanShared);
+#define IR_LAUNCH_SCAN(B)                                                                         \
+    do {                                                                                          \
+        cudaError_t e = cudaFuncSetAttribute(k_detect_scan<B>,                                    \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                           \
+        k_detect_scan<B><<<1, IR_SCAN_THREADS, smem, st>>>(c, state, base, hist, mag, n_frames,   \
+                                                           gone, gone_cap);                       \
+    } while (0)
+    switch (c.N / IR_SCAN_THREADS) {
+    case 1: IR_LAUNCH_SCAN(1); break;
+    case 2: IR_LAUNCH_SCAN(2); break;
+    case 4: IR_LAUNCH_SCAN(4); break;
+    case 8: IR_LAUNCH_SCAN(8); break;
+    case 16: IR_LAUNCH_SCAN(16); break;
+    default: return cudaErrorInvalidValue;
+    }
+#undef IR_LAUNCH_SCAN
+    return cudaGetLastError();
+}
+
+}  // namespace ir

@@ -1,0 +1,253 @@
+"""ctypes mirror of include/iridium_b200.h -- the host-side handle the tests and bench.py use.
+
+The arithmetic lives entirely in libiridium_b200.so (hand-written sm_100a kernels).  There
+is no Python / NumPy / oracle fallback: if the library or a CUDA device is missing, loading
+or creating a pipeline raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import List, Optional
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libiridium_b200.so")
+CSRC = os.path.join(HERE, "csrc")
+
+FMT_CF32, FMT_CI16, FMT_CI8 = 0, 1, 2
+FMT_BY_NAME = {"cf32": FMT_CF32, "ci16": FMT_CI16, "ci8": FMT_CI8}
+ABI_VERSION = 1
+
+
+class Config(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("device", C.c_int32),
+                ("center_frequency", C.c_double), ("sample_rate", C.c_int32),
+                ("fft_size", C.c_int32), ("burst_width_hz", C.c_int32),
+                ("threshold_db", C.c_float), ("use_gardner", C.c_int32),
+                ("feed_block", C.c_int32), ("start_time_ns", C.c_uint64),
+                ("max_samples", C.c_uint64), ("h2d_chunk", C.c_int32),
+                ("reserved", C.c_int32 * 7)]
+
+
+class Frame(C.Structure):
+    _fields_ = [("id", C.c_uint64), ("timestamp", C.c_uint64), ("center_frequency", C.c_double),
+                ("direction", C.c_int32), ("magnitude", C.c_float), ("noise", C.c_float),
+                ("confidence", C.c_int32), ("level", C.c_float), ("n_symbols", C.c_int32),
+                ("n_payload_symbols", C.c_int32), ("n_bits", C.c_int32),
+                ("bits_offset", C.c_uint32)]
+
+
+class Burst(C.Structure):
+    _fields_ = [("id", C.c_uint64), ("start", C.c_uint64), ("stop", C.c_uint64),
+                ("last_active", C.c_uint64), ("center_bin", C.c_int32), ("magnitude", C.c_float),
+                ("noise", C.c_float), ("num_samples", C.c_uint64), ("emit_count", C.c_uint64),
+                ("downmix_status", C.c_int32), ("demod_ok", C.c_int32),
+                ("center_offset", C.c_float), ("dm_start", C.c_int32), ("uw_start", C.c_int32),
+                ("frame_len", C.c_int32), ("uw_start_frac", C.c_float),
+                ("dm_direction", C.c_int32), ("dec_len", C.c_int32)]
+
+
+class Results(C.Structure):
+    _fields_ = [("n_bursts", C.c_size_t), ("bursts", C.POINTER(Burst)),
+                ("n_frames", C.c_size_t), ("frames", C.POINTER(Frame)),
+                ("bits", C.POINTER(C.c_uint8)), ("llr", C.POINTER(C.c_float)),
+                ("n_bits_total", C.c_size_t), ("ms_total", C.c_float),
+                ("ms_detect_fft", C.c_float), ("ms_detect_scan", C.c_float),
+                ("ms_downmix_fir", C.c_float), ("ms_downmix_chain", C.c_float),
+                ("ms_demod", C.c_float), ("kernel_launches", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("alg_bytes", C.c_uint64)]
+
+
+def build_library(verbose: bool = False) -> str:
+    """Compile csrc/ for sm_100a with nvcc (cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", CSRC, "-j4"], capture_output=not verbose, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libiridium_b200.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no fallback path)")
+    L = C.CDLL(LIB_PATH)
+    L.ir_last_error.restype = C.c_char_p
+    L.ir_device_count.restype = C.c_int
+    L.ir_pipeline_create.restype = C.c_void_p
+    L.ir_pipeline_create.argtypes = [C.POINTER(Config)]
+    L.ir_pipeline_destroy.argtypes = [C.c_void_p]
+    L.ir_pipeline_reset.argtypes = [C.c_void_p]
+    L.ir_pipeline_run_host.restype = C.c_int
+    L.ir_pipeline_run_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    L.ir_pipeline_run_device.restype = C.c_int
+    L.ir_pipeline_run_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    L.ir_pipeline_results.restype = C.c_int
+    L.ir_pipeline_results.argtypes = [C.c_void_p, C.POINTER(Results)]
+    L.ir_pipeline_copy_mag.restype = C.c_int
+    L.ir_pipeline_copy_mag.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+    for name in ("ir_pipeline_copy_frame_samples", "ir_pipeline_copy_decimated",
+                 "ir_pipeline_copy_burst_samples"):
+        f = getattr(L, name)
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    L.ir_format_raw.restype = C.c_int
+    L.ir_format_raw.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_uint64, C.POINTER(Frame),
+                                C.c_void_p]
+    L.ir_host_alloc.restype = C.c_void_p
+    L.ir_host_alloc.argtypes = [C.c_size_t]
+    L.ir_host_free.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "ir_last_error", "ir_device_count", "ir_pipeline_create", "ir_pipeline_destroy",
+    "ir_pipeline_reset", "ir_pipeline_run_host", "ir_pipeline_run_device", "ir_pipeline_results",
+    "ir_pipeline_copy_mag", "ir_pipeline_copy_frame_samples", "ir_pipeline_copy_decimated",
+    "ir_pipeline_copy_burst_samples", "ir_format_raw", "ir_host_alloc", "ir_host_free",
+]
+
+
+class RunResult:
+    """Python view of ir_results_t (copies everything out of the library's buffers)."""
+
+    def __init__(self, r: Results):
+        self.stats = {k: getattr(r, k) for k in (
+            "ms_total", "ms_detect_fft", "ms_detect_scan", "ms_downmix_fir", "ms_downmix_chain",
+            "ms_demod", "kernel_launches", "h2d_bytes", "d2h_bytes", "alg_bytes")}
+        self.bursts: List[dict] = []
+        for i in range(r.n_bursts):
+            b = r.bursts[i]
+            self.bursts.append({k: getattr(b, k) for k, _ in Burst._fields_})
+        allbits = np.ctypeslib.as_array(r.bits, (max(r.n_bits_total, 1),)).copy() if r.n_bits_total else np.zeros(0, np.uint8)
+        allllr = np.ctypeslib.as_array(r.llr, (max(r.n_bits_total, 1),)).copy() if r.n_bits_total else np.zeros(0, np.float32)
+        self.frames: List[dict] = []
+        self._cframes = []
+        for i in range(r.n_frames):
+            f = r.frames[i]
+            d = {k: getattr(f, k) for k, _ in Frame._fields_}
+            d["bits"] = allbits[f.bits_offset:f.bits_offset + f.n_bits]
+            d["llr"] = allllr[f.bits_offset:f.bits_offset + f.n_bits]
+            self.frames.append(d)
+            cf = Frame()
+            C.memmove(C.byref(cf), C.byref(f), C.sizeof(Frame))
+            self._cframes.append(cf)
+
+    def raw_lines(self, file_info: str = "T", t0: Optional[int] = None) -> List[str]:
+        """RAW: lines as frame_output_print would emit them (frame_output.c:144-199)."""
+        L = load_library()
+        if not self.frames:
+            return []
+        if t0 is None:      # ensure_initialized: first printed frame's timestamp floored to 1 s
+            t0 = (self.frames[0]["timestamp"] // 1_000_000_000) * 1_000_000_000
+        out = []
+        buf = C.create_string_buffer(4096)
+        for cf, d in zip(self._cframes, self.frames):
+            bits = np.ascontiguousarray(d["bits"], np.uint8)
+            n = L.ir_format_raw(buf, 4096, file_info.encode(), t0, C.byref(cf),
+                                bits.ctypes.data_as(C.c_void_p))
+            if n < 0:
+                raise RuntimeError("ir_format_raw failed")
+            out.append(buf.value.decode())
+        return out
+
+
+class Pipeline:
+    """detect -> downmix -> demod on one B200 (ir_pipeline_t)."""
+
+    def __init__(self, sample_rate: int = 10_000_000, center_frequency: float = 1_622_000_000.0,
+                 device: int = 0, threshold_db: float = 16.0, use_gardner: bool = True,
+                 fft_size: int = 0, feed_block: int = 32768, start_time_ns: int = 0,
+                 h2d_chunk: int = 0):
+        self.L = load_library()
+        cfg = Config()
+        cfg.abi_version = ABI_VERSION
+        cfg.device = device
+        cfg.center_frequency = center_frequency
+        cfg.sample_rate = sample_rate
+        cfg.fft_size = fft_size
+        cfg.threshold_db = threshold_db
+        cfg.use_gardner = int(use_gardner)
+        cfg.feed_block = feed_block
+        cfg.start_time_ns = start_time_ns
+        cfg.h2d_chunk = h2d_chunk
+        self.cfg = cfg
+        self.h = self.L.ir_pipeline_create(C.byref(cfg))
+        if not self.h:
+            raise RuntimeError("ir_pipeline_create failed: " + self.L.ir_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ir_pipeline_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed: " + self.L.ir_last_error().decode())
+
+    @staticmethod
+    def _as_raw(iq: np.ndarray, fmt: str):
+        if fmt == "cf32":
+            a = np.ascontiguousarray(iq, np.complex64)
+            return a, a.shape[0]
+        if fmt == "ci16":
+            a = np.ascontiguousarray(iq, np.int16)
+            return a, a.shape[0] // 2
+        a = np.ascontiguousarray(iq, np.int8)
+        return a, a.shape[0] // 2
+
+    def run_host(self, iq: np.ndarray, fmt: str = "cf32") -> RunResult:
+        a, n = self._as_raw(iq, fmt)
+        self._check(self.L.ir_pipeline_run_host(self.h, a.ctypes.data_as(C.c_void_p), n,
+                                                FMT_BY_NAME[fmt]), "ir_pipeline_run_host")
+        return self.results()
+
+    def run_host_ptr(self, ptr: int, n_samples: int, fmt: str = "cf32") -> RunResult:
+        self._check(self.L.ir_pipeline_run_host(self.h, C.c_void_p(ptr), n_samples,
+                                                FMT_BY_NAME[fmt]), "ir_pipeline_run_host")
+        return self.results()
+
+    def run_device_ptr(self, dev_ptr: int, n_samples: int, fmt: str = "cf32") -> RunResult:
+        self._check(self.L.ir_pipeline_run_device(self.h, C.c_void_p(dev_ptr), n_samples,
+                                                  FMT_BY_NAME[fmt]), "ir_pipeline_run_device")
+        return self.results()
+
+    def results(self) -> RunResult:
+        r = Results()
+        self._check(self.L.ir_pipeline_results(self.h, C.byref(r)), "ir_pipeline_results")
+        return RunResult(r)
+
+    # ---- parity taps
+    def mag(self, frame0: int, n_frames: int, fft_size: int) -> np.ndarray:
+        out = np.empty((n_frames, fft_size), np.float32)
+        self._check(self.L.ir_pipeline_copy_mag(self.h, frame0, n_frames,
+                                                out.ctypes.data_as(C.c_void_p)), "ir_pipeline_copy_mag")
+        return out
+
+    def _copy_cf(self, fn, index: int, cap: int) -> Optional[np.ndarray]:
+        out = np.empty(cap, np.complex64)
+        n = fn(self.h, index, out.ctypes.data_as(C.c_void_p), cap)
+        return None if n < 0 else out[:n].copy()
+
+    def frame_samples(self, burst_index: int) -> Optional[np.ndarray]:
+        return self._copy_cf(self.L.ir_pipeline_copy_frame_samples, burst_index, 4440)
+
+    def decimated(self, burst_index: int, cap: int = 60000) -> Optional[np.ndarray]:
+        return self._copy_cf(self.L.ir_pipeline_copy_decimated, burst_index, cap)
+
+    def burst_samples(self, burst_index: int, cap: int = 2 * 1024 * 1024 + 16) -> Optional[np.ndarray]:
+        return self._copy_cf(self.L.ir_pipeline_copy_burst_samples, burst_index, cap)

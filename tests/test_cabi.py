@@ -1,0 +1,50 @@
+"""The C-ABI library loads and exports every symbol include/iridium_b200.h declares (no GPU needed)."""
+import importlib
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:ir_|gpu_burst_fft_|burst_detector_|burst_downmix_|qpsk_demod)\w*)\s*\(", txt)))
+
+
+def test_library_exports_declared_symbols():
+    pl = importlib.import_module("iridium-sniffer_b200.pipeline")
+    if not os.path.exists(pl.LIB_PATH):
+        pl.build_library()
+    L = pl.load_library()
+    names = []
+    for h in os.listdir(os.path.join(ROOT, "include")):
+        if h.endswith(".h"):
+            names += _declared(h)
+    assert "ir_pipeline_create" in names and "ir_pipeline_run_host" in names
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/ but not exported"
+    for n in pl.EXPORTED_SYMBOLS:
+        assert n in names
+
+
+def test_no_device_fails_loudly():
+    """Without a CUDA device create must fail with a message, never fall back."""
+    import ctypes as C
+    pl = importlib.import_module("iridium-sniffer_b200.pipeline")
+    L = pl.load_library()
+    if L.ir_device_count() > 0:
+        return
+    try:
+        pl.Pipeline()
+    except RuntimeError as e:
+        assert "no CUDA device" in str(e) or "CUDA" in str(e)
+    else:
+        raise AssertionError("Pipeline() succeeded without a GPU")
+
+
+def test_struct_sizes_match_header():
+    import ctypes as C
+    pl = importlib.import_module("iridium-sniffer_b200.pipeline")
+    assert C.sizeof(pl.Frame) == 64 and C.sizeof(pl.Config) == 88
+    assert C.sizeof(pl.Burst) == 104 and C.sizeof(pl.Results) == 112
