@@ -292,9 +292,12 @@ def run_reference(args):
 
     def one():
         t = time.perf_counter()
+        # stdout/stderr go to files: a pipe nobody drains would block the child after 64 KiB
+        fo, fe = open(path + ".out", "wb"), open(path + ".err", "wb")
         pr = subprocess.Popen([ob.REF_BIN, "-f", path, "--format=cf32", "-r", str(FS), "--file-info=ref"],
-                              stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+                              stdout=fo, stderr=fe)
         busy = {}
+        deadline = time.time() + 600
         while pr.poll() is None:          # per-thread CPU time: robust to the 1 s exit quantum (main.c:405,794)
             try:
                 for tid in os.listdir(f"/proc/{pr.pid}/task"):
@@ -303,8 +306,14 @@ def run_reference(args):
             except Exception:
                 pass
             time.sleep(0.02)
-        out = pr.stdout.read().decode()
+            if time.time() > deadline:
+                pr.kill()
+                break
+        pr.wait()
         wall = time.perf_counter() - t
+        fo.close(); fe.close()
+        out = open(path + ".out", "rb").read().decode(errors="replace")
+        os.remove(path + ".out"); os.remove(path + ".err")
         lines = [l for l in out.splitlines() if l.startswith("RAW:")]
         return wall, (max(busy.values()) if busy else wall), len(lines), len(busy)
 

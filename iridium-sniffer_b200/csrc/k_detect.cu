@@ -5,8 +5,11 @@
 //                 simd_avx2.c:145-218) and the OpenCL window/VkFFT/fftshift_magnitude trio
 //                 (opencl/burst_fft.c:53-80,333-370).
 //  k_detect_scan: the burst state machine over the magnitude frames, strictly in frame order
-//                 (burst_detect.c:426-632), one persistent CTA with the noise baseline in
-//                 registers.  Emits burst descriptors; IQ never moves.
+//                 (burst_detect.c:426-632), one persistent CTA.  Magnitude rows stream into a
+//                 shared-memory ring by TMA bulk copies (one 4N-byte cp.async.bulk per frame,
+//                 mbarrier completion) several frames ahead of the consumer; the noise baseline
+//                 of a thread's bins lives in registers for the whole launch.  Emits burst
+//                 descriptors; IQ never moves.
 #include "ir_device.cuh"
 #include "ir_internal.h"
 
@@ -79,17 +82,21 @@ cudaError_t launch_detect_fft(int L, int fmt, const void *iq, int64_t first_samp
 
 // =========================================================================== state machine
 // Thread t owns bins t + 1024*u (u < BPT): one ballot per u yields 32 consecutive bins of the
-// "above threshold" bitmap.  The running noise baseline of the owned bins lives in registers
-// for the whole launch; the 512-frame history stays in HBM/L2 and is touched only on quiet
+// "above threshold" bitmap.  The 512-frame history stays in HBM/L2 and is touched only on quiet
 // frames (burst_detect.c:438-454).
+//
+// Threshold test: rel = mag/base > thr is the reference's (IEEE divide, simd_avx2.c:239-257).
+// A bin can only pass if mag > base*thr*(1-1e-5), so that cheap product comparison screens
+// every bin and the exact divide runs only for the survivors.
 
 struct ScanShared {
+    unsigned long long bar[8];    // mbarriers of the magnitude ring
     uint32_t above[512];
     uint32_t free_mask[512];      // 1 = no active burst covers the bin (burst_mask != 0)
     uint32_t valid[512];          // peak search range minus the DC notch (burst_detect.c:537-542)
     ArgMax red[32];
     int n_act;
-    int flags;
+    int flags[2];
     int squelch_count;
     unsigned long long next_id;
     uint32_t n_gone, n_squelch, overflow;
@@ -98,7 +105,7 @@ struct ScanShared {
 
 __device__ __forceinline__ bool bit_at(const uint32_t *bm, int bin) { return (bm[bin >> 5] >> (bin & 31)) & 1u; }
 
-__device__ __forceinline__ void clear_range(uint32_t *bm, int lo, int hi) {   // inclusive, single thread
+__device__ __forceinline__ void clear_range(uint32_t *bm, int lo, int hi) {   // inclusive
     for (int w = lo >> 5; w <= (hi >> 5); w++) {
         int a = max(lo, w << 5) & 31, b = min(hi, (w << 5) + 31) & 31;
         uint32_t m = (b == 31 ? 0xffffffffu : ((1u << (b + 1)) - 1u)) & ~((1u << a) - 1u);
@@ -106,21 +113,42 @@ __device__ __forceinline__ void clear_range(uint32_t *bm, int lo, int hi) {   //
     }
 }
 
-template <int BPT>
+__device__ __forceinline__ void push_gone(ScanShared &S, GoneBurst *gone, uint32_t gone_cap,
+                                          const ActBurst &b, uint64_t index) {
+    if (S.n_gone < gone_cap) {
+        GoneBurst g;
+        g.id = b.id; g.start = b.start; g.stop = index; g.last_active = b.last_active;
+        g.center_bin = b.center_bin; g.peak_rel = b.peak_rel; g.base_at_create = b.base_at_create;
+        g.pad = 0;
+        gone[S.n_gone] = g;
+    } else {
+        S.overflow = 1;
+    }
+    S.n_gone++;
+}
+
+template <int BPT, int DEPTH>
 __global__ void __launch_bounds__(IR_SCAN_THREADS, 1)
 k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g,
               float *__restrict__ hist, const float *__restrict__ mag, int64_t n_frames,
               GoneBurst *__restrict__ gone, uint32_t gone_cap) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    ScanShared &S = *reinterpret_cast<ScanShared *>(smem_raw);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *ring = reinterpret_cast<float *>(smem_raw);                       // [DEPTH][N]
+    ScanShared &S = *reinterpret_cast<ScanShared *>(smem_raw + (size_t)DEPTH * c.N * sizeof(float));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = c.N, W = N >> 5;
     const float thr = c.thr;
+    const float thr_lo = thr * 0.99999f;
+    const uint32_t row_bytes = (uint32_t)N * sizeof(float);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(S.bar);
 
     // ---- load state
-    float base[BPT];
+    float base[BPT], lim[BPT];
 #pragma unroll
-    for (int u = 0; u < BPT; u++) base[u] = base_g[u * IR_SCAN_THREADS + tid];
+    for (int u = 0; u < BPT; u++) {
+        base[u] = base_g[u * IR_SCAN_THREADS + tid];
+        lim[u] = base[u] > 0.0f ? base[u] * thr_lo : __int_as_float(0x7f800000);
+    }
     int hist_idx = gs->hist_idx, primed = gs->primed;
     uint64_t index = gs->index;
     if (tid == 0) {
@@ -130,7 +158,9 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
         S.n_gone = gs->n_gone;
         S.n_squelch = gs->n_squelch;
         S.overflow = gs->overflow;
-        S.flags = 0;
+        S.flags[0] = 0; S.flags[1] = 0;
+        for (int d = 0; d < DEPTH; d++) mbar_init(&bars[d], 1);
+        fence_mbar_init();
     }
     for (int i = tid; i < IR_MAX_ACTIVE; i += blockDim.x)
         if (i < gs->n_act) S.act[i] = gs->act[i];
@@ -146,27 +176,47 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
         S.above[w] = 0;
     }
     __syncthreads();
+    if (tid == 0) {                                        // prime the ring
+        for (int d = 0; d < DEPTH && d < n_frames; d++) {
+            mbar_expect_tx(&bars[d], row_bytes);
+            tma_load_1d(ring + (size_t)d * N, mag + (size_t)d * N, row_bytes, &bars[d]);
+        }
+    }
     if (tid < S.n_act) clear_range(S.free_mask, max(S.act[tid].center_bin - c.half_bw, 0),
                                    min(S.act[tid].center_bin + c.half_bw, N - 1));
     __syncthreads();
 
-    auto baseline_push = [&](const float *m) {          // burst_detect.c:438-454, simd_avx2.c:221-236
+    auto baseline_push = [&](const float *m, const float *old) {   // burst_detect.c:438-454, simd_avx2.c:221-236
         float *h = hist + (size_t)hist_idx * N;
 #pragma unroll
         for (int u = 0; u < BPT; u++) {
             const int bin = u * IR_SCAN_THREADS + tid;
-            float old = primed ? h[bin] : 0.0f;          // untouched history is zero (calloc / reset)
-            float v = base[u] - old;
+            float v = base[u] - old[u];
             base[u] = v + m[u];
+            lim[u] = base[u] > 0.0f ? base[u] * thr_lo : __int_as_float(0x7f800000);
             h[bin] = m[u];
         }
         if (++hist_idx == c.hist_size) { primed = 1; hist_idx = 0; }
     };
+    auto load_old = [&](float *old) {                      // untouched history is zero (calloc / reset)
+        const float *h = hist + (size_t)hist_idx * N;
+#pragma unroll
+        for (int u = 0; u < BPT; u++) old[u] = primed ? h[u * IR_SCAN_THREADS + tid] : 0.0f;
+    };
 
     for (int64_t f = 0; f < n_frames; f++, index += (uint64_t)N) {
+        const int slot = (int)(f % DEPTH);
+        const float *row = ring + (size_t)slot * N;
+        // a frame that starts with no active burst will most likely end in a baseline update:
+        // get the history row moving before waiting for the magnitudes
+        const bool expect_quiet = S.n_act == 0;
+        float old[BPT];
+        if (expect_quiet) load_old(old);
+        mbar_wait(&bars[slot], (uint32_t)((f / DEPTH) & 1));
         float m[BPT];
 #pragma unroll
-        for (int u = 0; u < BPT; u++) m[u] = mag[f * N + u * IR_SCAN_THREADS + tid];
+        for (int u = 0; u < BPT; u++) m[u] = row[u * IR_SCAN_THREADS + tid];
+        bool old_valid = expect_quiet;
 
         if (primed) {
             float rel[BPT];
@@ -174,14 +224,24 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
             uint32_t any = 0;
 #pragma unroll
             for (int u = 0; u < BPT; u++) {
-                rel[u] = base[u] > 0.0f ? m[u] / base[u] : 0.0f;      // simd_avx2.c:239-257
-                ab[u] = rel[u] > thr;
+                ab[u] = false;
+                rel[u] = 0.0f;
+                if (m[u] > lim[u]) {
+                    rel[u] = m[u] / base[u];                  // base > 0 here (lim is +inf otherwise)
+                    ab[u] = rel[u] > thr;
+                }
                 uint32_t bal = __ballot_sync(0xffffffffu, ab[u]);
                 if (lane == 0) S.above[u * 32 + warp] = bal;
                 any |= bal;
             }
-            if (tid == 0) S.flags = 0;
+            const int par = (int)(f & 1);
+            if (tid == 0) S.flags[par ^ 1] = 0;
             const int any_above = __syncthreads_or(any != 0);
+            // every thread has consumed its part of `row`: refill the slot DEPTH frames ahead
+            if (tid == 0 && f + DEPTH < n_frames) {
+                mbar_expect_tx(&bars[slot], row_bytes);
+                tma_load_1d(ring + (size_t)slot * N, mag + (size_t)(f + DEPTH) * N, row_bytes, &bars[slot]);
+            }
             int n_act = S.n_act;
             if (any_above || n_act > 0) {
                 int fl = 0;
@@ -206,9 +266,9 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
                     cand[u] = ab[u] && bit_at(S.free_mask, bin) && bit_at(S.valid, bin);
                     if (cand[u]) fl |= 1;
                 }
-                if (fl) atomicOr(&S.flags, fl);
+                if (fl) atomicOr(&S.flags[par], fl);
                 __syncthreads();
-                const int flags = S.flags;
+                const int flags = S.flags[par];
                 if (flags & 2) {
                     // delete_gone_bursts (:490-518): order-preserving, one thread
                     if (tid == 0) {
@@ -217,27 +277,20 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
                             ActBurst b = S.act[i];
                             bool too_long = c.max_burst_len > 0 &&
                                             b.last_active - b.start > (uint64_t)c.max_burst_len;
-                            if ((b.last_active + (uint64_t)c.post_len <= index) || too_long) {
-                                if (S.n_gone < gone_cap) {
-                                    GoneBurst g;
-                                    g.id = b.id; g.start = b.start; g.stop = index;
-                                    g.last_active = b.last_active; g.center_bin = b.center_bin;
-                                    g.peak_rel = b.peak_rel; g.base_at_create = b.base_at_create;
-                                    g.pad = 0;
-                                    gone[S.n_gone] = g;
-                                } else {
-                                    S.overflow = 1;
-                                }
-                                S.n_gone++;
-                            } else {
+                            if ((b.last_active + (uint64_t)c.post_len <= index) || too_long)
+                                push_gone(S, gone, gone_cap, b, index);
+                            else
                                 S.act[k++] = b;
-                            }
                         }
                         S.n_act = k;
                     }
                     __syncthreads();
                     n_act = S.n_act;
-                    if (flags & 4) baseline_push(m);                    // update_filters_post(d, 1)
+                    if (flags & 4) {                                    // update_filters_post(d, 1)
+                        load_old(old);
+                        baseline_push(m, old);
+                        old_valid = false;
+                    }
                     // update_burst_mask (:482-486)
                     for (int w = tid; w < W; w += blockDim.x) S.free_mask[w] = 0xffffffffu;
                     __syncthreads();
@@ -256,8 +309,8 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
                         best = block_argmax(best, S.red);
                         if (best.v < 0.0f) break;
                         const int bin = best.i;
-                        const int slot = S.n_act;
-                        if (slot < IR_MAX_ACTIVE) {
+                        const int slot_b = S.n_act;
+                        if (slot_b < IR_MAX_ACTIVE) {
                             if (tid == (bin & (IR_SCAN_THREADS - 1))) {
                                 ActBurst nb;
                                 nb.id = S.next_id;
@@ -270,7 +323,7 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
                                 for (int u = 0; u < BPT; u++) if (u == bin / IR_SCAN_THREADS) bs = base[u];
                                 nb.base_at_create = bs;
                                 nb.pad = 0;
-                                S.act[slot] = nb;
+                                S.act[slot_b] = nb;
                                 clear_range(S.free_mask, max(bin - c.half_bw, 0), min(bin + c.half_bw, N - 1));
                             }
                         }
@@ -282,32 +335,20 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
                         }
                         __syncthreads();
                         if (tid == 0) {
-                            if (slot < IR_MAX_ACTIVE) { S.n_act = slot + 1; S.next_id += 10; }
-                            else { S.overflow = 1; S.next_id += 10; }
+                            if (slot_b < IR_MAX_ACTIVE) S.n_act = slot_b + 1; else S.overflow = 1;
+                            S.next_id += 10;
                         }
                         __syncthreads();
                     }
                 }
                 // squelch (:593-631)
                 n_act = S.n_act;
-                bool reset_noise = false;
                 if (c.max_bursts > 0 && n_act > c.max_bursts) {
+                    __syncthreads();
                     if (tid == 0) {
                         for (int i = 0; i < n_act; i++) {
                             const ActBurst &b = S.act[i];
-                            if (b.start != index - (uint64_t)c.pre_len) {
-                                if (S.n_gone < gone_cap) {
-                                    GoneBurst g;
-                                    g.id = b.id; g.start = b.start; g.stop = index;
-                                    g.last_active = b.last_active; g.center_bin = b.center_bin;
-                                    g.peak_rel = b.peak_rel; g.base_at_create = b.base_at_create;
-                                    g.pad = 0;
-                                    gone[S.n_gone] = g;
-                                } else {
-                                    S.overflow = 1;
-                                }
-                                S.n_gone++;
-                            }
+                            if (b.start != index - (uint64_t)c.pre_len) push_gone(S, gone, gone_cap, b, index);
                         }
                         S.n_act = 0;
                         S.n_squelch++;
@@ -315,26 +356,37 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
                     }
                     for (int w = tid; w < W; w += blockDim.x) S.free_mask[w] = 0xffffffffu;
                     __syncthreads();
-                    if (S.squelch_count >= 10) reset_noise = true;
+                    const bool reset_noise = S.squelch_count >= 10;
                     __syncthreads();
                     if (reset_noise) {
                         hist_idx = 0; primed = 0;
 #pragma unroll
-                        for (int u = 0; u < BPT; u++) base[u] = 0.0f;
+                        for (int u = 0; u < BPT; u++) { base[u] = 0.0f; lim[u] = __int_as_float(0x7f800000); }
                         if (tid == 0) S.squelch_count = 0;
+                        old_valid = false;
                     }
+                    __syncthreads();
+                } else if (flags != 0) {
+                    if (tid == 0 && S.squelch_count > 0) S.squelch_count--;
+                    __syncthreads();              // S.n_act changed in this frame: publish before the read below
                 } else if (tid == 0 && S.squelch_count > 0) {
                     S.squelch_count--;
                 }
-                __syncthreads();
             } else if (tid == 0 && S.squelch_count > 0) {
                 S.squelch_count--;
             }
+        } else {
+            __syncthreads();                      // all threads done with `row`
+            if (tid == 0 && f + DEPTH < n_frames) {
+                mbar_expect_tx(&bars[slot], row_bytes);
+                tma_load_1d(ring + (size_t)slot * N, mag + (size_t)(f + DEPTH) * N, row_bytes, &bars[slot]);
+            }
         }
         // update_filters_post(d, 0) (:438-454)
-        if (S.n_act == 0) baseline_push(m);
-        // S.n_act is only written inside barrier-separated sections above; the next frame's
-        // first barrier (__syncthreads_or) orders this read against later writes.
+        if (S.n_act == 0) {
+            if (!old_valid) load_old(old);
+            baseline_push(m, old);
+        }
     }
 
     // ---- store state
@@ -349,29 +401,31 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
     }
 }
 
+template <int BPT, int DEPTH>
+static cudaError_t launch_scan_t(const DetConfig &c, DetState *state, float *base, float *hist,
+                                 const float *mag, int64_t n_frames, GoneBurst *gone,
+                                 uint32_t gone_cap, cudaStream_t st) {
+    const size_t smem = (size_t)DEPTH * c.N * sizeof(float) + sizeof(ScanShared);
+    cudaError_t e = cudaFuncSetAttribute(k_detect_scan<BPT, DEPTH>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_detect_scan<BPT, DEPTH><<<1, IR_SCAN_THREADS, smem, st>>>(c, state, base, hist, mag, n_frames,
+                                                                gone, gone_cap);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_detect_scan(const DetConfig &c, DetState *state, float *base, float *hist,
                                const float *mag, int64_t n_frames, GoneBurst *gone,
                                uint32_t gone_cap, cudaStream_t st) {
     if (n_frames <= 0) return cudaSuccess;
-    const size_t smem = sizeof(ScanShared);
-#define IR_LAUNCH_SCAN(B)                                                                         \
-    do {                                                                                          \
-        cudaError_t e = cudaFuncSetAttribute(k_detect_scan<B>,                                    \
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) return e;                                                           \
-        k_detect_scan<B><<<1, IR_SCAN_THREADS, smem, st>>>(c, state, base, hist, mag, n_frames,   \
-                                                           gone, gone_cap);                       \
-    } while (0)
     switch (c.N / IR_SCAN_THREADS) {
-    case 1: IR_LAUNCH_SCAN(1); break;
-    case 2: IR_LAUNCH_SCAN(2); break;
-    case 4: IR_LAUNCH_SCAN(4); break;
-    case 8: IR_LAUNCH_SCAN(8); break;
-    case 16: IR_LAUNCH_SCAN(16); break;
+    case 1: return launch_scan_t<1, 8>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
+    case 2: return launch_scan_t<2, 8>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
+    case 4: return launch_scan_t<4, 8>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
+    case 8: return launch_scan_t<8, 5>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
+    case 16: return launch_scan_t<16, 2>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
     default: return cudaErrorInvalidValue;
     }
-#undef IR_LAUNCH_SCAN
-    return cudaGetLastError();
 }
 
 }  // namespace ir

@@ -123,22 +123,32 @@ k_fir(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const BurstPa
 
     // A: stage the raw samples.  Positions the detector had not yet received when it emitted
     // the burst read the ring slot's previous content: one lap earlier, or zero.
+    // cf32 rows go global -> shared asynchronously (LDGSTS, 8 B each: burst starts are only
+    // guaranteed 8-byte aligned inside the pitched layout), so all ~86 copies of a thread are in
+    // flight at once instead of one L2 round trip per element.
+#pragma unroll 4
     for (int e = tid; e < fir_in_max<DEC>(); e += blockDim.x) {
-        float2 v = make_float2(0.0f, 0.0f);
+        float2 *dst = &s[fir_pi<DEC>(e)];
+        bool filled = false;
         if (e < n_in && e0 + e < P.n) {
             int64_t q = P.start + e0 + e;
             if (q >= P.emit_count) q -= (int64_t)ring;
-            if (q >= 0 && q < n_total) v = load_sample<FMT>(iq, q);
+            if (q >= 0 && q < n_total) {
+                if (FMT == IR_FMT_CF32) cp_async_8(dst, reinterpret_cast<const float2 *>(iq) + q);
+                else *dst = load_sample<FMT>(iq, q);
+                filled = true;
+            }
         }
-        s[fir_pi<DEC>(e)] = v;
+        if (!filled) *dst = make_float2(0.0f, 0.0f);
     }
+    if (FMT == IR_FMT_CF32) cp_async_wait_all();
     __syncthreads();
     // B: coarse frequency shift in place, 16 samples per checkpoint (rotator.h:36-42)
     {
         const int nseg = (n_in + IR_ROT_G - 1) / IR_ROT_G;
         for (int seg = tid; seg < nseg; seg += blockDim.x) {
             float2 ph = P.rot_table[(e0 >> 4) + seg];
-#pragma unroll 4
+#pragma unroll
             for (int i = 0; i < IR_ROT_G; i++) {
                 const int e = seg * IR_ROT_G + i;
                 if (e < n_in) {
