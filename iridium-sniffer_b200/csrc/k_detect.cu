@@ -127,8 +127,8 @@ __device__ __forceinline__ void push_gone(ScanShared &S, GoneBurst *gone, uint32
     S.n_gone++;
 }
 
-template <int BPT, int DEPTH>
-__global__ void __launch_bounds__(IR_SCAN_THREADS, 1)
+template <int BPT, int NT, int DEPTH>
+__global__ void __launch_bounds__(NT, 1)
 k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g,
               float *__restrict__ hist, const float *__restrict__ mag, int64_t n_frames,
               GoneBurst *__restrict__ gone, uint32_t gone_cap) {
@@ -146,7 +146,7 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
     float base[BPT], lim[BPT];
 #pragma unroll
     for (int u = 0; u < BPT; u++) {
-        base[u] = base_g[u * IR_SCAN_THREADS + tid];
+        base[u] = base_g[u * NT + tid];
         lim[u] = base[u] > 0.0f ? base[u] * thr_lo : __int_as_float(0x7f800000);
     }
     int hist_idx = gs->hist_idx, primed = gs->primed;
@@ -186,11 +186,11 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
                                    min(S.act[tid].center_bin + c.half_bw, N - 1));
     __syncthreads();
 
-    auto baseline_push = [&](const float *m, const float *old) {   // burst_detect.c:438-454, simd_avx2.c:221-236
+    auto baseline_push = [&](const float (&m)[BPT], const float (&old)[BPT]) {   // burst_detect.c:438-454, simd_avx2.c:221-236
         float *h = hist + (size_t)hist_idx * N;
 #pragma unroll
         for (int u = 0; u < BPT; u++) {
-            const int bin = u * IR_SCAN_THREADS + tid;
+            const int bin = u * NT + tid;
             float v = base[u] - old[u];
             base[u] = v + m[u];
             lim[u] = base[u] > 0.0f ? base[u] * thr_lo : __int_as_float(0x7f800000);
@@ -198,10 +198,10 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
         }
         if (++hist_idx == c.hist_size) { primed = 1; hist_idx = 0; }
     };
-    auto load_old = [&](float *old) {                      // untouched history is zero (calloc / reset)
+    auto load_old = [&](float (&old)[BPT]) {               // untouched history is zero (calloc / reset)
         const float *h = hist + (size_t)hist_idx * N;
 #pragma unroll
-        for (int u = 0; u < BPT; u++) old[u] = primed ? h[u * IR_SCAN_THREADS + tid] : 0.0f;
+        for (int u = 0; u < BPT; u++) old[u] = primed ? h[u * NT + tid] : 0.0f;
     };
 
     for (int64_t f = 0; f < n_frames; f++, index += (uint64_t)N) {
@@ -215,24 +215,29 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
         mbar_wait(&bars[slot], (uint32_t)((f / DEPTH) & 1));
         float m[BPT];
 #pragma unroll
-        for (int u = 0; u < BPT; u++) m[u] = row[u * IR_SCAN_THREADS + tid];
+        for (int u = 0; u < BPT; u++) m[u] = row[u * NT + tid];
         bool old_valid = expect_quiet;
 
         if (primed) {
-            float rel[BPT];
-            bool ab[BPT];
+            // bal[u]: the 32 "above threshold" bits of bins u*1024 + warp*32 .. +31 (warp-uniform)
+            uint32_t bal[BPT];
             uint32_t any = 0;
 #pragma unroll
             for (int u = 0; u < BPT; u++) {
-                ab[u] = false;
-                rel[u] = 0.0f;
-                if (m[u] > lim[u]) {
-                    rel[u] = m[u] / base[u];                  // base > 0 here (lim is +inf otherwise)
-                    ab[u] = rel[u] > thr;
+                const bool pass = m[u] > lim[u];
+                uint32_t b = __ballot_sync(0xffffffffu, pass);
+                if (b) {                                      // rare: run the reference's exact test
+                    const bool ab = pass && (m[u] / base[u] > thr);   // base > 0 (lim is +inf otherwise)
+                    b = __ballot_sync(0xffffffffu, ab);
                 }
-                uint32_t bal = __ballot_sync(0xffffffffu, ab[u]);
-                if (lane == 0) S.above[u * 32 + warp] = bal;
-                any |= bal;
+                bal[u] = b;
+                any |= b;
+            }
+            if (lane < BPT) {
+                uint32_t w = 0;
+#pragma unroll
+                for (int u = 0; u < BPT; u++) if (lane == u) w = bal[u];
+                S.above[lane * (NT / 32) + warp] = w;
             }
             const int par = (int)(f & 1);
             if (tid == 0) S.flags[par ^ 1] = 0;
@@ -258,14 +263,17 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
                     if (done) fl |= 2;
                     if (too_long) fl |= 4;
                 }
-                // peaks after masking with the mask left by the previous frame (:522-548)
-                bool cand[BPT];
+                // peaks after masking with the mask left by the previous frame (:522-548),
+                // one 32-bin word at a time (warp-uniform)
+                uint32_t cw[BPT];
+                uint32_t anyc = 0;
 #pragma unroll
                 for (int u = 0; u < BPT; u++) {
-                    const int bin = u * IR_SCAN_THREADS + tid;
-                    cand[u] = ab[u] && bit_at(S.free_mask, bin) && bit_at(S.valid, bin);
-                    if (cand[u]) fl |= 1;
+                    cw[u] = 0;
+                    if (bal[u]) cw[u] = bal[u] & S.free_mask[u * (NT / 32) + warp] & S.valid[u * (NT / 32) + warp];
+                    anyc |= cw[u];
                 }
+                if (anyc && lane == 0) fl |= 1;
                 if (fl) atomicOr(&S.flags[par], fl);
                 __syncthreads();
                 const int flags = S.flags[par];
@@ -301,17 +309,20 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
                 }
                 if (flags & 1) {
                     // create_new_bursts (:556-591): strongest remaining peak first
+                    bool cand[BPT];
+#pragma unroll
+                    for (int u = 0; u < BPT; u++) cand[u] = (cw[u] >> lane) & 1u;
                     for (;;) {
                         ArgMax best{-1.0f, 0x7fffffff};
 #pragma unroll
                         for (int u = 0; u < BPT; u++)
-                            if (cand[u]) best = argmax_pick(best, ArgMax{rel[u], u * IR_SCAN_THREADS + tid});
+                            if (cand[u]) best = argmax_pick(best, ArgMax{m[u] / base[u], u * NT + tid});
                         best = block_argmax(best, S.red);
                         if (best.v < 0.0f) break;
                         const int bin = best.i;
                         const int slot_b = S.n_act;
                         if (slot_b < IR_MAX_ACTIVE) {
-                            if (tid == (bin & (IR_SCAN_THREADS - 1))) {
+                            if (tid == (bin & (NT - 1))) {
                                 ActBurst nb;
                                 nb.id = S.next_id;
                                 nb.start = index - (uint64_t)c.pre_len;
@@ -320,7 +331,7 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
                                 nb.peak_rel = best.v;
                                 float bs = 0.0f;
 #pragma unroll
-                                for (int u = 0; u < BPT; u++) if (u == bin / IR_SCAN_THREADS) bs = base[u];
+                                for (int u = 0; u < BPT; u++) if (u == bin / NT) bs = base[u];
                                 nb.base_at_create = bs;
                                 nb.pad = 0;
                                 S.act[slot_b] = nb;
@@ -330,7 +341,7 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
                         const int lo = bin - c.half_bw, hi = bin + c.half_bw;
 #pragma unroll
                         for (int u = 0; u < BPT; u++) {
-                            const int b = u * IR_SCAN_THREADS + tid;
+                            const int b = u * NT + tid;
                             if (b >= lo && b <= hi) cand[u] = false;
                         }
                         __syncthreads();
@@ -392,7 +403,7 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
     // ---- store state
     __syncthreads();
 #pragma unroll
-    for (int u = 0; u < BPT; u++) base_g[u * IR_SCAN_THREADS + tid] = base[u];
+    for (int u = 0; u < BPT; u++) base_g[u * NT + tid] = base[u];
     for (int i = tid; i < S.n_act; i += blockDim.x) gs->act[i] = S.act[i];
     if (tid == 0) {
         gs->hist_idx = hist_idx; gs->primed = primed; gs->n_act = S.n_act;
@@ -401,29 +412,31 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
     }
 }
 
-template <int BPT, int DEPTH>
+template <int BPT, int NT, int DEPTH>
 static cudaError_t launch_scan_t(const DetConfig &c, DetState *state, float *base, float *hist,
                                  const float *mag, int64_t n_frames, GoneBurst *gone,
                                  uint32_t gone_cap, cudaStream_t st) {
     const size_t smem = (size_t)DEPTH * c.N * sizeof(float) + sizeof(ScanShared);
-    cudaError_t e = cudaFuncSetAttribute(k_detect_scan<BPT, DEPTH>,
+    cudaError_t e = cudaFuncSetAttribute(k_detect_scan<BPT, NT, DEPTH>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_detect_scan<BPT, DEPTH><<<1, IR_SCAN_THREADS, smem, st>>>(c, state, base, hist, mag, n_frames,
-                                                                gone, gone_cap);
+    k_detect_scan<BPT, NT, DEPTH><<<1, NT, smem, st>>>(c, state, base, hist, mag, n_frames,
+                                                       gone, gone_cap);
     return cudaGetLastError();
 }
 
+// Threads x bins-per-thread = N.  512 threads keep every per-bin value in registers (no
+// spills at <=128 registers); the 16384-point detector needs 1024 threads.
 cudaError_t launch_detect_scan(const DetConfig &c, DetState *state, float *base, float *hist,
                                const float *mag, int64_t n_frames, GoneBurst *gone,
                                uint32_t gone_cap, cudaStream_t st) {
     if (n_frames <= 0) return cudaSuccess;
-    switch (c.N / IR_SCAN_THREADS) {
-    case 1: return launch_scan_t<1, 8>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
-    case 2: return launch_scan_t<2, 8>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
-    case 4: return launch_scan_t<4, 8>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
-    case 8: return launch_scan_t<8, 5>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
-    case 16: return launch_scan_t<16, 2>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
+    switch (c.N) {
+    case 1024: return launch_scan_t<2, 512, 8>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
+    case 2048: return launch_scan_t<4, 512, 8>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
+    case 4096: return launch_scan_t<8, 512, 8>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
+    case 8192: return launch_scan_t<16, 512, 5>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
+    case 16384: return launch_scan_t<16, 1024, 2>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
     default: return cudaErrorInvalidValue;
     }
 }
