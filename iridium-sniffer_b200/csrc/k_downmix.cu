@@ -71,29 +71,57 @@ cudaError_t launch_rot_tables(const float2 *incr, float2 *const *tables, const i
 
 // ============================================================== rotate + FIR + decimate
 template <int DEC> __host__ __device__ constexpr int fir_in_max() { return (IR_FIR_TILE - 1) * DEC + IR_INPUT_NTAPS; }
-template <int DEC> __host__ __device__ constexpr int fir_pitch_elems() {
-    return fir_in_max<DEC>() + fir_in_max<DEC>() / (IR_FIR_R * DEC) + 2;
-}
-template <int DEC> __device__ __forceinline__ int fir_pi(int e) { return e + e / (IR_FIR_R * DEC); }
+// Shared-memory index of burst sample e.  Two access patterns must both be conflict-free for
+// 8-byte accesses: the rotate phase (lane stride 16 samples) and the FIR phase (lane stride
+// R*DEC samples).  e + e/16 + e/(R*DEC) gives lane strides of 17 and R*DEC*17/16+1 (341 for
+// DEC=40, 409 for DEC=48), both odd.
+template <int DEC> __host__ __device__ constexpr int fir_pi_c(int e) { return e + (e >> 4) + e / (IR_FIR_R * DEC); }
+template <int DEC> __device__ __forceinline__ int fir_pi(int e) { return e + (e >> 4) + e / (IR_FIR_R * DEC); }
+template <int DEC> __host__ __device__ constexpr int fir_pitch_elems() { return fir_pi_c<DEC>(fir_in_max<DEC>()) + 4; }
 
-template <int J, int DEC>
-__device__ __forceinline__ void fir_chains(const float2 *__restrict__ sl, float2 (&acc)[IR_FIR_R]) {
-    constexpr int BODY = IR_INPUT_NTAPS / 4;          // 200 four-tap groups
-    constexpr int D4 = DEC / 4;                       // step shift between neighbouring outputs
-    constexpr int NST = BODY + D4 * (IR_FIR_R - 1);
+// Zero-padded tap table in shared memory: hp[IR_FIR_HPAD + k] = taps[k] for 0 <= k < 800, else 0.
+#define IR_FIR_HPAD 0
+template <int DEC> __host__ __device__ constexpr int fir_nit() { return (IR_INPUT_NTAPS / 4 + DEC / 4 - 1) / (DEC / 4) + IR_FIR_R - 1; }
+template <int DEC> __host__ __device__ constexpr int fir_hp_elems() { return IR_FIR_HPAD + DEC * ((fir_nit<DEC>() + 7) / 8 * 8) + 8; }
+
+// One lane accumulates chain J (taps J, J+4, J+8, ... in ascending order, one FMA each --
+// simd_avx2.c:76-86) of 8 consecutive outputs.  Output i lags output 0 by DEC/4 steps, so the
+// tap a sample meets in chain i is the one chain i-1 used DEC/4 steps earlier: taps rotate
+// through 8 register sets of DEC/4 values, each loaded sample feeds 16 FMAs, and the whole
+// loop is ~1.5 K instructions shared by all warps (J is a run-time offset).  Before a chain
+// starts and after it ends it sees zero taps: fma(0, x, acc) leaves acc unchanged.
+template <int DEC>
+__device__ __forceinline__ void fir_chains(const float2 *__restrict__ sp, const float *__restrict__ hp,
+                                           float2 (&acc)[IR_FIR_R]) {
+    constexpr int D4 = DEC / 4;
+    constexpr int NIT = fir_nit<DEC>();
+    constexpr int ROW = IR_FIR_R * DEC + IR_FIR_R * DEC / 16 + 1;      // fir_pi advance per 8 iterations
+    float G[8][D4];
 #pragma unroll
-    for (int tau = 0; tau < NST; tau++) {
-        const int cidx = 4 * tau + J;
-        const float2 x = sl[cidx + cidx / (IR_FIR_R * DEC)];
+    for (int a = 0; a < 8; a++)
 #pragma unroll
-        for (int i = 0; i < IR_FIR_R; i++) {
-            const int m = tau - D4 * i;
-            if (m >= 0 && m < BODY) {
-                const float h = c_in_taps[4 * m + J];
-                acc[i].x = fmaf(h, x.x, acc[i].x);
-                acc[i].y = fmaf(h, x.y, acc[i].y);
+        for (int r = 0; r < D4; r++) G[a][r] = 0.0f;
+    for (int T = 0; T < (NIT + 7) / 8; T++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (8 * T + u < NIT) {                                     // warp-uniform
+#pragma unroll
+                for (int r = 0; r < D4; r++) G[u][r] = hp[DEC * u + 4 * r];
+#pragma unroll
+                for (int r = 0; r < D4; r++) {
+                    const int ql = D4 * u + r;
+                    const float2 x = sp[4 * ql + (ql >> 2)];
+#pragma unroll
+                    for (int i = 0; i < IR_FIR_R; i++) {
+                        const float h = G[(u - i + 8) & 7][r];
+                        acc[i].x = fmaf(h, x.x, acc[i].x);
+                        acc[i].y = fmaf(h, x.y, acc[i].y);
+                    }
+                }
             }
         }
+        sp += ROW;
+        hp += 8 * DEC;
     }
 }
 
@@ -106,7 +134,12 @@ k_fir(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const BurstPa
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *s = reinterpret_cast<float2 *>(smem_raw);
     float2 *part = s + fir_pitch_elems<DEC>();            // [4][IR_FIR_TILE]
+    float *hp = reinterpret_cast<float *>(part + 4 * IR_FIR_TILE);   // zero-padded body taps
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = tid; k < fir_hp_elems<DEC>(); k += blockDim.x) {
+        const int kk = k - IR_FIR_HPAD;
+        hp[k] = (kk >= 0 && kk < (IR_INPUT_NTAPS / 4) * 4) ? c_in_taps[kk] : 0.0f;
+    }
 
     // which burst owns this tile
     int lo = 0, hi = n_bursts;
@@ -165,13 +198,8 @@ k_fir(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const BurstPa
         float2 acc[IR_FIR_R];
 #pragma unroll
         for (int i = 0; i < IR_FIR_R; i++) acc[i] = make_float2(0.0f, 0.0f);
-        const float2 *sl = s + (IR_FIR_R * DEC + 1) * lane;
-        switch (warp) {
-        case 0: fir_chains<0, DEC>(sl, acc); break;
-        case 1: fir_chains<1, DEC>(sl, acc); break;
-        case 2: fir_chains<2, DEC>(sl, acc); break;
-        default: fir_chains<3, DEC>(sl, acc); break;
-        }
+        constexpr int ROW = IR_FIR_R * DEC + IR_FIR_R * DEC / 16 + 1;
+        fir_chains<DEC>(s + ROW * lane + warp, hp + IR_FIR_HPAD + warp, acc);     // chain J = warp
 #pragma unroll
         for (int i = 0; i < IR_FIR_R; i++) part[warp * IR_FIR_TILE + IR_FIR_R * lane + i] = acc[i];
     }
@@ -196,7 +224,7 @@ template <int FMT, int DEC>
 static cudaError_t launch_fir_t(const void *iq, int64_t n_total, uint64_t ring, const BurstParam *bp,
                                 const int *tile_start, int n_bursts, int n_tiles, float2 *dec_out,
                                 cudaStream_t st) {
-    const size_t smem = sizeof(float2) * (fir_pitch_elems<DEC>() + 4 * IR_FIR_TILE);
+    const size_t smem = sizeof(float2) * (fir_pitch_elems<DEC>() + 4 * IR_FIR_TILE) + sizeof(float) * fir_hp_elems<DEC>();
     cudaError_t e = cudaFuncSetAttribute(k_fir<FMT, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k_fir<FMT, DEC><<<n_tiles, 128, smem, st>>>(iq, n_total, ring, bp, tile_start, n_bursts, dec_out);
