@@ -204,40 +204,51 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
         for (int u = 0; u < BPT; u++) old[u] = primed ? h[u * NT + tid] : 0.0f;
     };
 
+    int slot = 0;
+    uint32_t slot_phase = 0;
+    bool warp_had_bits = true;          // this warp's words of S.above may be non-zero
     for (int64_t f = 0; f < n_frames; f++, index += (uint64_t)N) {
-        const int slot = (int)(f % DEPTH);
         const float *row = ring + (size_t)slot * N;
         // a frame that starts with no active burst will most likely end in a baseline update:
         // get the history row moving before waiting for the magnitudes
         const bool expect_quiet = S.n_act == 0;
         float old[BPT];
         if (expect_quiet) load_old(old);
-        mbar_wait(&bars[slot], (uint32_t)((f / DEPTH) & 1));
+        mbar_wait(&bars[slot], slot_phase);
         float m[BPT];
 #pragma unroll
         for (int u = 0; u < BPT; u++) m[u] = row[u * NT + tid];
         bool old_valid = expect_quiet;
 
         if (primed) {
-            // bal[u]: the 32 "above threshold" bits of bins u*1024 + warp*32 .. +31 (warp-uniform)
+            // Screen all of the thread's bins with one predicate and the warp with one vote;
+            // only warps that see a candidate build their 32-bin words bal[u] (bins
+            // u*NT + warp*32 .. +31) with the reference's exact divide test.
             uint32_t bal[BPT];
+            bool pass_any = false;
+#pragma unroll
+            for (int u = 0; u < BPT; u++) pass_any = pass_any || (m[u] > lim[u]);
             uint32_t any = 0;
+            const bool warp_pass = __any_sync(0xffffffffu, pass_any);
+            if (warp_pass) {
 #pragma unroll
-            for (int u = 0; u < BPT; u++) {
-                const bool pass = m[u] > lim[u];
-                uint32_t b = __ballot_sync(0xffffffffu, pass);
-                if (b) {                                      // rare: run the reference's exact test
-                    const bool ab = pass && (m[u] / base[u] > thr);   // base > 0 (lim is +inf otherwise)
-                    b = __ballot_sync(0xffffffffu, ab);
+                for (int u = 0; u < BPT; u++) {
+                    const bool ab = (m[u] > lim[u]) && (m[u] / base[u] > thr);   // base > 0 (lim is +inf otherwise)
+                    bal[u] = __ballot_sync(0xffffffffu, ab);
+                    any |= bal[u];
                 }
-                bal[u] = b;
-                any |= b;
-            }
-            if (lane < BPT) {
-                uint32_t w = 0;
+            } else {
 #pragma unroll
-                for (int u = 0; u < BPT; u++) if (lane == u) w = bal[u];
-                S.above[lane * (NT / 32) + warp] = w;
+                for (int u = 0; u < BPT; u++) bal[u] = 0;
+            }
+            if (any || warp_had_bits) {
+                if (lane < BPT) {
+                    uint32_t w = 0;
+#pragma unroll
+                    for (int u = 0; u < BPT; u++) if (lane == u) w = bal[u];
+                    S.above[lane * (NT / 32) + warp] = w;
+                }
+                warp_had_bits = any != 0;
             }
             const int par = (int)(f & 1);
             if (tid == 0) S.flags[par ^ 1] = 0;
@@ -267,11 +278,15 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
                 // one 32-bin word at a time (warp-uniform)
                 uint32_t cw[BPT];
                 uint32_t anyc = 0;
+                if (any) {
 #pragma unroll
-                for (int u = 0; u < BPT; u++) {
-                    cw[u] = 0;
-                    if (bal[u]) cw[u] = bal[u] & S.free_mask[u * (NT / 32) + warp] & S.valid[u * (NT / 32) + warp];
-                    anyc |= cw[u];
+                    for (int u = 0; u < BPT; u++) {
+                        cw[u] = bal[u] & S.free_mask[u * (NT / 32) + warp] & S.valid[u * (NT / 32) + warp];
+                        anyc |= cw[u];
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < BPT; u++) cw[u] = 0;
                 }
                 if (anyc && lane == 0) fl |= 1;
                 if (fl) atomicOr(&S.flags[par], fl);
@@ -398,6 +413,7 @@ k_detect_scan(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g
             if (!old_valid) load_old(old);
             baseline_push(m, old);
         }
+        if (++slot == DEPTH) { slot = 0; slot_phase ^= 1u; }
     }
 
     // ---- store state
