@@ -129,6 +129,14 @@ cudaError_t launch_detect_fft(int L, int fmt, const void *iq, int64_t first_samp
 cudaError_t launch_detect_scan(const DetConfig &c, DetState *state, float *base, float *hist,
                                const float *mag, int64_t n_frames, GoneBurst *gone,
                                uint32_t gone_cap, cudaStream_t st);
+// k_detect_cluster.cu: same state machine on an 8-CTA cluster with speculative frame batches
+cudaError_t launch_detect_scan_cluster(const DetConfig &c, DetState *state, float *base, float *hist,
+                                       const float *mag, int64_t n_frames, GoneBurst *gone,
+                                       uint32_t gone_cap, cudaStream_t st);
+// picks the cluster kernel for N >= 2048 unless IR_SCAN=single is set in the environment
+cudaError_t launch_detect_scan_auto(const DetConfig &c, DetState *state, float *base, float *hist,
+                                    const float *mag, int64_t n_frames, GoneBurst *gone,
+                                    uint32_t gone_cap, cudaStream_t st);
 // k_downmix.cu
 cudaError_t upload_input_taps(const float *taps, int ntaps);
 cudaError_t upload_chain_tables(const HostTables &t);

@@ -1,0 +1,459 @@
+// k_detect_cluster.cu -- the burst state machine (burst_detect.c:426-632) on a thread-block
+// cluster of 8 CTAs, frames processed in speculative batches.
+//
+// Why: one CTA walking the frames one by one is bound by barrier / dependency latency and by a
+// single SM's ingest rate (4N bytes per frame).  Here every CTA owns N/8 bins (baseline in
+// registers, its slice of every magnitude row) and the frame-to-frame dependency is broken by
+// the observation that the noise baseline changes only on "quiet" frames (no active burst,
+// burst_detect.c:438-454), on which nothing else happens:
+//
+//   batch type F (bursts active): the baseline is frozen, so the owners compute the
+//     "above threshold" bitmaps of K frames at once; the leader CTA then replays the K frames
+//     through the sparse state machine (hysteresis, deletion, masks, peak picking, squelch).
+//     The batch is cut after the first frame that ends with a baseline update.
+//   batch type Q (no burst active): the owners assume every frame is quiet, update their
+//     baselines frame by frame (per-bin serial, exactly the reference's two roundings) and
+//     produce the bitmaps along the way; the leader only has to confirm that no valid bin crossed
+//     the threshold.  The first frame that does cuts the batch: owners rewind to that frame
+//     (recompute from the batch start) and the next batch is of type F.
+//
+// Two cluster barriers per batch instead of two CTA barriers per frame; bitmaps travel to the
+// leader through distributed shared memory.  Results are identical to the single-CTA kernel in
+// k_detect.cu (kept for N < 2048 and as a cross-check; tests compare both with the CPU oracle).
+#include <cooperative_groups.h>
+
+#include "ir_device.cuh"
+#include "ir_internal.h"
+
+namespace cg = cooperative_groups;
+
+namespace ir {
+
+namespace {
+
+constexpr int CL = 8;          // CTAs per cluster
+constexpr int CT = 256;        // threads per CTA
+constexpr int KB = 32;         // frames per batch
+constexpr int MAXW = 512;      // bitmap words per frame (N <= 16384)
+
+struct ClShared {
+    uint32_t words[KB][MAXW];      // leader only: above-threshold bitmaps of the batch
+    uint32_t free_mask[MAXW];      // 1 = bin not covered by an active burst
+    uint32_t valid[MAXW];
+    uint32_t cand[MAXW];
+    ArgMax red[32];
+    // control block, written by the leader, read by every CTA after barrier B
+    int ctl_commit;                // frames of this batch that stand
+    int ctl_push_forced;           // baseline updates to apply at the last committed frame (type F)
+    int ctl_push_normal;
+    int ctl_reset_noise;           // squelch reset happened at the last committed frame
+    int ctl_next_type;             // 0 = F, 1 = Q
+    // leader machine state
+    int n_act;
+    int flags;
+    int squelch_count;
+    unsigned long long next_id;
+    uint32_t n_gone, n_squelch, overflow;
+    ActBurst act[IR_MAX_ACTIVE];
+};
+
+__device__ __forceinline__ bool cbit(const uint32_t *bm, int bin) { return (bm[bin >> 5] >> (bin & 31)) & 1u; }
+
+__device__ __forceinline__ void cclear(uint32_t *bm, int lo, int hi) {
+    for (int w = lo >> 5; w <= (hi >> 5); w++) {
+        int a = max(lo, w << 5) & 31, b = min(hi, (w << 5) + 31) & 31;
+        uint32_t m = (b == 31 ? 0xffffffffu : ((1u << (b + 1)) - 1u)) & ~((1u << a) - 1u);
+        atomicAnd(&bm[w], ~m);
+    }
+}
+
+__device__ __forceinline__ void cgone(ClShared &S, GoneBurst *gone, uint32_t cap, const ActBurst &b, uint64_t index) {
+    if (S.n_gone < cap) {
+        GoneBurst g;
+        g.id = b.id; g.start = b.start; g.stop = index; g.last_active = b.last_active;
+        g.center_bin = b.center_bin; g.peak_rel = b.peak_rel; g.base_at_create = b.base_at_create; g.pad = 0;
+        gone[S.n_gone] = g;
+    } else {
+        S.overflow = 1;
+    }
+    S.n_gone++;
+}
+
+}  // namespace
+
+// BPT = bins per thread = N / (CL * CT)
+template <int BPT>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 1)
+k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g,
+                      float *__restrict__ hist, const float *__restrict__ mag, int64_t n_frames,
+                      GoneBurst *__restrict__ gone, uint32_t gone_cap) {
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ClShared &S = *reinterpret_cast<ClShared *>(smem_raw);
+    ClShared &LS = *cluster.map_shared_rank(&S, 0);           // the leader's copy (DSMEM)
+    const int rank = (int)cluster.block_rank();
+    const bool leader = rank == 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = c.N, W = N >> 5;
+    constexpr int NB = BPT * CT;                              // bins per CTA
+    constexpr int WPC = NB / 32;                              // words per CTA per frame
+    const int bin0 = rank * NB;                               // first bin of this CTA
+    const float thr = c.thr;
+    const float thr_lo = thr * 0.99999f;
+    const float INF = __int_as_float(0x7f800000);
+
+    // ---- per-bin state: bin(u) = bin0 + u*CT + tid
+    float base[BPT];
+#pragma unroll
+    for (int u = 0; u < BPT; u++) base[u] = base_g[bin0 + u * CT + tid];
+    int hist_idx = gs->hist_idx, primed = gs->primed;         // replicated in every CTA
+    uint64_t index = gs->index;                               // sample index of frame k0
+
+    if (leader) {
+        if (tid == 0) {
+            S.n_act = gs->n_act; S.squelch_count = gs->squelch_count; S.next_id = gs->next_id;
+            S.n_gone = gs->n_gone; S.n_squelch = gs->n_squelch; S.overflow = gs->overflow; S.flags = 0;
+            S.ctl_next_type = gs->n_act > 0 ? 0 : 1;
+        }
+        for (int i = tid; i < gs->n_act && i < IR_MAX_ACTIVE; i += CT) S.act[i] = gs->act[i];
+        for (int w = tid; w < W; w += CT) {
+            uint32_t v = 0;
+            for (int b = 0; b < 32; b++) {
+                int bin = (w << 5) + b;
+                bool ok = bin >= c.half_bw && bin < N - c.half_bw && !(bin >= N / 2 - 3 && bin <= N / 2 + 3);
+                v |= ok ? (1u << b) : 0u;
+            }
+            S.valid[w] = v;
+            S.free_mask[w] = 0xffffffffu;
+        }
+        __syncthreads();
+        if (tid < S.n_act) cclear(S.free_mask, max(S.act[tid].center_bin - c.half_bw, 0),
+                                  min(S.act[tid].center_bin + c.half_bw, N - 1));
+    }
+    cluster.sync();
+    int type = LS.ctl_next_type;
+
+    // one baseline update of the owned bins with magnitude row `row` (burst_detect.c:438-454,
+    // simd_avx2.c:221-236); `write_hist` = also store the row into the history
+    auto push_row = [&](const float *__restrict__ row, bool write_hist) {
+        float *h = hist + (size_t)hist_idx * N + bin0;
+#pragma unroll
+        for (int u = 0; u < BPT; u++) {
+            const int o = u * CT + tid;
+            const float mv = row[bin0 + o];
+            const float old = primed ? h[o] : 0.0f;            // untouched history is zero
+            const float v = base[u] - old;
+            base[u] = v + mv;
+            if (write_hist) h[o] = mv;
+        }
+        if (++hist_idx == c.hist_size) { primed = 1; hist_idx = 0; }
+    };
+    // bitmap words of one frame for the owned bins -> leader's words[j]
+    auto screen_row = [&](const float *__restrict__ row, int j) {
+        bool pass_any = false;
+        float mv[BPT];
+#pragma unroll
+        for (int u = 0; u < BPT; u++) {
+            mv[u] = row[bin0 + u * CT + tid];
+            const float lim = base[u] > 0.0f ? base[u] * thr_lo : INF;
+            pass_any = pass_any || (mv[u] > lim);
+        }
+        const bool warp_pass = __any_sync(0xffffffffu, pass_any);
+#pragma unroll
+        for (int u = 0; u < BPT; u++) {
+            uint32_t b = 0;
+            if (warp_pass) {
+                const bool ab = base[u] > 0.0f && (mv[u] / base[u] > thr);      // simd_avx2.c:239-257
+                b = __ballot_sync(0xffffffffu, ab);
+            }
+            if (lane == 0) LS.words[j][rank * WPC + u * (CT / 32) + warp] = b;
+        }
+    };
+
+    int64_t k0 = 0;
+    while (k0 < n_frames) {
+        const int Kb = (int)min((int64_t)KB, n_frames - k0);
+        const float *rows = mag + (size_t)k0 * N;
+        // ---------------- phase 1: owners
+        float base0[BPT];
+        const int idx0 = hist_idx, primed0 = primed;
+#pragma unroll
+        for (int u = 0; u < BPT; u++) base0[u] = base[u];
+        if (type == 0) {
+            for (int j = 0; j < Kb; j++) screen_row(rows + (size_t)j * N, j);
+        } else {
+            for (int j = 0; j < Kb; j++) {
+                const float *row = rows + (size_t)j * N;
+                if (primed) {
+                    screen_row(row, j);
+                } else if (lane == 0) {
+#pragma unroll
+                    for (int u = 0; u < BPT; u++) LS.words[j][rank * WPC + u * (CT / 32) + warp] = 0;
+                }
+                push_row(row, false);                         // speculative: history written at commit
+            }
+        }
+        cluster.sync();                                        // (A) bitmaps are at the leader
+        // ---------------- phase 2: leader replays the batch
+        if (leader) {
+            int commit = Kb, push_forced = 0, push_normal = 0, reset_noise = 0;
+            if (type == 1) {
+                // confirm quietness: no valid bin may cross (the mask is all-free: n_act == 0)
+                int first = Kb;
+                for (int j = 0; j < Kb && first == Kb; j++) {
+                    uint32_t any = 0;
+                    for (int w = tid; w < W; w += CT) any |= S.words[j][w] & S.valid[w];
+                    if (__syncthreads_or(any != 0)) first = j;
+                }
+                commit = first;
+                if (tid == 0) {
+                    // create_new_bursts' else-branch runs on every primed frame (:628-631)
+                    int prim = primed0, idx = idx0;
+                    for (int j = 0; j < commit; j++) {
+                        if (prim && S.squelch_count > 0) S.squelch_count--;
+                        if (++idx == c.hist_size) { prim = 1; idx = 0; }
+                    }
+                    S.ctl_next_type = commit < Kb ? 0 : 1;
+                }
+            } else {
+                uint64_t fidx = index;
+                for (int j = 0; j < Kb; j++, fidx += (uint64_t)N) {
+                    const uint32_t *Wd = S.words[j];
+                    if (tid == 0) S.flags = 0;
+                    __syncthreads();
+                    int n_act = S.n_act;
+                    int fl = 0;
+                    // update_bursts (:458-469)
+                    for (int i = tid; i < n_act; i += CT) {
+                        ActBurst &b = S.act[i];
+                        const int cb = b.center_bin;
+                        bool hit = (cb > 0 && cbit(Wd, cb - 1)) || cbit(Wd, cb) || (cb < N - 1 && cbit(Wd, cb + 1));
+                        if (hit) b.last_active = fidx;
+                        bool too_long = c.max_burst_len > 0 && b.last_active - b.start > (uint64_t)c.max_burst_len;
+                        bool done = (b.last_active + (uint64_t)c.post_len <= fidx) || too_long;
+                        if (done) fl |= 2;
+                        if (too_long) fl |= 4;
+                    }
+                    // peaks: above & mask of the previous frame & search range (:522-548)
+                    for (int w = tid; w < W; w += CT) {
+                        uint32_t cw = Wd[w] & S.free_mask[w] & S.valid[w];
+                        S.cand[w] = cw;
+                        if (cw) fl |= 1;
+                    }
+                    if (fl) atomicOr(&S.flags, fl);
+                    __syncthreads();
+                    const int flags = S.flags;
+                    bool forced = false;
+                    if (flags & 2) {                           // delete_gone_bursts (:490-518)
+                        if (tid == 0) {
+                            int k = 0;
+                            for (int i = 0; i < n_act; i++) {
+                                ActBurst b = S.act[i];
+                                bool too_long = c.max_burst_len > 0 && b.last_active - b.start > (uint64_t)c.max_burst_len;
+                                if ((b.last_active + (uint64_t)c.post_len <= fidx) || too_long) cgone(S, gone, gone_cap, b, fidx);
+                                else S.act[k++] = b;
+                            }
+                            S.n_act = k;
+                        }
+                        __syncthreads();
+                        n_act = S.n_act;
+                        forced = (flags & 4) != 0;             // update_filters_post(d, 1): applied by the owners
+                        for (int w = tid; w < W; w += CT) S.free_mask[w] = 0xffffffffu;
+                        __syncthreads();
+                        for (int i = tid; i < n_act; i += CT)
+                            cclear(S.free_mask, max(S.act[i].center_bin - c.half_bw, 0), min(S.act[i].center_bin + c.half_bw, N - 1));
+                        __syncthreads();
+                    }
+                    // A forced update (too-long burst) changes the baseline between peak extraction
+                    // and create_new_bursts: peaks keep their pre-update relative magnitude, the
+                    // noise field reads the updated sum (:583).  The leader recomputes that one
+                    // value per new burst itself; the owners apply the update after the batch.
+                    if (flags & 1) {                            // create_new_bursts (:556-591)
+                        const float *row = rows + (size_t)j * N;
+                        const float *hold = hist + (size_t)hist_idx * N;
+                        for (;;) {
+                            ArgMax best{-1.0f, 0x7fffffff};
+                            for (int w = tid; w < W; w += CT) {
+                                uint32_t cw = S.cand[w];
+                                while (cw) {
+                                    const int b = __ffs(cw) - 1;
+                                    cw &= cw - 1;
+                                    const int bin = (w << 5) + b;
+                                    best = argmax_pick(best, ArgMax{row[bin] / base_g[bin], bin});
+                                }
+                            }
+                            best = block_argmax(best, S.red);
+                            if (best.v < 0.0f) break;
+                            const int bin = best.i;
+                            if (tid == 0) {
+                                const int slot = S.n_act;
+                                if (slot < IR_MAX_ACTIVE) {
+                                    ActBurst nb;
+                                    nb.id = S.next_id;
+                                    nb.start = fidx - (uint64_t)c.pre_len;
+                                    nb.last_active = nb.start;
+                                    nb.center_bin = bin;
+                                    nb.peak_rel = best.v;
+                                    float bs = base_g[bin];
+                                    if (forced) {
+                                        const float old = primed ? hold[bin] : 0.0f;
+                                        const float v = bs - old;
+                                        bs = v + row[bin];
+                                    }
+                                    nb.base_at_create = bs;
+                                    nb.pad = 0;
+                                    S.act[slot] = nb;
+                                    S.n_act = slot + 1;
+                                } else {
+                                    S.overflow = 1;
+                                }
+                                S.next_id += 10;
+                                const int lo = max(bin - c.half_bw, 0), hi = min(bin + c.half_bw, N - 1);
+                                cclear(S.free_mask, lo, hi);
+                                cclear(S.cand, lo, hi);
+                            }
+                            __syncthreads();
+                        }
+                    }
+                    // squelch (:593-631)
+                    n_act = S.n_act;
+                    {
+                        if (c.max_bursts > 0 && n_act > c.max_bursts) {
+                            __syncthreads();
+                            if (tid == 0) {
+                                for (int i = 0; i < n_act; i++) {
+                                    const ActBurst &b = S.act[i];
+                                    if (b.start != fidx - (uint64_t)c.pre_len) cgone(S, gone, gone_cap, b, fidx);
+                                }
+                                S.n_act = 0;
+                                S.n_squelch++;
+                                S.squelch_count += 3;
+                                if (S.squelch_count >= 10) { S.squelch_count = 0; S.flags |= 8; }
+                            }
+                            for (int w = tid; w < W; w += CT) S.free_mask[w] = 0xffffffffu;
+                            __syncthreads();
+                            if (S.flags & 8) reset_noise = 1;
+                        } else if (tid == 0 && S.squelch_count > 0) {
+                            S.squelch_count--;
+                        }
+                    }
+                    __syncthreads();
+                    // does this frame end the batch?  any baseline update does.
+                    const bool quiet_after = S.n_act == 0;
+                    if (forced || quiet_after || reset_noise) {
+                        commit = j + 1;
+                        push_forced = forced ? 1 : 0;
+                        push_normal = quiet_after ? 1 : 0;
+                        break;
+                    }
+                }
+                if (tid == 0) S.ctl_next_type = push_normal ? 1 : 0;
+            }
+            if (tid == 0) {
+                S.ctl_commit = commit;
+                S.ctl_push_forced = push_forced;
+                S.ctl_push_normal = push_normal;
+                S.ctl_reset_noise = reset_noise;
+            }
+        }
+        cluster.sync();                                        // (B) verdict is published
+        const int commit = LS.ctl_commit;
+        const int pushF = LS.ctl_push_forced, pushN = LS.ctl_push_normal, rst = LS.ctl_reset_noise;
+        const int next_type = LS.ctl_next_type;
+        // ---------------- phase 3: owners make their state match the verdict
+        bool publish = false;
+        if (type == 1) {
+            if (commit == Kb) {
+                // all quiet: the speculative baselines stand; write the history rows now
+                int idx = idx0;
+                for (int j = 0; j < Kb; j++) {
+                    const float *row = rows + (size_t)j * N + bin0;
+                    float *h = hist + (size_t)idx * N + bin0;
+#pragma unroll
+                    for (int u = 0; u < BPT; u++) h[u * CT + tid] = row[u * CT + tid];
+                    if (++idx == c.hist_size) idx = 0;
+                }
+            } else {
+                // rewind to the batch start and redo the frames that stand, this time for real
+#pragma unroll
+                for (int u = 0; u < BPT; u++) base[u] = base0[u];
+                hist_idx = idx0; primed = primed0;
+                for (int j = 0; j < commit; j++) push_row(rows + (size_t)j * N, true);
+                publish = true;                                // next batch is type F
+            }
+        } else {
+            // order inside the frame: forced update (:516-517), squelch reset (:618-627), regular
+            // update (:698)
+            if (pushF) { push_row(rows + (size_t)(commit - 1) * N, true); publish = true; }
+            if (rst) {
+                hist_idx = 0; primed = 0;
+#pragma unroll
+                for (int u = 0; u < BPT; u++) base[u] = 0.0f;
+                publish = true;
+            }
+            if (pushN) { push_row(rows + (size_t)(commit - 1) * N, true); publish = true; }
+        }
+        if (publish) {
+#pragma unroll
+            for (int u = 0; u < BPT; u++) base_g[bin0 + u * CT + tid] = base[u];
+            __threadfence();
+        }
+        k0 += commit;
+        index += (uint64_t)commit * (uint64_t)N;
+        type = next_type;
+        cluster.sync();                                        // base_g / history visible before the next batch
+    }
+
+    // ---- store state
+#pragma unroll
+    for (int u = 0; u < BPT; u++) base_g[bin0 + u * CT + tid] = base[u];
+    if (leader) {
+        __syncthreads();
+        for (int i = tid; i < S.n_act; i += CT) gs->act[i] = S.act[i];
+        if (tid == 0) {
+            gs->hist_idx = hist_idx; gs->primed = primed; gs->n_act = S.n_act;
+            gs->squelch_count = S.squelch_count; gs->next_id = S.next_id; gs->index = index;
+            gs->n_gone = S.n_gone; gs->n_squelch = S.n_squelch; gs->overflow = S.overflow;
+        }
+    }
+}
+
+template <int BPT>
+static cudaError_t launch_cluster_t(const DetConfig &c, DetState *state, float *base, float *hist,
+                                    const float *mag, int64_t n_frames, GoneBurst *gone,
+                                    uint32_t gone_cap, cudaStream_t st) {
+    const size_t smem = sizeof(ClShared);
+    cudaError_t e = cudaFuncSetAttribute(k_detect_scan_cluster<BPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_detect_scan_cluster<BPT><<<CL, CT, smem, st>>>(c, state, base, hist, mag, n_frames, gone, gone_cap);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_detect_scan_cluster(const DetConfig &c, DetState *state, float *base, float *hist,
+                                       const float *mag, int64_t n_frames, GoneBurst *gone,
+                                       uint32_t gone_cap, cudaStream_t st) {
+    if (n_frames <= 0) return cudaSuccess;
+    switch (c.N / (CL * CT)) {
+    case 1: return launch_cluster_t<1>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
+    case 2: return launch_cluster_t<2>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
+    case 4: return launch_cluster_t<4>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
+    case 8: return launch_cluster_t<8>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace ir
+
+#include <stdlib.h>
+#include <string.h>
+namespace ir {
+cudaError_t launch_detect_scan_auto(const DetConfig &c, DetState *state, float *base, float *hist,
+                                    const float *mag, int64_t n_frames, GoneBurst *gone,
+                                    uint32_t gone_cap, cudaStream_t st) {
+    const char *env = getenv("IR_SCAN");
+    const bool force_single = env && strcmp(env, "single") == 0;
+    if (c.N >= 2048 && !force_single)
+        return launch_detect_scan_cluster(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
+    return launch_detect_scan(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
+}
+}  // namespace ir

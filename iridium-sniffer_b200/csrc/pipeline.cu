@@ -471,7 +471,7 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
         CK(cudaEventRecord(a.b, p->st_fft));
         CK(cudaStreamWaitEvent(p->st_scan, a.b, 0));
         CK(cudaEventRecord(b.a, p->st_scan));
-        CK(launch_detect_scan(dc, p->d_state.p, p->d_base.p, p->d_hist.p, p->d_mag.p + f0 * N, f1 - f0,
+        CK(launch_detect_scan_auto(dc, p->d_state.p, p->d_base.p, p->d_hist.p, p->d_mag.p + f0 * N, f1 - f0,
                               p->d_gone.p, gone_cap, p->st_scan));
         CK(cudaEventRecord(b.b, p->st_scan));
         ev_fft.push_back(a); ev_scan.push_back(b);

@@ -267,7 +267,7 @@ static void detector_feed(_burst_detector *d, const void *host, size_t n, bool i
         }
         if ((e = launch_detect_fft(dc.L, IR_FMT_CF32, d->d_buf, (int64_t)(d->index - d->buf_base), d->d_window, d->d_tw,
                                    d->d_mag, nf, d->sm_count, d->st)) != cudaSuccess) die("k_detect_fft", e);
-        if ((e = launch_detect_scan(dc, d->d_state, d->d_base, d->d_hist, d->d_mag, nf, d->d_gone, d->gone_cap, d->st)) != cudaSuccess) die("k_detect_scan", e);
+        if ((e = launch_detect_scan_auto(dc, d->d_state, d->d_base, d->d_hist, d->d_mag, nf, d->d_gone, d->gone_cap, d->st)) != cudaSuccess) die("k_detect_scan", e);
         d->index += (uint64_t)nf * N;
     }
     DetState hs;
