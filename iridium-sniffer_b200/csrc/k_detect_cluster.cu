@@ -51,6 +51,7 @@ struct ClShared {
     // leader machine state
     int n_act;
     int flags;
+    int ff_frame;
     int squelch_count;
     unsigned long long next_id;
     uint32_t n_gone, n_squelch, overflow;
@@ -148,13 +149,11 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
         }
         if (++hist_idx == c.hist_size) { primed = 1; hist_idx = 0; }
     };
-    // bitmap words of one frame for the owned bins -> leader's words[j]
-    auto screen_row = [&](const float *__restrict__ row, int j) {
+    // bitmap words of one frame (values already in registers) for the owned bins -> leader's words[j]
+    auto screen_vals = [&](const float (&mv)[BPT], int j) {
         bool pass_any = false;
-        float mv[BPT];
 #pragma unroll
         for (int u = 0; u < BPT; u++) {
-            mv[u] = row[bin0 + u * CT + tid];
             const float lim = base[u] > 0.0f ? base[u] * thr_lo : INF;
             pass_any = pass_any || (mv[u] > lim);
         }
@@ -169,6 +168,10 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
             if (lane == 0) LS.words[j][rank * WPC + u * (CT / 32) + warp] = b;
         }
     };
+    // Frames are consumed in groups of G whose values (and, for quiet batches, the history rows
+    // they replace) are all requested before the first is used: one memory round trip per group
+    // instead of one per frame.
+    constexpr int G = BPT >= 8 ? 4 : (BPT == 4 ? 8 : 16);
 
     int64_t k0 = 0;
     while (k0 < n_frames) {
@@ -179,18 +182,45 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
         const int idx0 = hist_idx, primed0 = primed;
 #pragma unroll
         for (int u = 0; u < BPT; u++) base0[u] = base[u];
-        if (type == 0) {
-            for (int j = 0; j < Kb; j++) screen_row(rows + (size_t)j * N, j);
-        } else {
-            for (int j = 0; j < Kb; j++) {
-                const float *row = rows + (size_t)j * N;
-                if (primed) {
-                    screen_row(row, j);
-                } else if (lane == 0) {
+        for (int j0 = 0; j0 < Kb; j0 += G) {
+            float mv[G][BPT], ov[G][BPT];
 #pragma unroll
-                    for (int u = 0; u < BPT; u++) LS.words[j][rank * WPC + u * (CT / 32) + warp] = 0;
+            for (int g = 0; g < G; g++) {
+                const bool in = j0 + g < Kb;
+                const float *row = rows + (size_t)(j0 + g) * N + bin0;
+                int hrow = hist_idx + g;
+                if (hrow >= c.hist_size) hrow -= c.hist_size;
+                const float *h = hist + (size_t)hrow * N + bin0;
+                // a history row is live if the detector is primed now or wraps before reaching it
+                const bool live = primed || (hist_idx + g >= c.hist_size);
+#pragma unroll
+                for (int u = 0; u < BPT; u++) {
+                    mv[g][u] = in ? row[u * CT + tid] : 0.0f;
+                    ov[g][u] = (type == 1 && in && live) ? h[u * CT + tid] : 0.0f;
                 }
-                push_row(row, false);                         // speculative: history written at commit
+            }
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const int j = j0 + g;
+                if (j < Kb) {
+                    if (type == 0) {
+                        screen_vals(mv[g], j);
+                    } else {
+                        if (primed) {
+                            screen_vals(mv[g], j);
+                        } else if (lane == 0) {
+#pragma unroll
+                            for (int u = 0; u < BPT; u++) LS.words[j][rank * WPC + u * (CT / 32) + warp] = 0;
+                        }
+                        // speculative baseline update (history written at commit)
+#pragma unroll
+                        for (int u = 0; u < BPT; u++) {
+                            const float v = base[u] - ov[g][u];
+                            base[u] = v + mv[g][u];
+                        }
+                        if (++hist_idx == c.hist_size) { primed = 1; hist_idx = 0; }
+                    }
+                }
             }
         }
         cluster.sync();                                        // (A) bitmaps are at the leader
@@ -199,12 +229,18 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
             int commit = Kb, push_forced = 0, push_normal = 0, reset_noise = 0;
             if (type == 1) {
                 // confirm quietness: no valid bin may cross (the mask is all-free: n_act == 0)
-                int first = Kb;
-                for (int j = 0; j < Kb && first == Kb; j++) {
-                    uint32_t any = 0;
-                    for (int w = tid; w < W; w += CT) any |= S.words[j][w] & S.valid[w];
-                    if (__syncthreads_or(any != 0)) first = j;
+                if (tid == 0) S.ff_frame = Kb;
+                __syncthreads();
+                int mine = Kb;
+                for (int w = tid; w < W; w += CT) {
+                    const uint32_t v = S.valid[w];
+                    for (int j = 0; j < mine; j++)
+                        if (S.words[j][w] & v) { mine = j; break; }
                 }
+                mine = __reduce_min_sync(0xffffffffu, mine);
+                if (lane == 0 && mine < Kb) atomicMin(&S.ff_frame, mine);
+                __syncthreads();
+                const int first = S.ff_frame;
                 commit = first;
                 if (tid == 0) {
                     // create_new_bursts' else-branch runs on every primed frame (:628-631)
@@ -218,6 +254,47 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
             } else {
                 uint64_t fidx = index;
                 for (int j = 0; j < Kb; j++, fidx += (uint64_t)N) {
+                    // Fast-forward: warp 0 alone walks the frames on which nothing happens (no
+                    // candidate peak, no burst ending, some burst still active), applying their
+                    // only effects (hysteresis refresh, squelch count-down), and stops at the
+                    // first frame that needs the full machinery.
+                    if (warp == 0) {
+                        int jj = j;
+                        uint64_t fi = fidx;
+                        for (; jj < Kb; jj++, fi += (uint64_t)N) {
+                            const uint32_t *Wf = S.words[jj];
+                            const int na = S.n_act;
+                            int ev = na == 0 ? 16 : 0;
+                            uint32_t anyc = 0;
+                            for (int w = lane; w < W; w += 32) anyc |= Wf[w] & S.free_mask[w] & S.valid[w];
+                            if (anyc) ev |= 1;
+                            for (int i = lane; i < na; i += 32) {
+                                const ActBurst &b = S.act[i];
+                                const int cb = b.center_bin;
+                                const bool hit = (cb > 0 && cbit(Wf, cb - 1)) || cbit(Wf, cb) || (cb < N - 1 && cbit(Wf, cb + 1));
+                                const uint64_t la = hit ? fi : b.last_active;
+                                const bool too_long = c.max_burst_len > 0 && la - b.start > (uint64_t)c.max_burst_len;
+                                if ((la + (uint64_t)c.post_len <= fi) || too_long) ev |= 2;
+                            }
+                            ev = __reduce_or_sync(0xffffffffu, ev);
+                            if (ev) break;
+                            for (int i = lane; i < na; i += 32) {
+                                ActBurst &b = S.act[i];
+                                const int cb = b.center_bin;
+                                if ((cb > 0 && cbit(Wf, cb - 1)) || cbit(Wf, cb) || (cb < N - 1 && cbit(Wf, cb + 1))) b.last_active = fi;
+                            }
+                            if (lane == 0 && primed && S.squelch_count > 0) S.squelch_count--;
+                            __syncwarp();
+                        }
+                        if (lane == 0) S.ff_frame = jj;
+                    }
+                    __syncthreads();
+                    {
+                        const int jn = S.ff_frame;
+                        fidx += (uint64_t)(jn - j) * (uint64_t)N;
+                        j = jn;
+                    }
+                    if (j >= Kb) break;
                     const uint32_t *Wd = S.words[j];
                     if (tid == 0) S.flags = 0;
                     __syncthreads();
