@@ -62,6 +62,7 @@ struct DetState {
     uint32_t n_squelch;
     uint32_t overflow;             // IR_MAX_ACTIVE or gone list exceeded
     uint32_t pad;
+    unsigned long long dbg[24];    // cycle counters of the cluster state machine (IR_SCAN_DEBUG)
     ActBurst act[IR_MAX_ACTIVE];
 };
 

@@ -12,6 +12,7 @@
 // (burst_detect.c:401-422) does not exist here.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <time.h>
 
@@ -213,6 +214,14 @@ static int finish_run(ir_pipeline *p, const void *iq_dev, size_t n, int fmt, cud
     CK(cudaStreamSynchronize(st));
     p->res.d2h_bytes += offsetof(DetState, act);
     if (hs.overflow) { set_err("detector capacity exceeded (IR_MAX_ACTIVE or burst list)"); return -1; }
+    if (getenv("IR_SCAN_DEBUG")) {
+        fprintf(stderr, "scan cycles leader: p1 %llu waitA %llu p2 %llu waitB %llu p3 %llu waitC %llu batches %llu qbatches %llu\n",
+                hs.dbg[0], hs.dbg[1], hs.dbg[2], hs.dbg[3], hs.dbg[4], hs.dbg[5], hs.dbg[6], hs.dbg[7]);
+        fprintf(stderr, "scan leader p2 split: search %llu preflags %llu deletion %llu creation %llu squelch/end %llu | event frames %llu creates %llu deletes %llu\n",
+                hs.dbg[8], hs.dbg[9], hs.dbg[10], hs.dbg[11], hs.dbg[12], hs.dbg[13], hs.dbg[14], hs.dbg[15]);
+        fprintf(stderr, "scan owner(rank3) p1 split: issue %llu oldloads %llu wait+sync %llu lds+sync %llu compute %llu\n",
+                hs.dbg[16], hs.dbg[17], hs.dbg[18], hs.dbg[19], hs.dbg[20]);
+    }
     const size_t nb = hs.n_gone;
     p->h_gone.resize(nb);
     if (nb) {
