@@ -132,6 +132,22 @@ def make_recording_gpu(torch, synth, seed, duration_s, bursts_per_s, device):
     return iq, truth
 
 
+def reduce_over_ranks(torch, dist, device, times, counts):
+    """Job-level numbers from per-rank ones: MAX over ranks for every time, SUM for every count.
+    dist is None for a single process.  (tests/test_multirank_gloo.py runs this on gloo.)"""
+    t = torch.tensor(list(times), dtype=torch.float64, device=device)
+    c = torch.tensor(list(counts), dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    return [float(x) for x in t.tolist()], [int(x) for x in c.tolist()]
+
+
+def shard_seed(world, rank):
+    """Each rank decodes its own independent recording (different seed -> different bursts)."""
+    return 2 + 8 * (world > 1) + rank
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -146,7 +162,7 @@ def run_ours(args):
     pl = importlib.import_module("iridium-sniffer_b200.pipeline")
 
     t_gen = time.time()
-    iq_dev, truth = make_recording_gpu(torch, synth, 2 + 8 * (world > 1) + rank, args.seconds, args.bursts_per_s, dev)
+    iq_dev, truth = make_recording_gpu(torch, synth, shard_seed(world, rank), args.seconds, args.bursts_per_s, dev)
     n = iq_dev.shape[0]
     host = torch.empty((n, 2), dtype=torch.float32, pin_memory=True)
     host.copy_(iq_dev)
@@ -163,8 +179,11 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident leg (value)
+    # The timed loops call the C ABI only (run + per-step stats struct); result conversion to
+    # Python objects happens once, after the clocks stop.
+    iq_ptr, host_ptr = iq_dev.data_ptr(), host.data_ptr()
     for _ in range(args.warmup):
-        res = p.run_device_ptr(iq_dev.data_ptr(), n, "cf32")
+        p.run_device_raw(iq_ptr, n, "cf32")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -172,36 +191,36 @@ def run_ours(args):
     t0 = time.perf_counter()
     dev_ms, launches, stage = 0.0, 0, {}
     for _ in range(args.steps):
-        res = p.run_device_ptr(iq_dev.data_ptr(), n, "cf32")
-        dev_ms += res.stats["ms_total"]
-        launches += res.stats["kernel_launches"]
+        p.run_device_raw(iq_ptr, n, "cf32")
+        st = p.stats()
+        dev_ms += st["ms_total"]
+        launches += st["kernel_launches"]
         for k in ("ms_detect_fft", "ms_detect_scan", "ms_downmix_fir", "ms_downmix_chain", "ms_demod"):
-            stage[k] = stage.get(k, 0.0) + res.stats[k]
+            stage[k] = stage.get(k, 0.0) + st[k]
     barrier()
     wall = time.perf_counter() - t0
+    res = p.results()
     # ---------------- end-to-end leg: pinned host IQ -> RAW text lines
-    for _ in range(min(args.warmup, 2)):
-        p.run_host_ptr(host.data_ptr(), n, "cf32")
+    for _ in range(args.warmup):
+        p.run_host_raw(host_ptr, n, "cf32")
+        p.raw_text("b200")
     barrier()
     t1 = time.perf_counter()
     h2d = d2h = 0
-    n_lines = 0
+    text = b""
     for _ in range(args.steps):
-        r2 = p.run_host_ptr(host.data_ptr(), n, "cf32")
-        lines = r2.raw_lines("b200")
-        n_lines = len(lines)
-        h2d += r2.stats["h2d_bytes"]; d2h += r2.stats["d2h_bytes"]
+        p.run_host_raw(host_ptr, n, "cf32")
+        text = p.raw_text("b200")
+        st = p.stats()
+        h2d += st["h2d_bytes"]; d2h += st["d2h_bytes"]
     barrier()
     wall_e2e = time.perf_counter() - t1
+    n_lines = text.count(b"\n")
     clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([wall, wall_e2e, dev_ms / 1e3], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([len(res.bursts), len(res.frames), launches], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    wall, wall_e2e, dev_s = [float(x) for x in t.tolist()]
-    n_bursts, n_frames, launches = [int(x) for x in cnt.tolist()]
+    (wall, wall_e2e, dev_s), (n_bursts, n_frames, launches) = reduce_over_ranks(
+        torch, dist if world > 1 else None, dev, [wall, wall_e2e, dev_ms / 1e3],
+        [len(res.bursts), len(res.frames), launches])
 
     ok_bits = sum("".join(map(str, f["bits"])) in truth_set for f in res.frames)
     if rank == 0:
@@ -247,7 +266,7 @@ def run_ours(args):
             "e2e": {"value": round(total / wall_e2e / 1e6, 2), "unit": UNIT,
                     "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
                     "ms_per_step": round(wall_e2e / K * 1e3, 3), "raw_lines_per_step": n_lines,
-                    "api": "ir_pipeline_run_host (pinned host IQ -> frames) + ir_format_raw"},
+                    "api": "ir_pipeline_run_host (pinned host IQ -> frames) + ir_pipeline_format_raw_all"},
             "bursts_per_s": round(n_bursts / (wall / K), 1),
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
         }

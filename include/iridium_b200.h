@@ -154,6 +154,13 @@ int ir_pipeline_copy_burst_samples(ir_pipeline_t *p, size_t burst_index, float *
 int ir_format_raw(char *dst, size_t cap, const char *file_info, uint64_t t0,
                   const ir_frame_t *frame, const uint8_t *bits);
 
+/* All RAW: lines of the last run in one call, in frame order (the batched sink of SURVEY.md 8f
+ * rank 2).  t0 = 0 selects frame_output.c:144-158's rule (first frame's timestamp floored to
+ * 1 s).  Returns the number of bytes written (no trailing NUL counted); with dst == NULL the
+ * size a buffer must have; -1 on error. */
+long ir_pipeline_format_raw_all(ir_pipeline_t *p, const char *file_info, uint64_t t0, char *dst,
+                                size_t cap);
+
 /* Pinned host allocations for callers that want full-rate H2D. */
 void *ir_host_alloc(size_t bytes);
 void ir_host_free(void *p);

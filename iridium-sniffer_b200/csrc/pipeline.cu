@@ -584,6 +584,23 @@ extern "C" int ir_format_raw(char *dst, size_t cap, const char *file_info, uint6
     return (int)pos;
 }
 
+extern "C" long ir_pipeline_format_raw_all(ir_pipeline_t *p, const char *file_info, uint64_t t0, char *dst,
+                                           size_t cap) {
+    if (!p) return -1;
+    const size_t head = 128 + (file_info ? strlen(file_info) : 0);   // fixed-width fields < 100 chars
+    if (!dst) return (long)(p->frames.size() * head + p->bits.size() + 64);
+    if (p->frames.empty()) return 0;
+    if (t0 == 0) t0 = (p->frames[0].timestamp / 1000000000ULL) * 1000000000ULL;
+    size_t pos = 0;
+    for (const ir_frame_t &f : p->frames) {
+        if (pos + head + (size_t)f.n_bits + 2 > cap) { set_err("ir_pipeline_format_raw_all: buffer too small"); return -1; }
+        int n = ir_format_raw(dst + pos, cap - pos, file_info, t0, &f, p->bits.data() + f.bits_offset);
+        if (n < 0) return -1;
+        pos += (size_t)n;
+    }
+    return (long)pos;
+}
+
 extern "C" void *ir_host_alloc(size_t bytes) {
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;

@@ -101,6 +101,8 @@ def load_library() -> C.CDLL:
     L.ir_format_raw.restype = C.c_int
     L.ir_format_raw.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_uint64, C.POINTER(Frame),
                                 C.c_void_p]
+    L.ir_pipeline_format_raw_all.restype = C.c_long
+    L.ir_pipeline_format_raw_all.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_size_t]
     L.ir_host_alloc.restype = C.c_void_p
     L.ir_host_alloc.argtypes = [C.c_size_t]
     L.ir_host_free.argtypes = [C.c_void_p]
@@ -112,7 +114,8 @@ EXPORTED_SYMBOLS = [
     "ir_last_error", "ir_device_count", "ir_pipeline_create", "ir_pipeline_destroy",
     "ir_pipeline_reset", "ir_pipeline_run_host", "ir_pipeline_run_device", "ir_pipeline_results",
     "ir_pipeline_copy_mag", "ir_pipeline_copy_frame_samples", "ir_pipeline_copy_decimated",
-    "ir_pipeline_copy_burst_samples", "ir_format_raw", "ir_host_alloc", "ir_host_free",
+    "ir_pipeline_copy_burst_samples", "ir_format_raw", "ir_pipeline_format_raw_all", "ir_host_alloc",
+    "ir_host_free",
 ]
 
 
@@ -225,6 +228,37 @@ class Pipeline:
         self._check(self.L.ir_pipeline_run_device(self.h, C.c_void_p(dev_ptr), n_samples,
                                                   FMT_BY_NAME[fmt]), "ir_pipeline_run_device")
         return self.results()
+
+    # ---- bare calls (no Python-side result conversion): what bench.py times
+    def run_device_raw(self, dev_ptr: int, n_samples: int, fmt: str = "cf32") -> None:
+        self._check(self.L.ir_pipeline_run_device(self.h, C.c_void_p(dev_ptr), n_samples,
+                                                  FMT_BY_NAME[fmt]), "ir_pipeline_run_device")
+
+    def run_host_raw(self, ptr: int, n_samples: int, fmt: str = "cf32") -> None:
+        self._check(self.L.ir_pipeline_run_host(self.h, C.c_void_p(ptr), n_samples,
+                                                FMT_BY_NAME[fmt]), "ir_pipeline_run_host")
+
+    def raw_text(self, file_info: str = "T", t0: int = 0) -> bytes:
+        """Every RAW: line of the last run, formatted inside the library in one call."""
+        need = self.L.ir_pipeline_format_raw_all(self.h, file_info.encode(), t0, None, 0)
+        if need < 0:
+            raise RuntimeError("ir_pipeline_format_raw_all failed")
+        if getattr(self, "_txt_cap", 0) < need:
+            self._txt = C.create_string_buffer(need)
+            self._txt_cap = need
+        n = self.L.ir_pipeline_format_raw_all(self.h, file_info.encode(), t0, self._txt, self._txt_cap)
+        if n < 0:
+            raise RuntimeError("ir_pipeline_format_raw_all failed: " + self.L.ir_last_error().decode())
+        return self._txt.raw[:n]
+
+    def stats(self) -> dict:
+        r = Results()
+        self._check(self.L.ir_pipeline_results(self.h, C.byref(r)), "ir_pipeline_results")
+        d = {k: getattr(r, k) for k in ("ms_total", "ms_detect_fft", "ms_detect_scan", "ms_downmix_fir",
+                                        "ms_downmix_chain", "ms_demod", "kernel_launches", "h2d_bytes",
+                                        "d2h_bytes", "alg_bytes")}
+        d["n_bursts"], d["n_frames"] = r.n_bursts, r.n_frames
+        return d
 
     def results(self) -> RunResult:
         r = Results()

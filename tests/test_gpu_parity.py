@@ -162,6 +162,16 @@ def test_raw_lines_sorted_compare(run_small, port, rec_small):
     assert a == b     # freq, id, confidence, payload count, bits (level/N: compared with tolerance above)
 
 
+def test_batched_raw_text_equals_per_frame_lines(run_small):
+    """ir_pipeline_format_raw_all == ir_format_raw over every frame, and t0=0 picks
+    frame_output.c:144-158's rule (first frame's timestamp floored to one second)."""
+    p, res = run_small
+    t0 = (res.frames[0]["timestamp"] // 10**9) * 10**9
+    lines = res.raw_lines("T", t0)
+    assert p.raw_text("T", t0).decode() == "".join(l + "\n" for l in lines)
+    assert p.raw_text("T", 0) == p.raw_text("T", t0)
+
+
 def test_device_resident_run_equals_host_run(pl, rec_small, run_small):
     import torch
     _, res = run_small
@@ -178,6 +188,7 @@ def test_empty_and_tiny_inputs(pl):
     p = pl.Pipeline(sample_rate=10_000_000)
     r = p.run_host(np.zeros(100, np.complex64))          # shorter than one frame
     assert r.bursts == [] and r.frames == []
+    assert p.raw_text("T", 0) == b""                     # no frames -> empty text
     rng = np.random.default_rng(0)
     x = (rng.standard_normal(8192 * 600) + 1j * rng.standard_normal(8192 * 600)).astype(np.complex64) * 0.01
     r = p.run_host(x)                                    # noise only: nothing may be emitted
