@@ -69,6 +69,69 @@ struct RotTable { float2 *d = nullptr; int len = 0; float2 incr; };
 
 struct EvPair { cudaEvent_t a, b; };
 
+// Bump allocator over one big allocation (device memory or pinned host memory).  The per-wave
+// burst buffers come from here, so nothing is freed or reallocated while earlier waves are
+// still in flight; a request that does not fit gets its own allocation, and the next run (device
+// idle) regrows the arena to the size the previous run needed.
+struct Arena {
+    bool host = false;
+    unsigned char *base = nullptr;
+    size_t cap = 0, used = 0;
+    std::vector<std::pair<void *, size_t>> extra;
+    void *raw_alloc(size_t n) {
+        void *q = nullptr;
+        cudaError_t e = host ? cudaHostAlloc(&q, n, cudaHostAllocDefault) : cudaMalloc(&q, n);
+        if (e != cudaSuccess) { set_err(std::string(host ? "cudaHostAlloc: " : "cudaMalloc: ") + cudaGetErrorString(e)); return nullptr; }
+        return q;
+    }
+    void raw_free(void *q) { if (!q) return; if (host) cudaFreeHost(q); else cudaFree(q); }
+    int begin(size_t min_cap) {
+        size_t want = cap;
+        for (auto &e : extra) { raw_free(e.first); want += e.second; }
+        const bool grow = !extra.empty() || cap < min_cap;
+        extra.clear();
+        if (grow) {
+            want = std::max(want + want / 4, min_cap);
+            raw_free(base);
+            base = (unsigned char *)raw_alloc(want);
+            cap = base ? want : 0;
+            if (!base) return -1;
+        }
+        used = 0;
+        return 0;
+    }
+    template <class T>
+    T *take(size_t count) {
+        size_t n = (count * sizeof(T) + 255) & ~(size_t)255;
+        if (n == 0) n = 256;
+        if (used + n <= cap) { void *q = base + used; used += n; return (T *)q; }
+        void *q = raw_alloc(n);
+        if (q) extra.push_back({q, n});
+        return (T *)q;
+    }
+    void release() { for (auto &e : extra) raw_free(e.first); extra.clear(); raw_free(base); base = nullptr; cap = used = 0; }
+};
+
+// One wave = the bursts the detector emitted while scanning one chunk of the input.  Its
+// downmix / demod kernels run on st_burst while the detector is busy with the next chunk.
+struct Wave {
+    size_t b0 = 0, nb = 0;
+    int n_tiles = 0;
+    int64_t dec_total = 0;
+    BurstParam *d_bp = nullptr, *h_bp = nullptr;
+    int *d_tile_start = nullptr, *h_tile_start = nullptr;
+    float2 *d_dec = nullptr, *d_scrA = nullptr, *d_scrB = nullptr, *d_frames = nullptr;
+    ChainOut *d_co = nullptr, *h_co = nullptr;
+    DemodOut *d_do = nullptr, *h_do = nullptr;
+    unsigned char *d_bits = nullptr, *h_bits = nullptr;
+    float *d_llr = nullptr, *h_llr = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr, e_done = nullptr;
+};
+
+struct Chunk { size_t end = 0; cudaEvent_t e_hdr = nullptr; EvPair fft, scan; };
+
+constexpr size_t kHdrBytes = offsetof(DetState, act);
+
 }  // namespace
 
 struct ir_pipeline {
@@ -77,7 +140,7 @@ struct ir_pipeline {
     HostTables tab;
     int dev = 0, sm_count = 148;
     int dec = 40;
-    cudaStream_t st_copy = nullptr, st_fft = nullptr, st_scan = nullptr;
+    cudaStream_t st_copy = nullptr, st_fft = nullptr, st_scan = nullptr, st_burst = nullptr;
     // constants
     DevBuf<float> d_window;
     DevBuf<float2> d_tw_det, d_tw12, d_tw11, d_sync_dl, d_sync_ul;
@@ -85,30 +148,30 @@ struct ir_pipeline {
     DevBuf<unsigned char> d_iq;
     DevBuf<float> d_mag, d_base, d_hist;
     DevBuf<DetState> d_state;
-    DevBuf<GoneBurst> d_gone;
+    // burst list: pinned host memory mapped into the device; the scan kernel stores the (few,
+    // 56-byte) records straight into it, the host reads them after the chunk's event
+    GoneBurst *h_gone = nullptr, *d_gone = nullptr;
+    uint32_t gone_cap = 0;
+    unsigned char *h_hdr = nullptr;          // pinned: DetState header after every chunk
+    size_t hdr_slots = 0;
     // bursts
-    DevBuf<BurstParam> d_bp;
-    DevBuf<int> d_tile_start;
-    DevBuf<float2> d_dec, d_scrA, d_scrB, d_frames;
-    DevBuf<ChainOut> d_co;
-    DevBuf<DemodOut> d_do;
-    DevBuf<unsigned char> d_bits;
-    DevBuf<float> d_llr;
+    Arena dev_arena, pin_arena;
+    std::vector<Wave> waves;
+    std::vector<Chunk> chunks;
     std::unordered_map<int, RotTable> rot;
+    std::vector<std::pair<unsigned char *, size_t>> rot_slabs;   // (base, used); never freed before destroy
+    size_t rot_slab_cap = 0;                                      // capacity of rot_slabs.back()
     // last run (host)
     const void *last_iq = nullptr;
     size_t last_n = 0;
     int last_fmt = 0;
-    std::vector<GoneBurst> h_gone;
     std::vector<BurstParam> h_bp;
-    std::vector<ChainOut> h_co;
-    std::vector<DemodOut> h_do;
+    std::vector<float2 *> frame_ptr, dec_ptr;                     // per burst, device
     std::vector<ir_burst_t> bursts;
     std::vector<ir_frame_t> frames;
     std::vector<uint8_t> bits;
     std::vector<float> llr;
-    std::vector<uint8_t> h_bits_raw;
-    std::vector<float> h_llr_raw;
+    uint64_t alg = 0;
     ir_results_t res;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -159,8 +222,10 @@ extern "C" ir_pipeline_t *ir_pipeline_create(const ir_config_t *cfg) {
     if ((int)p->tab.h_input.size() != IR_INPUT_NTAPS) return fail("unexpected input filter length");
     if (cudaStreamCreateWithFlags(&p->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&p->st_fft, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&p->st_scan, cudaStreamNonBlocking) != cudaSuccess)
+        cudaStreamCreateWithFlags(&p->st_scan, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&p->st_burst, cudaStreamNonBlocking) != cudaSuccess)
         return fail("stream creation failed");
+    p->pin_arena.host = true;
     if (p->d_window.ensure(p->dc.N)) return fail(g_err);
     if (cudaMemcpy(p->d_window.p, p->tab.det_window.data(), sizeof(float) * p->dc.N, cudaMemcpyHostToDevice) != cudaSuccess)
         return fail("window upload failed");
@@ -181,17 +246,18 @@ extern "C" void ir_pipeline_destroy(ir_pipeline_t *p) {
     if (!p) return;
     cudaSetDevice(p->dev);
     cudaDeviceSynchronize();
-    for (auto &kv : p->rot) if (kv.second.d) cudaFree(kv.second.d);
+    for (auto &s : p->rot_slabs) cudaFree(s.first);
     p->d_window.release(); p->d_tw_det.release(); p->d_tw12.release(); p->d_tw11.release();
     p->d_sync_dl.release(); p->d_sync_ul.release(); p->d_iq.release(); p->d_mag.release();
-    p->d_base.release(); p->d_hist.release(); p->d_state.release(); p->d_gone.release();
-    p->d_bp.release(); p->d_tile_start.release(); p->d_dec.release(); p->d_scrA.release();
-    p->d_scrB.release(); p->d_frames.release(); p->d_co.release(); p->d_do.release();
-    p->d_bits.release(); p->d_llr.release();
+    p->d_base.release(); p->d_hist.release(); p->d_state.release();
+    p->dev_arena.release(); p->pin_arena.release();
+    if (p->h_gone) cudaFreeHost(p->h_gone);
+    if (p->h_hdr) cudaFreeHost(p->h_hdr);
     for (auto e : p->ev_pool) cudaEventDestroy(e);
     if (p->st_copy) cudaStreamDestroy(p->st_copy);
     if (p->st_fft) cudaStreamDestroy(p->st_fft);
     if (p->st_scan) cudaStreamDestroy(p->st_scan);
+    if (p->st_burst) cudaStreamDestroy(p->st_burst);
     delete p;
 }
 
@@ -204,43 +270,52 @@ extern "C" int ir_pipeline_reset(ir_pipeline_t *p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Everything after the detector: host bookkeeping + FIR + chain + demod + result assembly.
-static int finish_run(ir_pipeline *p, const void *iq_dev, size_t n, int fmt, cudaEvent_t ev_begin,
-                      std::vector<EvPair> &ev_fft, std::vector<EvPair> &ev_scan) {
+// NCO phase-checkpoint tables, one per detector bin that ever carried a burst; carved from slabs
+// that live until the pipeline is destroyed (no cudaFree while kernels are in flight).
+static float2 *rot_alloc(ir_pipeline *p, size_t count) {
+    const size_t bytes = (count * sizeof(float2) + 255) & ~(size_t)255;
+    if (p->rot_slabs.empty() || p->rot_slab_cap - p->rot_slabs.back().second < bytes) {
+        const size_t cap = std::max<size_t>((size_t)16 << 20, bytes);
+        void *q = nullptr;
+        cudaError_t e = cudaMalloc(&q, cap);
+        if (e != cudaSuccess) { set_err(std::string("cudaMalloc(rot tables): ") + cudaGetErrorString(e)); return nullptr; }
+        p->rot_slabs.push_back({(unsigned char *)q, 0});
+        p->rot_slab_cap = cap;
+    }
+    auto &s = p->rot_slabs.back();
+    float2 *r = (float2 *)(s.first + s.second);
+    s.second += bytes;
+    return r;
+}
+
+// Bursts [b0, b1) of the gone list: host bookkeeping (burst_data_t equivalents, decimation
+// geometry), then FIR + chain + demod + result copies enqueued on st_burst.  Does not wait.
+static int launch_wave(ir_pipeline *p, size_t b0, size_t b1, const void *iq_dev, size_t n, int fmt) {
     const DetConfig &dc = p->dc;
-    cudaStream_t st = p->st_scan;
-    DetState hs;                       // only the header is needed
-    CK(cudaMemcpyAsync(&hs, p->d_state.p, offsetof(DetState, act), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    p->res.d2h_bytes += offsetof(DetState, act);
-    if (hs.overflow) { set_err("detector capacity exceeded (IR_MAX_ACTIVE or burst list)"); return -1; }
-    if (getenv("IR_SCAN_DEBUG")) {
-        fprintf(stderr, "scan cycles leader: p1 %llu waitA %llu p2 %llu waitB %llu p3 %llu waitC %llu batches %llu qbatches %llu\n",
-                hs.dbg[0], hs.dbg[1], hs.dbg[2], hs.dbg[3], hs.dbg[4], hs.dbg[5], hs.dbg[6], hs.dbg[7]);
-        fprintf(stderr, "scan leader p2 split: search %llu preflags %llu deletion %llu creation %llu squelch/end %llu | event frames %llu creates %llu deletes %llu\n",
-                hs.dbg[8], hs.dbg[9], hs.dbg[10], hs.dbg[11], hs.dbg[12], hs.dbg[13], hs.dbg[14], hs.dbg[15]);
-        fprintf(stderr, "scan owner(rank3) p1 split: issue %llu oldloads %llu wait+sync %llu lds+sync %llu compute %llu\n",
-                hs.dbg[16], hs.dbg[17], hs.dbg[18], hs.dbg[19], hs.dbg[20]);
-    }
-    const size_t nb = hs.n_gone;
-    p->h_gone.resize(nb);
-    if (nb) {
-        CK(cudaMemcpyAsync(p->h_gone.data(), p->d_gone.p, nb * sizeof(GoneBurst), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        p->res.d2h_bytes += nb * sizeof(GoneBurst);
-    }
-    // ---- burst_data_t equivalents (burst_detect.c:703-742) and decimation geometry
+    cudaStream_t st = p->st_burst;
+    const size_t nb = b1 - b0;
     const uint64_t B = p->cfg.feed_block > 0 ? (uint64_t)p->cfg.feed_block : 32768;
     const uint64_t R = dc.ringbuf_size;
     const int fs = dc.sample_rate, N = dc.N;
-    p->bursts.assign(nb, ir_burst_t{});
-    p->h_bp.assign(nb, BurstParam{});
-    std::vector<int> tile_start(nb + 1, 0);
-    std::vector<int> need_bins;
+    Wave w;
+    w.b0 = b0; w.nb = nb;
+    const size_t nsym2 = 2 * (size_t)IR_MAX_SYMS;
+    w.h_bp = p->pin_arena.take<BurstParam>(nb);
+    w.h_tile_start = p->pin_arena.take<int>(nb + 1);
+    w.h_co = p->pin_arena.take<ChainOut>(nb);
+    w.h_do = p->pin_arena.take<DemodOut>(nb);
+    w.h_bits = p->pin_arena.take<unsigned char>(nb * nsym2);
+    w.h_llr = p->pin_arena.take<float>(nb * nsym2);
+    if (!w.h_bp || !w.h_tile_start || !w.h_co || !w.h_do || !w.h_bits || !w.h_llr) return -1;
+    p->bursts.resize(b1, ir_burst_t{});
+    p->h_bp.resize(b1, BurstParam{});
+    p->frame_ptr.resize(b1, nullptr);
+    p->dec_ptr.resize(b1, nullptr);
+    std::vector<size_t> need_bins;
     int64_t dec_total = 0;
     int n_tiles = 0;
-    uint64_t alg = (uint64_t)n * fmt_bytes(fmt);
-    for (size_t i = 0; i < nb; i++) {
+    // ---- burst_data_t equivalents (burst_detect.c:703-742) and decimation geometry
+    for (size_t i = b0; i < b1; i++) {
         const GoneBurst &g = p->h_gone[i];
         ir_burst_t &ob = p->bursts[i];
         ob.id = g.id; ob.start = g.start; ob.stop = g.stop; ob.last_active = g.last_active;
@@ -270,9 +345,9 @@ static int finish_run(ir_pipeline *p, const void *iq_dev, size_t n, int fmt, cud
             if (dlen < 0) dlen = 0;
         }
         bp.dec_len = dlen;
-        bp.dec_off = dec_total;
+        bp.dec_off = dec_total;                                // relative to this wave's arrays
         bp.tile0 = n_tiles;
-        tile_start[i] = n_tiles;
+        w.h_tile_start[i - b0] = n_tiles;
         const float rel = (g.center_bin - N / 2) / (float)N;   // :663-664
         const float ph = -2.0f * (float)M_PI * rel;
         float sn, cs;
@@ -285,103 +360,110 @@ static int finish_run(ir_pipeline *p, const void *iq_dev, size_t n, int fmt, cud
             dec_total += dlen;
             n_tiles += (dlen + IR_FIR_TILE - 1) / IR_FIR_TILE;
             auto it = p->rot.find(g.center_bin);
-            if (it == p->rot.end() || it->second.len < nn + IR_ROT_G) need_bins.push_back((int)i);
-            alg += 8ull * (uint64_t)nn + 8ull * (uint64_t)dlen;
+            if (it == p->rot.end() || it->second.len < nn + IR_ROT_G) need_bins.push_back(i);
+            p->alg += 8ull * (uint64_t)nn + 8ull * (uint64_t)dlen;
         } else {
             bp.dec_len = 0;        // chain reports status 2
         }
     }
-    tile_start[nb] = n_tiles;
+    w.h_tile_start[nb] = n_tiles;
+    w.n_tiles = n_tiles; w.dec_total = dec_total;
     // ---- NCO checkpoint tables for bins not cached yet (or cached too short)
     if (!need_bins.empty()) {
         std::unordered_map<int, int> want;     // bin -> samples
-        for (int i : need_bins) {
+        for (size_t i : need_bins) {
             int bin = p->h_gone[i].center_bin;
             int len = ((p->h_bp[i].n + IR_ROT_G + 65535) / 65536) * 65536;
-            auto w = want.find(bin);
-            if (w == want.end() || w->second < len) want[bin] = len;
+            auto wi = want.find(bin);
+            if (wi == want.end() || wi->second < len) want[bin] = len;
         }
-        std::vector<float2> incr;
-        std::vector<float2 *> ptrs;
-        std::vector<int> lens;
+        const size_t k = want.size();
+        float2 *h_incr = p->pin_arena.take<float2>(k), *d_incr = p->dev_arena.take<float2>(k);
+        float2 **h_ptrs = p->pin_arena.take<float2 *>(k), **d_ptrs = p->dev_arena.take<float2 *>(k);
+        int *h_lens = p->pin_arena.take<int>(k), *d_lens = p->dev_arena.take<int>(k);
+        if (!h_incr || !d_incr || !h_ptrs || !d_ptrs || !h_lens || !d_lens) return -1;
+        size_t j = 0;
         for (auto &kv : want) {
             RotTable &rt = p->rot[kv.first];
-            if (rt.d) cudaFree(rt.d);
             rt.len = kv.second;
-            CK(cudaMalloc(&rt.d, sizeof(float2) * (size_t)(rt.len / IR_ROT_G + 1)));
+            rt.d = rot_alloc(p, (size_t)(rt.len / IR_ROT_G + 1));
+            if (!rt.d) return -1;
             const float rel = (kv.first - N / 2) / (float)N;
             const float ph = -2.0f * (float)M_PI * rel;
             float sn, cs;
             sincosf(ph, &sn, &cs);
             rt.incr = make_float2(cs, sn);
-            incr.push_back(rt.incr); ptrs.push_back(rt.d); lens.push_back(rt.len);
+            h_incr[j] = rt.incr; h_ptrs[j] = rt.d; h_lens[j] = rt.len;
+            j++;
         }
-        float2 *d_incr; float2 **d_ptrs; int *d_lens;
-        const size_t k = incr.size();
-        CK(cudaMalloc(&d_incr, k * sizeof(float2)));
-        CK(cudaMalloc(&d_ptrs, k * sizeof(float2 *)));
-        CK(cudaMalloc(&d_lens, k * sizeof(int)));
-        CK(cudaMemcpyAsync(d_incr, incr.data(), k * sizeof(float2), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d_ptrs, ptrs.data(), k * sizeof(float2 *), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d_lens, lens.data(), k * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_incr, h_incr, k * sizeof(float2), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_ptrs, h_ptrs, k * sizeof(float2 *), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_lens, h_lens, k * sizeof(int), cudaMemcpyHostToDevice, st));
         CK(launch_rot_tables(d_incr, d_ptrs, d_lens, (int)k, st));
         p->res.kernel_launches++;
-        CK(cudaStreamSynchronize(st));
-        cudaFree(d_incr); cudaFree(d_ptrs); cudaFree(d_lens);
     }
-    for (size_t i = 0; i < nb; i++) {
+    for (size_t i = b0; i < b1; i++) {
         auto it = p->rot.find(p->h_gone[i].center_bin);
         p->h_bp[i].rot_table = it != p->rot.end() ? it->second.d : nullptr;
+        w.h_bp[i - b0] = p->h_bp[i];
     }
     // ---- device work for the bursts
-    cudaEvent_t e_fir0 = p->ev(), e_fir1 = p->ev(), e_ch1 = p->ev(), e_dm1 = p->ev();
-    p->h_co.assign(nb, ChainOut{});
-    p->h_do.assign(nb, DemodOut{});
-    if (nb) {
-        if (p->d_bp.ensure(nb) || p->d_tile_start.ensure(nb + 1) || p->d_dec.ensure((size_t)dec_total + 16) ||
-            p->d_scrA.ensure((size_t)dec_total + 16) || p->d_scrB.ensure((size_t)dec_total + 16) ||
-            p->d_frames.ensure(nb * (size_t)IR_MAX_FRAME) || p->d_co.ensure(nb) || p->d_do.ensure(nb) ||
-            p->d_bits.ensure(nb * 2 * (size_t)IR_MAX_SYMS) || p->d_llr.ensure(nb * 2 * (size_t)IR_MAX_SYMS))
-            return -1;
-        CK(cudaMemcpyAsync(p->d_bp.p, p->h_bp.data(), nb * sizeof(BurstParam), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(p->d_tile_start.p, tile_start.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-        p->res.h2d_bytes += nb * sizeof(BurstParam) + (nb + 1) * sizeof(int);
-        CK(cudaEventRecord(e_fir0, st));
-        CK(launch_fir(fmt, p->dec, iq_dev, (int64_t)n, R, p->d_bp.p, p->d_tile_start.p, (int)nb, n_tiles, p->d_dec.p, st));
-        CK(cudaEventRecord(e_fir1, st));
-        CK(launch_chain(p->d_bp.p, (int)nb, p->d_dec.p, p->d_scrA.p, p->d_scrB.p, p->d_tw12.p, p->d_tw11.p,
-                        p->d_sync_dl.p, p->d_sync_ul.p, p->d_co.p, p->d_frames.p, st));
-        CK(cudaEventRecord(e_ch1, st));
-        CK(launch_demod(p->d_co.p, (int)nb, p->d_frames.p, p->cfg.use_gardner, p->d_do.p, p->d_bits.p, p->d_llr.p, st));
-        CK(cudaEventRecord(e_dm1, st));
-        p->res.kernel_launches += (n_tiles > 0 ? 1 : 0) + 2;
-        p->h_bits_raw.resize(nb * 2 * (size_t)IR_MAX_SYMS);
-        p->h_llr_raw.resize(nb * 2 * (size_t)IR_MAX_SYMS);
-        CK(cudaMemcpyAsync(p->h_co.data(), p->d_co.p, nb * sizeof(ChainOut), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(p->h_do.data(), p->d_do.p, nb * sizeof(DemodOut), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(p->h_bits_raw.data(), p->d_bits.p, p->h_bits_raw.size(), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(p->h_llr_raw.data(), p->d_llr.p, p->h_llr_raw.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
-        p->res.d2h_bytes += nb * (sizeof(ChainOut) + sizeof(DemodOut)) + p->h_bits_raw.size() + p->h_llr_raw.size() * sizeof(float);
-    } else {
-        CK(cudaEventRecord(e_fir0, st)); CK(cudaEventRecord(e_fir1, st));
-        CK(cudaEventRecord(e_ch1, st)); CK(cudaEventRecord(e_dm1, st));
+    w.e0 = p->ev(); w.e1 = p->ev(); w.e2 = p->ev(); w.e3 = p->ev(); w.e_done = p->ev();
+    w.d_bp = p->dev_arena.take<BurstParam>(nb);
+    w.d_tile_start = p->dev_arena.take<int>(nb + 1);
+    w.d_dec = p->dev_arena.take<float2>((size_t)dec_total + 16);
+    w.d_scrA = p->dev_arena.take<float2>((size_t)dec_total + 16);
+    w.d_scrB = p->dev_arena.take<float2>((size_t)dec_total + 16);
+    w.d_frames = p->dev_arena.take<float2>(nb * (size_t)IR_MAX_FRAME);
+    w.d_co = p->dev_arena.take<ChainOut>(nb);
+    w.d_do = p->dev_arena.take<DemodOut>(nb);
+    w.d_bits = p->dev_arena.take<unsigned char>(nb * nsym2);
+    w.d_llr = p->dev_arena.take<float>(nb * nsym2);
+    if (!w.d_bp || !w.d_tile_start || !w.d_dec || !w.d_scrA || !w.d_scrB || !w.d_frames || !w.d_co || !w.d_do ||
+        !w.d_bits || !w.d_llr)
+        return -1;
+    for (size_t i = b0; i < b1; i++) {
+        p->frame_ptr[i] = w.d_frames + (i - b0) * (size_t)IR_MAX_FRAME;
+        p->dec_ptr[i] = w.d_dec + p->h_bp[i].dec_off;
     }
-    cudaEvent_t e_end = p->ev();
-    CK(cudaEventRecord(e_end, st));
-    CK(cudaStreamSynchronize(st));
-    // ---- assemble demod_frame_t equivalents (qpsk_demod.c:505-527) on the host, in double
-    p->frames.clear(); p->bits.clear(); p->llr.clear();
+    CK(cudaMemcpyAsync(w.d_bp, w.h_bp, nb * sizeof(BurstParam), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(w.d_tile_start, w.h_tile_start, (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    p->res.h2d_bytes += nb * sizeof(BurstParam) + (nb + 1) * sizeof(int);
+    CK(cudaEventRecord(w.e0, st));
+    CK(launch_fir(fmt, p->dec, iq_dev, (int64_t)n, R, w.d_bp, w.d_tile_start, (int)nb, n_tiles, w.d_dec, st));
+    CK(cudaEventRecord(w.e1, st));
+    CK(launch_chain(w.d_bp, (int)nb, w.d_dec, w.d_scrA, w.d_scrB, p->d_tw12.p, p->d_tw11.p, p->d_sync_dl.p,
+                    p->d_sync_ul.p, w.d_co, w.d_frames, st));
+    CK(cudaEventRecord(w.e2, st));
+    CK(launch_demod(w.d_co, (int)nb, w.d_frames, p->cfg.use_gardner, w.d_do, w.d_bits, w.d_llr, st));
+    CK(cudaEventRecord(w.e3, st));
+    p->res.kernel_launches += (n_tiles > 0 ? 1 : 0) + 2;
+    CK(cudaMemcpyAsync(w.h_co, w.d_co, nb * sizeof(ChainOut), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(w.h_do, w.d_do, nb * sizeof(DemodOut), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(w.h_bits, w.d_bits, nb * nsym2, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(w.h_llr, w.d_llr, nb * nsym2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    p->res.d2h_bytes += nb * (sizeof(GoneBurst) + sizeof(ChainOut) + sizeof(DemodOut) + nsym2 * 5);
+    CK(cudaEventRecord(w.e_done, st));
+    p->waves.push_back(w);
+    return 0;
+}
+
+// demod_frame_t equivalents (qpsk_demod.c:505-527) of one finished wave, on the host, in double
+static int assemble_wave(ir_pipeline *p, const Wave &w) {
+    CK(cudaEventSynchronize(w.e_done));
+    const int fs = p->dc.sample_rate;
     const uint64_t delay_ns = (uint64_t)((IR_INPUT_NTAPS / 2) * 1000000000ULL / fs);      // burst_downmix.c:431-433
-    for (size_t i = 0; i < nb; i++) {
+    const size_t nsym2 = 2 * (size_t)IR_MAX_SYMS;
+    for (size_t i = w.b0; i < w.b0 + w.nb; i++) {
         ir_burst_t &ob = p->bursts[i];
-        const ChainOut &c = p->h_co[i];
-        const DemodOut &d = p->h_do[i];
+        const ChainOut &c = w.h_co[i - w.b0];
+        const DemodOut &d = w.h_do[i - w.b0];
         ob.downmix_status = p->h_bp[i].dec_len >= 100 ? c.status : (ob.num_samples < 100 ? 1 : 2);
         ob.demod_ok = 0;
         ob.center_offset = c.center_offset; ob.dm_start = c.start; ob.uw_start = c.uw_start;
         ob.frame_len = c.frame_len; ob.uw_start_frac = c.uw_corr; ob.dm_direction = c.direction;
         if (ob.downmix_status != 0) continue;
-        alg += 8ull * (uint64_t)c.frame_len;
+        p->alg += 8ull * (uint64_t)c.frame_len;
         if (!d.ok) continue;
         ob.demod_ok = 1;
         ir_frame_t f;
@@ -402,30 +484,20 @@ static int finish_run(ir_pipeline *p, const void *iq_dev, size_t n, int fmt, cud
         f.n_symbols = d.n_symbols; f.n_payload_symbols = d.n_symbols - 12;
         f.n_bits = 2 * d.n_symbols;
         f.bits_offset = (uint32_t)p->bits.size();
-        const uint8_t *br = p->h_bits_raw.data() + i * 2 * (size_t)IR_MAX_SYMS;
-        const float *lr = p->h_llr_raw.data() + i * 2 * (size_t)IR_MAX_SYMS;
+        const uint8_t *br = w.h_bits + (i - w.b0) * nsym2;
+        const float *lr = w.h_llr + (i - w.b0) * nsym2;
         p->bits.insert(p->bits.end(), br, br + f.n_bits);
         p->llr.insert(p->llr.end(), lr, lr + f.n_bits);
         p->frames.push_back(f);
-        alg += 8ull * (uint64_t)c.frame_len + (uint64_t)f.n_bits;
+        p->alg += 8ull * (uint64_t)c.frame_len + (uint64_t)f.n_bits;
     }
-    // ---- timings
-    auto span = [&](cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; };
-    p->res.ms_detect_fft = 0; p->res.ms_detect_scan = 0;
-    for (auto &e : ev_fft) p->res.ms_detect_fft += span(e.a, e.b);
-    for (auto &e : ev_scan) p->res.ms_detect_scan += span(e.a, e.b);
-    p->res.ms_downmix_fir = span(e_fir0, e_fir1);
-    p->res.ms_downmix_chain = span(e_fir1, e_ch1);
-    p->res.ms_demod = span(e_ch1, e_dm1);
-    p->res.ms_total = span(ev_begin, e_end);
-    p->res.alg_bytes = alg;
-    p->res.n_bursts = p->bursts.size(); p->res.bursts = p->bursts.data();
-    p->res.n_frames = p->frames.size(); p->res.frames = p->frames.data();
-    p->res.bits = p->bits.data(); p->res.llr = p->llr.data(); p->res.n_bits_total = p->bits.size();
-    p->last_iq = iq_dev; p->last_n = n; p->last_fmt = fmt;
     return 0;
 }
 
+// Whole path over one block.  Every chunk's copy / FFT / scan is enqueued up front; the host then
+// follows the detector chunk by chunk and launches the downmix + demod of the bursts each chunk
+// emitted (a "wave") on a fourth stream, so that only the last wave runs after the detector is
+// done.  The state machine occupies 8 SMs; the waves and the FFTs of later chunks use the rest.
 static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, size_t n, int fmt) {
     if (!p) { set_err("null pipeline"); return -1; }
     if (fmt < 0 || fmt > 2) { set_err("bad sample format"); return -1; }
@@ -435,6 +507,7 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     const size_t bps = (size_t)fmt_bytes(fmt);
     p->ev_used = 0;
     p->res.kernel_launches = 0; p->res.h2d_bytes = 0; p->res.d2h_bytes = 0;
+    p->alg = (uint64_t)n * bps;
     if (p->cfg.start_time_ns) p->start_time_ns = p->cfg.start_time_ns;
     else {
         struct timespec ts;
@@ -445,21 +518,36 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     p->n_frames_last = n_frames;
     if (p->d_mag.ensure((size_t)std::max<int64_t>(n_frames, 1) * N)) return -1;
     const uint32_t gone_cap = (uint32_t)std::max<size_t>(4096, n / 20000 + 1024);
-    if (p->d_gone.ensure(gone_cap)) return -1;
+    if (gone_cap > p->gone_cap) {
+        if (p->h_gone) cudaFreeHost(p->h_gone);
+        p->h_gone = nullptr; p->gone_cap = 0;
+        CK(cudaHostAlloc((void **)&p->h_gone, (size_t)gone_cap * sizeof(GoneBurst), cudaHostAllocMapped));
+        CK(cudaHostGetDevicePointer((void **)&p->d_gone, p->h_gone, 0));
+        p->gone_cap = gone_cap;
+    }
     const void *iq_dev = dev_iq;
     if (host_iq) {
         if (p->d_iq.ensure(n * bps + 64)) return -1;
         iq_dev = p->d_iq.p;
     }
+    // chunking: copies (host input only) overlap the detector kernels of earlier chunks
+    size_t chunk = p->cfg.h2d_chunk > 0 ? (size_t)p->cfg.h2d_chunk : ((size_t)16 << 20);
+    chunk = std::max<size_t>(chunk / N, 1) * N;
+    const size_t n_chunks = std::max<size_t>((n + chunk - 1) / chunk, 1);
+    if (n_chunks > p->hdr_slots) {
+        if (p->h_hdr) cudaFreeHost(p->h_hdr);
+        p->h_hdr = nullptr; p->hdr_slots = 0;
+        CK(cudaHostAlloc((void **)&p->h_hdr, (n_chunks + 8) * kHdrBytes, cudaHostAllocDefault));
+        p->hdr_slots = n_chunks + 8;
+    }
+    if (p->dev_arena.begin((size_t)64 << 20) || p->pin_arena.begin((size_t)8 << 20)) return -1;
+    p->waves.clear(); p->chunks.clear();
+    p->bursts.clear(); p->h_bp.clear(); p->frame_ptr.clear(); p->dec_ptr.clear();
+    p->frames.clear(); p->bits.clear(); p->llr.clear();
     if (ir_pipeline_reset(p)) return -1;
     cudaEvent_t ev_begin = p->ev();
     CK(cudaEventRecord(ev_begin, p->st_scan));          // after the state reset
     CK(cudaStreamWaitEvent(p->st_fft, ev_begin, 0));
-    std::vector<EvPair> ev_fft, ev_scan;
-    // chunking: copies (host input only) overlap the detector kernels of earlier chunks
-    size_t chunk = p->cfg.h2d_chunk > 0 ? (size_t)p->cfg.h2d_chunk : ((size_t)16 << 20);
-    chunk = std::max<size_t>(chunk / N, 1) * N;
-    if (!host_iq) chunk = std::max<size_t>((size_t)64 << 20, chunk);    // resident input: few big launches
     for (size_t off = 0; off < n; off += chunk) {
         const size_t m = std::min(chunk, n - off);
         if (host_iq) {
@@ -472,26 +560,98 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
         }
         const int64_t f0 = (int64_t)(off / N);
         const int64_t f1 = std::min<int64_t>((int64_t)((off + m) / N), n_frames);
-        if (f1 <= f0) continue;
-        EvPair a{p->ev(), p->ev()}, b{p->ev(), p->ev()};
-        CK(cudaEventRecord(a.a, p->st_fft));
-        CK(launch_detect_fft(dc.L, fmt, iq_dev, f0 * N, p->d_window.p, p->d_tw_det.p, p->d_mag.p + f0 * N,
-                             f1 - f0, p->sm_count, p->st_fft));
-        CK(cudaEventRecord(a.b, p->st_fft));
-        CK(cudaStreamWaitEvent(p->st_scan, a.b, 0));
-        CK(cudaEventRecord(b.a, p->st_scan));
-        CK(launch_detect_scan_auto(dc, p->d_state.p, p->d_base.p, p->d_hist.p, p->d_mag.p + f0 * N, f1 - f0,
-                              p->d_gone.p, gone_cap, p->st_scan));
-        CK(cudaEventRecord(b.b, p->st_scan));
-        ev_fft.push_back(a); ev_scan.push_back(b);
-        p->res.kernel_launches += 2;
+        Chunk c;
+        c.end = off + m;
+        c.fft = EvPair{p->ev(), p->ev()};
+        c.scan = EvPair{p->ev(), p->ev()};
+        c.e_hdr = p->ev();
+        CK(cudaEventRecord(c.fft.a, p->st_fft));
+        if (f1 > f0) {
+            CK(launch_detect_fft(dc.L, fmt, iq_dev, f0 * N, p->d_window.p, p->d_tw_det.p, p->d_mag.p + f0 * N,
+                                 f1 - f0, p->sm_count, p->st_fft));
+            p->res.kernel_launches++;
+        }
+        CK(cudaEventRecord(c.fft.b, p->st_fft));
+        CK(cudaStreamWaitEvent(p->st_scan, c.fft.b, 0));
+        CK(cudaEventRecord(c.scan.a, p->st_scan));
+        if (f1 > f0) {
+            CK(launch_detect_scan_auto(dc, p->d_state.p, p->d_base.p, p->d_hist.p, p->d_mag.p + f0 * N, f1 - f0,
+                                       p->d_gone, p->gone_cap, p->st_scan));
+            p->res.kernel_launches++;
+        }
+        CK(cudaEventRecord(c.scan.b, p->st_scan));
+        CK(cudaMemcpyAsync(p->h_hdr + p->chunks.size() * kHdrBytes, p->d_state.p, kHdrBytes, cudaMemcpyDeviceToHost,
+                           p->st_scan));
+        CK(cudaEventRecord(c.e_hdr, p->st_scan));
+        p->res.d2h_bytes += kHdrBytes;
+        p->chunks.push_back(c);
     }
-    if (host_iq) {                                        // the FIR reads iq on st_scan: all copies must be in
-        cudaEvent_t e = p->ev();
-        CK(cudaEventRecord(e, p->st_copy));
-        CK(cudaStreamWaitEvent(p->st_scan, e, 0));
+    // ---- follow the detector: one wave of bursts per chunk
+    const uint64_t B = p->cfg.feed_block > 0 ? (uint64_t)p->cfg.feed_block : 32768;
+    size_t done = 0, assembled = 0;
+    DetState hs;
+    memset(&hs, 0, kHdrBytes);
+    for (size_t ci = 0; ci < p->chunks.size(); ci++) {
+        CK(cudaEventSynchronize(p->chunks[ci].e_hdr));
+        memcpy(&hs, p->h_hdr + ci * kHdrBytes, kHdrBytes);
+        if (hs.overflow || hs.n_gone > p->gone_cap) { set_err("detector capacity exceeded (IR_MAX_ACTIVE or burst list)"); return -1; }
+        const bool last = ci + 1 == p->chunks.size();
+        // a burst can be processed once every sample its extract reads is resident: its emit point
+        // (end of the emulated feed call) must lie inside what has been copied and scanned
+        size_t hi = done;
+        while (hi < hs.n_gone) {
+            if (!last) {
+                const uint64_t calls = (p->h_gone[hi].stop + (uint64_t)N + B - 1) / B;
+                if (std::min<uint64_t>(calls * B, n) > p->chunks[ci].end) break;
+            }
+            hi++;
+        }
+        if (hi > done) {
+            if (launch_wave(p, done, hi, iq_dev, n, fmt)) return -1;
+            done = hi;
+        }
+        // assemble earlier waves while this one runs
+        while (assembled + 1 < p->waves.size()) {
+            if (assemble_wave(p, p->waves[assembled])) return -1;
+            assembled++;
+        }
     }
-    return finish_run(p, iq_dev, n, fmt, ev_begin, ev_fft, ev_scan);
+    cudaEvent_t e_end = p->ev();
+    if (!p->chunks.empty()) CK(cudaStreamWaitEvent(p->st_burst, p->chunks.back().e_hdr, 0));
+    else CK(cudaStreamWaitEvent(p->st_burst, ev_begin, 0));
+    CK(cudaEventRecord(e_end, p->st_burst));
+    for (; assembled < p->waves.size(); assembled++)
+        if (assemble_wave(p, p->waves[assembled])) return -1;
+    if (host_iq) CK(cudaStreamSynchronize(p->st_copy));
+    CK(cudaStreamSynchronize(p->st_burst));
+    if (getenv("IR_SCAN_DEBUG")) {
+        fprintf(stderr, "scan cycles leader: p1 %llu waitA %llu p2 %llu waitB %llu p3 %llu waitC %llu batches %llu qbatches %llu\n",
+                hs.dbg[0], hs.dbg[1], hs.dbg[2], hs.dbg[3], hs.dbg[4], hs.dbg[5], hs.dbg[6], hs.dbg[7]);
+        fprintf(stderr, "scan leader p2 split: search %llu preflags %llu deletion %llu creation %llu squelch/end %llu | event frames %llu creates %llu deletes %llu\n",
+                hs.dbg[8], hs.dbg[9], hs.dbg[10], hs.dbg[11], hs.dbg[12], hs.dbg[13], hs.dbg[14], hs.dbg[15]);
+        fprintf(stderr, "scan owner(rank3) p1 split: issue %llu oldloads %llu wait+sync %llu lds+sync %llu compute %llu\n",
+                hs.dbg[16], hs.dbg[17], hs.dbg[18], hs.dbg[19], hs.dbg[20]);
+    }
+    // ---- timings: CUDA events on the launching streams
+    auto span = [&](cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; };
+    p->res.ms_detect_fft = 0; p->res.ms_detect_scan = 0;
+    p->res.ms_downmix_fir = 0; p->res.ms_downmix_chain = 0; p->res.ms_demod = 0;
+    for (auto &c : p->chunks) {
+        p->res.ms_detect_fft += span(c.fft.a, c.fft.b);
+        p->res.ms_detect_scan += span(c.scan.a, c.scan.b);
+    }
+    for (auto &w : p->waves) {
+        p->res.ms_downmix_fir += span(w.e0, w.e1);
+        p->res.ms_downmix_chain += span(w.e1, w.e2);
+        p->res.ms_demod += span(w.e2, w.e3);
+    }
+    p->res.ms_total = span(ev_begin, e_end);
+    p->res.alg_bytes = p->alg;
+    p->res.n_bursts = p->bursts.size(); p->res.bursts = p->bursts.data();
+    p->res.n_frames = p->frames.size(); p->res.frames = p->frames.data();
+    p->res.bits = p->bits.data(); p->res.llr = p->llr.data(); p->res.n_bits_total = p->bits.size();
+    p->last_iq = iq_dev; p->last_n = n; p->last_fmt = fmt;
+    return 0;
 }
 
 extern "C" int ir_pipeline_run_host(ir_pipeline_t *p, const void *iq, size_t n_samples, int fmt) {
@@ -523,7 +683,7 @@ extern "C" int ir_pipeline_copy_frame_samples(ir_pipeline_t *p, size_t bi, float
     const size_t nfl = (size_t)p->bursts[bi].frame_len;
     if (p->bursts[bi].downmix_status != 0 || nfl > cap) return -1;
     CK(cudaSetDevice(p->dev));
-    CK(cudaMemcpy(dst, p->d_frames.p + bi * (size_t)IR_MAX_FRAME, nfl * sizeof(float2), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(dst, p->frame_ptr[bi], nfl * sizeof(float2), cudaMemcpyDeviceToHost));
     return (int)nfl;
 }
 
@@ -532,7 +692,7 @@ extern "C" int ir_pipeline_copy_decimated(ir_pipeline_t *p, size_t bi, float *ds
     const size_t dl = (size_t)p->h_bp[bi].dec_len;
     if (dl == 0 || dl > cap) return -1;
     CK(cudaSetDevice(p->dev));
-    CK(cudaMemcpy(dst, p->d_dec.p + p->h_bp[bi].dec_off, dl * sizeof(float2), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(dst, p->dec_ptr[bi], dl * sizeof(float2), cudaMemcpyDeviceToHost));
     return (int)dl;
 }
 

@@ -168,7 +168,7 @@ def test_batched_raw_text_equals_per_frame_lines(run_small):
     p, res = run_small
     t0 = (res.frames[0]["timestamp"] // 10**9) * 10**9
     lines = res.raw_lines("T", t0)
-    assert p.raw_text("T", t0).decode() == "".join(l + "\n" for l in lines)
+    assert p.raw_text("T", t0).decode() == "".join(l.rstrip("\n") + "\n" for l in lines)
     assert p.raw_text("T", 0) == p.raw_text("T", t0)
 
 
