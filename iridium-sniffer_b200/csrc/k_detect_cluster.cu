@@ -8,19 +8,37 @@
 // burst_detect.c:438-454), on which nothing else happens:
 //
 //   batch type F (bursts active): the baseline is frozen, so the owners compute the
-//     "above threshold" bitmaps of K frames at once; the leader CTA then replays the K frames
-//     through the sparse state machine (hysteresis, deletion, masks, peak picking, squelch).
-//     The batch is cut after the first frame that ends with a baseline update.
+//     "above threshold" bitmaps of K frames at once; the leader CTA then works out what the
+//     state machine does on those K frames.  The batch is cut after the first frame that ends
+//     with a baseline update.
 //   batch type Q (no burst active): the owners assume every frame is quiet, update their
 //     baselines frame by frame (per-bin serial, exactly the reference's two roundings) and
 //     produce the bitmaps along the way; the leader only has to confirm that no valid bin crossed
 //     the threshold.  The first frame that does cuts the batch: owners rewind to that frame
 //     (recompute from the batch start) and the next batch is of type F.
 //
-// Two cluster barriers per batch instead of two CTA barriers per frame; bitmaps travel to the
+// Owners (phase 1) stream their slices straight from global memory into registers, one chunk of
+// frames ahead, and test them against per-bin thresholds; only a warp that sees a crossing builds
+// bitmap words (ballots) and lists them as (frame, word) entries.  Everything the leader does
+// is driven by those sparse entries.
+//
+// Leader, type F (phase 2): the frames of a batch are NOT replayed one by one.  With a frozen
+// baseline a burst's end frame depends only on its own bins (hysteresis replay: one warp per
+// burst, one lane per frame), so deletions need no sequential step at all.  What is sequential is
+// burst creation -- a new burst masks its neighbourhood in later frames -- so the leader iterates
+// "rounds": find the earliest frame with an eligible crossing given every burst known so far,
+// create that frame's bursts (strongest first), compute their end frames, repeat.  The plan is
+// applied (burst list, gone records, ids, mask) only at the end; anything unusual -- squelch,
+// a burst that could exceed max_burst_len, table overflow -- drops the plan and runs the plain
+// frame-by-frame replay instead, which is also the cross-check path (IR_SCAN=cluster_dense).
+//
+// Three cluster barriers per batch instead of two CTA barriers per frame; bitmaps travel to the
 // leader through distributed shared memory.  Results are identical to the single-CTA kernel in
-// k_detect.cu (kept for N < 2048 and as a cross-check; tests compare both with the CPU oracle).
+// k_detect.cu (kept for N < 2048 and as a cross-check; tests compare all variants with the CPU
+// oracle).
 #include <cooperative_groups.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "ir_device.cuh"
 #include "ir_internal.h"
@@ -34,13 +52,25 @@ namespace {
 constexpr int CL = 8;          // CTAs per cluster
 constexpr int CT = 256;        // threads per CTA
 constexpr int KB = 32;         // frames per batch
-static_assert(KB == 32, "the leader's frame search maps one frame to one lane");
+static_assert(KB == 32, "the leader maps one frame to one lane");
 constexpr int MAXW = 512;      // bitmap words per frame (N <= 16384)
-constexpr int MAXC = 2048;     // candidate peaks kept in shared memory per frame
+constexpr int MAXC = 1024;     // candidate peaks kept in shared memory per frame
+constexpr int ENT_PER = 256;   // non-zero bitmap words listed per CTA and batch
+constexpr int ENT_MAX = CL * ENT_PER;
+constexpr int PB_MAX = CT;     // bursts a plan can hold (one thread each when it is applied)
+constexpr int NOF = 64;        // "no frame"
+constexpr uint32_t FULL = 0xffffffffu;
 
 struct ClShared {
     uint32_t words[KB][MAXW];      // leader only: above-threshold bitmaps of the batch
     uint32_t myw[KB][MAXW / CL];   // every CTA: its own words of the batch, shipped once per batch
+    // sparse view of the same bitmaps: (frame << 16 | word) of every non-zero word
+    uint32_t my_ent[ENT_PER];      // every CTA: entries of its own words
+    uint32_t ent_r[CL][ENT_PER];   // leader only: as shipped by each CTA
+    uint32_t ent[ENT_MAX];         // leader only: compacted
+    int my_n_ent;
+    int n_ent_r[CL];
+    int fbits[KB];                 // leader: set valid bits per frame (bound on candidate peaks)
     uint32_t free_mask[MAXW];      // 1 = bin not covered by an active burst
     uint32_t valid[MAXW];
     uint32_t cand[MAXW];
@@ -51,6 +81,15 @@ struct ClShared {
     int ctl_push_normal;
     int ctl_reset_noise;           // squelch reset happened at the last committed frame
     int ctl_next_type;             // 0 = F, 1 = Q
+    // plan of a type-F batch
+    int pb_cb[PB_MAX];             // center bin
+    int pb_create[PB_MAX];         // frame of creation, -1 = active before the batch
+    int pb_end[PB_MAX];            // frame of deletion, NOF = survives the batch
+    uint32_t pb_hm[PB_MAX];        // frames with a hysteresis hit
+    float nb_rel[PB_MAX];          // new bursts: peak relative magnitude, baseline at creation
+    float nb_base[PB_MAX];
+    int pl_rank[PB_MAX];
+    int fstar, round_new, plan_abort;
     // leader machine state
     int n_cand;                    // candidate peaks of the frame being processed
     int cbin[MAXC];
@@ -67,12 +106,20 @@ struct ClShared {
 
 __device__ __forceinline__ bool cbit(const uint32_t *bm, int bin) { return (bm[bin >> 5] >> (bin & 31)) & 1u; }
 
+// bits of word w that lie in [lo, hi] (bin numbers)
+__device__ __forceinline__ uint32_t range_bits(int w, int lo, int hi) {
+    int a = max(lo, w << 5), b = min(hi, (w << 5) + 31);
+    if (a > b) return 0u;
+    a &= 31; b &= 31;
+    return (b == 31 ? FULL : ((1u << (b + 1)) - 1u)) & ~((1u << a) - 1u);
+}
+
 __device__ __forceinline__ void cclear(uint32_t *bm, int lo, int hi) {
-    for (int w = lo >> 5; w <= (hi >> 5); w++) {
-        int a = max(lo, w << 5) & 31, b = min(hi, (w << 5) + 31) & 31;
-        uint32_t m = (b == 31 ? 0xffffffffu : ((1u << (b + 1)) - 1u)) & ~((1u << a) - 1u);
-        atomicAnd(&bm[w], ~m);
-    }
+    for (int w = lo >> 5; w <= (hi >> 5); w++) atomicAnd(&bm[w], ~range_bits(w, lo, hi));
+}
+
+__device__ __forceinline__ bool hyst_hit(const uint32_t *Wf, int cb, int N) {
+    return (cb > 0 && cbit(Wf, cb - 1)) || cbit(Wf, cb) || (cb < N - 1 && cbit(Wf, cb + 1));
 }
 
 __device__ __forceinline__ void cgone(ClShared &S, GoneBurst *gone, uint32_t cap, const ActBurst &b, uint64_t index) {
@@ -94,7 +141,7 @@ template <int BPT>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 1)
 k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g,
                       float *__restrict__ hist, const float *__restrict__ mag, int64_t n_frames,
-                      GoneBurst *__restrict__ gone, uint32_t gone_cap) {
+                      GoneBurst *__restrict__ gone, uint32_t gone_cap, int force_dense) {
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ClShared &S = *reinterpret_cast<ClShared *>(smem_raw);
@@ -132,7 +179,7 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
                 v |= ok ? (1u << b) : 0u;
             }
             S.valid[w] = v;
-            S.free_mask[w] = 0xffffffffu;
+            S.free_mask[w] = FULL;
         }
         __syncthreads();
         if (tid < S.n_act) cclear(S.free_mask, max(S.act[tid].center_bin - c.half_bw, 0),
@@ -156,40 +203,29 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
         }
         if (++hist_idx == c.hist_size) { primed = 1; hist_idx = 0; }
     };
-    // bitmap words of one frame (values already in registers) for the owned bins -> leader's words[j]
-    auto screen_vals = [&](const float (&mv)[BPT], int j) {
-        bool pass_any = false;
-#pragma unroll
-        for (int u = 0; u < BPT; u++) {
-            const float lim = base[u] > 0.0f ? base[u] * thr_lo : INF;
-            pass_any = pass_any | (mv[u] > lim);
+    // rel = mag/base > thr (IEEE divide, simd_avx2.c:239-257).  Outside the band
+    // base*thr*(1 -+ 1e-5) the outcome is decided by a product; the divide runs only inside it.
+    auto above = [&](float mv, float bs) -> bool {
+        bool ab = false;
+        if (bs > 0.0f) {
+            if (mv > bs * thr_hi) ab = true;
+            else if (mv > bs * thr_lo) ab = mv / bs > thr;
         }
-        const bool warp_pass = __any_sync(0xffffffffu, pass_any);
-#pragma unroll
-        for (int u = 0; u < BPT; u++) {
-            uint32_t b = 0;
-            if (warp_pass) {
-                // rel = mag/base > thr (IEEE divide, simd_avx2.c:239-257).  Outside the band
-                // base*thr*(1 -+ 1e-5) the outcome is decided by a product; the divide runs only
-                // for values inside it.
-                bool ab = false;
-                if (base[u] > 0.0f) {
-                    if (mv[u] > base[u] * thr_hi) ab = true;
-                    else if (mv[u] > base[u] * thr_lo) ab = mv[u] / base[u] > thr;
-                }
-                b = __ballot_sync(0xffffffffu, ab);
-            }
-            if (lane == 0) S.myw[j][u * (CT / 32) + warp] = b;
+        return ab;
+    };
+    // one bitmap word (32 consecutive bins of this warp) of frame j: store + list it if non-zero
+    auto put_word = [&](int j, int u, bool ab) {
+        const uint32_t b = __ballot_sync(FULL, ab);
+        if (lane == 0 && b) {
+            S.myw[j][u * (CT / 32) + warp] = b;
+            const int s = atomicAdd(&S.my_n_ent, 1);
+            if (s < ENT_PER) S.my_ent[s] = ((uint32_t)j << 16) | (uint32_t)(rank * WPC + u * (CT / 32) + warp);
         }
     };
-    // Frames are consumed in groups of G whose values (and, for quiet batches, the history rows
-    // they replace) are all requested before the first is used: one memory round trip per group
-    // instead of one per frame.
-    constexpr int G = BPT >= 8 ? 4 : (BPT == 4 ? 8 : 16);
-    float *stage = reinterpret_cast<float *>(smem_raw + ((sizeof(ClShared) + 127) / 128) * 128);   // [2][G][NB]
+    constexpr int G = BPT >= 8 ? 4 : 8;                       // frames per register chunk
 
     unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    unsigned long long sub[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // leader phase-2 breakdown
+    unsigned long long sub[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // leader phase-2 breakdown
     unsigned long long p1s[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // owner phase-1 breakdown (rank 3)
     long long tsub = 0;
     long long tprev = clock64();
@@ -215,107 +251,115 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
         const int idx0 = hist_idx, primed0 = primed;
 #pragma unroll
         for (int u = 0; u < BPT; u++) base0[u] = base[u];
-        // The owned slices of the magnitude rows are staged through shared memory with 16-byte
-        // asynchronous copies, one group of G frames ahead of the group being consumed.
-        auto stage_group = [&](int j0s) {
-            float *dst = stage + (size_t)((j0s / G) & 1) * G * NB;
-            for (int g = 0; g < G; g++) {
-                if (j0s + g < Kb) {
-                    const float *src = rows + (size_t)(j0s + g) * N + bin0;
-                    for (int ch = tid; ch < NB / 4; ch += CT) cp_async_16(dst + (size_t)g * NB + 4 * ch, src + 4 * ch);
-                }
-            }
-            cp_async_commit();
-        };
         long long tq = clock64();
-        stage_group(0);
-        for (int j0 = 0; j0 < Kb; j0 += G) {
-            IR_P1(4);
-            const bool more = j0 + G < Kb;
-            if (more) stage_group(j0 + G);
-            IR_P1(0);
-            float mv[G][BPT], ov[G][BPT];
-            if (type == 1) {
+        if (tid == 0) S.my_n_ent = 0;
+        {
+            uint4 *mz = reinterpret_cast<uint4 *>(&S.myw[0][0]);
+            for (int i = tid; i < KB * (MAXW / CL) / 4; i += CT) mz[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+        auto load_chunk = [&](float (&dst)[G][BPT], int j0) {
 #pragma unroll
-                for (int g = 0; g < G; g++) {       // history rows of a quiet batch: plain loads, in flight
-                    const bool in = j0 + g < Kb;     // while the staged magnitudes are awaited
-                    int hrow = hist_idx + g;
-                    if (hrow >= c.hist_size) hrow -= c.hist_size;
-                    const float *h = hist + (size_t)hrow * N + bin0;
-                    // a history row is live if the detector is primed now or wraps before reaching it
-                    const bool live = primed || (hist_idx + g >= c.hist_size);
+            for (int g = 0; g < G; g++) {
+                const float *row = rows + (size_t)(j0 + g) * N + bin0 + tid;
 #pragma unroll
-                    for (int u = 0; u < BPT; u++) ov[g][u] = (in && live) ? h[u * CT + tid] : 0.0f;
+                for (int u = 0; u < BPT; u++) dst[g][u] = (j0 + g < Kb) ? row[u * CT] : 0.0f;
+            }
+        };
+        float lim[BPT];                                       // type F: per-bin pre-screen threshold
+#pragma unroll
+        for (int u = 0; u < BPT; u++) lim[u] = base[u] > 0.0f ? base[u] * thr_lo : INF;
+        float nx[G][BPT];
+        load_chunk(nx, 0);
+        IR_P1(0);
+#pragma unroll
+        for (int j0 = 0; j0 < KB; j0 += G) {
+            if (j0 >= Kb) break;
+            float mv[G][BPT];
+#pragma unroll
+            for (int g = 0; g < G; g++)
+#pragma unroll
+                for (int u = 0; u < BPT; u++) mv[g][u] = nx[g][u];
+            if (j0 + G < Kb) load_chunk(nx, j0 + G);          // next chunk in flight while this one is used
+            if (type == 0) {
+                // frozen baseline: frames (bits) on which this thread's bins pass the pre-screen
+                uint32_t fm[BPT];
+                uint32_t anyb = 0;
+#pragma unroll
+                for (int u = 0; u < BPT; u++) {
+                    fm[u] = 0;
+#pragma unroll
+                    for (int g = 0; g < G; g++) fm[u] |= (mv[g][u] > lim[u]) ? (1u << g) : 0u;
+                    anyb |= fm[u];
+                }
+                if (__any_sync(FULL, anyb != 0u)) {              // only where a burst sits
+#pragma unroll
+                    for (int u = 0; u < BPT; u++) {
+                        const uint32_t fr = __reduce_or_sync(FULL, fm[u]);
+#pragma unroll
+                        for (int g = 0; g < G; g++)
+                            if ((fr >> g) & 1u) put_word(j0 + g, u, above(mv[g][u], base[u]));
+                    }
                 }
             } else {
-#pragma unroll
-                for (int g = 0; g < G; g++)
-#pragma unroll
-                    for (int u = 0; u < BPT; u++) ov[g][u] = 0.0f;
-            }
-            IR_P1(1);
-            if (more) cp_async_wait_group<1>(); else cp_async_wait_group<0>();
-            __syncthreads();
-            IR_P1(2);
-            {
-                const float *srcs = stage + (size_t)((j0 / G) & 1) * G * NB;
+                float ov[G][BPT];
 #pragma unroll
                 for (int g = 0; g < G; g++) {
                     const bool in = j0 + g < Kb;
+                    int hrow = hist_idx + g;
+                    if (hrow >= c.hist_size) hrow -= c.hist_size;
+                    const float *h = hist + (size_t)hrow * N + bin0 + tid;
+                    // a history row is live if the detector is primed now or wraps before reaching it
+                    const bool live = primed || (hist_idx + g >= c.hist_size);
 #pragma unroll
-                    for (int u = 0; u < BPT; u++) mv[g][u] = in ? srcs[(size_t)g * NB + u * CT + tid] : 0.0f;
+                    for (int u = 0; u < BPT; u++) ov[g][u] = (in && live) ? h[u * CT] : 0.0f;
                 }
-            }
-            __syncthreads();                         // buffer may be refilled two groups later
-            IR_P1(3);
-            // Frozen baseline: one vote decides for the whole group whether this warp's bins need
-            // the per-frame test at all (they do only where a burst sits).
-            bool group_quiet = false;
-            if (type == 0) {
-                bool pass_any = false;
+                // speculative pass: update the baselines frame by frame, note pre-screen passes
+                float bs0[BPT];
 #pragma unroll
-                for (int u = 0; u < BPT; u++) {
-                    const float lim = base[u] > 0.0f ? base[u] * thr_lo : INF;
+                for (int u = 0; u < BPT; u++) bs0[u] = base[u];
+                const int hi0 = hist_idx, pr0 = primed;
+                uint32_t anyb = 0;
 #pragma unroll
-                    for (int g = 0; g < G; g++) pass_any = pass_any | (mv[g][u] > lim);
-                }
-                group_quiet = !__any_sync(0xffffffffu, pass_any);
-                if (group_quiet) {                      // G*BPT == 32 zero words, one per lane
-                    const int g = lane / BPT, u = lane % BPT;
-                    if (G * BPT == 32) {
-                        if (j0 + g < Kb) S.myw[j0 + g][u * (CT / 32) + warp] = 0;
-                    } else {
-                        for (int q = lane; q < G * BPT; q += 32)
-                            if (j0 + q / BPT < Kb) S.myw[j0 + q / BPT][(q % BPT) * (CT / 32) + warp] = 0;
-                    }
-                }
-            }
-#pragma unroll
-            for (int g = 0; g < G; g++) {
-                const int j = j0 + g;
-                if (j < Kb) {
-                    if (type == 0) {
-                        if (!group_quiet) screen_vals(mv[g], j);
-                    } else {
-                        if (primed) {
-                            screen_vals(mv[g], j);
-                        } else if (lane == 0) {
-#pragma unroll
-                            for (int u = 0; u < BPT; u++) S.myw[j][u * (CT / 32) + warp] = 0;
-                        }
-                        // speculative baseline update (history written at commit)
+                for (int g = 0; g < G; g++) {
+                    if (j0 + g < Kb) {
 #pragma unroll
                         for (int u = 0; u < BPT; u++) {
+                            // (a non-positive baseline passes here and is sorted out by the exact test)
+                            if (primed) anyb |= (mv[g][u] > base[u] * thr_lo) ? 1u : 0u;
                             const float v = base[u] - ov[g][u];
                             base[u] = v + mv[g][u];
                         }
                         if (++hist_idx == c.hist_size) { primed = 1; hist_idx = 0; }
                     }
                 }
+                if (__any_sync(FULL, anyb != 0u)) {              // rare: redo this chunk with the exact test
+#pragma unroll
+                    for (int u = 0; u < BPT; u++) base[u] = bs0[u];
+                    hist_idx = hi0; primed = pr0;
+#pragma unroll
+                    for (int g = 0; g < G; g++) {
+                        if (j0 + g < Kb) {
+                            if (primed) {
+#pragma unroll
+                                for (int u = 0; u < BPT; u++) {
+                                    const bool pass = base[u] > 0.0f ? (mv[g][u] > base[u] * thr_lo) : false;
+                                    if (__any_sync(FULL, pass)) put_word(j0 + g, u, above(mv[g][u], base[u]));
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < BPT; u++) {
+                                const float v = base[u] - ov[g][u];
+                                base[u] = v + mv[g][u];
+                            }
+                            if (++hist_idx == c.hist_size) { primed = 1; hist_idx = 0; }
+                        }
+                    }
+                }
             }
         }
-        IR_P1(4);
-        // ship this CTA's words of the whole batch to the leader: 16-byte DSMEM stores
+        IR_P1(1);
+        // ship this CTA's words and entries of the whole batch to the leader (DSMEM)
         __syncthreads();
         if (WPC >= 4) {
             constexpr int CH = WPC >= 4 ? WPC / 4 : 1;                 // 16-byte chunks per frame
@@ -327,23 +371,50 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
         } else {
             for (int i = tid; i < Kb * WPC; i += CT) LS.words[i / WPC][rank * WPC + i % WPC] = S.myw[i / WPC][i % WPC];
         }
+        {
+            const int my_n = S.my_n_ent;
+            for (int i = tid; i < my_n && i < ENT_PER; i += CT) LS.ent_r[rank][i] = S.my_ent[i];
+            if (tid == 0) LS.n_ent_r[rank] = my_n;
+        }
+        IR_P1(2);
         IR_TICK(0);
         cluster.sync();                                        // (A) bitmaps are at the leader
         IR_TICK(1);
-        // ---------------- phase 2: leader replays the batch
+        // ---------------- phase 2: leader
         if (leader) {
             int commit = Kb, push_forced = 0, push_normal = 0, reset_noise = 0;
+            // compact the per-CTA lists of non-zero words; sparse = they are complete
+            bool sparse = true;
+            int n_ent = 0;
+#pragma unroll
+            for (int r = 0; r < CL; r++) sparse = sparse && S.n_ent_r[r] <= ENT_PER;
+            if (sparse) {
+#pragma unroll
+                for (int r = 0; r < CL; r++) {
+                    const int nr = S.n_ent_r[r];
+                    for (int i = tid; i < nr; i += CT) S.ent[n_ent + i] = S.ent_r[r][i];
+                    n_ent += nr;
+                }
+            }
             if (type == 1) {
                 // confirm quietness: no valid bin may cross (the mask is all-free: n_act == 0)
                 if (tid == 0) S.ff_frame = Kb;
                 __syncthreads();
                 int mine = Kb;
-                for (int w = tid; w < W; w += CT) {
-                    const uint32_t v = S.valid[w];
-                    for (int j = 0; j < mine; j++)
-                        if (S.words[j][w] & v) { mine = j; break; }
+                if (sparse) {
+                    for (int e = tid; e < n_ent; e += CT) {
+                        const uint32_t en = S.ent[e];
+                        const int ej = (int)(en >> 16), w = (int)(en & 0xffffu);
+                        if (ej < mine && (S.words[ej][w] & S.valid[w])) mine = ej;
+                    }
+                } else {
+                    for (int w = tid; w < W; w += CT) {
+                        const uint32_t v = S.valid[w];
+                        for (int j = 0; j < mine; j++)
+                            if (S.words[j][w] & v) { mine = j; break; }
+                    }
                 }
-                mine = __reduce_min_sync(0xffffffffu, mine);
+                mine = __reduce_min_sync(FULL, mine);
                 if (lane == 0 && mine < Kb) atomicMin(&S.ff_frame, mine);
                 __syncthreads();
                 const int first = S.ff_frame;
@@ -358,25 +429,263 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
                     S.ctl_next_type = commit < Kb ? 0 : 1;
                 }
             } else {
-                uint64_t fidx = index;
                 tsub = clock64();
+                // ======== plan: rounds over burst creations (see the header)
+                bool planned = false;
+                {
+                    const int n_old = S.n_act;
+                    bool ok = sparse && primed && !force_dense && n_old <= PB_MAX - 64 &&
+                              (c.max_burst_len <= 0 ||
+                               (uint64_t)Kb * (uint64_t)N + (uint64_t)c.pre_len <= (uint64_t)c.max_burst_len);
+                    const uint64_t batch_end = index + (uint64_t)Kb * (uint64_t)N;
+                    int bad = 0;
+                    if (ok && c.max_burst_len > 0)
+                        for (int i = tid; i < n_old; i += CT)
+                            if (batch_end - S.act[i].start > (uint64_t)c.max_burst_len) bad = 1;   // could become too long
+                    if (tid < KB) S.fbits[tid] = 0;
+                    if (tid == 0) { S.plan_abort = 0; S.round_new = 0; }
+                    __syncthreads();                              // also orders the compaction of S.ent
+                    if (ok)
+                        for (int e = tid; e < n_ent; e += CT) {
+                            const uint32_t en = S.ent[e];
+                            const int ej = (int)(en >> 16), w = (int)(en & 0xffffu);
+                            atomicAdd(&S.fbits[ej], __popc(S.words[ej][w] & S.valid[w]));
+                        }
+                    __syncthreads();
+                    if (tid < KB && S.fbits[tid] > MAXC) bad = 1;  // a frame could overflow the peak list
+                    ok = !__syncthreads_or(bad) && ok;
+                    IR_SUB(0);
+                    if (ok) {
+                        const uint32_t *Wf = S.words[lane];       // lane = frame
+                        const uint64_t fi = index + (uint64_t)lane * (uint64_t)N;
+                        // bursts active before the batch: hysteresis replay -> end frame
+                        for (int i = warp; i < n_old; i += CT / 32) {
+                            const int cb = S.act[i].center_bin;
+                            const uint64_t b_la = S.act[i].last_active;
+                            const bool inr = lane < Kb;
+                            const uint32_t H = __ballot_sync(FULL, inr && hyst_hit(Wf, cb, N));
+                            const uint32_t Hle = H & (FULL >> (31 - lane));
+                            const uint64_t la = Hle ? index + (uint64_t)(31 - __clz(Hle)) * (uint64_t)N : b_la;
+                            const uint32_t D = __ballot_sync(FULL, inr && (la + (uint64_t)c.post_len <= fi));
+                            if (lane == 0) {
+                                S.pb_cb[i] = cb; S.pb_create[i] = -1; S.pb_end[i] = D ? __ffs(D) - 1 : NOF; S.pb_hm[i] = H;
+                            }
+                        }
+                        int n_pb = n_old, f_done = -1, n_new = 0, q = NOF;
+                        bool abort_plan = false;
+                        __syncthreads();
+                        IR_SUB(1);
+                        for (;;) {
+                            IR_COUNT(sub[9] += 1);
+                            if (tid == 0) { S.fstar = NOF; S.n_cand = 0; }
+                            // first frame after which no burst is left (every warp works it out)
+                            bool alive = lane >= Kb;
+                            for (int k = 0; k < n_pb; k++) alive = alive || (S.pb_create[k] <= lane && lane < S.pb_end[k]);
+                            const uint32_t am = __ballot_sync(FULL, alive);
+                            q = (~am) ? __ffs(~am) - 1 : NOF;
+                            const int flim = min(q, Kb - 1);
+                            __syncthreads();
+                            // earliest frame after f_done with a crossing no known burst masks.  A burst
+                            // masks the peaks of frames (create, end]: the mask is the previous frame's.
+                            for (int e = tid; e < n_ent; e += CT) {
+                                const uint32_t en = S.ent[e];
+                                const int f = (int)(en >> 16), w = (int)(en & 0xffffu);
+                                if (f > f_done && f <= flim) {
+                                    uint32_t m = S.words[f][w] & S.valid[w];
+                                    for (int k = 0; k < n_pb && m; k++)
+                                        if (S.pb_create[k] < f && f <= S.pb_end[k])
+                                            m &= ~range_bits(w, S.pb_cb[k] - c.half_bw, S.pb_cb[k] + c.half_bw);
+                                    if (m) atomicMin(&S.fstar, f);
+                                }
+                            }
+                            __syncthreads();
+                            const int fs = S.fstar;
+                            IR_SUB(2);
+                            if (fs >= NOF) break;
+                            // peaks of frame fs (:522-548)
+                            for (int e = tid; e < n_ent; e += CT) {
+                                const uint32_t en = S.ent[e];
+                                const int f = (int)(en >> 16), w = (int)(en & 0xffffu);
+                                if (f == fs) {
+                                    uint32_t m = S.words[f][w] & S.valid[w];
+                                    for (int k = 0; k < n_pb && m; k++)
+                                        if (S.pb_create[k] < f && f <= S.pb_end[k])
+                                            m &= ~range_bits(w, S.pb_cb[k] - c.half_bw, S.pb_cb[k] + c.half_bw);
+                                    if (m) {
+                                        int slot = atomicAdd(&S.n_cand, __popc(m));
+                                        while (m) {
+                                            const int b = __ffs(m) - 1;
+                                            m &= m - 1;
+                                            if (slot < MAXC) S.cbin[slot] = (w << 5) + b;
+                                            slot++;
+                                        }
+                                    }
+                                }
+                            }
+                            __syncthreads();
+                            const int nc = min(S.n_cand, MAXC);
+                            IR_SUB(3);
+                            {
+                                const float *row = rows + (size_t)fs * N;
+                                for (int i = tid; i < nc; i += CT) {
+                                    const int bin = S.cbin[i];
+                                    const float bs = base_g[bin];
+                                    S.crel[i] = row[bin] / bs;
+                                    S.cbase[i] = bs;
+                                }
+                            }
+                            __syncthreads();
+                            IR_SUB(4);
+                            if (warp == 0) {                      // create_new_bursts (:556-591): strongest first
+                                int t = 0;
+                                for (;;) {
+                                    ArgMax best{-1.0f, 0x7fffffff};
+                                    int bslot = -1;
+                                    for (int i = lane; i < nc; i += 32) {
+                                        const int bin = S.cbin[i];
+                                        if (bin >= 0) {
+                                            const ArgMax cur{S.crel[i], bin};
+                                            const ArgMax nb = argmax_pick(best, cur);
+                                            if (nb.i != best.i) bslot = i;
+                                            best = nb;
+                                        }
+                                    }
+                                    const ArgMax wbest = warp_argmax(best);
+                                    if (wbest.v < 0.0f) break;
+                                    const int bin = wbest.i;
+                                    const unsigned owner = __ballot_sync(FULL, best.i == bin && bslot >= 0);
+                                    const int src = __ffs(owner) - 1;
+                                    const float bc = __shfl_sync(FULL, bslot >= 0 ? S.cbase[bslot] : 0.0f, src);
+                                    if (n_pb + t >= PB_MAX) { if (lane == 0) S.plan_abort = 1; break; }
+                                    if (lane == 0) {
+                                        const int k = n_pb + t;
+                                        S.pb_cb[k] = bin; S.pb_create[k] = fs; S.pb_end[k] = NOF; S.pb_hm[k] = 0u;
+                                        S.nb_rel[n_new + t] = wbest.v; S.nb_base[n_new + t] = bc;
+                                    }
+                                    t++;
+                                    for (int i = lane; i < nc; i += 32) {
+                                        const int bb = S.cbin[i];
+                                        if (bb >= bin - c.half_bw && bb <= bin + c.half_bw) S.cbin[i] = -1;
+                                    }
+                                    __syncwarp();
+                                }
+                                if (lane == 0) S.round_new = t;
+                            }
+                            __syncthreads();
+                            const int t_new = S.round_new;
+                            IR_SUB(5);
+                            if (S.plan_abort) { abort_plan = true; break; }
+                            // end frames of the new bursts: they are updated from the next frame on
+                            for (int t = warp; t < t_new; t += CT / 32) {
+                                const int k = n_pb + t;
+                                const int cb = S.pb_cb[k];
+                                const bool inr = lane > fs && lane < Kb;
+                                const uint32_t H = __ballot_sync(FULL, inr && hyst_hit(Wf, cb, N));
+                                const uint32_t Hle = H & (FULL >> (31 - lane));
+                                const uint64_t start = index + (uint64_t)fs * (uint64_t)N - (uint64_t)c.pre_len;
+                                const uint64_t la = Hle ? index + (uint64_t)(31 - __clz(Hle)) * (uint64_t)N : start;
+                                const uint32_t D = __ballot_sync(FULL, inr && (la + (uint64_t)c.post_len <= fi));
+                                if (lane == 0) { S.pb_end[k] = D ? __ffs(D) - 1 : NOF; S.pb_hm[k] = H; }
+                            }
+                            __syncthreads();
+                            n_pb += t_new; n_new += t_new; f_done = fs;
+                            if (c.max_bursts > 0) {               // squelch (:593-631) is left to the replay
+                                int cnt = 0;
+                                for (int k = lane; k < n_pb; k += 32) cnt += (S.pb_create[k] <= fs && fs < S.pb_end[k]) ? 1 : 0;
+                                cnt = __reduce_add_sync(FULL, cnt);
+                                if (cnt > c.max_bursts) { abort_plan = true; break; }
+                            }
+                            if (n_pb > PB_MAX - 64) { abort_plan = true; break; }
+                            IR_SUB(6);
+                        }
+                        if (!abort_plan) {
+                            // ---- apply the plan: one thread per burst
+                            planned = true;
+                            const int C = q < Kb ? q + 1 : Kb;    // the batch is cut after the first quiet frame
+                            commit = C;
+                            push_normal = q < Kb ? 1 : 0;
+                            ActBurst mine;
+                            const bool have = tid < n_pb;
+                            int endf = NOF;
+                            bool ended = false;
+                            if (have) {
+                                endf = S.pb_end[tid];
+                                const int cr = S.pb_create[tid];
+                                if (cr < 0) {
+                                    mine = S.act[tid];
+                                } else {
+                                    const int t = tid - n_old;
+                                    mine.id = S.next_id + 10ull * (unsigned long long)t;
+                                    mine.start = index + (uint64_t)cr * (uint64_t)N - (uint64_t)c.pre_len;
+                                    mine.last_active = mine.start;
+                                    mine.center_bin = S.pb_cb[tid];
+                                    mine.peak_rel = S.nb_rel[t];
+                                    mine.base_at_create = S.nb_base[t];
+                                    mine.pad = 0;
+                                }
+                                ended = endf < C;
+                                const int lastf = ended ? endf : C - 1;
+                                const uint32_t hits = S.pb_hm[tid] & (lastf >= 31 ? FULL : ((1u << (lastf + 1)) - 1u));
+                                if (hits) mine.last_active = index + (uint64_t)(31 - __clz(hits)) * (uint64_t)N;
+                            }
+                            S.pl_rank[tid] = have ? (ended ? endf : -1) : -2;
+                            __syncthreads();
+                            int pos = 0;
+                            if (have) {
+                                // gone records in the replay's order: by deletion frame, then list order;
+                                // survivors keep their list order
+                                for (int k = 0; k < n_pb; k++) {
+                                    const int e2 = S.pl_rank[k];
+                                    if (ended) pos += (e2 >= 0 && (e2 < endf || (e2 == endf && k < tid))) ? 1 : 0;
+                                    else pos += (e2 == -1 && k < tid) ? 1 : 0;
+                                }
+                                if (ended) {
+                                    const uint32_t slot = S.n_gone + (uint32_t)pos;
+                                    if (slot < gone_cap) {
+                                        GoneBurst g;
+                                        g.id = mine.id; g.start = mine.start; g.stop = index + (uint64_t)endf * (uint64_t)N;
+                                        g.last_active = mine.last_active; g.center_bin = mine.center_bin;
+                                        g.peak_rel = mine.peak_rel; g.base_at_create = mine.base_at_create; g.pad = 0;
+                                        gone[slot] = g;
+                                    } else {
+                                        S.overflow = 1;
+                                    }
+                                }
+                            }
+                            const int n_end = __syncthreads_count(have && ended);     // also: every S.act read is done
+                            if (have && !ended) S.act[pos] = mine;
+                            for (int w = tid; w < W; w += CT) S.free_mask[w] = FULL;
+                            if (tid == 0) {
+                                S.n_act = n_pb - n_end;
+                                S.n_gone += (uint32_t)n_end;
+                                S.next_id += 10ull * (unsigned long long)n_new;
+                                S.squelch_count = max(S.squelch_count - C, 0);
+                            }
+                            __syncthreads();
+                            if (have && !ended)
+                                cclear(S.free_mask, max(mine.center_bin - c.half_bw, 0), min(mine.center_bin + c.half_bw, N - 1));
+                            __syncthreads();
+                        }
+                    }
+                }
+                IR_SUB(7);
+                IR_COUNT(sub[planned ? 10 : 11] += 1);
+                if (!planned) {
+                // ======== plain replay, frame by frame (every case)
+                uint64_t fidx = index;
                 for (int j = 0; j < Kb; j++, fidx += (uint64_t)N) {
-                    // Fast-forward: warp 0 alone walks the frames on which nothing happens (no
-                    // candidate peak, no burst ending, some burst still active), applying their
-                    // only effects (hysteresis refresh, squelch count-down), and stops at the
-                    // first frame that needs the full machinery.
-                    // The search is parallel: one thread per bitmap word looks for the first frame
-                    // with an unmasked valid crossing, one thread per active burst replays its
-                    // hysteresis to find the frame on which it ends; the earliest wins.
+                    // Fast-forward over the frames on which nothing happens (no candidate peak, no
+                    // burst ending, some burst still active), applying their only effects (hysteresis
+                    // refresh, squelch count-down).  The search is parallel: one thread per bitmap word
+                    // looks for the first frame with an unmasked valid crossing, one warp per active
+                    // burst replays its hysteresis to find the frame on which it ends; the earliest wins.
                     if (tid == 0) S.ff_frame = Kb;
                     __syncthreads();
                     const int na_ff = S.n_act;
                     // frames [j, Kb) of the batch as a bit range (KB == 32 == warp width)
-                    const uint32_t range = (Kb >= 32 ? 0xffffffffu : ((1u << Kb) - 1u)) & ~((1u << j) - 1u);
+                    const uint32_t range = (Kb >= 32 ? FULL : ((1u << Kb) - 1u)) & ~((1u << j) - 1u);
                     {
                         int mine = na_ff == 0 ? j : Kb;
-                        // candidates: one thread per word reads that word of all 32 frames (independent
-                        // loads, fully pipelined) and builds the mask of frames with an eligible bit
                         for (int w = tid; w < W; w += CT) {
                             const uint32_t mk = S.free_mask[w] & S.valid[w];
                             if (mk) {
@@ -394,30 +703,29 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
                             const int cb = b.center_bin;
                             const uint32_t *Wf = S.words[lane];
                             const bool inr = (range >> lane) & 1u;
-                            const bool hit = inr && ((cb > 0 && cbit(Wf, cb - 1)) || cbit(Wf, cb) || (cb < N - 1 && cbit(Wf, cb + 1)));
-                            const uint32_t H = __ballot_sync(0xffffffffu, hit);
-                            const uint32_t Hle = H & (0xffffffffu >> (31 - lane));
+                            const bool hit = inr && hyst_hit(Wf, cb, N);
+                            const uint32_t H = __ballot_sync(FULL, hit);
+                            const uint32_t Hle = H & (FULL >> (31 - lane));
                             const uint64_t fi = index + (uint64_t)lane * (uint64_t)N;
                             const uint64_t la = Hle ? index + (uint64_t)(31 - __clz(Hle)) * (uint64_t)N : b.last_active;
                             const bool too_long = c.max_burst_len > 0 && la - b.start > (uint64_t)c.max_burst_len;
                             const bool done = inr && ((la + (uint64_t)c.post_len <= fi) || too_long);
-                            const uint32_t D = __ballot_sync(0xffffffffu, done);
+                            const uint32_t D = __ballot_sync(FULL, done);
                             if (D) mine = min(mine, __ffs(D) - 1);
                         }
-                        mine = __reduce_min_sync(0xffffffffu, mine);
+                        mine = __reduce_min_sync(FULL, mine);
                         if (lane == 0 && mine < Kb) atomicMin(&S.ff_frame, mine);
                     }
                     __syncthreads();
                     {
                         const int jn = S.ff_frame;
                         // effects of the skipped frames [j, jn): hysteresis refresh, squelch count-down
-                        const uint32_t skipped = range & (jn >= 32 ? 0xffffffffu : ((1u << jn) - 1u));
+                        const uint32_t skipped = range & (jn >= 32 ? FULL : ((1u << jn) - 1u));
                         for (int i = warp; i < na_ff; i += CT / 32) {
                             const int cb = S.act[i].center_bin;
                             const uint32_t *Wf = S.words[lane];
-                            const bool hit = ((skipped >> lane) & 1u) &&
-                                             ((cb > 0 && cbit(Wf, cb - 1)) || cbit(Wf, cb) || (cb < N - 1 && cbit(Wf, cb + 1)));
-                            const uint32_t H = __ballot_sync(0xffffffffu, hit);
+                            const bool hit = ((skipped >> lane) & 1u) && hyst_hit(Wf, cb, N);
+                            const uint32_t H = __ballot_sync(FULL, hit);
                             if (lane == 0 && H) S.act[i].last_active = index + (uint64_t)(31 - __clz(H)) * (uint64_t)N;
                         }
                         if (tid == 0 && primed) {
@@ -427,9 +735,7 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
                         fidx += (uint64_t)(jn - j) * (uint64_t)N;
                         j = jn;
                     }
-                    IR_SUB(0);
                     if (j >= Kb) break;
-                    IR_COUNT(sub[5] += 1);
                     const uint32_t *Wd = S.words[j];
                     if (tid == 0) S.flags = 0;
                     __syncthreads();
@@ -439,8 +745,7 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
                     for (int i = tid; i < n_act; i += CT) {
                         ActBurst &b = S.act[i];
                         const int cb = b.center_bin;
-                        bool hit = (cb > 0 && cbit(Wd, cb - 1)) || cbit(Wd, cb) || (cb < N - 1 && cbit(Wd, cb + 1));
-                        if (hit) b.last_active = fidx;
+                        if (hyst_hit(Wd, cb, N)) b.last_active = fidx;
                         bool too_long = c.max_burst_len > 0 && b.last_active - b.start > (uint64_t)c.max_burst_len;
                         bool done = (b.last_active + (uint64_t)c.post_len <= fidx) || too_long;
                         if (done) fl |= 2;
@@ -456,7 +761,6 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
                     __syncthreads();
                     const int flags = S.flags;
                     bool forced = false;
-                    IR_SUB(1);
                     if (flags & 2) {                           // delete_gone_bursts (:490-518)
                         if (tid == 0) {
                             int k = 0;
@@ -471,7 +775,7 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
                         __syncthreads();
                         n_act = S.n_act;
                         forced = (flags & 4) != 0;             // update_filters_post(d, 1): applied by the owners
-                        for (int w = tid; w < W; w += CT) S.free_mask[w] = 0xffffffffu;
+                        for (int w = tid; w < W; w += CT) S.free_mask[w] = FULL;
                         __syncthreads();
                         for (int i = tid; i < n_act; i += CT)
                             cclear(S.free_mask, max(S.act[i].center_bin - c.half_bw, 0), min(S.act[i].center_bin + c.half_bw, N - 1));
@@ -481,9 +785,6 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
                     // and create_new_bursts: peaks keep their pre-update relative magnitude, the
                     // noise field reads the updated sum (:583).  The leader recomputes that one
                     // value per new burst itself; the owners apply the update after the batch.
-                    IR_SUB(2);
-                    IR_COUNT(if (flags & 1) sub[6] += 1);
-                    IR_COUNT(if (flags & 2) sub[7] += 1);
                     bool created_fast = false;
                     if (flags & 1) {
                         // Gather the candidate peaks once (bin, relative magnitude, baseline the
@@ -491,8 +792,6 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
                         // out of shared memory in a single warp.
                         const float *row = rows + (size_t)j * N;
                         const float *hold = hist + (size_t)hist_idx * N;
-                        // one candidate per thread, so that their global reads overlap: list the
-                        // bins first (cheap, shared memory only), then fetch in parallel
                         if (tid == 0) S.n_cand = 0;
                         __syncthreads();
                         for (int w = tid; w < W; w += CT) {
@@ -541,9 +840,9 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
                                     if (wbest.v < 0.0f) break;
                                     const int bin = wbest.i;
                                     // the lane that holds the winner publishes its baseline
-                                    const unsigned owner = __ballot_sync(0xffffffffu, best.i == bin && bslot >= 0);
+                                    const unsigned owner = __ballot_sync(FULL, best.i == bin && bslot >= 0);
                                     const int src = __ffs(owner) - 1;
-                                    const float bc = __shfl_sync(0xffffffffu, bslot >= 0 ? S.cbase[bslot] : 0.0f, src);
+                                    const float bc = __shfl_sync(FULL, bslot >= 0 ? S.cbase[bslot] : 0.0f, src);
                                     if (lane == 0) {
                                         const int slot = S.n_act;
                                         if (slot < IR_MAX_ACTIVE) {
@@ -620,7 +919,6 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
                             __syncthreads();
                         }
                     }
-                    IR_SUB(3);
                     // squelch (:593-631)
                     n_act = S.n_act;
                     {
@@ -636,7 +934,7 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
                                 S.squelch_count += 3;
                                 if (S.squelch_count >= 10) { S.squelch_count = 0; S.flags |= 8; }
                             }
-                            for (int w = tid; w < W; w += CT) S.free_mask[w] = 0xffffffffu;
+                            for (int w = tid; w < W; w += CT) S.free_mask[w] = FULL;
                             __syncthreads();
                             if (S.flags & 8) reset_noise = 1;
                         } else if (tid == 0 && S.squelch_count > 0) {
@@ -645,7 +943,6 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
                     }
                     __syncthreads();
                     // does this frame end the batch?  any baseline update does.
-                    IR_SUB(4);
                     const bool quiet_after = S.n_act == 0;
                     if (forced || quiet_after || reset_noise) {
                         commit = j + 1;
@@ -654,6 +951,8 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
                         break;
                     }
                 }
+                }
+                IR_SUB(8);
                 if (tid == 0) S.ctl_next_type = push_normal ? 1 : 0;
             }
             if (tid == 0) {
@@ -769,19 +1068,20 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
             for (int i = 0; i < 8; i++) gs->dbg[i] += tacc[i];
         }
     }
-    if (rank == 0 && tid == 0) for (int i = 0; i < 8; i++) gs->dbg[8 + i] += sub[i];
-    if (rank == 3 && tid == 0) for (int i = 0; i < 8; i++) gs->dbg[16 + i] += p1s[i];
+    if (rank == 0 && tid == 0) for (int i = 0; i < 12; i++) gs->dbg[8 + i] += sub[i];
+    if (rank == 3 && tid == 0) for (int i = 0; i < 4; i++) gs->dbg[20 + i] += p1s[i];
 }
 
 template <int BPT>
 static cudaError_t launch_cluster_t(const DetConfig &c, DetState *state, float *base, float *hist,
                                     const float *mag, int64_t n_frames, GoneBurst *gone,
                                     uint32_t gone_cap, cudaStream_t st) {
-    constexpr int G = BPT >= 8 ? 4 : (BPT == 4 ? 8 : 16);
-    const size_t smem = ((sizeof(ClShared) + 127) / 128) * 128 + sizeof(float) * 2 * G * BPT * CT;
+    const size_t smem = ((sizeof(ClShared) + 127) / 128) * 128;
     cudaError_t e = cudaFuncSetAttribute(k_detect_scan_cluster<BPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_detect_scan_cluster<BPT><<<CL, CT, smem, st>>>(c, state, base, hist, mag, n_frames, gone, gone_cap);
+    const char *env = getenv("IR_SCAN");
+    const int force_dense = env && strcmp(env, "cluster_dense") == 0;      // cross-check path of the tests
+    k_detect_scan_cluster<BPT><<<CL, CT, smem, st>>>(c, state, base, hist, mag, n_frames, gone, gone_cap, force_dense);
     return cudaGetLastError();
 }
 
@@ -798,11 +1098,6 @@ cudaError_t launch_detect_scan_cluster(const DetConfig &c, DetState *state, floa
     }
 }
 
-}  // namespace ir
-
-#include <stdlib.h>
-#include <string.h>
-namespace ir {
 cudaError_t launch_detect_scan_auto(const DetConfig &c, DetState *state, float *base, float *hist,
                                     const float *mag, int64_t n_frames, GoneBurst *gone,
                                     uint32_t gone_cap, cudaStream_t st) {
@@ -812,4 +1107,5 @@ cudaError_t launch_detect_scan_auto(const DetConfig &c, DetState *state, float *
         return launch_detect_scan_cluster(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
     return launch_detect_scan(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
 }
+
 }  // namespace ir

@@ -627,10 +627,10 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     if (getenv("IR_SCAN_DEBUG")) {
         fprintf(stderr, "scan cycles leader: p1 %llu waitA %llu p2 %llu waitB %llu p3 %llu waitC %llu batches %llu qbatches %llu\n",
                 hs.dbg[0], hs.dbg[1], hs.dbg[2], hs.dbg[3], hs.dbg[4], hs.dbg[5], hs.dbg[6], hs.dbg[7]);
-        fprintf(stderr, "scan leader p2 split: search %llu preflags %llu deletion %llu creation %llu squelch/end %llu | event frames %llu creates %llu deletes %llu\n",
-                hs.dbg[8], hs.dbg[9], hs.dbg[10], hs.dbg[11], hs.dbg[12], hs.dbg[13], hs.dbg[14], hs.dbg[15]);
-        fprintf(stderr, "scan owner(rank3) p1 split: issue %llu oldloads %llu wait+sync %llu lds+sync %llu compute %llu\n",
-                hs.dbg[16], hs.dbg[17], hs.dbg[18], hs.dbg[19], hs.dbg[20]);
+        fprintf(stderr, "scan leader p2 (type F): precheck %llu old-replay %llu | per round: eligible %llu peaks %llu fetch %llu greedy %llu new-replay %llu | apply %llu | frame replay %llu | rounds %llu planned %llu replayed %llu\n",
+                hs.dbg[8], hs.dbg[9], hs.dbg[10], hs.dbg[11], hs.dbg[12], hs.dbg[13], hs.dbg[14], hs.dbg[15], hs.dbg[16],
+                hs.dbg[17], hs.dbg[18], hs.dbg[19]);
+        fprintf(stderr, "scan owner(rank3) p1 split: setup %llu chunks %llu ship %llu\n", hs.dbg[20], hs.dbg[21], hs.dbg[22]);
     }
     // ---- timings: CUDA events on the launching streams
     auto span = [&](cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; };

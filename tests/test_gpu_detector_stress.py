@@ -1,6 +1,6 @@
-"""Detector edge cases on the GPU against the CPU oracle, for BOTH state-machine kernels
-(8-CTA cluster with speculative batches, and the single-CTA reference implementation selected
-with IR_SCAN=single): dense traffic (BASELINE config 4), squelch (> max_bursts simultaneous
+"""Detector edge cases on the GPU against the CPU oracle, for every state-machine variant
+(8-CTA cluster with speculative batches and the one-warp sparse leader; the same cluster with the
+block-wide dense leader, IR_SCAN=cluster_dense; the single-CTA implementation, IR_SCAN=single): dense traffic (BASELINE config 4), squelch (> max_bursts simultaneous
 bursts, burst_detect.c:593-631), a too-long burst forcing a baseline update
 (burst_detect.c:498-517), recordings that are not a whole number of frames / feed blocks."""
 import importlib
@@ -15,6 +15,9 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def pl():
     return importlib.import_module("iridium-sniffer_b200.pipeline")
+
+
+MODES = ["cluster", "cluster_dense", "single"]
 
 
 def _burst_key(b):
@@ -32,8 +35,8 @@ def _check(pl, port, iq, mode, expect_squelch=None, min_bursts=1):
     assert len(want) >= min_bursts
     old = os.environ.get("IR_SCAN")
     try:
-        if mode == "single":
-            os.environ["IR_SCAN"] = "single"
+        if mode != "cluster":
+            os.environ["IR_SCAN"] = mode
         else:
             os.environ.pop("IR_SCAN", None)
         p = pl.Pipeline(sample_rate=10_000_000, start_time_ns=77)
@@ -57,7 +60,7 @@ def dense(synth):
     return synth.make_dense_recording(1234)
 
 
-@pytest.mark.parametrize("mode", ["cluster", "single"])
+@pytest.mark.parametrize("mode", MODES)
 def test_dense_672_bursts(pl, port, dense, mode):
     res = _check(pl, port, dense.iq, mode, expect_squelch=False, min_bursts=600)
     truth = {t.bits for t in dense.truth}
@@ -81,20 +84,20 @@ def _tones(seed, n_tones, dur_s, t0_s, total_s=0.62, snr_db=20.0):
     return x
 
 
-@pytest.mark.parametrize("mode", ["cluster", "single"])
+@pytest.mark.parametrize("mode", MODES)
 def test_squelch(pl, port, mode):
     iq = _tones(5, 236, 0.02, 0.5)          # 236 carriers at once > max_bursts = 200
     _check(pl, port, iq, mode, expect_squelch=True, min_bursts=0)
 
 
-@pytest.mark.parametrize("mode", ["cluster", "single"])
+@pytest.mark.parametrize("mode", MODES)
 def test_too_long_burst_forces_baseline_update(pl, port, mode):
     iq = _tones(6, 1, 0.13, 0.45, total_s=0.75)      # 130 ms carrier > max_burst_len (90 ms)
     res = _check(pl, port, iq, mode, expect_squelch=False, min_bursts=1)
     assert any(b["stop"] - b["start"] > 900000 for b in res.bursts)
 
 
-@pytest.mark.parametrize("mode", ["cluster", "single"])
+@pytest.mark.parametrize("mode", MODES)
 def test_ragged_length_and_leading_bursts(pl, port, synth, mode):
     """Length not a multiple of the frame or of the feed block; bursts inside the first 512 frames
     (invisible to the detector but polluting the baseline, SURVEY.md D10 v)."""
