@@ -140,6 +140,14 @@ int ir_pipeline_run_device(ir_pipeline_t *p, const void *iq_dev, size_t n_sample
 /* Results of the last run; pointers stay valid until the next run/reset/destroy. */
 int ir_pipeline_results(ir_pipeline_t *p, ir_results_t *out);
 
+/* Counters of the detector's state machine over the last run: out[0] launches the streaming
+ * state machine completed, [1] launches it handed to the general cluster kernel (squelch,
+ * too-long burst, baseline outside the guard band ...), [2] baseline commands, [3] event frames,
+ * [4] bitmap words resolved with the exact divide, [5] waits for the baseline workers, [6] frame
+ * of the last hand-over.  Returns 1 if the streaming state machine is in use, 0 if IR_SCAN
+ * selected another variant, -1 on error. */
+int ir_pipeline_scan_stats(ir_pipeline_t *p, uint64_t *out, int n);
+
 /* Debug / parity taps on the last run (host copies; caller provides the buffers). */
 int ir_pipeline_copy_mag(ir_pipeline_t *p, size_t frame0, size_t n_frames, float *dst);
 int ir_pipeline_copy_frame_samples(ir_pipeline_t *p, size_t burst_index, float *dst_cf32,

@@ -9,6 +9,8 @@
 
 #define IR_MAX_ACTIVE 1024      // device-side cap on simultaneously tracked bursts
 #define IR_SCAN_THREADS 1024
+#define IR_STREAM_CL 8          // CTAs of the streaming state machine's cluster
+#define IR_STREAM_MAX_FRAMES 4096   // frames per launch of the streaming state machine
 #define IR_ROT_G 16             // samples between NCO phase checkpoints
 #define IR_FIR_TILE 256         // decimated outputs per FIR CTA
 #define IR_FIR_R 8              // outputs per lane
@@ -64,6 +66,18 @@ struct DetState {
     uint32_t pad;
     unsigned long long dbg[24];    // cycle counters of the cluster state machine (IR_SCAN_DEBUG)
     ActBurst act[IR_MAX_ACTIVE];
+};
+
+// control block of the streaming state machine (k_detect_stream.cu), device memory
+struct StreamCtl {
+    unsigned long long cmd[IR_STREAM_MAX_FRAMES + 8];   // leader -> workers: ranges of quiet frames
+    unsigned int done[IR_STREAM_CL];                    // workers -> leader: commands finished per CTA
+    unsigned int guard_bad;                             // a baseline left the band the bitmaps were made for
+    int bailed;                                         // last launch gave up: restore + fallback must run
+    int reason;                                         // why (1 primed priming launch, 2 guard band, 3 too-long burst,
+                                                        //  4 peak list, 5/7 burst table, 6 squelch, 8 primed in mid-launch)
+    unsigned long long stats[8];                        // 0 launches kept, 1 bailed, 2 commands, 3 event frames,
+                                                        // 4 words resolved exactly, 5 waits for the workers, 6 frame of last bail
 };
 
 // ------------------------------------------------------------------ downmix
@@ -134,6 +148,22 @@ cudaError_t launch_detect_scan(const DetConfig &c, DetState *state, float *base,
 cudaError_t launch_detect_scan_cluster(const DetConfig &c, DetState *state, float *base, float *hist,
                                        const float *mag, int64_t n_frames, GoneBurst *gone,
                                        uint32_t gone_cap, cudaStream_t st);
+// the same, but a no-op unless *run_if != 0 (device flag; the fallback of the streaming scan)
+cudaError_t launch_detect_scan_cluster_if(const DetConfig &c, DetState *state, float *base, float *hist,
+                                          const float *mag, int64_t n_frames, GoneBurst *gone,
+                                          uint32_t gone_cap, const int *run_if, cudaStream_t st);
+// k_detect_stream.cu: bitmaps against a reference baseline on all SMs + a one-warp state machine
+// with baseline workers (see the file header).  Caller snapshots / restores around it.
+bool stream_scan_supported(const DetConfig &c);
+cudaError_t launch_detect_classify(const float *mag, const float *base, float thr, int N, int n_frames,
+                                   uint32_t *xu, float *ref_out, int sm_count, cudaStream_t st);
+cudaError_t launch_detect_scan_stream(const DetConfig &c, DetState *state, float *base, float *hist,
+                                      const float *mag, const uint32_t *xu, const float *ref, int n_frames,
+                                      GoneBurst *gone, uint32_t gone_cap, StreamCtl *ctl, unsigned epoch,
+                                      cudaStream_t st);
+cudaError_t launch_scan_restore(const StreamCtl *ctl, float *hist, const float *hist_snap, size_t n_hist,
+                                float *base, const float *base_snap, int N, DetState *gs,
+                                const DetState *gs_snap, int sm_count, cudaStream_t st);
 // picks the cluster kernel for N >= 2048 unless IR_SCAN=single is set in the environment
 cudaError_t launch_detect_scan_auto(const DetConfig &c, DetState *state, float *base, float *hist,
                                     const float *mag, int64_t n_frames, GoneBurst *gone,

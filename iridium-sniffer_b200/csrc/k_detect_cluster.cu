@@ -141,7 +141,8 @@ template <int BPT>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 1)
 k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g,
                       float *__restrict__ hist, const float *__restrict__ mag, int64_t n_frames,
-                      GoneBurst *__restrict__ gone, uint32_t gone_cap, int force_dense) {
+                      GoneBurst *__restrict__ gone, uint32_t gone_cap, int force_dense, const int *run_if) {
+    if (run_if != nullptr && *run_if == 0) return;            // uniform over the cluster: nobody reaches a barrier
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ClShared &S = *reinterpret_cast<ClShared *>(smem_raw);
@@ -1075,27 +1076,33 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
 template <int BPT>
 static cudaError_t launch_cluster_t(const DetConfig &c, DetState *state, float *base, float *hist,
                                     const float *mag, int64_t n_frames, GoneBurst *gone,
-                                    uint32_t gone_cap, cudaStream_t st) {
+                                    uint32_t gone_cap, const int *run_if, cudaStream_t st) {
     const size_t smem = ((sizeof(ClShared) + 127) / 128) * 128;
     cudaError_t e = cudaFuncSetAttribute(k_detect_scan_cluster<BPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const char *env = getenv("IR_SCAN");
     const int force_dense = env && strcmp(env, "cluster_dense") == 0;      // cross-check path of the tests
-    k_detect_scan_cluster<BPT><<<CL, CT, smem, st>>>(c, state, base, hist, mag, n_frames, gone, gone_cap, force_dense);
+    k_detect_scan_cluster<BPT><<<CL, CT, smem, st>>>(c, state, base, hist, mag, n_frames, gone, gone_cap, force_dense, run_if);
     return cudaGetLastError();
+}
+
+cudaError_t launch_detect_scan_cluster_if(const DetConfig &c, DetState *state, float *base, float *hist,
+                                          const float *mag, int64_t n_frames, GoneBurst *gone,
+                                          uint32_t gone_cap, const int *run_if, cudaStream_t st) {
+    if (n_frames <= 0) return cudaSuccess;
+    switch (c.N / (CL * CT)) {
+    case 1: return launch_cluster_t<1>(c, state, base, hist, mag, n_frames, gone, gone_cap, run_if, st);
+    case 2: return launch_cluster_t<2>(c, state, base, hist, mag, n_frames, gone, gone_cap, run_if, st);
+    case 4: return launch_cluster_t<4>(c, state, base, hist, mag, n_frames, gone, gone_cap, run_if, st);
+    case 8: return launch_cluster_t<8>(c, state, base, hist, mag, n_frames, gone, gone_cap, run_if, st);
+    default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t launch_detect_scan_cluster(const DetConfig &c, DetState *state, float *base, float *hist,
                                        const float *mag, int64_t n_frames, GoneBurst *gone,
                                        uint32_t gone_cap, cudaStream_t st) {
-    if (n_frames <= 0) return cudaSuccess;
-    switch (c.N / (CL * CT)) {
-    case 1: return launch_cluster_t<1>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
-    case 2: return launch_cluster_t<2>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
-    case 4: return launch_cluster_t<4>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
-    case 8: return launch_cluster_t<8>(c, state, base, hist, mag, n_frames, gone, gone_cap, st);
-    default: return cudaErrorInvalidValue;
-    }
+    return launch_detect_scan_cluster_if(c, state, base, hist, mag, n_frames, gone, gone_cap, nullptr, st);
 }
 
 cudaError_t launch_detect_scan_auto(const DetConfig &c, DetState *state, float *base, float *hist,

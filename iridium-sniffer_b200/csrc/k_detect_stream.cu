@@ -1,0 +1,623 @@
+// k_detect_stream.cu -- the burst state machine (burst_detect.c:426-632) as two cooperating
+// kernels that take the dense magnitude data off the serial path.
+//
+// The frame-to-frame dependency of the reference is carried by two things only: the list of
+// active bursts (a handful of integers) and the noise baseline, which changes on "quiet" frames
+// (no burst active, burst_detect.c:438-454) and is frozen otherwise.  Everything else is a
+// per-(frame, bin) threshold test.  So:
+//
+//  k_detect_classify (all SMs): tests every magnitude of a run of frames against a REFERENCE
+//      baseline `ref` (the baseline as it stood when the kernel ran) with a guard band:
+//         X bit: mag > thr * 1.5*ref      -> certainly above for any baseline in [0.5, 1.5]*ref
+//         U bit: neither that nor mag < thr * 0.5*ref   -> "uncertain", needs the exact test
+//      and writes two bitmaps per frame (N/32 words each) -- 1/16 of the magnitude bytes.
+//
+//  k_detect_scan_stream (one 8-CTA cluster):
+//      * leader = one warp.  Walks the frames in order reading only the bitmaps (streamed into a
+//        shared-memory ring by TMA bulk copies, several frames ahead).  A frame on which no
+//        unmasked bit is set, no burst ends and every hysteresis test is decided by an X bit
+//        costs ~100 cycles.  Otherwise ("event") the leader runs the reference's steps for that
+//        frame exactly: IEEE divide against the true baseline for the few bins concerned, peaks
+//        sorted strongest first, deletions in list order, mask, creations.
+//      * workers = the other 4096 threads of the cluster, one to four bins each, baseline in
+//        registers.  The leader hands them ranges of quiet frames; they apply the reference's
+//        update (two roundings per bin, in frame order), keep the 512-row history, publish the
+//        baseline, and check that it stays inside the guard band the bitmaps were made for.
+//      The leader waits for the workers only when it needs baseline values: at the first event
+//      after a quiet run.
+//
+//  Anything unusual -- guard band violated, squelch, a burst exceeding max_burst_len (forced
+//  baseline update), the history priming in mid-launch, table overflow -- makes the leader bail:
+//  the launch's effects are undone from a snapshot and the frames are redone by the cluster
+//  kernel of k_detect_cluster.cu, which handles every case.  Both produce the reference's result
+//  bit for bit; tests compare all variants with the CPU oracle.
+#include <stdlib.h>
+#include <string.h>
+
+#include "ir_device.cuh"
+#include "ir_internal.h"
+
+namespace ir {
+
+namespace {
+
+constexpr int SCL = IR_STREAM_CL;      // CTAs per cluster
+constexpr int SWT = 512;               // worker threads per CTA
+constexpr int SNT = SWT + 32;          // + one more warp (the leader, in CTA 0)
+constexpr int SD = 16;                 // bitmap rows in flight
+constexpr int SMAXW = 512;             // bitmap words per frame (N <= 16384)
+constexpr int SMAXC = 1024;            // candidate peaks of one frame
+constexpr int SQCH = 128;              // quiet frames per worker command
+constexpr int SGMAX = 8;               // frames per worker register chunk (4 when a thread owns 4 bins)
+constexpr uint32_t FULL = 0xffffffffu;
+
+struct StShared {
+    unsigned long long bar[SD];
+    uint32_t ring[SD][2 * SMAXW];
+    uint32_t free_mask[SMAXW];         // 1 = bin not covered by an active burst
+    uint32_t valid[SMAXW];             // peak search range minus the DC notch
+    int cw[SMAXW];                     // words of the frame with a possible unmasked crossing
+    int n_cw;
+    int n_cand;
+    int cbin[SMAXC];
+    float crel[SMAXC];
+    float cbase[SMAXC];
+    unsigned long long a_id[IR_MAX_ACTIVE], a_start[IR_MAX_ACTIVE], a_last[IR_MAX_ACTIVE];
+    int a_cb[IR_MAX_ACTIVE];
+    float a_rel[IR_MAX_ACTIVE], a_base[IR_MAX_ACTIVE];
+    unsigned long long wcmd;           // workers: the command being executed
+};
+
+__device__ __forceinline__ unsigned long long ld_vol64(const unsigned long long *p) {
+    return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+__device__ __forceinline__ unsigned ld_vol32(const unsigned *p) { return *reinterpret_cast<const volatile unsigned *>(p); }
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(SWT) : "memory"); }
+
+__device__ __forceinline__ uint32_t st_range_bits(int w, int lo, int hi) {
+    int a = max(lo, w << 5), b = min(hi, (w << 5) + 31);
+    if (a > b) return 0u;
+    a &= 31; b &= 31;
+    return (b == 31 ? FULL : ((1u << (b + 1)) - 1u)) & ~((1u << a) - 1u);
+}
+__device__ __forceinline__ void st_clear(uint32_t *bm, int lo, int hi) {
+    for (int w = lo >> 5; w <= (hi >> 5); w++) atomicAnd(&bm[w], ~st_range_bits(w, lo, hi));
+}
+
+// command word: bit 0 exit, bits 1..20 first frame, 21..41 end frame, 42..63 launch epoch
+__device__ __forceinline__ unsigned long long pack_cmd(unsigned epoch, int s, int e, int ex) {
+    return ((unsigned long long)(epoch & 0x3fffffu) << 42) | ((unsigned long long)e << 21) |
+           ((unsigned long long)s << 1) | (unsigned long long)ex;
+}
+
+}  // namespace
+
+// =========================================================================== classification
+// One warp = 1024 consecutive bins (32 bitmap words) of a run of frames.
+__global__ void __launch_bounds__(128)
+k_detect_classify(const float *__restrict__ mag, const float *base_g, float thr, int N, int n_frames,
+                  int frames_per_warp, uint32_t *__restrict__ xu, float *__restrict__ ref_out) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int ncol = N >> 10;
+    const int col = gw % ncol, part = gw / ncol;
+    const int f0 = part * frames_per_warp;
+    if (f0 >= n_frames) return;
+    const int f1 = min(f0 + frames_per_warp, n_frames);
+    const int W = N >> 5;
+    const float INF = __int_as_float(0x7f800000);
+    float thi[32], tlo[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const int bin = (col << 10) + (j << 5) + lane;
+        const float r = *reinterpret_cast<const volatile float *>(base_g + bin);
+        if (part == 0) ref_out[bin] = r;
+        if (r > 0.0f) {
+            thi[j] = thr * (r * 1.5f) * 1.0001f;
+            tlo[j] = thr * (r * 0.5f) * 0.9999f;
+        } else {
+            thi[j] = INF; tlo[j] = INF;        // rel is 0 while the baseline is not positive
+        }
+    }
+    for (int f = f0; f < f1; f++) {
+        const float *row = mag + (size_t)f * N + (col << 10) + lane;
+        float m[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) m[j] = __ldg(row + (j << 5));
+        uint32_t xw = 0, uw = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const bool hi = m[j] > thi[j];
+            const bool un = !hi && !(m[j] < tlo[j]);
+            const uint32_t bx = __ballot_sync(FULL, hi), bu = __ballot_sync(FULL, un);
+            if (lane == j) { xw = bx; uw = bu; }
+        }
+        uint32_t *o = xu + (size_t)f * (2 * W) + (col << 5) + lane;
+        o[0] = xw;
+        o[W] = uw;
+    }
+}
+
+// =========================================================================== state machine
+// BPT = bins per worker thread = N / (SCL * SWT)
+template <int BPT>
+__global__ void __cluster_dims__(SCL, 1, 1) __launch_bounds__(SNT, 1)
+k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, float *hist,
+                     const float *__restrict__ mag, const uint32_t *__restrict__ xu,
+                     const float *__restrict__ ref, int n_frames, GoneBurst *__restrict__ gone,
+                     uint32_t gone_cap, StreamCtl *ctl, unsigned epoch) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    StShared &S = *reinterpret_cast<StShared *>(smem_raw);
+    const int rank = (int)blockIdx.x;
+    const int N = c.N, W = N >> 5, H = c.hist_size;
+    const bool classified = xu != nullptr;
+
+    if (threadIdx.x < SWT) {
+        // ------------------------------------------------------------------ workers
+        const int wt = threadIdx.x;
+        constexpr int NB = BPT * SWT;
+        constexpr int SG = BPT >= 4 ? 4 : SGMAX;
+        const int bin0 = rank * NB;
+        float base[BPT], glo[BPT], ghi[BPT];
+        int bad = 0;
+#pragma unroll
+        for (int u = 0; u < BPT; u++) {
+            const int bin = bin0 + u * SWT + wt;
+            base[u] = base_g[bin];
+            glo[u] = 0.0f; ghi[u] = 0.0f;
+            if (classified) {
+                const float r = ref[bin];
+                const float a = r * 0.5f, b = r * 1.5f;
+                glo[u] = fminf(a, b); ghi[u] = fmaxf(a, b);
+                bad |= !(base[u] >= glo[u] && base[u] <= ghi[u]);
+            }
+        }
+        int hist_idx = gs->hist_idx, primed = gs->primed;
+        unsigned my = 0;
+        for (;;) {
+            if (wt == 0) {
+                unsigned long long v;
+                for (;;) {
+                    v = ld_vol64(&ctl->cmd[my]);
+                    if ((unsigned)(v >> 42) == (epoch & 0x3fffffu) && v != 0ull) break;
+                    __nanosleep(64);
+                }
+                S.wcmd = v;
+            }
+            worker_bar();
+            const unsigned long long v = S.wcmd;
+            if (v & 1ull) break;
+            const int s = (int)((v >> 1) & 0xfffffu), e = (int)((v >> 21) & 0x1fffffu);
+            for (int f = s; f < e; f += SG) {
+                float mv[SG][BPT], ov[SG][BPT];
+#pragma unroll
+                for (int g = 0; g < SG; g++) {
+                    const bool in = f + g < e;
+                    const float *row = mag + (size_t)(f + g) * N + bin0 + wt;
+                    int hrow = hist_idx + g;
+                    if (hrow >= H) hrow -= H;
+                    const float *h = hist + (size_t)hrow * N + bin0 + wt;
+                    // a history row is live if the detector is primed or wraps before reaching it
+                    const bool live = primed || (hist_idx + g >= H);
+#pragma unroll
+                    for (int u = 0; u < BPT; u++) {
+                        mv[g][u] = in ? __ldg(row + u * SWT) : 0.0f;
+                        ov[g][u] = (in && live) ? h[u * SWT] : 0.0f;
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < SG; g++) {
+                    if (f + g < e) {
+                        float *h = hist + (size_t)hist_idx * N + bin0 + wt;
+#pragma unroll
+                        for (int u = 0; u < BPT; u++) {
+                            const float t = base[u] - ov[g][u];            // simd_avx2.c:221-236: two roundings
+                            base[u] = t + mv[g][u];
+                            h[u * SWT] = mv[g][u];
+                            if (classified) bad |= !(base[u] >= glo[u] && base[u] <= ghi[u]);
+                        }
+                        if (++hist_idx == H) { primed = 1; hist_idx = 0; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < BPT; u++) __stcg(base_g + bin0 + u * SWT + wt, base[u]);
+            if (bad) { atomicOr(&ctl->guard_bad, 1u); bad = 0; }
+            __threadfence();
+            worker_bar();
+            my++;
+            if (wt == 0) *reinterpret_cast<volatile unsigned *>(&ctl->done[rank]) = my;
+        }
+        return;
+    }
+    if (rank != 0) return;
+
+    // ---------------------------------------------------------------------- leader (one warp)
+    constexpr int WPL = 4 * BPT;                              // bitmap words per lane = W / 32
+    const int lane = threadIdx.x & 31;
+    const float thr = c.thr;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(S.bar);
+    const uint32_t row_bytes = (uint32_t)(2 * W) * sizeof(uint32_t);
+    int n_act = gs->n_act, sq = gs->squelch_count, hist_idx = gs->hist_idx, primed = gs->primed;
+    unsigned long long next_id = gs->next_id;
+    const uint64_t index0 = gs->index;
+    uint32_t n_gone = gs->n_gone;
+    uint32_t overflow = gs->overflow;
+    int bail = 0;
+    unsigned n_cmd = 0, n_waited = 0;
+    unsigned long long st_events = 0, st_exact = 0, st_waits = 0;
+
+    for (int i = lane; i < n_act; i += 32) {
+        const ActBurst b = gs->act[i];
+        S.a_id[i] = b.id; S.a_start[i] = b.start; S.a_last[i] = b.last_active;
+        S.a_cb[i] = b.center_bin; S.a_rel[i] = b.peak_rel; S.a_base[i] = b.base_at_create;
+    }
+    for (int w = lane; w < W; w += 32) {
+        uint32_t v = 0;
+        for (int b = 0; b < 32; b++) {
+            const int bin = (w << 5) + b;
+            const bool ok = bin >= c.half_bw && bin < N - c.half_bw && !(bin >= N / 2 - 3 && bin <= N / 2 + 3);
+            v |= ok ? (1u << b) : 0u;
+        }
+        S.valid[w] = v;
+        S.free_mask[w] = FULL;
+    }
+    if (lane < SCL) *reinterpret_cast<volatile unsigned *>(&ctl->done[lane]) = 0u;
+    if (lane == 0) {
+        *reinterpret_cast<volatile unsigned *>(&ctl->guard_bad) = 0u;
+        for (int d = 0; d < SD; d++) mbar_init(&bars[d], 1);
+        fence_mbar_init();
+    }
+    __threadfence();
+    __syncwarp();
+    for (int i = lane; i < n_act; i += 32)
+        st_clear(S.free_mask, max(S.a_cb[i] - c.half_bw, 0), min(S.a_cb[i] + c.half_bw, N - 1));
+    __syncwarp();
+    uint32_t fv[WPL];
+#pragma unroll
+    for (int k = 0; k < WPL; k++) fv[k] = S.free_mask[lane * WPL + k] & S.valid[lane * WPL + k];
+    int n_loaded = 0, n_landed = 0;                           // bitmap rows requested / waited for
+    if (classified) {
+        n_loaded = min(SD, n_frames);
+        if (lane == 0)
+            for (int d = 0; d < n_loaded; d++) {
+                mbar_expect_tx(&bars[d], row_bytes);
+                tma_load_1d(S.ring[d], xu + (size_t)d * (2 * W), row_bytes, &bars[d]);
+            }
+    }
+    if (!classified && primed) bail = 1;                      // a priming launch on a primed detector
+    if (n_act >= IR_MAX_ACTIVE - 64) bail = 7;
+
+    auto issue = [&](int s, int e, int ex) {
+        if (lane == 0) *reinterpret_cast<volatile unsigned long long *>(&ctl->cmd[n_cmd]) = pack_cmd(epoch, s, e, ex);
+        n_cmd++;
+    };
+    // the baseline the workers hold is published and inside the guard band
+    auto wait_all = [&]() -> bool {
+        if (n_waited == n_cmd) return true;
+        if (lane < SCL)
+            while (ld_vol32(&ctl->done[lane]) < n_cmd) __nanosleep(32);
+        __syncwarp();
+        __threadfence();
+        n_waited = n_cmd;
+        st_waits++;
+        return ld_vol32(&ctl->guard_bad) == 0u;
+    };
+
+    int qs = -1;                                              // first frame of the quiet range not yet handed out
+    int f = 0;
+    for (; f < n_frames && !bail; f++) {
+        const uint64_t idx = index0 + (uint64_t)f * (uint64_t)N;
+        const int slot = f % SD;
+        const uint32_t *X = S.ring[slot], *U = X + W;
+        bool quiet;
+        if (classified) { mbar_wait(&bars[slot], (uint32_t)((f / SD) & 1)); n_landed = f + 1; }
+        if (!primed) {
+            quiet = true;                                     // nothing is detected before 512 frames (:426-428)
+        } else {
+            // ---- the three questions of a frame, from the bitmaps alone
+            uint32_t anyc = 0;
+#pragma unroll
+            for (int k4 = 0; k4 < WPL / 4; k4++) {
+                const uint4 x = *reinterpret_cast<const uint4 *>(&X[lane * WPL + 4 * k4]);
+                const uint4 u = *reinterpret_cast<const uint4 *>(&U[lane * WPL + 4 * k4]);
+                anyc |= ((x.x | u.x) & fv[4 * k4]) | ((x.y | u.y) & fv[4 * k4 + 1]) |
+                        ((x.z | u.z) & fv[4 * k4 + 2]) | ((x.w | u.w) & fv[4 * k4 + 3]);
+            }
+            int ev = anyc != 0u;
+            for (int i = lane; i < n_act; i += 32) {
+                const int cb = S.a_cb[i];
+                const int lo = max(cb - 1, 0), hi = min(cb + 1, N - 1);
+                const int w0 = lo >> 5, w1 = hi >> 5;
+                const unsigned long long msk = ((1ull << (hi - lo + 1)) - 1ull) << (lo & 31);
+                const unsigned long long xx = (unsigned long long)X[w0] | (w1 != w0 ? (unsigned long long)X[w1] << 32 : 0ull);
+                unsigned long long la = S.a_last[i];
+                if (xx & msk) {
+                    la = idx;                                 // update_bursts (:458-469)
+                    S.a_last[i] = idx;
+                } else {
+                    const unsigned long long uu = (unsigned long long)U[w0] | (w1 != w0 ? (unsigned long long)U[w1] << 32 : 0ull);
+                    if (uu & msk) ev = 1;
+                }
+                if (la + (unsigned long long)c.post_len <= idx ||
+                    (c.max_burst_len > 0 && la - S.a_start[i] > (unsigned long long)c.max_burst_len))
+                    ev = 1;
+            }
+            if (__any_sync(FULL, ev)) {
+                // ================= event frame: the reference's steps, exactly
+                st_events++;
+                if (qs >= 0) { issue(qs, f, 0); qs = -1; }
+                if (!wait_all()) { bail = 2; break; }
+                const float *row = mag + (size_t)f * N;
+                // update_bursts for the tests an X bit did not decide
+                int too_long = 0, any_done = 0;
+                for (int i = lane; i < n_act; i += 32) {
+                    const int cb = S.a_cb[i];
+                    unsigned long long la = S.a_last[i];
+                    if (la != idx) {
+                        bool hit = false;
+                        for (int b = max(cb - 1, 0); b <= min(cb + 1, N - 1); b++) {
+                            if ((U[b >> 5] >> (b & 31)) & 1u) {
+                                const float bs = __ldcg(base_g + b);
+                                if (bs > 0.0f && row[b] / bs > thr) hit = true;
+                            }
+                        }
+                        if (hit) { la = idx; S.a_last[i] = idx; }
+                    }
+                    const bool tl = c.max_burst_len > 0 && la - S.a_start[i] > (unsigned long long)c.max_burst_len;
+                    if (tl) too_long = 1;
+                    if (la + (unsigned long long)c.post_len <= idx || tl) any_done = 1;
+                }
+                if (__any_sync(FULL, too_long)) { bail = 3; break; }     // forced baseline update (:498-517)
+                any_done = __any_sync(FULL, any_done);
+                // peaks: exact crossings & mask of the previous frame & search range (:522-548)
+                if (lane == 0) { S.n_cw = 0; S.n_cand = 0; }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < WPL; k++) {
+                    const int w = lane * WPL + k;
+                    if ((X[w] | U[w]) & fv[k]) S.cw[atomicAdd(&S.n_cw, 1)] = w;
+                }
+                __syncwarp();
+                const int n_cw = S.n_cw;
+                int n_cand = 0;
+                for (int j = 0; j < n_cw; j++) {
+                    const int w = S.cw[j];
+                    const int bin = (w << 5) + lane;
+                    const float mv = row[bin];
+                    const float bs = __ldcg(base_g + bin);
+                    float rel = 0.0f;
+                    bool ex = false;
+                    if (bs > 0.0f) { rel = mv / bs; ex = rel > thr; }                // simd_avx2.c:239-257
+                    ex = ex && (((S.free_mask[w] & S.valid[w]) >> lane) & 1u);
+                    const uint32_t bal = __ballot_sync(FULL, ex);
+                    if (ex) {
+                        const int pos = n_cand + __popc(bal & ((1u << lane) - 1u));
+                        if (pos < SMAXC) { S.cbin[pos] = bin; S.crel[pos] = rel; S.cbase[pos] = bs; }
+                    }
+                    n_cand += __popc(bal);
+                }
+                st_exact += (unsigned long long)n_cw;
+                if (n_cand > SMAXC) { bail = 4; break; }
+                __syncwarp();
+                bool mask_changed = false;
+                if (any_done) {
+                    // delete_gone_bursts (:490-518): gone records and survivors keep the list order
+                    int kept = 0;
+                    for (int i0 = 0; i0 < n_act; i0 += 32) {
+                        const int i = i0 + lane;
+                        const bool have = i < n_act;
+                        unsigned long long id = 0, start = 0, la = 0;
+                        int cb = 0;
+                        float rel = 0.0f, bsc = 0.0f;
+                        if (have) {
+                            id = S.a_id[i]; start = S.a_start[i]; la = S.a_last[i];
+                            cb = S.a_cb[i]; rel = S.a_rel[i]; bsc = S.a_base[i];
+                        }
+                        const bool done = have && (la + (unsigned long long)c.post_len <= idx);
+                        const uint32_t dm = __ballot_sync(FULL, done), km = __ballot_sync(FULL, have && !done);
+                        const uint32_t below = (1u << lane) - 1u;
+                        if (done) {
+                            const uint32_t slot_g = n_gone + (uint32_t)__popc(dm & below);
+                            if (slot_g < gone_cap) {
+                                GoneBurst g;
+                                g.id = id; g.start = start; g.stop = idx; g.last_active = la;
+                                g.center_bin = cb; g.peak_rel = rel; g.base_at_create = bsc; g.pad = 0;
+                                gone[slot_g] = g;
+                            } else {
+                                overflow = 1;
+                            }
+                        }
+                        overflow = __any_sync(FULL, overflow) ? 1u : 0u;
+                        __syncwarp();
+                        if (have && !done) {
+                            const int pos = kept + __popc(km & below);
+                            S.a_id[pos] = id; S.a_start[pos] = start; S.a_last[pos] = la;
+                            S.a_cb[pos] = cb; S.a_rel[pos] = rel; S.a_base[pos] = bsc;
+                        }
+                        n_gone += (uint32_t)__popc(dm);
+                        kept += __popc(km);
+                        __syncwarp();
+                    }
+                    n_act = kept;
+                    // update_burst_mask (:482-486)
+                    for (int w = lane; w < W; w += 32) S.free_mask[w] = FULL;
+                    __syncwarp();
+                    for (int i = lane; i < n_act; i += 32)
+                        st_clear(S.free_mask, max(S.a_cb[i] - c.half_bw, 0), min(S.a_cb[i] + c.half_bw, N - 1));
+                    __syncwarp();
+                    mask_changed = true;
+                }
+                if (n_cand > 0) {
+                    // create_new_bursts (:556-591): strongest remaining peak first, ties by bin
+                    const int nc = n_cand;
+                    for (;;) {
+                        ArgMax best{-1.0f, 0x7fffffff};
+                        int bslot = -1;
+                        for (int i = lane; i < nc; i += 32) {
+                            const int bin = S.cbin[i];
+                            if (bin >= 0) {
+                                const ArgMax cur{S.crel[i], bin};
+                                const ArgMax nb = argmax_pick(best, cur);
+                                if (nb.i != best.i) bslot = i;
+                                best = nb;
+                            }
+                        }
+                        const ArgMax wbest = warp_argmax(best);
+                        if (wbest.v < 0.0f) break;
+                        const int bin = wbest.i;
+                        const unsigned owner = __ballot_sync(FULL, best.i == bin && bslot >= 0);
+                        const int src = __ffs(owner) - 1;
+                        const float bc = __shfl_sync(FULL, bslot >= 0 ? S.cbase[bslot] : 0.0f, src);
+                        if (lane == 0) {
+                            S.a_id[n_act] = next_id;
+                            S.a_start[n_act] = idx - (unsigned long long)c.pre_len;
+                            S.a_last[n_act] = idx - (unsigned long long)c.pre_len;
+                            S.a_cb[n_act] = bin; S.a_rel[n_act] = wbest.v; S.a_base[n_act] = bc;
+                            st_clear(S.free_mask, max(bin - c.half_bw, 0), min(bin + c.half_bw, N - 1));
+                        }
+                        n_act++;
+                        next_id += 10ull;
+                        for (int i = lane; i < nc; i += 32) {
+                            const int bb = S.cbin[i];
+                            if (bb >= bin - c.half_bw && bb <= bin + c.half_bw) S.cbin[i] = -1;
+                        }
+                        __syncwarp();
+                        if (n_act >= IR_MAX_ACTIVE - 64) break;
+                    }
+                    mask_changed = true;
+                    if (n_act >= IR_MAX_ACTIVE - 64) { bail = 5; break; }
+                }
+                if (c.max_bursts > 0 && n_act > c.max_bursts) { bail = 6; break; }    // squelch (:593-631)
+                if (mask_changed) {
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < WPL; k++) fv[k] = S.free_mask[lane * WPL + k] & S.valid[lane * WPL + k];
+                }
+            }
+            if (sq > 0) sq--;                                 // :628-631
+            quiet = n_act == 0;
+        }
+        // every lane is done with the ring slot: refill it SD frames ahead
+        __syncwarp();
+        if (classified && f + SD < n_frames) {
+            if (lane == 0) {
+                mbar_expect_tx(&bars[slot], row_bytes);
+                tma_load_1d(S.ring[slot], xu + (size_t)(f + SD) * (2 * W), row_bytes, &bars[slot]);
+            }
+            n_loaded = f + SD + 1;
+        }
+        if (quiet) {                                          // update_filters_post (:438-454), by the workers
+            if (qs < 0) qs = f;
+            if (f + 1 - qs >= SQCH) { issue(qs, f + 1, 0); qs = -1; }
+            if (++hist_idx == H) {
+                hist_idx = 0;
+                if (!primed) {
+                    primed = 1;
+                    if (f + 1 < n_frames) { bail = 8; break; }   // the bitmaps were not made for this baseline
+                }
+            }
+        }
+    }
+    // ---- wrap up
+    if (!bail) {
+        if (qs >= 0) { issue(qs, n_frames, 0); qs = -1; }
+        if (!wait_all()) bail = 2;
+    }
+    issue(0, 0, 1);
+    if (lane < SCL)
+        while (ld_vol32(&ctl->done[lane]) < n_cmd - 1) __nanosleep(32);     // every real command is finished
+    __syncwarp();
+    // bulk copies still in flight (a bailed launch) must land before the shared memory is released
+    for (int g = n_landed; g < n_loaded; g++) mbar_wait(&bars[g % SD], (uint32_t)((g / SD) & 1));
+    if (!bail) {
+        for (int i = lane; i < n_act; i += 32) {
+            ActBurst b;
+            b.id = S.a_id[i]; b.start = S.a_start[i]; b.last_active = S.a_last[i];
+            b.center_bin = S.a_cb[i]; b.peak_rel = S.a_rel[i]; b.base_at_create = S.a_base[i]; b.pad = 0;
+            gs->act[i] = b;
+        }
+        if (lane == 0) {
+            gs->hist_idx = hist_idx; gs->primed = primed; gs->n_act = n_act; gs->squelch_count = sq;
+            gs->next_id = next_id; gs->index = index0 + (uint64_t)n_frames * (uint64_t)N;
+            gs->n_gone = n_gone; gs->overflow = overflow;
+        }
+    }
+    if (lane == 0) {
+        ctl->bailed = bail ? 1 : 0;
+        if (bail) { ctl->reason = bail; ctl->stats[1] += 1; ctl->stats[6] = (unsigned long long)f; } else ctl->stats[0] += 1;
+        ctl->stats[2] += n_cmd; ctl->stats[3] += st_events; ctl->stats[4] += st_exact; ctl->stats[5] += st_waits;
+    }
+}
+
+// Undo a bailed launch: history, baseline and state back to the snapshot taken before it.
+__global__ void k_scan_restore(const StreamCtl *ctl, float *hist, const float *hist_snap, size_t n_hist,
+                               float *base, const float *base_snap, int N, DetState *gs, const DetState *gs_snap) {
+    if (!ctl->bailed) return;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const float4 *s4 = reinterpret_cast<const float4 *>(hist_snap);
+    float4 *d4 = reinterpret_cast<float4 *>(hist);
+    for (size_t i = t; i < n_hist / 4; i += stride) d4[i] = s4[i];
+    for (size_t i = t; i < (size_t)N; i += stride) base[i] = base_snap[i];
+    const uint32_t *gsrc = reinterpret_cast<const uint32_t *>(gs_snap);
+    uint32_t *gdst = reinterpret_cast<uint32_t *>(gs);
+    for (size_t i = t; i < sizeof(DetState) / 4; i += stride) gdst[i] = gsrc[i];
+}
+
+size_t stream_ctl_bytes() { return sizeof(StreamCtl); }
+
+cudaError_t launch_detect_classify(const float *mag, const float *base, float thr, int N, int n_frames,
+                                   uint32_t *xu, float *ref_out, int sm_count, cudaStream_t st) {
+    if (n_frames <= 0) return cudaSuccess;
+    const int ncol = N >> 10;
+    // enough warps for every SM, not so many that the per-warp threshold setup dominates
+    int parts = (sm_count * 16 + ncol - 1) / ncol;
+    int fpw = (n_frames + parts - 1) / parts;
+    if (fpw < 8) fpw = 8;
+    parts = (n_frames + fpw - 1) / fpw;
+    const int warps = parts * ncol;
+    const int blocks = (warps + 3) / 4;
+    k_detect_classify<<<blocks, 128, 0, st>>>(mag, base, thr, N, n_frames, fpw, xu, ref_out);
+    return cudaGetLastError();
+}
+
+template <int BPT>
+static cudaError_t launch_stream_t(const DetConfig &c, DetState *state, float *base, float *hist, const float *mag,
+                                   const uint32_t *xu, const float *ref, int n_frames, GoneBurst *gone,
+                                   uint32_t gone_cap, StreamCtl *ctl, unsigned epoch, cudaStream_t st) {
+    const size_t smem = ((sizeof(StShared) + 127) / 128) * 128;
+    cudaError_t e = cudaFuncSetAttribute(k_detect_scan_stream<BPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_detect_scan_stream<BPT><<<SCL, SNT, smem, st>>>(c, state, base, hist, mag, xu, ref, n_frames, gone, gone_cap, ctl, epoch);
+    return cudaGetLastError();
+}
+
+bool stream_scan_supported(const DetConfig &c) {
+    const int bpt = c.N / (SCL * SWT);
+    return c.N % (SCL * SWT) == 0 && (bpt == 1 || bpt == 2 || bpt == 4) && c.hist_size >= 2 * SGMAX;
+}
+
+// One launch of the streaming state machine over frames [0, n_frames) of `mag` (n_frames <=
+// IR_STREAM_MAX_FRAMES).  xu == nullptr: priming launch (detector not primed, every frame quiet).
+// The snapshot / restore / fallback around it is the caller's (pipeline.cu).
+cudaError_t launch_detect_scan_stream(const DetConfig &c, DetState *state, float *base, float *hist, const float *mag,
+                                      const uint32_t *xu, const float *ref, int n_frames, GoneBurst *gone,
+                                      uint32_t gone_cap, StreamCtl *ctl, unsigned epoch, cudaStream_t st) {
+    if (n_frames <= 0) return cudaSuccess;
+    if (n_frames > IR_STREAM_MAX_FRAMES) return cudaErrorInvalidValue;
+    switch (c.N / (SCL * SWT)) {
+    case 1: return launch_stream_t<1>(c, state, base, hist, mag, xu, ref, n_frames, gone, gone_cap, ctl, epoch, st);
+    case 2: return launch_stream_t<2>(c, state, base, hist, mag, xu, ref, n_frames, gone, gone_cap, ctl, epoch, st);
+    case 4: return launch_stream_t<4>(c, state, base, hist, mag, xu, ref, n_frames, gone, gone_cap, ctl, epoch, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_scan_restore(const StreamCtl *ctl, float *hist, const float *hist_snap, size_t n_hist, float *base,
+                                const float *base_snap, int N, DetState *gs, const DetState *gs_snap, int sm_count,
+                                cudaStream_t st) {
+    k_scan_restore<<<sm_count * 2, 256, 0, st>>>(ctl, hist, hist_snap, n_hist, base, base_snap, N, gs, gs_snap);
+    return cudaGetLastError();
+}
+
+}  // namespace ir

@@ -148,6 +148,15 @@ struct ir_pipeline {
     DevBuf<unsigned char> d_iq;
     DevBuf<float> d_mag, d_base, d_hist;
     DevBuf<DetState> d_state;
+    // streaming state machine (k_detect_stream.cu): bitmaps of one launch, the reference baseline
+    // they were made against, the snapshot a bailed launch is undone from, the control block
+    DevBuf<uint32_t> d_xu;
+    DevBuf<float> d_ref, d_hist_snap, d_base_snap;
+    DevBuf<DetState> d_state_snap;
+    DevBuf<StreamCtl> d_ctl;
+    unsigned scan_epoch = 1;
+    int scan_mode = 0;                       // 0 = streaming (default where supported), 1 = cluster / single (IR_SCAN)
+    uint64_t scan_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // burst list: pinned host memory mapped into the device; the scan kernel stores the (few,
     // 56-byte) records straight into it, the host reads them after the chunk's event
     GoneBurst *h_gone = nullptr, *d_gone = nullptr;
@@ -238,6 +247,18 @@ extern "C" ir_pipeline_t *ir_pipeline_create(const ir_config_t *cfg) {
         return fail("constant upload failed");
     if (p->d_base.ensure(p->dc.N) || p->d_hist.ensure((size_t)p->dc.N * p->dc.hist_size) || p->d_state.ensure(1))
         return fail(g_err);
+    {
+        const char *env = getenv("IR_SCAN");
+        p->scan_mode = (env && *env && strcmp(env, "stream") != 0) || !stream_scan_supported(p->dc) ? 1 : 0;
+        if (p->scan_mode == 0) {
+            const size_t W2 = (size_t)p->dc.N / 16;
+            if (p->d_xu.ensure((size_t)IR_STREAM_MAX_FRAMES * W2) || p->d_ref.ensure(p->dc.N) ||
+                p->d_hist_snap.ensure((size_t)p->dc.N * p->dc.hist_size) || p->d_base_snap.ensure(p->dc.N) ||
+                p->d_state_snap.ensure(1) || p->d_ctl.ensure(1))
+                return fail(g_err);
+            if (cudaMemset(p->d_ctl.p, 0, sizeof(StreamCtl)) != cudaSuccess) return fail("control block init failed");
+        }
+    }
     memset(&p->res, 0, sizeof(p->res));
     return p;
 }
@@ -250,6 +271,8 @@ extern "C" void ir_pipeline_destroy(ir_pipeline_t *p) {
     p->d_window.release(); p->d_tw_det.release(); p->d_tw12.release(); p->d_tw11.release();
     p->d_sync_dl.release(); p->d_sync_ul.release(); p->d_iq.release(); p->d_mag.release();
     p->d_base.release(); p->d_hist.release(); p->d_state.release();
+    p->d_xu.release(); p->d_ref.release(); p->d_hist_snap.release(); p->d_base_snap.release();
+    p->d_state_snap.release(); p->d_ctl.release();
     p->dev_arena.release(); p->pin_arena.release();
     if (p->h_gone) cudaFreeHost(p->h_gone);
     if (p->h_hdr) cudaFreeHost(p->h_hdr);
@@ -494,6 +517,39 @@ static int assemble_wave(ir_pipeline *p, const Wave &w) {
     return 0;
 }
 
+// Frames [f0, f1) of the run through the streaming state machine, on st_scan.  The run starts
+// from a reset detector, so the first hist_size frames are the priming launch (every frame quiet,
+// no bitmaps); after that each launch is: bitmaps against the current baseline, snapshot, state
+// machine, and -- both no-ops unless the launch bailed -- restore + the cluster kernel.
+static int scan_stream_range(ir_pipeline *p, int64_t f0, int64_t f1) {
+    const DetConfig &dc = p->dc;
+    const int N = dc.N;
+    cudaStream_t st = p->st_scan;
+    const size_t n_hist = (size_t)N * dc.hist_size;
+    for (int64_t a = f0; a < f1;) {
+        const bool priming = a < dc.hist_size;
+        const int64_t b = priming ? std::min<int64_t>(f1, dc.hist_size) : std::min<int64_t>(f1, a + IR_STREAM_MAX_FRAMES);
+        const int nf = (int)(b - a);
+        const float *mag = p->d_mag.p + a * N;
+        if (!priming) {
+            CK(launch_detect_classify(mag, p->d_base.p, dc.thr, N, nf, p->d_xu.p, p->d_ref.p, p->sm_count, st));
+            p->res.kernel_launches++;
+        }
+        CK(cudaMemcpyAsync(p->d_hist_snap.p, p->d_hist.p, n_hist * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(p->d_base_snap.p, p->d_base.p, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(p->d_state_snap.p, p->d_state.p, sizeof(DetState), cudaMemcpyDeviceToDevice, st));
+        CK(launch_detect_scan_stream(dc, p->d_state.p, p->d_base.p, p->d_hist.p, mag, priming ? nullptr : p->d_xu.p,
+                                     p->d_ref.p, nf, p->d_gone, p->gone_cap, p->d_ctl.p, p->scan_epoch++, st));
+        CK(launch_scan_restore(p->d_ctl.p, p->d_hist.p, p->d_hist_snap.p, n_hist, p->d_base.p, p->d_base_snap.p, N,
+                               p->d_state.p, p->d_state_snap.p, p->sm_count, st));
+        CK(launch_detect_scan_cluster_if(dc, p->d_state.p, p->d_base.p, p->d_hist.p, mag, nf, p->d_gone, p->gone_cap,
+                                         &p->d_ctl.p->bailed, st));
+        p->res.kernel_launches += 3;
+        a = b;
+    }
+    return 0;
+}
+
 // Whole path over one block.  Every chunk's copy / FFT / scan is enqueued up front; the host then
 // follows the detector chunk by chunk and launches the downmix + demod of the bursts each chunk
 // emitted (a "wave") on a fourth stream, so that only the last wave runs after the detector is
@@ -545,6 +601,7 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     p->bursts.clear(); p->h_bp.clear(); p->frame_ptr.clear(); p->dec_ptr.clear();
     p->frames.clear(); p->bits.clear(); p->llr.clear();
     if (ir_pipeline_reset(p)) return -1;
+    if (p->scan_mode == 0) CK(cudaMemsetAsync(p->d_ctl.p, 0, sizeof(StreamCtl), p->st_scan));
     cudaEvent_t ev_begin = p->ev();
     CK(cudaEventRecord(ev_begin, p->st_scan));          // after the state reset
     CK(cudaStreamWaitEvent(p->st_fft, ev_begin, 0));
@@ -574,10 +631,12 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
         CK(cudaEventRecord(c.fft.b, p->st_fft));
         CK(cudaStreamWaitEvent(p->st_scan, c.fft.b, 0));
         CK(cudaEventRecord(c.scan.a, p->st_scan));
-        if (f1 > f0) {
+        if (f1 > f0 && p->scan_mode != 0) {
             CK(launch_detect_scan_auto(dc, p->d_state.p, p->d_base.p, p->d_hist.p, p->d_mag.p + f0 * N, f1 - f0,
                                        p->d_gone, p->gone_cap, p->st_scan));
             p->res.kernel_launches++;
+        } else if (f1 > f0) {
+            if (scan_stream_range(p, f0, f1)) return -1;
         }
         CK(cudaEventRecord(c.scan.b, p->st_scan));
         CK(cudaMemcpyAsync(p->h_hdr + p->chunks.size() * kHdrBytes, p->d_state.p, kHdrBytes, cudaMemcpyDeviceToHost,
@@ -624,7 +683,20 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
         if (assemble_wave(p, p->waves[assembled])) return -1;
     if (host_iq) CK(cudaStreamSynchronize(p->st_copy));
     CK(cudaStreamSynchronize(p->st_burst));
-    if (getenv("IR_SCAN_DEBUG")) {
+    if (p->scan_mode == 0)
+        CK(cudaMemcpy(p->scan_stats, p->d_ctl.p->stats, sizeof(p->scan_stats), cudaMemcpyDeviceToHost));
+    else
+        memset(p->scan_stats, 0, sizeof(p->scan_stats));
+    if (getenv("IR_SCAN_DEBUG") && p->scan_mode == 0) {
+        int reason = 0;
+        cudaMemcpy(&reason, &p->d_ctl.p->reason, sizeof(int), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "stream scan: launches kept %llu bailed %llu (last reason %d at frame %llu) commands %llu events %llu exact words %llu waits %llu\n",
+                (unsigned long long)p->scan_stats[0], (unsigned long long)p->scan_stats[1], reason,
+                (unsigned long long)p->scan_stats[6], (unsigned long long)p->scan_stats[2],
+                (unsigned long long)p->scan_stats[3], (unsigned long long)p->scan_stats[4],
+                (unsigned long long)p->scan_stats[5]);
+    }
+    if (getenv("IR_SCAN_DEBUG") && p->scan_mode != 0) {
         fprintf(stderr, "scan cycles leader: p1 %llu waitA %llu p2 %llu waitB %llu p3 %llu waitC %llu batches %llu qbatches %llu\n",
                 hs.dbg[0], hs.dbg[1], hs.dbg[2], hs.dbg[3], hs.dbg[4], hs.dbg[5], hs.dbg[6], hs.dbg[7]);
         fprintf(stderr, "scan leader p2 (type F): precheck %llu old-replay %llu | per round: eligible %llu peaks %llu fetch %llu greedy %llu new-replay %llu | apply %llu | frame replay %llu | rounds %llu planned %llu replayed %llu\n",
@@ -668,6 +740,12 @@ extern "C" int ir_pipeline_results(ir_pipeline_t *p, ir_results_t *out) {
     if (!p || !out) return -1;
     *out = p->res;
     return 0;
+}
+
+extern "C" int ir_pipeline_scan_stats(ir_pipeline_t *p, uint64_t *out, int n) {
+    if (!p || !out) return -1;
+    for (int i = 0; i < n && i < 8; i++) out[i] = p->scan_stats[i];
+    return p->scan_mode == 0 ? 1 : 0;
 }
 
 extern "C" int ir_pipeline_copy_mag(ir_pipeline_t *p, size_t frame0, size_t n_frames, float *dst) {

@@ -106,6 +106,8 @@ def load_library() -> C.CDLL:
     L.ir_host_alloc.restype = C.c_void_p
     L.ir_host_alloc.argtypes = [C.c_size_t]
     L.ir_host_free.argtypes = [C.c_void_p]
+    L.ir_pipeline_scan_stats.restype = C.c_int
+    L.ir_pipeline_scan_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
     _lib = L
     return L
 
@@ -115,7 +117,7 @@ EXPORTED_SYMBOLS = [
     "ir_pipeline_reset", "ir_pipeline_run_host", "ir_pipeline_run_device", "ir_pipeline_results",
     "ir_pipeline_copy_mag", "ir_pipeline_copy_frame_samples", "ir_pipeline_copy_decimated",
     "ir_pipeline_copy_burst_samples", "ir_format_raw", "ir_pipeline_format_raw_all", "ir_host_alloc",
-    "ir_host_free",
+    "ir_host_free", "ir_pipeline_scan_stats",
 ]
 
 
@@ -250,6 +252,17 @@ class Pipeline:
         if n < 0:
             raise RuntimeError("ir_pipeline_format_raw_all failed: " + self.L.ir_last_error().decode())
         return self._txt.raw[:n]
+
+    def scan_stats(self) -> dict:
+        """Counters of the detector state machine over the last run (ir_pipeline_scan_stats)."""
+        a = (C.c_uint64 * 8)()
+        rc = self.L.ir_pipeline_scan_stats(self.h, a, 8)
+        if rc < 0:
+            raise RuntimeError("ir_pipeline_scan_stats failed")
+        keys = ("launches_kept", "launches_bailed", "commands", "event_frames", "exact_words", "waits", "last_bail_frame")
+        d = {k: int(a[i]) for i, k in enumerate(keys)}
+        d["streaming"] = bool(rc)
+        return d
 
     def stats(self) -> dict:
         r = Results()
