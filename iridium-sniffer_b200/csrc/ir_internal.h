@@ -11,6 +11,10 @@
 #define IR_SCAN_THREADS 1024
 #define IR_STREAM_CL 8          // CTAs of the streaming state machine's cluster
 #define IR_STREAM_MAX_FRAMES 4096   // frames per launch of the streaming state machine
+// guard band of the bitmaps: valid while every baseline stays inside [LO, HI] x its reference value.
+// LO also sets how often pure noise lands in the uncertain band (e^(-23.1*LO) per bin and frame at 16 dB).
+#define IR_GUARD_LO 0.65f
+#define IR_GUARD_HI 1.5f
 #define IR_ROT_G 16             // samples between NCO phase checkpoints
 #define IR_FIR_TILE 256         // decimated outputs per FIR CTA
 #define IR_FIR_R 8              // outputs per lane
@@ -76,8 +80,10 @@ struct StreamCtl {
     int bailed;                                         // last launch gave up: restore + fallback must run
     int reason;                                         // why (1 primed priming launch, 2 guard band, 3 too-long burst,
                                                         //  4 peak list, 5/7 burst table, 6 squelch, 8 primed in mid-launch)
-    unsigned long long stats[8];                        // 0 launches kept, 1 bailed, 2 commands, 3 event frames,
-                                                        // 4 words resolved exactly, 5 waits for the workers, 6 frame of last bail
+    unsigned long long stats[16];                       // 0 launches kept, 1 bailed, 2 commands, 3 event frames,
+                                                        // 4 words resolved exactly, 5 waits for the workers, 6 frame of last bail,
+                                                        // 7 ns inside the kernel, 8-11 leader cycles: ring wait, bitmap pass,
+                                                        // wait for workers, event body
 };
 
 // ------------------------------------------------------------------ downmix

@@ -8,9 +8,10 @@
 //
 //  k_detect_classify (all SMs): tests every magnitude of a run of frames against a REFERENCE
 //      baseline `ref` (the baseline as it stood when the kernel ran) with a guard band:
-//         X bit: mag > thr * 1.5*ref      -> certainly above for any baseline in [0.5, 1.5]*ref
-//         U bit: neither that nor mag < thr * 0.5*ref   -> "uncertain", needs the exact test
-//      and writes two bitmaps per frame (N/32 words each) -- 1/16 of the magnitude bytes.
+//         X  bit: mag > thr * HI*ref            -> certainly above for any baseline in [LO, HI]*ref
+//         XU bit: not (mag < thr * LO*ref)      -> above or "uncertain" (needs the exact test)
+//      (LO, HI = IR_GUARD_LO, IR_GUARD_HI) and writes two bitmaps per frame (N/32 words each) --
+//      1/16 of the magnitude bytes.
 //
 //  k_detect_scan_stream (one 8-CTA cluster):
 //      * leader = one warp.  Walks the frames in order reading only the bitmaps (streamed into a
@@ -42,9 +43,11 @@ namespace ir {
 namespace {
 
 constexpr int SCL = IR_STREAM_CL;      // CTAs per cluster
-constexpr int SWT = 512;               // worker threads per CTA
+constexpr int SWT = 256;               // worker threads per CTA (few threads = many registers for the leader)
 constexpr int SNT = SWT + 32;          // + one more warp (the leader, in CTA 0)
-constexpr int SD = 16;                 // bitmap rows in flight
+constexpr int SGF = 8;                 // frames per leader group = rows per ring block
+constexpr int SPF = 4;                 // candidate words whose loads are in flight together
+constexpr int SACT = 512;              // bursts the leader can track (squelch sets in long before)
 constexpr int SMAXW = 512;             // bitmap words per frame (N <= 16384)
 constexpr int SMAXC = 1024;            // candidate peaks of one frame
 constexpr int SQCH = 128;              // quiet frames per worker command
@@ -52,19 +55,22 @@ constexpr int SGMAX = 8;               // frames per worker register chunk (4 wh
 constexpr uint32_t FULL = 0xffffffffu;
 
 struct StShared {
-    unsigned long long bar[SD];
-    uint32_t ring[SD][2 * SMAXW];
+    unsigned long long bar[8];         // one per ring block
     uint32_t free_mask[SMAXW];         // 1 = bin not covered by an active burst
     uint32_t valid[SMAXW];             // peak search range minus the DC notch
     int cw[SMAXW];                     // words of the frame with a possible unmasked crossing
     int n_cw;
-    int n_cand;
     int cbin[SMAXC];
     float crel[SMAXC];
     float cbase[SMAXC];
-    unsigned long long a_id[IR_MAX_ACTIVE], a_start[IR_MAX_ACTIVE], a_last[IR_MAX_ACTIVE];
-    int a_cb[IR_MAX_ACTIVE];
-    float a_rel[IR_MAX_ACTIVE], a_base[IR_MAX_ACTIVE];
+    // active bursts (burst_detect.c:39-48) + their times in frames of this launch
+    unsigned long long a_id[SACT], a_start[SACT], a_last[SACT];   // a_last: last_active at launch start
+    int a_cb[SACT];
+    int a_dl[SACT];                    // first frame on which the burst is deleted unless a hit comes
+    int a_lah[SACT];                   // frame of the latest hit in this launch (NONE: see a_last)
+    int a_tl[SACT];                    // last frame on which it cannot be "too long" yet
+    uint32_t a_hm[SACT];               // hits in the frames of the current group
+    float a_rel[SACT], a_base[SACT];
     unsigned long long wcmd;           // workers: the command being executed
 };
 
@@ -72,6 +78,14 @@ __device__ __forceinline__ unsigned long long ld_vol64(const unsigned long long 
     return *reinterpret_cast<const volatile unsigned long long *>(p);
 }
 __device__ __forceinline__ unsigned ld_vol32(const unsigned *p) { return *reinterpret_cast<const volatile unsigned *>(p); }
+__device__ __forceinline__ unsigned ld_acq32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_rel32(unsigned *p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(SWT) : "memory"); }
 
 __device__ __forceinline__ uint32_t st_range_bits(int w, int lo, int hi) {
@@ -113,8 +127,8 @@ k_detect_classify(const float *__restrict__ mag, const float *base_g, float thr,
         const float r = *reinterpret_cast<const volatile float *>(base_g + bin);
         if (part == 0) ref_out[bin] = r;
         if (r > 0.0f) {
-            thi[j] = thr * (r * 1.5f) * 1.0001f;
-            tlo[j] = thr * (r * 0.5f) * 0.9999f;
+            thi[j] = thr * (r * IR_GUARD_HI) * 1.0001f;
+            tlo[j] = thr * (r * IR_GUARD_LO) * 0.9999f;
         } else {
             thi[j] = INF; tlo[j] = INF;        // rel is 0 while the baseline is not positive
         }
@@ -128,13 +142,13 @@ k_detect_classify(const float *__restrict__ mag, const float *base_g, float thr,
 #pragma unroll
         for (int j = 0; j < 32; j++) {
             const bool hi = m[j] > thi[j];
-            const bool un = !hi && !(m[j] < tlo[j]);
+            const bool un = !(m[j] < tlo[j]);                  // certain or uncertain (NaN: uncertain)
             const uint32_t bx = __ballot_sync(FULL, hi), bu = __ballot_sync(FULL, un);
             if (lane == j) { xw = bx; uw = bu; }
         }
         uint32_t *o = xu + (size_t)f * (2 * W) + (col << 5) + lane;
-        o[0] = xw;
-        o[W] = uw;
+        o[0] = uw;                                             // row = [XU][X]
+        o[W] = xw;
     }
 }
 
@@ -156,7 +170,7 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
         // ------------------------------------------------------------------ workers
         const int wt = threadIdx.x;
         constexpr int NB = BPT * SWT;
-        constexpr int SG = BPT >= 4 ? 4 : SGMAX;
+        constexpr int SG = BPT >= 8 ? 4 : SGMAX;
         const int bin0 = rank * NB;
         float base[BPT], glo[BPT], ghi[BPT];
         int bad = 0;
@@ -167,7 +181,7 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
             glo[u] = 0.0f; ghi[u] = 0.0f;
             if (classified) {
                 const float r = ref[bin];
-                const float a = r * 0.5f, b = r * 1.5f;
+                const float a = r * IR_GUARD_LO, b = r * IR_GUARD_HI;
                 glo[u] = fminf(a, b); ghi[u] = fmaxf(a, b);
                 bad |= !(base[u] >= glo[u] && base[u] <= ghi[u]);
             }
@@ -180,7 +194,7 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
                 for (;;) {
                     v = ld_vol64(&ctl->cmd[my]);
                     if ((unsigned)(v >> 42) == (epoch & 0x3fffffu) && v != 0ull) break;
-                    __nanosleep(64);
+                    __nanosleep(20);
                 }
                 S.wcmd = v;
             }
@@ -223,21 +237,29 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
 #pragma unroll
             for (int u = 0; u < BPT; u++) __stcg(base_g + bin0 + u * SWT + wt, base[u]);
             if (bad) { atomicOr(&ctl->guard_bad, 1u); bad = 0; }
-            __threadfence();
-            worker_bar();
+            worker_bar();                                     // the CTA's stores are ordered before thread 0's release
             my++;
-            if (wt == 0) *reinterpret_cast<volatile unsigned *>(&ctl->done[rank]) = my;
+            if (wt == 0) st_rel32(&ctl->done[rank], my);
         }
         return;
     }
     if (rank != 0) return;
 
     // ---------------------------------------------------------------------- leader (one warp)
-    constexpr int WPL = 4 * BPT;                              // bitmap words per lane = W / 32
+    // Frames are taken in groups of SGF: the questions "does any unmasked bit show up" and "does a
+    // burst end / need an exact hysteresis test" are answered for the whole group with independent
+    // instruction streams (one warp hides its own latencies that way), the frames before the
+    // first event are committed in one step, the event frame is processed exactly, and the next
+    // group starts right after it.  Times are kept in frames relative to this launch.
+    constexpr int WPL = 2 * BPT;                              // bitmap words per lane = W / 32
+    constexpr int RB = BPT >= 8 ? 4 : 8;                      // ring blocks of SGF rows
+    constexpr int RROWS = RB * SGF;
     const int lane = threadIdx.x & 31;
     const float thr = c.thr;
     uint64_t *bars = reinterpret_cast<uint64_t *>(S.bar);
-    const uint32_t row_bytes = (uint32_t)(2 * W) * sizeof(uint32_t);
+    uint32_t *ring = reinterpret_cast<uint32_t *>(smem_raw + ((sizeof(StShared) + 127) / 128) * 128);
+    const int RW = 2 * W;                                     // words per row: [XU][X]
+    const uint32_t row_bytes = (uint32_t)RW * sizeof(uint32_t);
     int n_act = gs->n_act, sq = gs->squelch_count, hist_idx = gs->hist_idx, primed = gs->primed;
     unsigned long long next_id = gs->next_id;
     const uint64_t index0 = gs->index;
@@ -246,11 +268,34 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     int bail = 0;
     unsigned n_cmd = 0, n_waited = 0;
     unsigned long long st_events = 0, st_exact = 0, st_waits = 0;
+    // cycle counters (lane 0's clock): ring wait, bitmap pass, wait for workers, event body
+    unsigned long long cy_ring = 0, cy_scan = 0, cy_wait = 0, cy_event = 0, cy_e1 = 0, cy_e2 = 0, cy_e3 = 0;
+    unsigned long long t_glob0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_glob0));
+    long long tk = clock64();
+#define ST_TICK(acc) do { const long long _t = clock64(); acc += (unsigned long long)(_t - tk); tk = _t; } while (0)
+    // frames a burst survives without a hit: idx - la >= post_len  <=>  frames >= PF (la = a frame's
+    // index) resp. PF0 (la = start = creation frame's index - pre_len)
+    const int PF = (c.post_len + N - 1) / N;
+    const int PF0 = max(1, (c.post_len - c.pre_len + N - 1) / N);
+    constexpr int NONE = -0x40000000;
+    // deadline (first frame on which the burst is deleted) and too-long horizon of a burst
+    auto deadline_of = [&](unsigned long long la) -> int {
+        const long long d = (long long)(la + (unsigned long long)c.post_len) - (long long)index0;
+        return d <= 0 ? 0 : (int)min((long long)0x3fffffff, (d + N - 1) / N);
+    };
+    auto horizon_of = [&](unsigned long long start) -> int {   // la <= index of frame f <= start + max_len for f <= this
+        if (c.max_burst_len <= 0) return 0x3fffffff;
+        const long long d = (long long)(start + (unsigned long long)c.max_burst_len) - (long long)index0;
+        return d < 0 ? -1 : (int)min((long long)0x3fffffff, d / N);
+    };
 
+    if (n_act > SACT - 64) { bail = 7; n_act = 0; }
     for (int i = lane; i < n_act; i += 32) {
         const ActBurst b = gs->act[i];
         S.a_id[i] = b.id; S.a_start[i] = b.start; S.a_last[i] = b.last_active;
         S.a_cb[i] = b.center_bin; S.a_rel[i] = b.peak_rel; S.a_base[i] = b.base_at_create;
+        S.a_dl[i] = deadline_of(b.last_active); S.a_lah[i] = NONE; S.a_tl[i] = horizon_of(b.start);
     }
     for (int w = lane; w < W; w += 32) {
         uint32_t v = 0;
@@ -265,7 +310,7 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     if (lane < SCL) *reinterpret_cast<volatile unsigned *>(&ctl->done[lane]) = 0u;
     if (lane == 0) {
         *reinterpret_cast<volatile unsigned *>(&ctl->guard_bad) = 0u;
-        for (int d = 0; d < SD; d++) mbar_init(&bars[d], 1);
+        for (int d = 0; d < RB; d++) mbar_init(&bars[d], 1);
         fence_mbar_init();
     }
     __threadfence();
@@ -276,17 +321,28 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     uint32_t fv[WPL];
 #pragma unroll
     for (int k = 0; k < WPL; k++) fv[k] = S.free_mask[lane * WPL + k] & S.valid[lane * WPL + k];
-    int n_loaded = 0, n_landed = 0;                           // bitmap rows requested / waited for
-    if (classified) {
-        n_loaded = min(SD, n_frames);
-        if (lane == 0)
-            for (int d = 0; d < n_loaded; d++) {
-                mbar_expect_tx(&bars[d], row_bytes);
-                tma_load_1d(S.ring[d], xu + (size_t)d * (2 * W), row_bytes, &bars[d]);
+    auto min_horizon = [&]() -> int {
+        int t = 0x3fffffff;
+        for (int i = lane; i < n_act; i += 32) t = min(t, S.a_tl[i]);
+        return __reduce_min_sync(FULL, t);
+    };
+    int Tmin = min_horizon();
+
+    // ring of bitmap rows, filled a block (SGF rows, one bulk copy, one mbarrier) at a time
+    const int n_blocks = classified ? (n_frames + SGF - 1) / SGF : 0;
+    int blk_issued = 0, blk_landed = 0;
+    auto fill_blocks = [&](int fcur) {                        // every block whose slot is free
+        while (blk_issued < n_blocks && (blk_issued < RB || (blk_issued - RB + 1) * SGF <= fcur)) {
+            if (lane == 0) {
+                const int r0 = blk_issued * SGF, nr = min(SGF, n_frames - r0);
+                uint64_t *bar = &bars[blk_issued % RB];
+                mbar_expect_tx(bar, row_bytes * (uint32_t)nr);
+                tma_load_1d(ring + (size_t)(r0 % RROWS) * RW, xu + (size_t)r0 * RW, row_bytes * (uint32_t)nr, bar);
             }
-    }
+            blk_issued++;
+        }
+    };
     if (!classified && primed) bail = 1;                      // a priming launch on a primed detector
-    if (n_act >= IR_MAX_ACTIVE - 64) bail = 7;
 
     auto issue = [&](int s, int e, int ex) {
         if (lane == 0) *reinterpret_cast<volatile unsigned long long *>(&ctl->cmd[n_cmd]) = pack_cmd(epoch, s, e, ex);
@@ -296,228 +352,312 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     auto wait_all = [&]() -> bool {
         if (n_waited == n_cmd) return true;
         if (lane < SCL)
-            while (ld_vol32(&ctl->done[lane]) < n_cmd) __nanosleep(32);
+            while (ld_acq32(&ctl->done[lane]) < n_cmd) __nanosleep(20);
         __syncwarp();
-        __threadfence();
         n_waited = n_cmd;
         st_waits++;
         return ld_vol32(&ctl->guard_bad) == 0u;
     };
-
     int qs = -1;                                              // first frame of the quiet range not yet handed out
+    // frames [a, b) end with no burst active: update_filters_post (:438-454), by the workers
+    auto quiet_frames = [&](int a, int b) {
+        if (qs < 0) qs = a;
+        if (b - qs >= SQCH) { issue(qs, b, 0); qs = -1; }
+        hist_idx += b - a;
+        if (hist_idx >= H) {                                  // (a group never crosses the priming point, see below)
+            hist_idx -= H;
+            if (!primed) {
+                primed = 1;
+                if (b < n_frames) bail = 8;                   // the bitmaps were not made for this baseline
+            }
+        }
+    };
+
     int f = 0;
-    for (; f < n_frames && !bail; f++) {
-        const uint64_t idx = index0 + (uint64_t)f * (uint64_t)N;
-        const int slot = f % SD;
-        const uint32_t *X = S.ring[slot], *U = X + W;
-        bool quiet;
-        if (classified) { mbar_wait(&bars[slot], (uint32_t)((f / SD) & 1)); n_landed = f + 1; }
-        if (!primed) {
-            quiet = true;                                     // nothing is detected before 512 frames (:426-428)
-        } else {
-            // ---- the three questions of a frame, from the bitmaps alone
-            uint32_t anyc = 0;
+    while (f < n_frames && !bail) {
+        ST_TICK(cy_scan);
+        if (!primed) {                                        // nothing is detected before 512 frames (:426-428)
+            const int G = min(min(SQCH, n_frames - f), H - hist_idx);
+            quiet_frames(f, f + G);
+            f += G;
+            continue;
+        }
+        const int G = min(SGF, n_frames - f);
+        __syncwarp();
+        fill_blocks(f);
+        while (blk_landed <= ((f + G - 1) / SGF)) {
+            mbar_wait(&bars[blk_landed % RB], (uint32_t)((blk_landed / RB) & 1));
+            blk_landed++;
+        }
+        ST_TICK(cy_ring);
+        if (f + G - 1 > Tmin) { bail = 3; break; }            // a burst may exceed max_burst_len (:498-517)
+        // ---- (1) unmasked bits, (2) bursts ending or needing the exact test: one flag bit per frame.
+        // Branch-free over the SGF rows (rows past the end of the launch hold stale bits and are
+        // masked off below) so that all loads of a group are in flight together.
+        uint32_t flags = 0;
+        {
+            uint32_t acc[SGF];
+#pragma unroll
+            for (int g = 0; g < SGF; g++) {
+                const uint32_t *XU = ring + (size_t)((f + g) % RROWS) * RW;
+                acc[g] = 0;
+#pragma unroll
+                for (int k4 = 0; k4 < WPL / 4; k4++) {
+                    const uint4 x = *reinterpret_cast<const uint4 *>(&XU[lane * WPL + 4 * k4]);
+                    acc[g] |= (x.x & fv[4 * k4]) | (x.y & fv[4 * k4 + 1]) | (x.z & fv[4 * k4 + 2]) | (x.w & fv[4 * k4 + 3]);
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < SGF; g++) flags |= acc[g] ? (1u << g) : 0u;
+        }
+        for (int i = lane; i < n_act; i += 32) {
+            const int cb = S.a_cb[i];
+            const int w0 = (cb - 1) >> 5, sh = (cb - 1) & 31, w1 = min(w0 + 1, W - 1);
+            int dl = S.a_dl[i];
+            uint32_t x3[SGF], u3[SGF];
+#pragma unroll
+            for (int g = 0; g < SGF; g++) {
+                const uint32_t *XU = ring + (size_t)((f + g) % RROWS) * RW;
+                const uint32_t *X = XU + W;
+                x3[g] = __funnelshift_r(X[w0], X[w1], sh) & 7u;
+                u3[g] = __funnelshift_r(XU[w0], XU[w1], sh) & 7u;
+            }
+            uint32_t hm = 0;
+#pragma unroll
+            for (int g = 0; g < SGF; g++) {
+                const bool hit = x3[g] != 0u;                              // update_bursts (:458-469), certain
+                const bool ev = !hit && (u3[g] != 0u || f + g >= dl);      // exact test needed / burst ends
+                hm |= hit ? (1u << g) : 0u;
+                flags |= ev ? (1u << g) : 0u;
+                dl = hit ? f + g + PF : dl;
+            }
+            S.a_hm[i] = hm;
+        }
+        flags &= (1u << G) - 1u;
+        flags = __reduce_or_sync(FULL, flags);
+        const int e = flags ? __ffs(flags) - 1 : G;
+        // event frame: list the words with a possible unmasked crossing and get their magnitudes
+        // moving now; they land while the frames before the event are committed
+        int n_cw = 0;
+        float mvp[SPF];
+#pragma unroll
+        for (int j = 0; j < SPF; j++) mvp[j] = 0.0f;
+        if (e < G) {
+            const uint32_t *XUe = ring + (size_t)((f + e) % RROWS) * RW;
+            uint32_t wmask = 0;
 #pragma unroll
             for (int k4 = 0; k4 < WPL / 4; k4++) {
-                const uint4 x = *reinterpret_cast<const uint4 *>(&X[lane * WPL + 4 * k4]);
-                const uint4 u = *reinterpret_cast<const uint4 *>(&U[lane * WPL + 4 * k4]);
-                anyc |= ((x.x | u.x) & fv[4 * k4]) | ((x.y | u.y) & fv[4 * k4 + 1]) |
-                        ((x.z | u.z) & fv[4 * k4 + 2]) | ((x.w | u.w) & fv[4 * k4 + 3]);
+                const uint4 x = *reinterpret_cast<const uint4 *>(&XUe[lane * WPL + 4 * k4]);
+                wmask |= ((x.x & fv[4 * k4]) ? 1u : 0u) << (4 * k4) | ((x.y & fv[4 * k4 + 1]) ? 2u : 0u) << (4 * k4) |
+                         ((x.z & fv[4 * k4 + 2]) ? 4u : 0u) << (4 * k4) | ((x.w & fv[4 * k4 + 3]) ? 8u : 0u) << (4 * k4);
             }
-            int ev = anyc != 0u;
+            int off = __popc(wmask);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {                // inclusive scan of the per-lane counts
+                const int t = __shfl_up_sync(FULL, off, o);
+                if (lane >= o) off += t;
+            }
+            n_cw = __shfl_sync(FULL, off, 31);
+            off -= __popc(wmask);
+            while (wmask) {
+                const int k = __ffs(wmask) - 1;
+                wmask &= wmask - 1;
+                S.cw[off++] = lane * WPL + k;
+            }
+            __syncwarp();
+            const float *rowe = mag + (size_t)(f + e) * N;
+#pragma unroll
+            for (int j = 0; j < SPF; j++)
+                if (j < n_cw) mvp[j] = rowe[(S.cw[j] << 5) + lane];
+        }
+        // ---- commit the frames before the first event
+        if (e > 0) {
+            const uint32_t below = (1u << e) - 1u;
+            for (int i = lane; i < n_act; i += 32) {
+                const uint32_t hm = S.a_hm[i] & below;
+                if (hm) {
+                    const int h = f + 31 - __clz(hm);
+                    S.a_lah[i] = h; S.a_dl[i] = h + PF;
+                }
+            }
+            sq = max(sq - e, 0);                              // :628-631
+            if (n_act == 0) quiet_frames(f, f + e);
+        }
+        f += e;
+        if (e == G) continue;
+        // ================= event frame f: the reference's steps, exactly
+        st_events++;
+        ST_TICK(cy_scan);
+        if (qs >= 0) { issue(qs, f, 0); qs = -1; }
+        if (!wait_all()) { bail = 2; break; }
+        ST_TICK(cy_wait);
+        {
+            const uint64_t idx = index0 + (uint64_t)f * (uint64_t)N;
+            const uint32_t *XU = ring + (size_t)(f % RROWS) * RW;
+            const uint32_t *X = XU + W;
+            const float *row = mag + (size_t)f * N;
+            __syncwarp();
+            // update_bursts incl. the tests an X bit does not decide
+            int any_done = 0;
             for (int i = lane; i < n_act; i += 32) {
                 const int cb = S.a_cb[i];
-                const int lo = max(cb - 1, 0), hi = min(cb + 1, N - 1);
-                const int w0 = lo >> 5, w1 = hi >> 5;
-                const unsigned long long msk = ((1ull << (hi - lo + 1)) - 1ull) << (lo & 31);
-                const unsigned long long xx = (unsigned long long)X[w0] | (w1 != w0 ? (unsigned long long)X[w1] << 32 : 0ull);
-                unsigned long long la = S.a_last[i];
-                if (xx & msk) {
-                    la = idx;                                 // update_bursts (:458-469)
-                    S.a_last[i] = idx;
-                } else {
-                    const unsigned long long uu = (unsigned long long)U[w0] | (w1 != w0 ? (unsigned long long)U[w1] << 32 : 0ull);
-                    if (uu & msk) ev = 1;
-                }
-                if (la + (unsigned long long)c.post_len <= idx ||
-                    (c.max_burst_len > 0 && la - S.a_start[i] > (unsigned long long)c.max_burst_len))
-                    ev = 1;
-            }
-            if (__any_sync(FULL, ev)) {
-                // ================= event frame: the reference's steps, exactly
-                st_events++;
-                if (qs >= 0) { issue(qs, f, 0); qs = -1; }
-                if (!wait_all()) { bail = 2; break; }
-                const float *row = mag + (size_t)f * N;
-                // update_bursts for the tests an X bit did not decide
-                int too_long = 0, any_done = 0;
-                for (int i = lane; i < n_act; i += 32) {
-                    const int cb = S.a_cb[i];
-                    unsigned long long la = S.a_last[i];
-                    if (la != idx) {
-                        bool hit = false;
-                        for (int b = max(cb - 1, 0); b <= min(cb + 1, N - 1); b++) {
-                            if ((U[b >> 5] >> (b & 31)) & 1u) {
-                                const float bs = __ldcg(base_g + b);
-                                if (bs > 0.0f && row[b] / bs > thr) hit = true;
-                            }
-                        }
-                        if (hit) { la = idx; S.a_last[i] = idx; }
+                const int w0 = (cb - 1) >> 5, sh = (cb - 1) & 31, w1 = min(w0 + 1, W - 1);
+                bool hit = (__funnelshift_r(X[w0], X[w1], sh) & 7u) != 0u;
+                if (!hit) {
+                    uint32_t u3 = __funnelshift_r(XU[w0], XU[w1], sh) & 7u;
+                    while (u3) {
+                        const int b = cb - 1 + __ffs(u3) - 1;
+                        u3 &= u3 - 1;
+                        const float bs = __ldcg(base_g + b);
+                        if (bs > 0.0f && row[b] / bs > thr) hit = true;
                     }
-                    const bool tl = c.max_burst_len > 0 && la - S.a_start[i] > (unsigned long long)c.max_burst_len;
-                    if (tl) too_long = 1;
-                    if (la + (unsigned long long)c.post_len <= idx || tl) any_done = 1;
                 }
-                if (__any_sync(FULL, too_long)) { bail = 3; break; }     // forced baseline update (:498-517)
-                any_done = __any_sync(FULL, any_done);
-                // peaks: exact crossings & mask of the previous frame & search range (:522-548)
-                if (lane == 0) { S.n_cw = 0; S.n_cand = 0; }
-                __syncwarp();
+                if (hit) { S.a_lah[i] = f; S.a_dl[i] = f + PF; }
+                else if (f >= S.a_dl[i]) any_done = 1;
+            }
+            any_done = __any_sync(FULL, any_done);
+            // peaks: exact crossings & mask of the previous frame & search range (:522-548)
+            int n_cand = 0;
+            for (int j0 = 0; j0 < n_cw; j0 += SPF) {
+                float mv[SPF], bs[SPF];
+                int wj[SPF];
 #pragma unroll
-                for (int k = 0; k < WPL; k++) {
-                    const int w = lane * WPL + k;
-                    if ((X[w] | U[w]) & fv[k]) S.cw[atomicAdd(&S.n_cw, 1)] = w;
+                for (int j = 0; j < SPF; j++) {
+                    wj[j] = j0 + j < n_cw ? S.cw[j0 + j] : -1;
+                    mv[j] = 0.0f; bs[j] = 0.0f;
+                    if (wj[j] >= 0) {
+                        const int bin = (wj[j] << 5) + lane;
+                        mv[j] = j0 == 0 ? mvp[j] : row[bin];
+                        bs[j] = __ldcg(base_g + bin);
+                    }
                 }
-                __syncwarp();
-                const int n_cw = S.n_cw;
-                int n_cand = 0;
-                for (int j = 0; j < n_cw; j++) {
-                    const int w = S.cw[j];
-                    const int bin = (w << 5) + lane;
-                    const float mv = row[bin];
-                    const float bs = __ldcg(base_g + bin);
+#pragma unroll
+                for (int j = 0; j < SPF; j++) {
+                    if (wj[j] < 0) break;
+                    const int w = wj[j];
                     float rel = 0.0f;
                     bool ex = false;
-                    if (bs > 0.0f) { rel = mv / bs; ex = rel > thr; }                // simd_avx2.c:239-257
+                    if (bs[j] > 0.0f) { rel = mv[j] / bs[j]; ex = rel > thr; }       // simd_avx2.c:239-257
                     ex = ex && (((S.free_mask[w] & S.valid[w]) >> lane) & 1u);
                     const uint32_t bal = __ballot_sync(FULL, ex);
                     if (ex) {
                         const int pos = n_cand + __popc(bal & ((1u << lane) - 1u));
-                        if (pos < SMAXC) { S.cbin[pos] = bin; S.crel[pos] = rel; S.cbase[pos] = bs; }
+                        if (pos < SMAXC) { S.cbin[pos] = (w << 5) + lane; S.crel[pos] = rel; S.cbase[pos] = bs[j]; }
                     }
                     n_cand += __popc(bal);
                 }
-                st_exact += (unsigned long long)n_cw;
-                if (n_cand > SMAXC) { bail = 4; break; }
+            }
+            st_exact += (unsigned long long)n_cw;
+            if (n_cand > SMAXC) { bail = 4; break; }
+            __syncwarp();
+            ST_TICK(cy_e1);
+            bool list_changed = false;
+            if (any_done) {
+                // delete_gone_bursts (:490-518): gone records and survivors keep the list order
+                int kept = 0;
+                for (int i0 = 0; i0 < n_act; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool have = i < n_act;
+                    unsigned long long id = 0, start = 0, la = 0;
+                    int cb = 0, dl = 0, lah = NONE, tl = 0;
+                    float rel = 0.0f, bsc = 0.0f;
+                    if (have) {
+                        id = S.a_id[i]; start = S.a_start[i]; la = S.a_last[i];
+                        cb = S.a_cb[i]; rel = S.a_rel[i]; bsc = S.a_base[i];
+                        dl = S.a_dl[i]; lah = S.a_lah[i]; tl = S.a_tl[i];
+                    }
+                    const bool done = have && f >= dl;
+                    const uint32_t dm = __ballot_sync(FULL, done), km = __ballot_sync(FULL, have && !done);
+                    const uint32_t below = (1u << lane) - 1u;
+                    if (done) {
+                        const uint32_t slot_g = n_gone + (uint32_t)__popc(dm & below);
+                        if (slot_g < gone_cap) {
+                            GoneBurst g;
+                            g.id = id; g.start = start; g.stop = idx;
+                            g.last_active = lah == NONE ? la : index0 + (uint64_t)lah * (uint64_t)N;
+                            g.center_bin = cb; g.peak_rel = rel; g.base_at_create = bsc; g.pad = 0;
+                            gone[slot_g] = g;
+                        } else {
+                            overflow = 1;
+                        }
+                    }
+                    overflow = __any_sync(FULL, overflow) ? 1u : 0u;
+                    __syncwarp();
+                    if (have && !done) {
+                        const int pos = kept + __popc(km & below);
+                        S.a_id[pos] = id; S.a_start[pos] = start; S.a_last[pos] = la;
+                        S.a_cb[pos] = cb; S.a_rel[pos] = rel; S.a_base[pos] = bsc;
+                        S.a_dl[pos] = dl; S.a_lah[pos] = lah; S.a_tl[pos] = tl;
+                    }
+                    n_gone += (uint32_t)__popc(dm);
+                    kept += __popc(km);
+                    __syncwarp();
+                }
+                n_act = kept;
+                // update_burst_mask (:482-486)
+                for (int w = lane; w < W; w += 32) S.free_mask[w] = FULL;
                 __syncwarp();
-                bool mask_changed = false;
-                if (any_done) {
-                    // delete_gone_bursts (:490-518): gone records and survivors keep the list order
-                    int kept = 0;
-                    for (int i0 = 0; i0 < n_act; i0 += 32) {
-                        const int i = i0 + lane;
-                        const bool have = i < n_act;
-                        unsigned long long id = 0, start = 0, la = 0;
-                        int cb = 0;
-                        float rel = 0.0f, bsc = 0.0f;
-                        if (have) {
-                            id = S.a_id[i]; start = S.a_start[i]; la = S.a_last[i];
-                            cb = S.a_cb[i]; rel = S.a_rel[i]; bsc = S.a_base[i];
+                for (int i = lane; i < n_act; i += 32)
+                    st_clear(S.free_mask, max(S.a_cb[i] - c.half_bw, 0), min(S.a_cb[i] + c.half_bw, N - 1));
+                __syncwarp();
+                list_changed = true;
+            }
+            ST_TICK(cy_e2);
+            if (n_cand > 0) {
+                // create_new_bursts (:556-591): strongest remaining peak first, ties by bin
+                const int nc = n_cand;
+                for (;;) {
+                    ArgMax best{-1.0f, 0x7fffffff};
+                    int bslot = -1;
+                    for (int i = lane; i < nc; i += 32) {
+                        const int bin = S.cbin[i];
+                        if (bin >= 0) {
+                            const ArgMax cur{S.crel[i], bin};
+                            const ArgMax nb = argmax_pick(best, cur);
+                            if (nb.i != best.i) bslot = i;
+                            best = nb;
                         }
-                        const bool done = have && (la + (unsigned long long)c.post_len <= idx);
-                        const uint32_t dm = __ballot_sync(FULL, done), km = __ballot_sync(FULL, have && !done);
-                        const uint32_t below = (1u << lane) - 1u;
-                        if (done) {
-                            const uint32_t slot_g = n_gone + (uint32_t)__popc(dm & below);
-                            if (slot_g < gone_cap) {
-                                GoneBurst g;
-                                g.id = id; g.start = start; g.stop = idx; g.last_active = la;
-                                g.center_bin = cb; g.peak_rel = rel; g.base_at_create = bsc; g.pad = 0;
-                                gone[slot_g] = g;
-                            } else {
-                                overflow = 1;
-                            }
-                        }
-                        overflow = __any_sync(FULL, overflow) ? 1u : 0u;
-                        __syncwarp();
-                        if (have && !done) {
-                            const int pos = kept + __popc(km & below);
-                            S.a_id[pos] = id; S.a_start[pos] = start; S.a_last[pos] = la;
-                            S.a_cb[pos] = cb; S.a_rel[pos] = rel; S.a_base[pos] = bsc;
-                        }
-                        n_gone += (uint32_t)__popc(dm);
-                        kept += __popc(km);
-                        __syncwarp();
                     }
-                    n_act = kept;
-                    // update_burst_mask (:482-486)
-                    for (int w = lane; w < W; w += 32) S.free_mask[w] = FULL;
-                    __syncwarp();
-                    for (int i = lane; i < n_act; i += 32)
-                        st_clear(S.free_mask, max(S.a_cb[i] - c.half_bw, 0), min(S.a_cb[i] + c.half_bw, N - 1));
-                    __syncwarp();
-                    mask_changed = true;
-                }
-                if (n_cand > 0) {
-                    // create_new_bursts (:556-591): strongest remaining peak first, ties by bin
-                    const int nc = n_cand;
-                    for (;;) {
-                        ArgMax best{-1.0f, 0x7fffffff};
-                        int bslot = -1;
-                        for (int i = lane; i < nc; i += 32) {
-                            const int bin = S.cbin[i];
-                            if (bin >= 0) {
-                                const ArgMax cur{S.crel[i], bin};
-                                const ArgMax nb = argmax_pick(best, cur);
-                                if (nb.i != best.i) bslot = i;
-                                best = nb;
-                            }
-                        }
-                        const ArgMax wbest = warp_argmax(best);
-                        if (wbest.v < 0.0f) break;
-                        const int bin = wbest.i;
-                        const unsigned owner = __ballot_sync(FULL, best.i == bin && bslot >= 0);
-                        const int src = __ffs(owner) - 1;
-                        const float bc = __shfl_sync(FULL, bslot >= 0 ? S.cbase[bslot] : 0.0f, src);
-                        if (lane == 0) {
-                            S.a_id[n_act] = next_id;
-                            S.a_start[n_act] = idx - (unsigned long long)c.pre_len;
-                            S.a_last[n_act] = idx - (unsigned long long)c.pre_len;
-                            S.a_cb[n_act] = bin; S.a_rel[n_act] = wbest.v; S.a_base[n_act] = bc;
-                            st_clear(S.free_mask, max(bin - c.half_bw, 0), min(bin + c.half_bw, N - 1));
-                        }
-                        n_act++;
-                        next_id += 10ull;
-                        for (int i = lane; i < nc; i += 32) {
-                            const int bb = S.cbin[i];
-                            if (bb >= bin - c.half_bw && bb <= bin + c.half_bw) S.cbin[i] = -1;
-                        }
-                        __syncwarp();
-                        if (n_act >= IR_MAX_ACTIVE - 64) break;
+                    const ArgMax wbest = warp_argmax(best);
+                    if (wbest.v < 0.0f) break;
+                    const int bin = wbest.i;
+                    const unsigned owner = __ballot_sync(FULL, best.i == bin && bslot >= 0);
+                    const int src = __ffs(owner) - 1;
+                    const float bc = __shfl_sync(FULL, bslot >= 0 ? S.cbase[bslot] : 0.0f, src);
+                    if (lane == 0) {
+                        const unsigned long long start = idx - (unsigned long long)c.pre_len;
+                        S.a_id[n_act] = next_id;
+                        S.a_start[n_act] = start;
+                        S.a_last[n_act] = start;
+                        S.a_cb[n_act] = bin; S.a_rel[n_act] = wbest.v; S.a_base[n_act] = bc;
+                        S.a_dl[n_act] = f + PF0; S.a_lah[n_act] = NONE; S.a_tl[n_act] = horizon_of(start);
+                        st_clear(S.free_mask, max(bin - c.half_bw, 0), min(bin + c.half_bw, N - 1));
                     }
-                    mask_changed = true;
-                    if (n_act >= IR_MAX_ACTIVE - 64) { bail = 5; break; }
-                }
-                if (c.max_bursts > 0 && n_act > c.max_bursts) { bail = 6; break; }    // squelch (:593-631)
-                if (mask_changed) {
+                    n_act++;
+                    next_id += 10ull;
+                    for (int i = lane; i < nc; i += 32) {
+                        const int bb = S.cbin[i];
+                        if (bb >= bin - c.half_bw && bb <= bin + c.half_bw) S.cbin[i] = -1;
+                    }
                     __syncwarp();
+                    if (n_act > SACT - 64) break;
+                }
+                list_changed = true;
+                if (n_act > SACT - 64) { bail = 5; break; }
+            }
+            if (c.max_bursts > 0 && n_act > c.max_bursts) { bail = 6; break; }      // squelch (:593-631)
+            ST_TICK(cy_e3);
+            if (list_changed) {
+                __syncwarp();
 #pragma unroll
-                    for (int k = 0; k < WPL; k++) fv[k] = S.free_mask[lane * WPL + k] & S.valid[lane * WPL + k];
-                }
+                for (int k = 0; k < WPL; k++) fv[k] = S.free_mask[lane * WPL + k] & S.valid[lane * WPL + k];
+                Tmin = min_horizon();
             }
             if (sq > 0) sq--;                                 // :628-631
-            quiet = n_act == 0;
+            if (n_act == 0) quiet_frames(f, f + 1);
+            f++;
         }
-        // every lane is done with the ring slot: refill it SD frames ahead
-        __syncwarp();
-        if (classified && f + SD < n_frames) {
-            if (lane == 0) {
-                mbar_expect_tx(&bars[slot], row_bytes);
-                tma_load_1d(S.ring[slot], xu + (size_t)(f + SD) * (2 * W), row_bytes, &bars[slot]);
-            }
-            n_loaded = f + SD + 1;
-        }
-        if (quiet) {                                          // update_filters_post (:438-454), by the workers
-            if (qs < 0) qs = f;
-            if (f + 1 - qs >= SQCH) { issue(qs, f + 1, 0); qs = -1; }
-            if (++hist_idx == H) {
-                hist_idx = 0;
-                if (!primed) {
-                    primed = 1;
-                    if (f + 1 < n_frames) { bail = 8; break; }   // the bitmaps were not made for this baseline
-                }
-            }
-        }
+        ST_TICK(cy_event);
     }
     // ---- wrap up
     if (!bail) {
@@ -529,11 +669,13 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
         while (ld_vol32(&ctl->done[lane]) < n_cmd - 1) __nanosleep(32);     // every real command is finished
     __syncwarp();
     // bulk copies still in flight (a bailed launch) must land before the shared memory is released
-    for (int g = n_landed; g < n_loaded; g++) mbar_wait(&bars[g % SD], (uint32_t)((g / SD) & 1));
+    for (; blk_landed < blk_issued; blk_landed++) mbar_wait(&bars[blk_landed % RB], (uint32_t)((blk_landed / RB) & 1));
     if (!bail) {
         for (int i = lane; i < n_act; i += 32) {
             ActBurst b;
-            b.id = S.a_id[i]; b.start = S.a_start[i]; b.last_active = S.a_last[i];
+            const int lah = S.a_lah[i];
+            b.id = S.a_id[i]; b.start = S.a_start[i];
+            b.last_active = lah == NONE ? S.a_last[i] : index0 + (uint64_t)lah * (uint64_t)N;
             b.center_bin = S.a_cb[i]; b.peak_rel = S.a_rel[i]; b.base_at_create = S.a_base[i]; b.pad = 0;
             gs->act[i] = b;
         }
@@ -547,6 +689,11 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
         ctl->bailed = bail ? 1 : 0;
         if (bail) { ctl->reason = bail; ctl->stats[1] += 1; ctl->stats[6] = (unsigned long long)f; } else ctl->stats[0] += 1;
         ctl->stats[2] += n_cmd; ctl->stats[3] += st_events; ctl->stats[4] += st_exact; ctl->stats[5] += st_waits;
+        unsigned long long t_glob1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_glob1));
+        ctl->stats[7] += t_glob1 - t_glob0;
+        ctl->stats[8] += cy_ring; ctl->stats[9] += cy_scan; ctl->stats[10] += cy_wait; ctl->stats[11] += cy_event;
+        ctl->stats[12] += cy_e1; ctl->stats[13] += cy_e2; ctl->stats[14] += cy_e3;
     }
 }
 
@@ -585,7 +732,8 @@ template <int BPT>
 static cudaError_t launch_stream_t(const DetConfig &c, DetState *state, float *base, float *hist, const float *mag,
                                    const uint32_t *xu, const float *ref, int n_frames, GoneBurst *gone,
                                    uint32_t gone_cap, StreamCtl *ctl, unsigned epoch, cudaStream_t st) {
-    const size_t smem = ((sizeof(StShared) + 127) / 128) * 128;
+    constexpr int RB = BPT >= 8 ? 4 : 8;
+    const size_t smem = ((sizeof(StShared) + 127) / 128) * 128 + (size_t)RB * SGF * (size_t)(c.N / 16) * sizeof(uint32_t);
     cudaError_t e = cudaFuncSetAttribute(k_detect_scan_stream<BPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k_detect_scan_stream<BPT><<<SCL, SNT, smem, st>>>(c, state, base, hist, mag, xu, ref, n_frames, gone, gone_cap, ctl, epoch);
@@ -594,7 +742,7 @@ static cudaError_t launch_stream_t(const DetConfig &c, DetState *state, float *b
 
 bool stream_scan_supported(const DetConfig &c) {
     const int bpt = c.N / (SCL * SWT);
-    return c.N % (SCL * SWT) == 0 && (bpt == 1 || bpt == 2 || bpt == 4) && c.hist_size >= 2 * SGMAX;
+    return c.N % (SCL * SWT) == 0 && (bpt == 2 || bpt == 4 || bpt == 8) && c.hist_size >= 2 * SGMAX;
 }
 
 // One launch of the streaming state machine over frames [0, n_frames) of `mag` (n_frames <=
@@ -606,9 +754,9 @@ cudaError_t launch_detect_scan_stream(const DetConfig &c, DetState *state, float
     if (n_frames <= 0) return cudaSuccess;
     if (n_frames > IR_STREAM_MAX_FRAMES) return cudaErrorInvalidValue;
     switch (c.N / (SCL * SWT)) {
-    case 1: return launch_stream_t<1>(c, state, base, hist, mag, xu, ref, n_frames, gone, gone_cap, ctl, epoch, st);
     case 2: return launch_stream_t<2>(c, state, base, hist, mag, xu, ref, n_frames, gone, gone_cap, ctl, epoch, st);
     case 4: return launch_stream_t<4>(c, state, base, hist, mag, xu, ref, n_frames, gone, gone_cap, ctl, epoch, st);
+    case 8: return launch_stream_t<8>(c, state, base, hist, mag, xu, ref, n_frames, gone, gone_cap, ctl, epoch, st);
     default: return cudaErrorInvalidValue;
     }
 }

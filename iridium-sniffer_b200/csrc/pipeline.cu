@@ -156,7 +156,7 @@ struct ir_pipeline {
     DevBuf<StreamCtl> d_ctl;
     unsigned scan_epoch = 1;
     int scan_mode = 0;                       // 0 = streaming (default where supported), 1 = cluster / single (IR_SCAN)
-    uint64_t scan_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t scan_stats[16] = {0};
     // burst list: pinned host memory mapped into the device; the scan kernel stores the (few,
     // 56-byte) records straight into it, the host reads them after the chunk's event
     GoneBurst *h_gone = nullptr, *d_gone = nullptr;
@@ -229,9 +229,12 @@ extern "C" ir_pipeline_t *ir_pipeline_create(const ir_config_t *cfg) {
     if (p->dec != 40 && p->dec != 48) return fail("decimation ratio (sample_rate/250k) must be 40 or 48 in this build");
     build_host_tables(p->tab, p->dc.N);
     if ((int)p->tab.h_input.size() != IR_INPUT_NTAPS) return fail("unexpected input filter length");
+    // the state machine is the serial spine of a run: its launches go first when SMs free up
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithFlags(&p->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&p->st_fft, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&p->st_scan, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&p->st_scan, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithFlags(&p->st_burst, cudaStreamNonBlocking) != cudaSuccess)
         return fail("stream creation failed");
     p->pin_arena.host = true;
@@ -695,6 +698,9 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
                 (unsigned long long)p->scan_stats[6], (unsigned long long)p->scan_stats[2],
                 (unsigned long long)p->scan_stats[3], (unsigned long long)p->scan_stats[4],
                 (unsigned long long)p->scan_stats[5]);
+        fprintf(stderr, "stream scan: kernel %.3f ms; leader Mcycles: ring wait %.2f bitmap pass %.2f worker wait %.2f events: hyst+peaks %.2f delete %.2f create %.2f tail %.2f\n",
+                p->scan_stats[7] * 1e-6, p->scan_stats[8] * 1e-6, p->scan_stats[9] * 1e-6, p->scan_stats[10] * 1e-6,
+                p->scan_stats[12] * 1e-6, p->scan_stats[13] * 1e-6, p->scan_stats[14] * 1e-6, p->scan_stats[11] * 1e-6);
     }
     if (getenv("IR_SCAN_DEBUG") && p->scan_mode != 0) {
         fprintf(stderr, "scan cycles leader: p1 %llu waitA %llu p2 %llu waitB %llu p3 %llu waitC %llu batches %llu qbatches %llu\n",
