@@ -125,7 +125,7 @@ struct Wave {
     DemodOut *d_do = nullptr, *h_do = nullptr;
     unsigned char *d_bits = nullptr, *h_bits = nullptr;
     float *d_llr = nullptr, *h_llr = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr, e_done = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e1a = nullptr, e1b = nullptr, e2 = nullptr, e3 = nullptr, e_done = nullptr;
 };
 
 struct Chunk { size_t end = 0; cudaEvent_t e_hdr = nullptr; EvPair fft, scan; };
@@ -140,7 +140,11 @@ struct ir_pipeline {
     HostTables tab;
     int dev = 0, sm_count = 148;
     int dec = 40;
-    cudaStream_t st_copy = nullptr, st_fft = nullptr, st_scan = nullptr, st_burst = nullptr;
+    cudaStream_t st_copy = nullptr, st_fft = nullptr, st_scan = nullptr, st_burst = nullptr, st_chain = nullptr;
+    // the symbol slicer is a serial recurrence per frame (long latency, few warps): its launches go
+    // round-robin over a few streams of their own so that they overlap the FIR / chain of later waves
+    static constexpr int kDemodStreams = 4;
+    cudaStream_t st_demod[kDemodStreams] = {nullptr, nullptr, nullptr, nullptr};
     // constants
     DevBuf<float> d_window;
     DevBuf<float2> d_tw_det, d_tw12, d_tw11, d_sync_dl, d_sync_ul;
@@ -235,8 +239,11 @@ extern "C" ir_pipeline_t *ir_pipeline_create(const ir_config_t *cfg) {
     if (cudaStreamCreateWithFlags(&p->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&p->st_fft, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithPriority(&p->st_scan, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&p->st_burst, cudaStreamNonBlocking) != cudaSuccess)
+        cudaStreamCreateWithFlags(&p->st_burst, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&p->st_chain, cudaStreamNonBlocking) != cudaSuccess)
         return fail("stream creation failed");
+    for (int i = 0; i < ir_pipeline::kDemodStreams; i++)
+        if (cudaStreamCreateWithFlags(&p->st_demod[i], cudaStreamNonBlocking) != cudaSuccess) return fail("stream creation failed");
     p->pin_arena.host = true;
     if (p->d_window.ensure(p->dc.N)) return fail(g_err);
     if (cudaMemcpy(p->d_window.p, p->tab.det_window.data(), sizeof(float) * p->dc.N, cudaMemcpyHostToDevice) != cudaSuccess)
@@ -284,6 +291,9 @@ extern "C" void ir_pipeline_destroy(ir_pipeline_t *p) {
     if (p->st_fft) cudaStreamDestroy(p->st_fft);
     if (p->st_scan) cudaStreamDestroy(p->st_scan);
     if (p->st_burst) cudaStreamDestroy(p->st_burst);
+    if (p->st_chain) cudaStreamDestroy(p->st_chain);
+    for (int i = 0; i < ir_pipeline::kDemodStreams; i++)
+        if (p->st_demod[i]) cudaStreamDestroy(p->st_demod[i]);
     delete p;
 }
 
@@ -434,7 +444,7 @@ static int launch_wave(ir_pipeline *p, size_t b0, size_t b1, const void *iq_dev,
         w.h_bp[i - b0] = p->h_bp[i];
     }
     // ---- device work for the bursts
-    w.e0 = p->ev(); w.e1 = p->ev(); w.e2 = p->ev(); w.e3 = p->ev(); w.e_done = p->ev();
+    w.e0 = p->ev(); w.e1 = p->ev(); w.e1a = p->ev(); w.e1b = p->ev(); w.e2 = p->ev(); w.e3 = p->ev(); w.e_done = p->ev();
     w.d_bp = p->dev_arena.take<BurstParam>(nb);
     w.d_tile_start = p->dev_arena.take<int>(nb + 1);
     w.d_dec = p->dev_arena.take<float2>((size_t)dec_total + 16);
@@ -458,18 +468,24 @@ static int launch_wave(ir_pipeline *p, size_t b0, size_t b1, const void *iq_dev,
     CK(cudaEventRecord(w.e0, st));
     CK(launch_fir(fmt, p->dec, iq_dev, (int64_t)n, R, w.d_bp, w.d_tile_start, (int)nb, n_tiles, w.d_dec, st));
     CK(cudaEventRecord(w.e1, st));
+    // the 250 kHz chain of this wave overlaps the FIR of the next one
+    CK(cudaStreamWaitEvent(p->st_chain, w.e1, 0));
+    CK(cudaEventRecord(w.e1a, p->st_chain));
     CK(launch_chain(w.d_bp, (int)nb, w.d_dec, w.d_scrA, w.d_scrB, p->d_tw12.p, p->d_tw11.p, p->d_sync_dl.p,
-                    p->d_sync_ul.p, w.d_co, w.d_frames, st));
-    CK(cudaEventRecord(w.e2, st));
-    CK(launch_demod(w.d_co, (int)nb, w.d_frames, p->cfg.use_gardner, w.d_do, w.d_bits, w.d_llr, st));
-    CK(cudaEventRecord(w.e3, st));
+                    p->d_sync_ul.p, w.d_co, w.d_frames, p->st_chain));
+    CK(cudaEventRecord(w.e1b, p->st_chain));
+    cudaStream_t sd = p->st_demod[p->waves.size() % ir_pipeline::kDemodStreams];
+    CK(cudaStreamWaitEvent(sd, w.e1b, 0));
+    CK(cudaEventRecord(w.e2, sd));
+    CK(launch_demod(w.d_co, (int)nb, w.d_frames, p->cfg.use_gardner, w.d_do, w.d_bits, w.d_llr, sd));
+    CK(cudaEventRecord(w.e3, sd));
     p->res.kernel_launches += (n_tiles > 0 ? 1 : 0) + 2;
-    CK(cudaMemcpyAsync(w.h_co, w.d_co, nb * sizeof(ChainOut), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(w.h_do, w.d_do, nb * sizeof(DemodOut), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(w.h_bits, w.d_bits, nb * nsym2, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(w.h_llr, w.d_llr, nb * nsym2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(w.h_co, w.d_co, nb * sizeof(ChainOut), cudaMemcpyDeviceToHost, sd));
+    CK(cudaMemcpyAsync(w.h_do, w.d_do, nb * sizeof(DemodOut), cudaMemcpyDeviceToHost, sd));
+    CK(cudaMemcpyAsync(w.h_bits, w.d_bits, nb * nsym2, cudaMemcpyDeviceToHost, sd));
+    CK(cudaMemcpyAsync(w.h_llr, w.d_llr, nb * nsym2 * sizeof(float), cudaMemcpyDeviceToHost, sd));
     p->res.d2h_bytes += nb * (sizeof(GoneBurst) + sizeof(ChainOut) + sizeof(DemodOut) + nsym2 * 5);
-    CK(cudaEventRecord(w.e_done, st));
+    CK(cudaEventRecord(w.e_done, sd));
     p->waves.push_back(w);
     return 0;
 }
@@ -681,6 +697,9 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     cudaEvent_t e_end = p->ev();
     if (!p->chunks.empty()) CK(cudaStreamWaitEvent(p->st_burst, p->chunks.back().e_hdr, 0));
     else CK(cudaStreamWaitEvent(p->st_burst, ev_begin, 0));
+    for (size_t wi = p->waves.size() > (size_t)ir_pipeline::kDemodStreams ? p->waves.size() - ir_pipeline::kDemodStreams : 0;
+         wi < p->waves.size(); wi++)
+        CK(cudaStreamWaitEvent(p->st_burst, p->waves[wi].e_done, 0));     // the last wave of every demod stream
     CK(cudaEventRecord(e_end, p->st_burst));
     for (; assembled < p->waves.size(); assembled++)
         if (assemble_wave(p, p->waves[assembled])) return -1;
@@ -720,7 +739,7 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     }
     for (auto &w : p->waves) {
         p->res.ms_downmix_fir += span(w.e0, w.e1);
-        p->res.ms_downmix_chain += span(w.e1, w.e2);
+        p->res.ms_downmix_chain += span(w.e1a, w.e1b);
         p->res.ms_demod += span(w.e2, w.e3);
     }
     p->res.ms_total = span(ev_begin, e_end);
