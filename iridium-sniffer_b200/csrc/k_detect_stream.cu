@@ -45,7 +45,8 @@ namespace {
 constexpr int SCL = IR_STREAM_CL;      // CTAs per cluster
 constexpr int SWT = 256;               // worker threads per CTA (few threads = many registers for the leader)
 constexpr int SNT = SWT + 32;          // + one more warp (the leader, in CTA 0)
-constexpr int SGF = 8;                 // frames per leader group = rows per ring block
+constexpr int SGF = 8;                 // rows per ring block
+constexpr int SGS = 4;                 // frames per leader group
 constexpr int SPF = 4;                 // candidate words whose loads are in flight together
 constexpr int SACT = 512;              // bursts the leader can track (squelch sets in long before)
 constexpr int SMAXW = 512;             // bitmap words per frame (N <= 16384)
@@ -58,6 +59,7 @@ struct StShared {
     unsigned long long bar[8];         // one per ring block
     uint32_t free_mask[SMAXW];         // 1 = bin not covered by an active burst
     uint32_t valid[SMAXW];             // peak search range minus the DC notch
+    uint32_t fvs[SMAXW];               // free & valid, mirrored from the owner lanes' registers
     int cw[SMAXW];                     // words of the frame with a possible unmasked crossing
     int n_cw;
     int cbin[SMAXC];
@@ -273,7 +275,13 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     unsigned long long t_glob0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_glob0));
     long long tk = clock64();
+// per-phase cycle counters of the leader: compiled in only with -DIR_SCAN_TIMING (reading the
+// clock is a scheduling barrier and costs the leader ~10 %)
+#ifdef IR_SCAN_TIMING
 #define ST_TICK(acc) do { const long long _t = clock64(); acc += (unsigned long long)(_t - tk); tk = _t; } while (0)
+#else
+#define ST_TICK(acc) do { (void)tk; } while (0)
+#endif
     // frames a burst survives without a hit: idx - la >= post_len  <=>  frames >= PF (la = a frame's
     // index) resp. PF0 (la = start = creation frame's index - pre_len)
     const int PF = (c.post_len + N - 1) / N;
@@ -318,15 +326,38 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     for (int i = lane; i < n_act; i += 32)
         st_clear(S.free_mask, max(S.a_cb[i] - c.half_bw, 0), min(S.a_cb[i] + c.half_bw, N - 1));
     __syncwarp();
-    uint32_t fv[WPL];
+    // free & valid mask: lane l owns words l*WPL .. l*WPL+WPL-1 in registers (fv) and mirrors them
+    // in S.fvs for the lookups by word index
+    uint32_t fv[WPL], vl[WPL];
 #pragma unroll
-    for (int k = 0; k < WPL; k++) fv[k] = S.free_mask[lane * WPL + k] & S.valid[lane * WPL + k];
+    for (int k = 0; k < WPL; k++) {
+        vl[k] = S.valid[lane * WPL + k];
+        fv[k] = S.free_mask[lane * WPL + k] & vl[k];
+        S.fvs[lane * WPL + k] = fv[k];
+    }
+    // clear (burst created) / set (burst deleted) the bins lo..hi in the owned words
+    auto mask_bins = [&](int lo, int hi, bool set) {
+        const int wl = lo >> 5;
+        const uint32_t m0 = st_range_bits(wl, lo, hi), m1 = st_range_bits(wl + 1, lo, hi), m2 = st_range_bits(wl + 2, lo, hi);
+#pragma unroll
+        for (int k = 0; k < WPL; k++) {
+            const int d = lane * WPL + k - wl;
+            const uint32_t m = d == 0 ? m0 : (d == 1 ? m1 : (d == 2 ? m2 : 0u));
+            if (m) {
+                fv[k] = set ? (fv[k] | (m & vl[k])) : (fv[k] & ~m);
+                S.fvs[lane * WPL + k] = fv[k];
+            }
+        }
+    };
     auto min_horizon = [&]() -> int {
         int t = 0x3fffffff;
         for (int i = lane; i < n_act; i += 32) t = min(t, S.a_tl[i]);
         return __reduce_min_sync(FULL, t);
     };
     int Tmin = min_horizon();
+    // a new burst's too-long horizon, in frames after its creation frame (start = idx - pre_len)
+    // la <= index of frame f', so la - start <= (f' - f)*N + pre_len <= max_burst_len while f' - f <= TLF
+    const int TLF = c.max_burst_len <= 0 ? 0x20000000 : (c.max_burst_len >= c.pre_len ? (c.max_burst_len - c.pre_len) / N : -1);
 
     // ring of bitmap rows, filled a block (SGF rows, one bulk copy, one mbarrier) at a time
     const int n_blocks = classified ? (n_frames + SGF - 1) / SGF : 0;
@@ -374,6 +405,7 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     };
 
     int f = 0;
+    int fill_mark = -1;                                       // block index of f at the last fill_blocks call
     while (f < n_frames && !bail) {
         ST_TICK(cy_scan);
         if (!primed) {                                        // nothing is detected before 512 frames (:426-428)
@@ -382,23 +414,26 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
             f += G;
             continue;
         }
-        const int G = min(SGF, n_frames - f);
-        __syncwarp();
-        fill_blocks(f);
-        while (blk_landed <= ((f + G - 1) / SGF)) {
-            mbar_wait(&bars[blk_landed % RB], (uint32_t)((blk_landed / RB) & 1));
-            blk_landed++;
+        const int G = min(SGS, n_frames - f);
+        if ((f + G - 1) / SGF != fill_mark) {
+            fill_mark = (f + G - 1) / SGF;
+            __syncwarp();
+            fill_blocks(f);
+            while (blk_landed <= fill_mark) {
+                mbar_wait(&bars[blk_landed % RB], (uint32_t)((blk_landed / RB) & 1));
+                blk_landed++;
+            }
+            ST_TICK(cy_ring);
         }
-        ST_TICK(cy_ring);
         if (f + G - 1 > Tmin) { bail = 3; break; }            // a burst may exceed max_burst_len (:498-517)
         // ---- (1) unmasked bits, (2) bursts ending or needing the exact test: one flag bit per frame.
-        // Branch-free over the SGF rows (rows past the end of the launch hold stale bits and are
+        // Branch-free over the SGS rows (rows past the end of the launch hold stale bits and are
         // masked off below) so that all loads of a group are in flight together.
         uint32_t flags = 0;
         {
-            uint32_t acc[SGF];
+            uint32_t acc[SGS];
 #pragma unroll
-            for (int g = 0; g < SGF; g++) {
+            for (int g = 0; g < SGS; g++) {
                 const uint32_t *XU = ring + (size_t)((f + g) % RROWS) * RW;
                 acc[g] = 0;
 #pragma unroll
@@ -408,15 +443,15 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
                 }
             }
 #pragma unroll
-            for (int g = 0; g < SGF; g++) flags |= acc[g] ? (1u << g) : 0u;
+            for (int g = 0; g < SGS; g++) flags |= acc[g] ? (1u << g) : 0u;
         }
         for (int i = lane; i < n_act; i += 32) {
             const int cb = S.a_cb[i];
             const int w0 = (cb - 1) >> 5, sh = (cb - 1) & 31, w1 = min(w0 + 1, W - 1);
             int dl = S.a_dl[i];
-            uint32_t x3[SGF], u3[SGF];
+            uint32_t x3[SGS], u3[SGS];
 #pragma unroll
-            for (int g = 0; g < SGF; g++) {
+            for (int g = 0; g < SGS; g++) {
                 const uint32_t *XU = ring + (size_t)((f + g) % RROWS) * RW;
                 const uint32_t *X = XU + W;
                 x3[g] = __funnelshift_r(X[w0], X[w1], sh) & 7u;
@@ -424,7 +459,7 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
             }
             uint32_t hm = 0;
 #pragma unroll
-            for (int g = 0; g < SGF; g++) {
+            for (int g = 0; g < SGS; g++) {
                 const bool hit = x3[g] != 0u;                              // update_bursts (:458-469), certain
                 const bool ev = !hit && (u3[g] != 0u || f + g >= dl);      // exact test needed / burst ends
                 hm |= hit ? (1u << g) : 0u;
@@ -437,11 +472,13 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
         flags = __reduce_or_sync(FULL, flags);
         const int e = flags ? __ffs(flags) - 1 : G;
         // event frame: list the words with a possible unmasked crossing and get their magnitudes
-        // moving now; they land while the frames before the event are committed
+        // (and, while no baseline update is pending, baselines) moving now; they land while the
+        // frames before the event are committed
         int n_cw = 0;
-        float mvp[SPF];
+        float mvp[SPF], bsp[SPF];
+        const bool base_ok = qs < 0 && n_waited == n_cmd;
 #pragma unroll
-        for (int j = 0; j < SPF; j++) mvp[j] = 0.0f;
+        for (int j = 0; j < SPF; j++) { mvp[j] = 0.0f; bsp[j] = 0.0f; }
         if (e < G) {
             const uint32_t *XUe = ring + (size_t)((f + e) % RROWS) * RW;
             uint32_t wmask = 0;
@@ -451,24 +488,30 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
                 wmask |= ((x.x & fv[4 * k4]) ? 1u : 0u) << (4 * k4) | ((x.y & fv[4 * k4 + 1]) ? 2u : 0u) << (4 * k4) |
                          ((x.z & fv[4 * k4 + 2]) ? 4u : 0u) << (4 * k4) | ((x.w & fv[4 * k4 + 3]) ? 8u : 0u) << (4 * k4);
             }
-            int off = __popc(wmask);
+            if (__any_sync(FULL, wmask != 0u)) {
+                int off = __popc(wmask);
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {                // inclusive scan of the per-lane counts
-                const int t = __shfl_up_sync(FULL, off, o);
-                if (lane >= o) off += t;
-            }
-            n_cw = __shfl_sync(FULL, off, 31);
-            off -= __popc(wmask);
-            while (wmask) {
-                const int k = __ffs(wmask) - 1;
-                wmask &= wmask - 1;
-                S.cw[off++] = lane * WPL + k;
-            }
-            __syncwarp();
-            const float *rowe = mag + (size_t)(f + e) * N;
+                for (int o = 1; o < 32; o <<= 1) {            // inclusive scan of the per-lane counts
+                    const int t = __shfl_up_sync(FULL, off, o);
+                    if (lane >= o) off += t;
+                }
+                n_cw = __shfl_sync(FULL, off, 31);
+                off -= __popc(wmask);
+                while (wmask) {
+                    const int k = __ffs(wmask) - 1;
+                    wmask &= wmask - 1;
+                    S.cw[off++] = lane * WPL + k;
+                }
+                __syncwarp();
+                const float *rowe = mag + (size_t)(f + e) * N;
 #pragma unroll
-            for (int j = 0; j < SPF; j++)
-                if (j < n_cw) mvp[j] = rowe[(S.cw[j] << 5) + lane];
+                for (int j = 0; j < SPF; j++)
+                    if (j < n_cw) {
+                        const int bin = (S.cw[j] << 5) + lane;
+                        mvp[j] = rowe[bin];
+                        if (base_ok) bsp[j] = __ldcg(base_g + bin);
+                    }
+            }
         }
         // ---- commit the frames before the first event
         if (e > 0) {
@@ -516,45 +559,50 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
                 else if (f >= S.a_dl[i]) any_done = 1;
             }
             any_done = __any_sync(FULL, any_done);
-            // peaks: exact crossings & mask of the previous frame & search range (:522-548)
+            // peaks: exact crossings & mask of the previous frame & search range (:522-548).  Up to SPF
+            // words stay in registers (lane = bin inside the word); more go through shared memory.
+            const bool fast = n_cw <= SPF;
+            float relj[SPF], bsj[SPF];
+            int wj[SPF];
+            bool exj[SPF];
             int n_cand = 0;
             for (int j0 = 0; j0 < n_cw; j0 += SPF) {
-                float mv[SPF], bs[SPF];
-                int wj[SPF];
 #pragma unroll
                 for (int j = 0; j < SPF; j++) {
                     wj[j] = j0 + j < n_cw ? S.cw[j0 + j] : -1;
-                    mv[j] = 0.0f; bs[j] = 0.0f;
+                    relj[j] = 0.0f; bsj[j] = 0.0f; exj[j] = false;
+                }
+                float mv[SPF];
+#pragma unroll
+                for (int j = 0; j < SPF; j++) {
+                    mv[j] = 0.0f;
                     if (wj[j] >= 0) {
                         const int bin = (wj[j] << 5) + lane;
                         mv[j] = j0 == 0 ? mvp[j] : row[bin];
-                        bs[j] = __ldcg(base_g + bin);
+                        bsj[j] = (j0 == 0 && base_ok) ? bsp[j] : __ldcg(base_g + bin);
                     }
                 }
 #pragma unroll
                 for (int j = 0; j < SPF; j++) {
-                    if (wj[j] < 0) break;
-                    const int w = wj[j];
-                    float rel = 0.0f;
-                    bool ex = false;
-                    if (bs[j] > 0.0f) { rel = mv[j] / bs[j]; ex = rel > thr; }       // simd_avx2.c:239-257
-                    ex = ex && (((S.free_mask[w] & S.valid[w]) >> lane) & 1u);
-                    const uint32_t bal = __ballot_sync(FULL, ex);
-                    if (ex) {
-                        const int pos = n_cand + __popc(bal & ((1u << lane) - 1u));
-                        if (pos < SMAXC) { S.cbin[pos] = (w << 5) + lane; S.crel[pos] = rel; S.cbase[pos] = bs[j]; }
+                    if (wj[j] >= 0) {
+                        if (bsj[j] > 0.0f) { relj[j] = mv[j] / bsj[j]; exj[j] = relj[j] > thr; }   // simd_avx2.c:239-257
+                        exj[j] = exj[j] && ((S.fvs[wj[j]] >> lane) & 1u);
+                        const uint32_t bal = __ballot_sync(FULL, exj[j]);
+                        if (!fast && exj[j]) {
+                            const int pos = n_cand + __popc(bal & ((1u << lane) - 1u));
+                            if (pos < SMAXC) { S.cbin[pos] = (wj[j] << 5) + lane; S.crel[pos] = relj[j]; S.cbase[pos] = bsj[j]; }
+                        }
+                        n_cand += __popc(bal);
                     }
-                    n_cand += __popc(bal);
                 }
             }
             st_exact += (unsigned long long)n_cw;
             if (n_cand > SMAXC) { bail = 4; break; }
             __syncwarp();
             ST_TICK(cy_e1);
-            bool list_changed = false;
             if (any_done) {
                 // delete_gone_bursts (:490-518): gone records and survivors keep the list order
-                int kept = 0;
+                int kept = 0, n_del = 0;
                 for (int i0 = 0; i0 < n_act; i0 += 32) {
                     const int i = i0 + lane;
                     const bool have = i < n_act;
@@ -570,7 +618,8 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
                     const uint32_t dm = __ballot_sync(FULL, done), km = __ballot_sync(FULL, have && !done);
                     const uint32_t below = (1u << lane) - 1u;
                     if (done) {
-                        const uint32_t slot_g = n_gone + (uint32_t)__popc(dm & below);
+                        const int dpos = n_del + __popc(dm & below);
+                        const uint32_t slot_g = n_gone + (uint32_t)dpos;
                         if (slot_g < gone_cap) {
                             GoneBurst g;
                             g.id = id; g.start = start; g.stop = idx;
@@ -580,6 +629,7 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
                         } else {
                             overflow = 1;
                         }
+                        S.cw[dpos] = cb;                       // (the word list is consumed: reuse it for the deleted bins)
                     }
                     overflow = __any_sync(FULL, overflow) ? 1u : 0u;
                     __syncwarp();
@@ -589,22 +639,87 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
                         S.a_cb[pos] = cb; S.a_rel[pos] = rel; S.a_base[pos] = bsc;
                         S.a_dl[pos] = dl; S.a_lah[pos] = lah; S.a_tl[pos] = tl;
                     }
-                    n_gone += (uint32_t)__popc(dm);
+                    n_del += __popc(dm);
                     kept += __popc(km);
                     __syncwarp();
                 }
+                n_gone += (uint32_t)n_del;
                 n_act = kept;
-                // update_burst_mask (:482-486)
-                for (int w = lane; w < W; w += 32) S.free_mask[w] = FULL;
+                // update_burst_mask (:482-486): free the deleted ranges, then re-cover what the
+                // survivors next to them still mask
+                if (n_del <= 8) {
+                    for (int d = 0; d < n_del; d++) {
+                        const int cbd = S.cw[d];
+                        mask_bins(max(cbd - c.half_bw, 0), min(cbd + c.half_bw, N - 1), true);
+                    }
+                    for (int i = 0; i < n_act; i++) {
+                        const int cbi = S.a_cb[i];
+                        bool near = false;
+                        for (int d = 0; d < n_del; d++) near = near || abs(cbi - S.cw[d]) <= 2 * c.half_bw;
+                        if (near) mask_bins(max(cbi - c.half_bw, 0), min(cbi + c.half_bw, N - 1), false);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < WPL; k++) fv[k] = vl[k];
+                    for (int i = 0; i < n_act; i++) {
+                        const int cbi = S.a_cb[i];
+                        const int lo = max(cbi - c.half_bw, 0), hi = min(cbi + c.half_bw, N - 1);
+                        const int wl = lo >> 5;
+#pragma unroll
+                        for (int k = 0; k < WPL; k++) {
+                            const int w = lane * WPL + k;
+                            if (w >= wl && w <= wl + 2) fv[k] &= ~st_range_bits(w, lo, hi);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < WPL; k++) S.fvs[lane * WPL + k] = fv[k];
+                }
                 __syncwarp();
-                for (int i = lane; i < n_act; i += 32)
-                    st_clear(S.free_mask, max(S.a_cb[i] - c.half_bw, 0), min(S.a_cb[i] + c.half_bw, N - 1));
-                __syncwarp();
-                list_changed = true;
+                Tmin = min_horizon();
             }
             ST_TICK(cy_e2);
-            if (n_cand > 0) {
-                // create_new_bursts (:556-591): strongest remaining peak first, ties by bin
+            if (n_cand > 0 && fast) {
+                // create_new_bursts (:556-591): strongest remaining peak first, ties by bin; the
+                // candidates never leave the registers
+                for (;;) {
+                    uint32_t key = 0;
+                    int kb = 0x7fffffff;
+#pragma unroll
+                    for (int j = 0; j < SPF; j++) {
+                        const uint32_t kj = exj[j] ? __float_as_uint(relj[j]) : 0u;   // rel > thr > 0: bit order = value order
+                        const int bj = (wj[j] << 5) + lane;
+                        if (kj > key || (kj != 0u && kj == key && bj < kb)) { key = kj; kb = bj; }
+                    }
+                    const uint32_t m = __reduce_max_sync(FULL, key);
+                    if (m == 0u) break;
+                    const int bin = __reduce_min_sync(FULL, key == m ? kb : 0x7fffffff);
+                    float bcl = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < SPF; j++) bcl = wj[j] == (bin >> 5) ? bsj[j] : bcl;
+                    const float bc = __shfl_sync(FULL, bcl, bin & 31);
+                    if (lane == 0) {
+                        const unsigned long long start = idx - (unsigned long long)c.pre_len;
+                        S.a_id[n_act] = next_id;
+                        S.a_start[n_act] = start;
+                        S.a_last[n_act] = start;
+                        S.a_cb[n_act] = bin; S.a_rel[n_act] = __uint_as_float(m); S.a_base[n_act] = bc;
+                        S.a_dl[n_act] = f + PF0; S.a_lah[n_act] = NONE; S.a_tl[n_act] = f + TLF;
+                    }
+                    Tmin = min(Tmin, f + TLF);
+                    n_act++;
+                    next_id += 10ull;
+                    mask_bins(max(bin - c.half_bw, 0), min(bin + c.half_bw, N - 1), false);
+#pragma unroll
+                    for (int j = 0; j < SPF; j++) {
+                        const int bj = (wj[j] << 5) + lane;
+                        if (bj >= bin - c.half_bw && bj <= bin + c.half_bw) exj[j] = false;
+                    }
+                    if (n_act > SACT - 64) break;
+                }
+                __syncwarp();
+                if (n_act > SACT - 64) { bail = 5; break; }
+            } else if (n_cand > 0) {
+                // the same through the shared-memory candidate list (many words)
                 const int nc = n_cand;
                 for (;;) {
                     ArgMax best{-1.0f, 0x7fffffff};
@@ -630,11 +745,12 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
                         S.a_start[n_act] = start;
                         S.a_last[n_act] = start;
                         S.a_cb[n_act] = bin; S.a_rel[n_act] = wbest.v; S.a_base[n_act] = bc;
-                        S.a_dl[n_act] = f + PF0; S.a_lah[n_act] = NONE; S.a_tl[n_act] = horizon_of(start);
-                        st_clear(S.free_mask, max(bin - c.half_bw, 0), min(bin + c.half_bw, N - 1));
+                        S.a_dl[n_act] = f + PF0; S.a_lah[n_act] = NONE; S.a_tl[n_act] = f + TLF;
                     }
+                    Tmin = min(Tmin, f + TLF);
                     n_act++;
                     next_id += 10ull;
+                    mask_bins(max(bin - c.half_bw, 0), min(bin + c.half_bw, N - 1), false);
                     for (int i = lane; i < nc; i += 32) {
                         const int bb = S.cbin[i];
                         if (bb >= bin - c.half_bw && bb <= bin + c.half_bw) S.cbin[i] = -1;
@@ -642,20 +758,14 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
                     __syncwarp();
                     if (n_act > SACT - 64) break;
                 }
-                list_changed = true;
                 if (n_act > SACT - 64) { bail = 5; break; }
             }
             if (c.max_bursts > 0 && n_act > c.max_bursts) { bail = 6; break; }      // squelch (:593-631)
             ST_TICK(cy_e3);
-            if (list_changed) {
-                __syncwarp();
-#pragma unroll
-                for (int k = 0; k < WPL; k++) fv[k] = S.free_mask[lane * WPL + k] & S.valid[lane * WPL + k];
-                Tmin = min_horizon();
-            }
             if (sq > 0) sq--;                                 // :628-631
             if (n_act == 0) quiet_frames(f, f + 1);
             f++;
+            __syncwarp();
         }
         ST_TICK(cy_event);
     }
