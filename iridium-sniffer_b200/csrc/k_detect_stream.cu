@@ -46,7 +46,6 @@ constexpr int SCL = IR_STREAM_CL;      // CTAs per cluster
 constexpr int SWT = 256;               // worker threads per CTA (few threads = many registers for the leader)
 constexpr int SNT = SWT + 32;          // + one more warp (the leader, in CTA 0)
 constexpr int SGF = 8;                 // rows per ring block
-constexpr int SGS = 4;                 // frames per leader group
 constexpr int SPF = 4;                 // candidate words whose loads are in flight together
 constexpr int SACT = 512;              // bursts the leader can track (squelch sets in long before)
 constexpr int SMAXW = 512;             // bitmap words per frame (N <= 16384)
@@ -57,9 +56,8 @@ constexpr uint32_t FULL = 0xffffffffu;
 
 struct StShared {
     unsigned long long bar[8];         // one per ring block
-    uint32_t free_mask[SMAXW];         // 1 = bin not covered by an active burst
     uint32_t valid[SMAXW];             // peak search range minus the DC notch
-    uint32_t fvs[SMAXW];               // free & valid, mirrored from the owner lanes' registers
+    uint32_t fvs[SMAXW];               // valid & not covered by an active burst (the lanes cache their words)
     int cw[SMAXW];                     // words of the frame with a possible unmasked crossing
     int n_cw;
     int cbin[SMAXC];
@@ -71,7 +69,6 @@ struct StShared {
     int a_dl[SACT];                    // first frame on which the burst is deleted unless a hit comes
     int a_lah[SACT];                   // frame of the latest hit in this launch (NONE: see a_last)
     int a_tl[SACT];                    // last frame on which it cannot be "too long" yet
-    uint32_t a_hm[SACT];               // hits in the frames of the current group
     float a_rel[SACT], a_base[SACT];
     unsigned long long wcmd;           // workers: the command being executed
 };
@@ -88,6 +85,17 @@ __device__ __forceinline__ unsigned ld_acq32(const unsigned *p) {
 __device__ __forceinline__ void st_rel32(unsigned *p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// shared-memory loads by 32-bit address (the leader's hot loop keeps its row addresses in registers)
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(SWT) : "memory"); }
 
 __device__ __forceinline__ uint32_t st_range_bits(int w, int lo, int hi) {
@@ -95,9 +103,6 @@ __device__ __forceinline__ uint32_t st_range_bits(int w, int lo, int hi) {
     if (a > b) return 0u;
     a &= 31; b &= 31;
     return (b == 31 ? FULL : ((1u << (b + 1)) - 1u)) & ~((1u << a) - 1u);
-}
-__device__ __forceinline__ void st_clear(uint32_t *bm, int lo, int hi) {
-    for (int w = lo >> 5; w <= (hi >> 5); w++) atomicAnd(&bm[w], ~st_range_bits(w, lo, hi));
 }
 
 // command word: bit 0 exit, bits 1..20 first frame, 21..41 end frame, 42..63 launch epoch
@@ -248,11 +253,10 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     if (rank != 0) return;
 
     // ---------------------------------------------------------------------- leader (one warp)
-    // Frames are taken in groups of SGF: the questions "does any unmasked bit show up" and "does a
-    // burst end / need an exact hysteresis test" are answered for the whole group with independent
-    // instruction streams (one warp hides its own latencies that way), the frames before the
-    // first event are committed in one step, the event frame is processed exactly, and the next
-    // group starts right after it.  Times are kept in frames relative to this launch.
+    // One frame per trip through a loop small enough to stay in the instruction cache: the
+    // frame's bitmap words are already in registers (loaded one frame ahead), the first 32
+    // bursts live one per lane, and a single vote decides whether anything happens.  Only then
+    // ("event") does the warp run the reference's steps for that frame.
     constexpr int WPL = 2 * BPT;                              // bitmap words per lane = W / 32
     constexpr int RB = BPT >= 8 ? 4 : 8;                      // ring blocks of SGF rows
     constexpr int RROWS = RB * SGF;
@@ -270,13 +274,11 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     int bail = 0;
     unsigned n_cmd = 0, n_waited = 0;
     unsigned long long st_events = 0, st_exact = 0, st_waits = 0;
-    // cycle counters (lane 0's clock): ring wait, bitmap pass, wait for workers, event body
-    unsigned long long cy_ring = 0, cy_scan = 0, cy_wait = 0, cy_event = 0, cy_e1 = 0, cy_e2 = 0, cy_e3 = 0;
     unsigned long long t_glob0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_glob0));
+    // per-phase cycle counters of the leader, compiled in only with -DIR_SCAN_TIMING
+    unsigned long long cy_scan = 0, cy_wait = 0, cy_e1 = 0, cy_e2 = 0, cy_e3 = 0, cy_e4 = 0;
     long long tk = clock64();
-// per-phase cycle counters of the leader: compiled in only with -DIR_SCAN_TIMING (reading the
-// clock is a scheduling barrier and costs the leader ~10 %)
 #ifdef IR_SCAN_TIMING
 #define ST_TICK(acc) do { const long long _t = clock64(); acc += (unsigned long long)(_t - tk); tk = _t; } while (0)
 #else
@@ -287,24 +289,24 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     const int PF = (c.post_len + N - 1) / N;
     const int PF0 = max(1, (c.post_len - c.pre_len + N - 1) / N);
     constexpr int NONE = -0x40000000;
-    // deadline (first frame on which the burst is deleted) and too-long horizon of a burst
-    auto deadline_of = [&](unsigned long long la) -> int {
-        const long long d = (long long)(la + (unsigned long long)c.post_len) - (long long)index0;
-        return d <= 0 ? 0 : (int)min((long long)0x3fffffff, (d + N - 1) / N);
-    };
-    auto horizon_of = [&](unsigned long long start) -> int {   // la <= index of frame f <= start + max_len for f <= this
-        if (c.max_burst_len <= 0) return 0x3fffffff;
-        const long long d = (long long)(start + (unsigned long long)c.max_burst_len) - (long long)index0;
-        return d < 0 ? -1 : (int)min((long long)0x3fffffff, d / N);
-    };
+    // la <= index of frame f', so la - start <= (f' - f)*N + pre_len <= max_burst_len while f' - f <= TLF
+    const int TLF = c.max_burst_len <= 0 ? 0x20000000 : (c.max_burst_len >= c.pre_len ? (c.max_burst_len - c.pre_len) / N : -1);
 
     if (n_act > SACT - 64) { bail = 7; n_act = 0; }
+#pragma unroll 1
     for (int i = lane; i < n_act; i += 32) {
         const ActBurst b = gs->act[i];
         S.a_id[i] = b.id; S.a_start[i] = b.start; S.a_last[i] = b.last_active;
         S.a_cb[i] = b.center_bin; S.a_rel[i] = b.peak_rel; S.a_base[i] = b.base_at_create;
-        S.a_dl[i] = deadline_of(b.last_active); S.a_lah[i] = NONE; S.a_tl[i] = horizon_of(b.start);
+        // first frame on which the burst is deleted unless a hit comes; last frame on which
+        // last_active - start cannot exceed max_burst_len yet
+        const long long d = (long long)(b.last_active + (unsigned long long)c.post_len) - (long long)index0;
+        S.a_dl[i] = d <= 0 ? 0 : (int)min((long long)0x3fffffff, (d + N - 1) / N);
+        S.a_lah[i] = NONE;
+        const long long t = (long long)(b.start + (unsigned long long)c.max_burst_len) - (long long)index0;
+        S.a_tl[i] = c.max_burst_len <= 0 ? 0x3fffffff : (t < 0 ? -1 : (int)min((long long)0x3fffffff, t / N));
     }
+#pragma unroll 1
     for (int w = lane; w < W; w += 32) {
         uint32_t v = 0;
         for (int b = 0; b < 32; b++) {
@@ -313,7 +315,7 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
             v |= ok ? (1u << b) : 0u;
         }
         S.valid[w] = v;
-        S.free_mask[w] = FULL;
+        S.fvs[w] = v;
     }
     if (lane < SCL) *reinterpret_cast<volatile unsigned *>(&ctl->done[lane]) = 0u;
     if (lane == 0) {
@@ -323,46 +325,47 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     }
     __threadfence();
     __syncwarp();
-    for (int i = lane; i < n_act; i += 32)
-        st_clear(S.free_mask, max(S.a_cb[i] - c.half_bw, 0), min(S.a_cb[i] + c.half_bw, N - 1));
-    __syncwarp();
-    // free & valid mask: lane l owns words l*WPL .. l*WPL+WPL-1 in registers (fv) and mirrors them
-    // in S.fvs for the lookups by word index
-    uint32_t fv[WPL], vl[WPL];
-#pragma unroll
-    for (int k = 0; k < WPL; k++) {
-        vl[k] = S.valid[lane * WPL + k];
-        fv[k] = S.free_mask[lane * WPL + k] & vl[k];
-        S.fvs[lane * WPL + k] = fv[k];
-    }
-    // clear (burst created) / set (burst deleted) the bins lo..hi in the owned words
+    // free & valid mask (S.fvs): clear / set the bins lo..hi (at most three words), one lane per word
     auto mask_bins = [&](int lo, int hi, bool set) {
-        const int wl = lo >> 5;
-        const uint32_t m0 = st_range_bits(wl, lo, hi), m1 = st_range_bits(wl + 1, lo, hi), m2 = st_range_bits(wl + 2, lo, hi);
+        const int w = (lo >> 5) + lane;
+        if (lane < 3 && w <= (hi >> 5)) {
+            const uint32_t m = st_range_bits(w, lo, hi);
+            S.fvs[w] = set ? (S.fvs[w] | (m & S.valid[w])) : (S.fvs[w] & ~m);
+        }
+        __syncwarp();
+    };
+#pragma unroll 1
+    for (int i = 0; i < n_act; i++) mask_bins(max(S.a_cb[i] - c.half_bw, 0), min(S.a_cb[i] + c.half_bw, N - 1), false);
+    uint32_t fv[WPL];                                         // this lane's words of S.fvs
+    // lane-resident copy of burst `lane`: word / shift of its hysteresis window, deadline, latest hit
+    // (a lane without a burst has an empty window mask and deadlines that never come)
+    uint32_t b_o0 = 0, b_o1 = 0, b_msk = 0;                   // byte offsets of the two window words in a row
+    int b_sh = 0, b_dl = 0x3fffffff, b_lah = NONE, b_tl = 0x3fffffff;
+    bool have = false;
+    auto reload_state = [&]() {
+        __syncwarp();
 #pragma unroll
-        for (int k = 0; k < WPL; k++) {
-            const int d = lane * WPL + k - wl;
-            const uint32_t m = d == 0 ? m0 : (d == 1 ? m1 : (d == 2 ? m2 : 0u));
-            if (m) {
-                fv[k] = set ? (fv[k] | (m & vl[k])) : (fv[k] & ~m);
-                S.fvs[lane * WPL + k] = fv[k];
-            }
+        for (int k4 = 0; k4 < WPL / 4; k4++) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(&S.fvs[lane * WPL + 4 * k4]);
+            fv[4 * k4] = v.x; fv[4 * k4 + 1] = v.y; fv[4 * k4 + 2] = v.z; fv[4 * k4 + 3] = v.w;
+        }
+        have = lane < n_act;
+        b_o0 = 0; b_o1 = 0; b_msk = 0; b_sh = 0; b_dl = 0x3fffffff; b_lah = NONE; b_tl = 0x3fffffff;
+        if (have) {
+            const int cb = S.a_cb[lane];
+            const int w0 = (cb - 1) >> 5;
+            b_o0 = (uint32_t)w0 * 4u; b_o1 = (uint32_t)min(w0 + 1, W - 1) * 4u; b_sh = (cb - 1) & 31; b_msk = 7u;
+            b_dl = S.a_dl[lane]; b_lah = S.a_lah[lane]; b_tl = S.a_tl[lane];
         }
     };
-    auto min_horizon = [&]() -> int {
-        int t = 0x3fffffff;
-        for (int i = lane; i < n_act; i += 32) t = min(t, S.a_tl[i]);
-        return __reduce_min_sync(FULL, t);
-    };
-    int Tmin = min_horizon();
-    // a new burst's too-long horizon, in frames after its creation frame (start = idx - pre_len)
-    // la <= index of frame f', so la - start <= (f' - f)*N + pre_len <= max_burst_len while f' - f <= TLF
-    const int TLF = c.max_burst_len <= 0 ? 0x20000000 : (c.max_burst_len >= c.pre_len ? (c.max_burst_len - c.pre_len) / N : -1);
+    reload_state();
 
     // ring of bitmap rows, filled a block (SGF rows, one bulk copy, one mbarrier) at a time
     const int n_blocks = classified ? (n_frames + SGF - 1) / SGF : 0;
     int blk_issued = 0, blk_landed = 0;
-    auto fill_blocks = [&](int fcur) {                        // every block whose slot is free
+    // rows up to frame `upto` are in shared memory; blocks wholly before frame `fcur` may be refilled
+    auto ring_advance = [&](int fcur, int upto) {
+        __syncwarp();
         while (blk_issued < n_blocks && (blk_issued < RB || (blk_issued - RB + 1) * SGF <= fcur)) {
             if (lane == 0) {
                 const int r0 = blk_issued * SGF, nr = min(SGF, n_frames - r0);
@@ -371,6 +374,10 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
                 tma_load_1d(ring + (size_t)(r0 % RROWS) * RW, xu + (size_t)r0 * RW, row_bytes * (uint32_t)nr, bar);
             }
             blk_issued++;
+        }
+        while (blk_landed <= upto / SGF) {
+            mbar_wait(&bars[blk_landed % RB], (uint32_t)((blk_landed / RB) & 1));
+            blk_landed++;
         }
     };
     if (!classified && primed) bail = 1;                      // a priming launch on a primed detector
@@ -395,7 +402,7 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
         if (qs < 0) qs = a;
         if (b - qs >= SQCH) { issue(qs, b, 0); qs = -1; }
         hist_idx += b - a;
-        if (hist_idx >= H) {                                  // (a group never crosses the priming point, see below)
+        if (hist_idx >= H) {                                  // (a run of unprimed frames never crosses the priming point)
             hist_idx -= H;
             if (!primed) {
                 primed = 1;
@@ -404,91 +411,77 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
         }
     };
 
+    // bitmap words of one frame: this lane's XU words, and the 3-bin hysteresis window of burst `lane`
+    struct FrameRegs { uint32_t xu[WPL]; uint32_t bx0, bx1, bu0, bu1; };
+    const uint32_t ring_a = smem_u32(ring), ring_end_a = ring_a + (uint32_t)RROWS * row_bytes;
+    const uint32_t my_off = (uint32_t)(lane * WPL) * 4u, x_off = (uint32_t)W * 4u;
+    auto load_frame = [&](FrameRegs &r, uint32_t ra) {        // ra = shared address of the frame's row
+#pragma unroll
+        for (int k4 = 0; k4 < WPL / 4; k4++) {
+            const uint4 v = lds128(ra + my_off + 16u * k4);
+            r.xu[4 * k4] = v.x; r.xu[4 * k4 + 1] = v.y; r.xu[4 * k4 + 2] = v.z; r.xu[4 * k4 + 3] = v.w;
+        }
+        r.bu0 = lds32(ra + b_o0); r.bu1 = lds32(ra + b_o1);
+        r.bx0 = lds32(ra + x_off + b_o0); r.bx1 = lds32(ra + x_off + b_o1);
+    };
+
     int f = 0;
-    int fill_mark = -1;                                       // block index of f at the last fill_blocks call
+    // ---- frames before the detector is primed: nothing is detected (:426-428), every frame is quiet
+    while (f < n_frames && !bail && !primed) {
+        const int G = min(min(SQCH, n_frames - f), H - hist_idx);
+        quiet_frames(f, f + G);
+        f += G;
+    }
+    FrameRegs cur;
+    uint32_t ra = ring_a + (uint32_t)(f % RROWS) * row_bytes;   // shared address of frame f's row
+    if (f < n_frames && !bail && (f & (SGF - 1)) != 0) ring_advance(f, f);
+    // (no software pipelining of the loads: a single warp pays more for the register moves of a
+    // double buffer than for one shared-memory latency per frame)
+#pragma unroll 1
     while (f < n_frames && !bail) {
-        ST_TICK(cy_scan);
-        if (!primed) {                                        // nothing is detected before 512 frames (:426-428)
-            const int G = min(min(SQCH, n_frames - f), H - hist_idx);
-            quiet_frames(f, f + G);
-            f += G;
-            continue;
+        if ((f & (SGF - 1)) == 0) ring_advance(f, f);         // frame f's block has landed; older blocks are refilled
+        load_frame(cur, ra);
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < WPL; k++) acc |= cur.xu[k] & fv[k];
+        const uint32_t x3 = __funnelshift_r(cur.bx0, cur.bx1, b_sh) & b_msk;
+        const uint32_t u3 = __funnelshift_r(cur.bu0, cur.bu1, b_sh) & b_msk;
+        const bool hit = x3 != 0u;                            // update_bursts (:458-469), decided by an X bit
+        bool ev = acc != 0u || (!hit && (u3 != 0u || f >= b_dl)) || f > b_tl;
+        if (n_act > 32) {                                     // bursts beyond the lane-resident 32
+#pragma unroll 1
+            for (int i = 32 + lane; i < n_act; i += 32) {
+                const uint32_t *XU = ring + (size_t)(f % RROWS) * RW;
+                const int cb = S.a_cb[i];
+                const int w0 = (cb - 1) >> 5, sh = (cb - 1) & 31, w1 = min(w0 + 1, W - 1);
+                if (__funnelshift_r(XU[W + w0], XU[W + w1], sh) & 7u) { S.a_dl[i] = f + PF; S.a_lah[i] = f; }
+                else if ((__funnelshift_r(XU[w0], XU[w1], sh) & 7u) != 0u || f >= S.a_dl[i]) ev = true;
+                if (f > S.a_tl[i]) ev = true;
+            }
         }
-        const int G = min(SGS, n_frames - f);
-        if ((f + G - 1) / SGF != fill_mark) {
-            fill_mark = (f + G - 1) / SGF;
-            __syncwarp();
-            fill_blocks(f);
-            while (blk_landed <= fill_mark) {
-                mbar_wait(&bars[blk_landed % RB], (uint32_t)((blk_landed / RB) & 1));
-                blk_landed++;
-            }
-            ST_TICK(cy_ring);
-        }
-        if (f + G - 1 > Tmin) { bail = 3; break; }            // a burst may exceed max_burst_len (:498-517)
-        // ---- (1) unmasked bits, (2) bursts ending or needing the exact test: one flag bit per frame.
-        // Branch-free over the SGS rows (rows past the end of the launch hold stale bits and are
-        // masked off below) so that all loads of a group are in flight together.
-        uint32_t flags = 0;
-        {
-            uint32_t acc[SGS];
+        if (!__any_sync(FULL, ev)) {
+            // ---- nothing happens on this frame
+            if (hit) { b_dl = f + PF; b_lah = f; }
+            sq = max(sq - 1, 0);                              // :628-631
+            if (n_act == 0) quiet_frames(f, f + 1);
+        } else {
+            // ================= event frame f: the reference's steps, exactly
+            st_events++;
+            ST_TICK(cy_scan);
+            if (have) { S.a_dl[lane] = b_dl; S.a_lah[lane] = b_lah; }
+            // words with a possible unmasked crossing; get their magnitudes (and, while no baseline
+            // update is pending, baselines) moving before anything else
+            const float *row = mag + (size_t)f * N;
+            int n_cw = 0;
+            float mvp[SPF], bsp[SPF];
+            int wj[SPF];
 #pragma unroll
-            for (int g = 0; g < SGS; g++) {
-                const uint32_t *XU = ring + (size_t)((f + g) % RROWS) * RW;
-                acc[g] = 0;
+            for (int j = 0; j < SPF; j++) { mvp[j] = 0.0f; bsp[j] = 0.0f; wj[j] = -1; }
+            const bool base_ok = qs < 0 && n_waited == n_cmd;
+            if (__any_sync(FULL, acc != 0u)) {
+                uint32_t wmask = 0;
 #pragma unroll
-                for (int k4 = 0; k4 < WPL / 4; k4++) {
-                    const uint4 x = *reinterpret_cast<const uint4 *>(&XU[lane * WPL + 4 * k4]);
-                    acc[g] |= (x.x & fv[4 * k4]) | (x.y & fv[4 * k4 + 1]) | (x.z & fv[4 * k4 + 2]) | (x.w & fv[4 * k4 + 3]);
-                }
-            }
-#pragma unroll
-            for (int g = 0; g < SGS; g++) flags |= acc[g] ? (1u << g) : 0u;
-        }
-        for (int i = lane; i < n_act; i += 32) {
-            const int cb = S.a_cb[i];
-            const int w0 = (cb - 1) >> 5, sh = (cb - 1) & 31, w1 = min(w0 + 1, W - 1);
-            int dl = S.a_dl[i];
-            uint32_t x3[SGS], u3[SGS];
-#pragma unroll
-            for (int g = 0; g < SGS; g++) {
-                const uint32_t *XU = ring + (size_t)((f + g) % RROWS) * RW;
-                const uint32_t *X = XU + W;
-                x3[g] = __funnelshift_r(X[w0], X[w1], sh) & 7u;
-                u3[g] = __funnelshift_r(XU[w0], XU[w1], sh) & 7u;
-            }
-            uint32_t hm = 0;
-#pragma unroll
-            for (int g = 0; g < SGS; g++) {
-                const bool hit = x3[g] != 0u;                              // update_bursts (:458-469), certain
-                const bool ev = !hit && (u3[g] != 0u || f + g >= dl);      // exact test needed / burst ends
-                hm |= hit ? (1u << g) : 0u;
-                flags |= ev ? (1u << g) : 0u;
-                dl = hit ? f + g + PF : dl;
-            }
-            S.a_hm[i] = hm;
-        }
-        flags &= (1u << G) - 1u;
-        flags = __reduce_or_sync(FULL, flags);
-        const int e = flags ? __ffs(flags) - 1 : G;
-        // event frame: list the words with a possible unmasked crossing and get their magnitudes
-        // (and, while no baseline update is pending, baselines) moving now; they land while the
-        // frames before the event are committed
-        int n_cw = 0;
-        float mvp[SPF], bsp[SPF];
-        const bool base_ok = qs < 0 && n_waited == n_cmd;
-#pragma unroll
-        for (int j = 0; j < SPF; j++) { mvp[j] = 0.0f; bsp[j] = 0.0f; }
-        if (e < G) {
-            const uint32_t *XUe = ring + (size_t)((f + e) % RROWS) * RW;
-            uint32_t wmask = 0;
-#pragma unroll
-            for (int k4 = 0; k4 < WPL / 4; k4++) {
-                const uint4 x = *reinterpret_cast<const uint4 *>(&XUe[lane * WPL + 4 * k4]);
-                wmask |= ((x.x & fv[4 * k4]) ? 1u : 0u) << (4 * k4) | ((x.y & fv[4 * k4 + 1]) ? 2u : 0u) << (4 * k4) |
-                         ((x.z & fv[4 * k4 + 2]) ? 4u : 0u) << (4 * k4) | ((x.w & fv[4 * k4 + 3]) ? 8u : 0u) << (4 * k4);
-            }
-            if (__any_sync(FULL, wmask != 0u)) {
+                for (int k = 0; k < WPL; k++) wmask |= (cur.xu[k] & fv[k]) ? (1u << k) : 0u;
                 int off = __popc(wmask);
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {            // inclusive scan of the per-lane counts
@@ -503,79 +496,56 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
                     S.cw[off++] = lane * WPL + k;
                 }
                 __syncwarp();
-                const float *rowe = mag + (size_t)(f + e) * N;
 #pragma unroll
                 for (int j = 0; j < SPF; j++)
                     if (j < n_cw) {
-                        const int bin = (S.cw[j] << 5) + lane;
-                        mvp[j] = rowe[bin];
-                        if (base_ok) bsp[j] = __ldcg(base_g + bin);
+                        wj[j] = S.cw[j];
+                        mvp[j] = row[(wj[j] << 5) + lane];
+                        if (base_ok) bsp[j] = __ldcg(base_g + (wj[j] << 5) + lane);
                     }
             }
-        }
-        // ---- commit the frames before the first event
-        if (e > 0) {
-            const uint32_t below = (1u << e) - 1u;
-            for (int i = lane; i < n_act; i += 32) {
-                const uint32_t hm = S.a_hm[i] & below;
-                if (hm) {
-                    const int h = f + 31 - __clz(hm);
-                    S.a_lah[i] = h; S.a_dl[i] = h + PF;
-                }
-            }
-            sq = max(sq - e, 0);                              // :628-631
-            if (n_act == 0) quiet_frames(f, f + e);
-        }
-        f += e;
-        if (e == G) continue;
-        // ================= event frame f: the reference's steps, exactly
-        st_events++;
-        ST_TICK(cy_scan);
-        if (qs >= 0) { issue(qs, f, 0); qs = -1; }
-        if (!wait_all()) { bail = 2; break; }
-        ST_TICK(cy_wait);
-        {
+            ST_TICK(cy_e1);
+            if (qs >= 0) { issue(qs, f, 0); qs = -1; }
+            if (!wait_all()) { bail = 2; break; }
+            ST_TICK(cy_wait);
             const uint64_t idx = index0 + (uint64_t)f * (uint64_t)N;
             const uint32_t *XU = ring + (size_t)(f % RROWS) * RW;
-            const uint32_t *X = XU + W;
-            const float *row = mag + (size_t)f * N;
             __syncwarp();
-            // update_bursts incl. the tests an X bit does not decide
-            int any_done = 0;
+            // update_bursts incl. the tests an X bit does not decide; which bursts end
+            int any_done = 0, too_long = 0;
+#pragma unroll 1
             for (int i = lane; i < n_act; i += 32) {
                 const int cb = S.a_cb[i];
                 const int w0 = (cb - 1) >> 5, sh = (cb - 1) & 31, w1 = min(w0 + 1, W - 1);
-                bool hit = (__funnelshift_r(X[w0], X[w1], sh) & 7u) != 0u;
-                if (!hit) {
-                    uint32_t u3 = __funnelshift_r(XU[w0], XU[w1], sh) & 7u;
-                    while (u3) {
-                        const int b = cb - 1 + __ffs(u3) - 1;
-                        u3 &= u3 - 1;
+                bool h = (__funnelshift_r(XU[W + w0], XU[W + w1], sh) & 7u) != 0u;
+                if (!h) {
+                    uint32_t q = __funnelshift_r(XU[w0], XU[w1], sh) & 7u;
+                    while (q) {
+                        const int b = cb - 1 + __ffs(q) - 1;
+                        q &= q - 1;
                         const float bs = __ldcg(base_g + b);
-                        if (bs > 0.0f && row[b] / bs > thr) hit = true;
+                        if (bs > 0.0f && row[b] / bs > thr) h = true;
                     }
                 }
-                if (hit) { S.a_lah[i] = f; S.a_dl[i] = f + PF; }
+                if (h) { S.a_lah[i] = f; S.a_dl[i] = f + PF; }
                 else if (f >= S.a_dl[i]) any_done = 1;
+                if (f > S.a_tl[i]) too_long = 1;
             }
+            if (__any_sync(FULL, too_long)) { bail = 3; break; }   // a burst may exceed max_burst_len (:498-517)
             any_done = __any_sync(FULL, any_done);
             // peaks: exact crossings & mask of the previous frame & search range (:522-548).  Up to SPF
             // words stay in registers (lane = bin inside the word); more go through shared memory.
             const bool fast = n_cw <= SPF;
             float relj[SPF], bsj[SPF];
-            int wj[SPF];
             bool exj[SPF];
             int n_cand = 0;
+#pragma unroll 1
             for (int j0 = 0; j0 < n_cw; j0 += SPF) {
-#pragma unroll
-                for (int j = 0; j < SPF; j++) {
-                    wj[j] = j0 + j < n_cw ? S.cw[j0 + j] : -1;
-                    relj[j] = 0.0f; bsj[j] = 0.0f; exj[j] = false;
-                }
                 float mv[SPF];
 #pragma unroll
                 for (int j = 0; j < SPF; j++) {
-                    mv[j] = 0.0f;
+                    relj[j] = 0.0f; bsj[j] = 0.0f; exj[j] = false; mv[j] = 0.0f;
+                    if (j0 > 0) wj[j] = j0 + j < n_cw ? S.cw[j0 + j] : -1;
                     if (wj[j] >= 0) {
                         const int bin = (wj[j] << 5) + lane;
                         mv[j] = j0 == 0 ? mvp[j] : row[bin];
@@ -599,23 +569,24 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
             st_exact += (unsigned long long)n_cw;
             if (n_cand > SMAXC) { bail = 4; break; }
             __syncwarp();
-            ST_TICK(cy_e1);
+            ST_TICK(cy_e2);
             if (any_done) {
                 // delete_gone_bursts (:490-518): gone records and survivors keep the list order
                 int kept = 0, n_del = 0;
+#pragma unroll 1
                 for (int i0 = 0; i0 < n_act; i0 += 32) {
                     const int i = i0 + lane;
-                    const bool have = i < n_act;
+                    const bool hv = i < n_act;
                     unsigned long long id = 0, start = 0, la = 0;
                     int cb = 0, dl = 0, lah = NONE, tl = 0;
                     float rel = 0.0f, bsc = 0.0f;
-                    if (have) {
+                    if (hv) {
                         id = S.a_id[i]; start = S.a_start[i]; la = S.a_last[i];
                         cb = S.a_cb[i]; rel = S.a_rel[i]; bsc = S.a_base[i];
                         dl = S.a_dl[i]; lah = S.a_lah[i]; tl = S.a_tl[i];
                     }
-                    const bool done = have && f >= dl;
-                    const uint32_t dm = __ballot_sync(FULL, done), km = __ballot_sync(FULL, have && !done);
+                    const bool done = hv && f >= dl;
+                    const uint32_t dm = __ballot_sync(FULL, done), km = __ballot_sync(FULL, hv && !done);
                     const uint32_t below = (1u << lane) - 1u;
                     if (done) {
                         const int dpos = n_del + __popc(dm & below);
@@ -633,7 +604,7 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
                     }
                     overflow = __any_sync(FULL, overflow) ? 1u : 0u;
                     __syncwarp();
-                    if (have && !done) {
+                    if (hv && !done) {
                         const int pos = kept + __popc(km & below);
                         S.a_id[pos] = id; S.a_start[pos] = start; S.a_last[pos] = la;
                         S.a_cb[pos] = cb; S.a_rel[pos] = rel; S.a_base[pos] = bsc;
@@ -647,40 +618,34 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
                 n_act = kept;
                 // update_burst_mask (:482-486): free the deleted ranges, then re-cover what the
                 // survivors next to them still mask
-                if (n_del <= 8) {
-                    for (int d = 0; d < n_del; d++) {
-                        const int cbd = S.cw[d];
-                        mask_bins(max(cbd - c.half_bw, 0), min(cbd + c.half_bw, N - 1), true);
-                    }
-                    for (int i = 0; i < n_act; i++) {
-                        const int cbi = S.a_cb[i];
+                if (n_del <= 4) {
+#pragma unroll 1
+                    for (int d = 0; d < n_del; d++) mask_bins(max(S.cw[d] - c.half_bw, 0), min(S.cw[d] + c.half_bw, N - 1), true);
+#pragma unroll 1
+                    for (int i0 = 0; i0 < n_act; i0 += 32) {
                         bool near = false;
-                        for (int d = 0; d < n_del; d++) near = near || abs(cbi - S.cw[d]) <= 2 * c.half_bw;
-                        if (near) mask_bins(max(cbi - c.half_bw, 0), min(cbi + c.half_bw, N - 1), false);
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < WPL; k++) fv[k] = vl[k];
-                    for (int i = 0; i < n_act; i++) {
-                        const int cbi = S.a_cb[i];
-                        const int lo = max(cbi - c.half_bw, 0), hi = min(cbi + c.half_bw, N - 1);
-                        const int wl = lo >> 5;
-#pragma unroll
-                        for (int k = 0; k < WPL; k++) {
-                            const int w = lane * WPL + k;
-                            if (w >= wl && w <= wl + 2) fv[k] &= ~st_range_bits(w, lo, hi);
+                        if (i0 + lane < n_act)
+                            for (int d = 0; d < n_del; d++) near = near || abs(S.a_cb[i0 + lane] - S.cw[d]) <= 2 * c.half_bw;
+                        uint32_t nm = __ballot_sync(FULL, near);
+                        while (nm) {
+                            const int cbi = S.a_cb[i0 + __ffs(nm) - 1];
+                            nm &= nm - 1;
+                            mask_bins(max(cbi - c.half_bw, 0), min(cbi + c.half_bw, N - 1), false);
                         }
                     }
-#pragma unroll
-                    for (int k = 0; k < WPL; k++) S.fvs[lane * WPL + k] = fv[k];
+                } else {
+#pragma unroll 1
+                    for (int w = lane; w < W; w += 32) S.fvs[w] = S.valid[w];
+                    __syncwarp();
+#pragma unroll 1
+                    for (int i = 0; i < n_act; i++) mask_bins(max(S.a_cb[i] - c.half_bw, 0), min(S.a_cb[i] + c.half_bw, N - 1), false);
                 }
-                __syncwarp();
-                Tmin = min_horizon();
             }
-            ST_TICK(cy_e2);
+            ST_TICK(cy_e3);
             if (n_cand > 0 && fast) {
                 // create_new_bursts (:556-591): strongest remaining peak first, ties by bin; the
                 // candidates never leave the registers
+#pragma unroll 1
                 for (;;) {
                     uint32_t key = 0;
                     int kb = 0x7fffffff;
@@ -705,7 +670,6 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
                         S.a_cb[n_act] = bin; S.a_rel[n_act] = __uint_as_float(m); S.a_base[n_act] = bc;
                         S.a_dl[n_act] = f + PF0; S.a_lah[n_act] = NONE; S.a_tl[n_act] = f + TLF;
                     }
-                    Tmin = min(Tmin, f + TLF);
                     n_act++;
                     next_id += 10ull;
                     mask_bins(max(bin - c.half_bw, 0), min(bin + c.half_bw, N - 1), false);
@@ -716,19 +680,19 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
                     }
                     if (n_act > SACT - 64) break;
                 }
-                __syncwarp();
                 if (n_act > SACT - 64) { bail = 5; break; }
             } else if (n_cand > 0) {
                 // the same through the shared-memory candidate list (many words)
                 const int nc = n_cand;
+#pragma unroll 1
                 for (;;) {
                     ArgMax best{-1.0f, 0x7fffffff};
                     int bslot = -1;
                     for (int i = lane; i < nc; i += 32) {
                         const int bin = S.cbin[i];
                         if (bin >= 0) {
-                            const ArgMax cur{S.crel[i], bin};
-                            const ArgMax nb = argmax_pick(best, cur);
+                            const ArgMax cur2{S.crel[i], bin};
+                            const ArgMax nb = argmax_pick(best, cur2);
                             if (nb.i != best.i) bslot = i;
                             best = nb;
                         }
@@ -747,7 +711,6 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
                         S.a_cb[n_act] = bin; S.a_rel[n_act] = wbest.v; S.a_base[n_act] = bc;
                         S.a_dl[n_act] = f + PF0; S.a_lah[n_act] = NONE; S.a_tl[n_act] = f + TLF;
                     }
-                    Tmin = min(Tmin, f + TLF);
                     n_act++;
                     next_id += 10ull;
                     mask_bins(max(bin - c.half_bw, 0), min(bin + c.half_bw, N - 1), false);
@@ -761,16 +724,19 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
                 if (n_act > SACT - 64) { bail = 5; break; }
             }
             if (c.max_bursts > 0 && n_act > c.max_bursts) { bail = 6; break; }      // squelch (:593-631)
-            ST_TICK(cy_e3);
             if (sq > 0) sq--;                                 // :628-631
             if (n_act == 0) quiet_frames(f, f + 1);
-            f++;
-            __syncwarp();
+            reload_state();
+            ST_TICK(cy_e4);
         }
-        ST_TICK(cy_event);
+        f++;
+        ra += row_bytes;
+        if (ra == ring_end_a) ra = ring_a;
     }
     // ---- wrap up
     if (!bail) {
+        if (have) { S.a_dl[lane] = b_dl; S.a_lah[lane] = b_lah; }   // hits since the last event
+        __syncwarp();
         if (qs >= 0) { issue(qs, n_frames, 0); qs = -1; }
         if (!wait_all()) bail = 2;
     }
@@ -802,8 +768,8 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
         unsigned long long t_glob1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_glob1));
         ctl->stats[7] += t_glob1 - t_glob0;
-        ctl->stats[8] += cy_ring; ctl->stats[9] += cy_scan; ctl->stats[10] += cy_wait; ctl->stats[11] += cy_event;
-        ctl->stats[12] += cy_e1; ctl->stats[13] += cy_e2; ctl->stats[14] += cy_e3;
+        ctl->stats[8] += cy_scan; ctl->stats[9] += cy_e1; ctl->stats[10] += cy_wait; ctl->stats[11] += cy_e2;
+        ctl->stats[12] += cy_e3; ctl->stats[13] += cy_e4;
     }
 }
 

@@ -717,9 +717,9 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
                 (unsigned long long)p->scan_stats[6], (unsigned long long)p->scan_stats[2],
                 (unsigned long long)p->scan_stats[3], (unsigned long long)p->scan_stats[4],
                 (unsigned long long)p->scan_stats[5]);
-        fprintf(stderr, "stream scan: kernel %.3f ms; leader Mcycles: ring wait %.2f bitmap pass %.2f worker wait %.2f events: hyst+peaks %.2f delete %.2f create %.2f tail %.2f\n",
+        fprintf(stderr, "stream scan: kernel %.3f ms; leader Mcycles (IR_SCAN_TIMING builds): frames %.2f list+prefetch %.2f worker wait %.2f hyst+peaks %.2f delete %.2f create+reload %.2f\n",
                 p->scan_stats[7] * 1e-6, p->scan_stats[8] * 1e-6, p->scan_stats[9] * 1e-6, p->scan_stats[10] * 1e-6,
-                p->scan_stats[12] * 1e-6, p->scan_stats[13] * 1e-6, p->scan_stats[14] * 1e-6, p->scan_stats[11] * 1e-6);
+                p->scan_stats[11] * 1e-6, p->scan_stats[12] * 1e-6, p->scan_stats[13] * 1e-6);
     }
     if (getenv("IR_SCAN_DEBUG") && p->scan_mode != 0) {
         fprintf(stderr, "scan cycles leader: p1 %llu waitA %llu p2 %llu waitB %llu p3 %llu waitC %llu batches %llu qbatches %llu\n",

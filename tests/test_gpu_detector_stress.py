@@ -112,3 +112,34 @@ def test_ragged_length_and_leading_bursts(pl, port, synth, mode):
     rec = synth.make_recording(21, duration_s=0.9, n_bursts=10, starts_s=np.linspace(0.05, 0.8, 10))
     iq = rec.iq[:-12345]
     _check(pl, port, iq, mode, min_bursts=1)      # (the polluted baseline may leave the guard band: either path)
+
+
+@pytest.mark.parametrize("mode", ["stream", "cluster"])
+def test_many_launches_bursts_across_launch_boundaries(pl, port, synth, mode):
+    """1 Mi-sample chunks = 128-frame launches of the state machine: priming spread over four launches,
+    bursts alive across launch boundaries (their latest hit must survive the hand-over of the state)."""
+    rec = synth.make_recording(33, duration_s=1.1, n_bursts=24)
+    P = port.det_params()
+    pb, _, _ = port.detect(P, rec.iq)
+    want = [(o.id, o.start, o.stop, o.last_active, o.center_bin, o.magnitude, o.noise) for o in pb]
+    assert len(want) >= 15
+    old = os.environ.get("IR_SCAN")
+    try:
+        if mode != "stream":
+            os.environ["IR_SCAN"] = mode
+        else:
+            os.environ.pop("IR_SCAN", None)
+        p = pl.Pipeline(sample_rate=10_000_000, start_time_ns=77, h2d_chunk=1 << 20)
+        res = p.run_host(rec.iq, "cf32")
+        got = [(b["id"], b["start"], b["stop"], b["last_active"], b["center_bin"], b["magnitude"], b["noise"])
+               for b in res.bursts]
+        ss = p.scan_stats()
+        p.close()
+        assert got == want, ss
+        if mode == "stream":
+            assert ss["launches_kept"] >= 8 and ss["launches_bailed"] == 0, ss
+    finally:
+        if old is None:
+            os.environ.pop("IR_SCAN", None)
+        else:
+            os.environ["IR_SCAN"] = old
