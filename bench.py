@@ -217,6 +217,17 @@ def run_ours(args):
     wall_e2e = time.perf_counter() - t1
     n_lines = text.count(b"\n")
     clocks = sampler.stop() if rank == 0 else None
+    # context for e2e: the bare pinned->device copy of one step's input (PCIe floor of this box)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    floor_ms = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        ev0.record()
+        iq_dev.copy_(host, non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        floor_ms.append(ev0.elapsed_time(ev1))
+    h2d_floor_ms = min(floor_ms)
 
     (wall, wall_e2e, dev_s), (n_bursts, n_frames, launches) = reduce_over_ranks(
         torch, dist if world > 1 else None, dev, [wall, wall_e2e, dev_ms / 1e3],
@@ -266,6 +277,8 @@ def run_ours(args):
             "e2e": {"value": round(total / wall_e2e / 1e6, 2), "unit": UNIT,
                     "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
                     "ms_per_step": round(wall_e2e / K * 1e3, 3), "raw_lines_per_step": n_lines,
+                    "h2d_copy_alone_ms": round(h2d_floor_ms, 3),
+                    "h2d_copy_alone_gbs": round(n * 8 / h2d_floor_ms / 1e6, 1),
                     "api": "ir_pipeline_run_host (pinned host IQ -> frames) + ir_pipeline_format_raw_all"},
             "bursts_per_s": round(n_bursts / (wall / K), 1),
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,

@@ -468,6 +468,16 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
             // ================= event frame f: the reference's steps, exactly
             st_events++;
             ST_TICK(cy_scan);
+            // "simple": every hysteresis test of this frame is decided by an X bit and every burst
+            // lives in a lane -- update_bursts happens in registers and no baseline value is needed
+            // unless there are candidate peaks
+            const bool cand_any = __any_sync(FULL, acc != 0u);
+            const bool simple = n_act <= 32 && !__any_sync(FULL, (!hit && u3 != 0u) || f > b_tl);
+            int any_done = 0;
+            if (simple) {
+                if (hit) { b_dl = f + PF; b_lah = f; }
+                any_done = __any_sync(FULL, !hit && f >= b_dl);
+            }
             if (have) { S.a_dl[lane] = b_dl; S.a_lah[lane] = b_lah; }
             // words with a possible unmasked crossing; get their magnitudes (and, while no baseline
             // update is pending, baselines) moving before anything else
@@ -478,61 +488,69 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
 #pragma unroll
             for (int j = 0; j < SPF; j++) { mvp[j] = 0.0f; bsp[j] = 0.0f; wj[j] = -1; }
             const bool base_ok = qs < 0 && n_waited == n_cmd;
-            if (__any_sync(FULL, acc != 0u)) {
+            if (cand_any) {
                 uint32_t wmask = 0;
 #pragma unroll
                 for (int k = 0; k < WPL; k++) wmask |= (cur.xu[k] & fv[k]) ? (1u << k) : 0u;
-                int off = __popc(wmask);
+                // the (few) lanes with such words take turns; every lane learns the whole list
+                uint32_t lm = __ballot_sync(FULL, wmask != 0u);
+                while (lm) {
+                    const int src = __ffs(lm) - 1;
+                    lm &= lm - 1;
+                    uint32_t wm = __shfl_sync(FULL, wmask, src);
+                    while (wm) {
+                        const int w = src * WPL + __ffs(wm) - 1;
+                        wm &= wm - 1;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {            // inclusive scan of the per-lane counts
-                    const int t = __shfl_up_sync(FULL, off, o);
-                    if (lane >= o) off += t;
+                        for (int j = 0; j < SPF; j++) if (j == n_cw) wj[j] = w;
+                        if (n_cw >= SPF && lane == 0) S.cw[n_cw] = w;
+                        n_cw++;
+                    }
                 }
-                n_cw = __shfl_sync(FULL, off, 31);
-                off -= __popc(wmask);
-                while (wmask) {
-                    const int k = __ffs(wmask) - 1;
-                    wmask &= wmask - 1;
-                    S.cw[off++] = lane * WPL + k;
+                if (n_cw > SPF && lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < SPF; j++) S.cw[j] = wj[j];
                 }
-                __syncwarp();
 #pragma unroll
                 for (int j = 0; j < SPF; j++)
-                    if (j < n_cw) {
-                        wj[j] = S.cw[j];
+                    if (wj[j] >= 0) {
                         mvp[j] = row[(wj[j] << 5) + lane];
                         if (base_ok) bsp[j] = __ldcg(base_g + (wj[j] << 5) + lane);
                     }
             }
             ST_TICK(cy_e1);
-            if (qs >= 0) { issue(qs, f, 0); qs = -1; }
-            if (!wait_all()) { bail = 2; break; }
+            if (cand_any || !simple) {                        // baseline values are about to be used
+                if (qs >= 0) { issue(qs, f, 0); qs = -1; }
+                if (!wait_all()) { bail = 2; break; }
+            }
             ST_TICK(cy_wait);
             const uint64_t idx = index0 + (uint64_t)f * (uint64_t)N;
-            const uint32_t *XU = ring + (size_t)(f % RROWS) * RW;
             __syncwarp();
-            // update_bursts incl. the tests an X bit does not decide; which bursts end
-            int any_done = 0, too_long = 0;
+            if (!simple) {
+                // update_bursts incl. the tests an X bit does not decide; which bursts end
+                const uint32_t *XU = ring + (size_t)(f % RROWS) * RW;
+                int too_long = 0;
 #pragma unroll 1
-            for (int i = lane; i < n_act; i += 32) {
-                const int cb = S.a_cb[i];
-                const int w0 = (cb - 1) >> 5, sh = (cb - 1) & 31, w1 = min(w0 + 1, W - 1);
-                bool h = (__funnelshift_r(XU[W + w0], XU[W + w1], sh) & 7u) != 0u;
-                if (!h) {
-                    uint32_t q = __funnelshift_r(XU[w0], XU[w1], sh) & 7u;
-                    while (q) {
-                        const int b = cb - 1 + __ffs(q) - 1;
-                        q &= q - 1;
-                        const float bs = __ldcg(base_g + b);
-                        if (bs > 0.0f && row[b] / bs > thr) h = true;
+                for (int i = lane; i < n_act; i += 32) {
+                    const int cb = S.a_cb[i];
+                    const int w0 = (cb - 1) >> 5, sh = (cb - 1) & 31, w1 = min(w0 + 1, W - 1);
+                    bool h = (__funnelshift_r(XU[W + w0], XU[W + w1], sh) & 7u) != 0u;
+                    if (!h) {
+                        uint32_t q = __funnelshift_r(XU[w0], XU[w1], sh) & 7u;
+                        while (q) {
+                            const int b = cb - 1 + __ffs(q) - 1;
+                            q &= q - 1;
+                            const float bs = __ldcg(base_g + b);
+                            if (bs > 0.0f && row[b] / bs > thr) h = true;
+                        }
                     }
+                    if (h) { S.a_lah[i] = f; S.a_dl[i] = f + PF; }
+                    else if (f >= S.a_dl[i]) any_done = 1;
+                    if (f > S.a_tl[i]) too_long = 1;
                 }
-                if (h) { S.a_lah[i] = f; S.a_dl[i] = f + PF; }
-                else if (f >= S.a_dl[i]) any_done = 1;
-                if (f > S.a_tl[i]) too_long = 1;
+                if (__any_sync(FULL, too_long)) { bail = 3; break; }   // a burst may exceed max_burst_len (:498-517)
+                any_done = __any_sync(FULL, any_done);
             }
-            if (__any_sync(FULL, too_long)) { bail = 3; break; }   // a burst may exceed max_burst_len (:498-517)
-            any_done = __any_sync(FULL, any_done);
             // peaks: exact crossings & mask of the previous frame & search range (:522-548).  Up to SPF
             // words stay in registers (lane = bin inside the word); more go through shared memory.
             const bool fast = n_cw <= SPF;

@@ -184,6 +184,11 @@ struct ir_pipeline {
     std::vector<ir_frame_t> frames;
     std::vector<uint8_t> bits;
     std::vector<float> llr;
+    // RAW: lines formatted while the run is still in flight (everything after the file_info field,
+    // with t0 = frame_output.c:144-158's rule), so that the batched sink is a copy
+    std::string raw_rest;
+    std::vector<size_t> raw_off;
+    uint64_t raw_t0 = 0;
     uint64_t alg = 0;
     ir_results_t res;
     std::vector<cudaEvent_t> ev_pool;
@@ -490,6 +495,22 @@ static int launch_wave(ir_pipeline *p, size_t b0, size_t b1, const void *iq_dev,
     return 0;
 }
 
+// frame_output_print's line (frame_output.c:160-199) from the field after file_info on
+static int format_raw_rest(char *dst, size_t cap, uint64_t t0, const ir_frame_t *f, const uint8_t *bits) {
+    const double ts_ms = (double)(f->timestamp - t0) / 1000000.0;
+    const int fhz = (int)(f->center_frequency + 0.5);
+    int pay = f->n_payload_symbols;
+    if (pay < 0) pay = 0;
+    int k = snprintf(dst, cap, " %012.4f %010d N:%05.2f%+06.2f I:%011llu %3d%% %.5f %3d ", ts_ms, fhz, f->magnitude,
+                     f->noise, (unsigned long long)f->id, f->confidence, f->level, pay);
+    if (k < 0) return -1;
+    size_t pos = (size_t)k < cap ? (size_t)k : cap - 1;
+    for (int i = 0; i < f->n_bits && pos + 2 < cap; i++) dst[pos++] = (char)('0' + bits[i]);
+    if (pos + 1 < cap) dst[pos++] = '\n';
+    dst[pos] = 0;
+    return (int)pos;
+}
+
 // demod_frame_t equivalents (qpsk_demod.c:505-527) of one finished wave, on the host, in double
 static int assemble_wave(ir_pipeline *p, const Wave &w) {
     CK(cudaEventSynchronize(w.e_done));
@@ -532,6 +553,13 @@ static int assemble_wave(ir_pipeline *p, const Wave &w) {
         p->llr.insert(p->llr.end(), lr, lr + f.n_bits);
         p->frames.push_back(f);
         p->alg += 8ull * (uint64_t)c.frame_len + (uint64_t)f.n_bits;
+        {   // its RAW: line, while the GPU is busy with later waves
+            if (p->frames.size() == 1) p->raw_t0 = (f.timestamp / 1000000000ULL) * 1000000000ULL;
+            char line[160 + 2 * IR_MAX_SYMS];
+            const int ln = format_raw_rest(line, sizeof(line), p->raw_t0, &f, br);
+            p->raw_off.push_back(p->raw_rest.size());
+            if (ln > 0) p->raw_rest.append(line, (size_t)ln);
+        }
     }
     return 0;
 }
@@ -608,7 +636,23 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     // chunking: copies (host input only) overlap the detector kernels of earlier chunks
     size_t chunk = p->cfg.h2d_chunk > 0 ? (size_t)p->cfg.h2d_chunk : ((size_t)16 << 20);
     chunk = std::max<size_t>(chunk / N, 1) * N;
-    const size_t n_chunks = std::max<size_t>((n + chunk - 1) / chunk, 1);
+    // chunk boundaries: full chunks, then the last stretch in halves (8, 4, 2, 1, 1 Mi samples for
+    // the default): what runs after the last copy / the last scan launch -- one wave of
+    // FIR + chain + demod, the result copies, the RAW text -- shrinks with the last chunk
+    std::vector<size_t> bounds;
+    {
+        size_t off = 0;
+        const size_t min_piece = std::max<size_t>(((size_t)1 << 20) / N, 1) * N;
+        while (off < n) {
+            size_t m = std::min(chunk, n - off);
+            if (n - off <= chunk)                              // inside the last chunk
+                while (m > min_piece && m / 2 >= min_piece && (n - off) - m < m) m = std::max<size_t>(m / 2 / N, 1) * N;
+            off += m;
+            bounds.push_back(off);
+        }
+        if (bounds.empty()) bounds.push_back(0);
+    }
+    const size_t n_chunks = bounds.size();
     if (n_chunks > p->hdr_slots) {
         if (p->h_hdr) cudaFreeHost(p->h_hdr);
         p->h_hdr = nullptr; p->hdr_slots = 0;
@@ -619,13 +663,14 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     p->waves.clear(); p->chunks.clear();
     p->bursts.clear(); p->h_bp.clear(); p->frame_ptr.clear(); p->dec_ptr.clear();
     p->frames.clear(); p->bits.clear(); p->llr.clear();
+    p->raw_rest.clear(); p->raw_off.clear(); p->raw_t0 = 0;
     if (ir_pipeline_reset(p)) return -1;
     if (p->scan_mode == 0) CK(cudaMemsetAsync(p->d_ctl.p, 0, sizeof(StreamCtl), p->st_scan));
     cudaEvent_t ev_begin = p->ev();
     CK(cudaEventRecord(ev_begin, p->st_scan));          // after the state reset
     CK(cudaStreamWaitEvent(p->st_fft, ev_begin, 0));
-    for (size_t off = 0; off < n; off += chunk) {
-        const size_t m = std::min(chunk, n - off);
+    for (size_t bi = 0, off = 0; bi < bounds.size() && off < n; off = bounds[bi], bi++) {
+        const size_t m = bounds[bi] - off;
         if (host_iq) {
             CK(cudaMemcpyAsync((unsigned char *)p->d_iq.p + off * bps, (const unsigned char *)host_iq + off * bps,
                                m * bps, cudaMemcpyHostToDevice, p->st_copy));
@@ -832,19 +877,12 @@ extern "C" int ir_pipeline_copy_burst_samples(ir_pipeline_t *p, size_t bi, float
 extern "C" int ir_format_raw(char *dst, size_t cap, const char *file_info, uint64_t t0,
                              const ir_frame_t *f, const uint8_t *bits) {
     if (!dst || !f || cap < 64) return -1;
-    const double ts_ms = (double)(f->timestamp - t0) / 1000000.0;
-    const int fhz = (int)(f->center_frequency + 0.5);
-    int pay = f->n_payload_symbols;
-    if (pay < 0) pay = 0;
-    int k = snprintf(dst, cap, "RAW: %s %012.4f %010d N:%05.2f%+06.2f I:%011llu %3d%% %.5f %3d ",
-                     file_info ? file_info : "", ts_ms, fhz, f->magnitude, f->noise,
-                     (unsigned long long)f->id, f->confidence, f->level, pay);
+    int k = snprintf(dst, cap, "RAW: %s", file_info ? file_info : "");
     if (k < 0) return -1;
-    size_t pos = (size_t)k < cap ? (size_t)k : cap - 1;
-    for (int i = 0; i < f->n_bits && pos + 2 < cap; i++) dst[pos++] = (char)('0' + bits[i]);
-    if (pos + 1 < cap) dst[pos++] = '\n';
-    dst[pos] = 0;
-    return (int)pos;
+    const size_t pos = (size_t)k < cap ? (size_t)k : cap - 1;
+    if (cap - pos < 8) { dst[pos] = 0; return (int)pos; }
+    const int r = format_raw_rest(dst + pos, cap - pos, t0, f, bits);
+    return r < 0 ? -1 : (int)pos + r;
 }
 
 extern "C" long ir_pipeline_format_raw_all(ir_pipeline_t *p, const char *file_info, uint64_t t0, char *dst,
@@ -855,6 +893,19 @@ extern "C" long ir_pipeline_format_raw_all(ir_pipeline_t *p, const char *file_in
     if (p->frames.empty()) return 0;
     if (t0 == 0) t0 = (p->frames[0].timestamp / 1000000000ULL) * 1000000000ULL;
     size_t pos = 0;
+    if (t0 == p->raw_t0 && p->raw_off.size() == p->frames.size()) {
+        // the lines were formatted during the run: "RAW: " + file_info + the cached remainder
+        const size_t fl = file_info ? strlen(file_info) : 0;
+        for (size_t i = 0; i < p->frames.size(); i++) {
+            const size_t a = p->raw_off[i], b = i + 1 < p->raw_off.size() ? p->raw_off[i + 1] : p->raw_rest.size();
+            if (pos + 5 + fl + (b - a) + 1 > cap) { set_err("ir_pipeline_format_raw_all: buffer too small"); return -1; }
+            memcpy(dst + pos, "RAW: ", 5); pos += 5;
+            if (fl) { memcpy(dst + pos, file_info, fl); pos += fl; }
+            memcpy(dst + pos, p->raw_rest.data() + a, b - a); pos += b - a;
+        }
+        dst[pos < cap ? pos : cap - 1] = 0;
+        return (long)pos;
+    }
     for (const ir_frame_t &f : p->frames) {
         if (pos + head + (size_t)f.n_bits + 2 > cap) { set_err("ir_pipeline_format_raw_all: buffer too small"); return -1; }
         int n = ir_format_raw(dst + pos, cap - pos, file_info, t0, &f, p->bits.data() + f.bits_offset);
