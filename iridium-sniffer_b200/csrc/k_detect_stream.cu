@@ -47,7 +47,6 @@ constexpr int SWT = 256;               // worker threads per CTA (few threads = 
 constexpr int SNT = SWT + 32;          // + one more warp (the leader, in CTA 0)
 constexpr int SGF = 8;                 // rows per ring block
 constexpr int SPF = 4;                 // candidate words whose loads are in flight together
-constexpr int SACT = 512;              // bursts the leader can track (squelch sets in long before)
 constexpr int SMAXW = 512;             // bitmap words per frame (N <= 16384)
 constexpr int SMAXC = 1024;            // candidate peaks of one frame
 constexpr int SQCH = 128;              // quiet frames per worker command
@@ -58,18 +57,10 @@ struct StShared {
     unsigned long long bar[8];         // one per ring block
     uint32_t valid[SMAXW];             // peak search range minus the DC notch
     uint32_t fvs[SMAXW];               // valid & not covered by an active burst (the lanes cache their words)
-    int cw[SMAXW];                     // words of the frame with a possible unmasked crossing
-    int n_cw;
-    int cbin[SMAXC];
+    int cw[SMAXW];                     // words of the frame with a possible unmasked crossing (beyond SPF)
+    int cbin[SMAXC];                   // candidate peaks of one frame when they do not fit the registers
     float crel[SMAXC];
     float cbase[SMAXC];
-    // active bursts (burst_detect.c:39-48) + their times in frames of this launch
-    unsigned long long a_id[SACT], a_start[SACT], a_last[SACT];   // a_last: last_active at launch start
-    int a_cb[SACT];
-    int a_dl[SACT];                    // first frame on which the burst is deleted unless a hit comes
-    int a_lah[SACT];                   // frame of the latest hit in this launch (NONE: see a_last)
-    int a_tl[SACT];                    // last frame on which it cannot be "too long" yet
-    float a_rel[SACT], a_base[SACT];
     unsigned long long wcmd;           // workers: the command being executed
 };
 
@@ -253,10 +244,13 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     if (rank != 0) return;
 
     // ---------------------------------------------------------------------- leader (one warp)
-    // One frame per trip through a loop small enough to stay in the instruction cache: the
-    // frame's bitmap words are already in registers (loaded one frame ahead), the first 32
-    // bursts live one per lane, and a single vote decides whether anything happens.  Only then
-    // ("event") does the warp run the reference's steps for that frame.
+    // One frame per trip through a loop small enough to stay in the instruction cache.  A lone
+    // warp pays ~6 cycles per instruction, so everything is organised to execute few of them: up
+    // to 32 active bursts live entirely in registers, one per lane (the reference's list order is
+    // creation order, i.e. ascending id, so no list needs to be kept: deletion frees a lane,
+    // creation takes a free one); one vote per frame decides whether anything happens; only then
+    // ("event") does the warp run the reference's steps for that frame.  More than 32 concurrent
+    // bursts is the cluster kernel's business (bail).
     constexpr int WPL = 2 * BPT;                              // bitmap words per lane = W / 32
     constexpr int RB = BPT >= 8 ? 4 : 8;                      // ring blocks of SGF rows
     constexpr int RROWS = RB * SGF;
@@ -292,20 +286,32 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     // la <= index of frame f', so la - start <= (f' - f)*N + pre_len <= max_burst_len while f' - f <= TLF
     const int TLF = c.max_burst_len <= 0 ? 0x20000000 : (c.max_burst_len >= c.pre_len ? (c.max_burst_len - c.pre_len) / N : -1);
 
-    if (n_act > SACT - 64) { bail = 7; n_act = 0; }
-#pragma unroll 1
-    for (int i = lane; i < n_act; i += 32) {
-        const ActBurst b = gs->act[i];
-        S.a_id[i] = b.id; S.a_start[i] = b.start; S.a_last[i] = b.last_active;
-        S.a_cb[i] = b.center_bin; S.a_rel[i] = b.peak_rel; S.a_base[i] = b.base_at_create;
-        // first frame on which the burst is deleted unless a hit comes; last frame on which
-        // last_active - start cannot exceed max_burst_len yet
+    // ---- the burst of this lane (burst_detect.c:39-48) and its times in frames of this launch
+    bool r_have = false;
+    unsigned long long r_id = 0, r_start = 0, r_last0 = 0;    // r_last0: last_active unless a hit came in this launch
+    int r_cb = 0;
+    float r_rel = 0.0f, r_base = 0.0f;
+    int b_dl = 0x3fffffff;        // first frame on which the burst is deleted unless a hit comes
+    int b_lah = NONE;             // frame of the latest hit in this launch
+    int b_tl = 0x3fffffff;        // last frame on which it cannot be "too long" yet
+    uint32_t b_o0 = 0, b_o1 = 0, b_msk = 0;                   // hysteresis window: byte offsets of its two words, bit mask
+    int b_sh = 0;
+    auto set_window = [&]() {
+        const int w0 = (r_cb - 1) >> 5;
+        b_o0 = (uint32_t)w0 * 4u; b_o1 = (uint32_t)min(w0 + 1, W - 1) * 4u; b_sh = (r_cb - 1) & 31; b_msk = 7u;
+    };
+    if (n_act > 32) { bail = 7; n_act = 0; }
+    if (lane < n_act) {
+        const ActBurst b = gs->act[lane];
+        r_have = true;
+        r_id = b.id; r_start = b.start; r_last0 = b.last_active; r_cb = b.center_bin; r_rel = b.peak_rel; r_base = b.base_at_create;
         const long long d = (long long)(b.last_active + (unsigned long long)c.post_len) - (long long)index0;
-        S.a_dl[i] = d <= 0 ? 0 : (int)min((long long)0x3fffffff, (d + N - 1) / N);
-        S.a_lah[i] = NONE;
+        b_dl = d <= 0 ? 0 : (int)min((long long)0x3fffffff, (d + N - 1) / N);
         const long long t = (long long)(b.start + (unsigned long long)c.max_burst_len) - (long long)index0;
-        S.a_tl[i] = c.max_burst_len <= 0 ? 0x3fffffff : (t < 0 ? -1 : (int)min((long long)0x3fffffff, t / N));
+        b_tl = c.max_burst_len <= 0 ? 0x3fffffff : (t < 0 ? -1 : (int)min((long long)0x3fffffff, t / N));
+        set_window();
     }
+    uint32_t have_mask = __ballot_sync(FULL, r_have);
 #pragma unroll 1
     for (int w = lane; w < W; w += 32) {
         uint32_t v = 0;
@@ -334,31 +340,18 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
         }
         __syncwarp();
     };
-#pragma unroll 1
-    for (int i = 0; i < n_act; i++) mask_bins(max(S.a_cb[i] - c.half_bw, 0), min(S.a_cb[i] + c.half_bw, N - 1), false);
+    auto mask_burst = [&](int cb, bool set) { mask_bins(max(cb - c.half_bw, 0), min(cb + c.half_bw, N - 1), set); };
+    for (uint32_t hm = have_mask; hm; hm &= hm - 1) mask_burst(__shfl_sync(FULL, r_cb, __ffs(hm) - 1), false);
     uint32_t fv[WPL];                                         // this lane's words of S.fvs
-    // lane-resident copy of burst `lane`: word / shift of its hysteresis window, deadline, latest hit
-    // (a lane without a burst has an empty window mask and deadlines that never come)
-    uint32_t b_o0 = 0, b_o1 = 0, b_msk = 0;                   // byte offsets of the two window words in a row
-    int b_sh = 0, b_dl = 0x3fffffff, b_lah = NONE, b_tl = 0x3fffffff;
-    bool have = false;
-    auto reload_state = [&]() {
+    auto reload_fv = [&]() {
         __syncwarp();
 #pragma unroll
         for (int k4 = 0; k4 < WPL / 4; k4++) {
             const uint4 v = *reinterpret_cast<const uint4 *>(&S.fvs[lane * WPL + 4 * k4]);
             fv[4 * k4] = v.x; fv[4 * k4 + 1] = v.y; fv[4 * k4 + 2] = v.z; fv[4 * k4 + 3] = v.w;
         }
-        have = lane < n_act;
-        b_o0 = 0; b_o1 = 0; b_msk = 0; b_sh = 0; b_dl = 0x3fffffff; b_lah = NONE; b_tl = 0x3fffffff;
-        if (have) {
-            const int cb = S.a_cb[lane];
-            const int w0 = (cb - 1) >> 5;
-            b_o0 = (uint32_t)w0 * 4u; b_o1 = (uint32_t)min(w0 + 1, W - 1) * 4u; b_sh = (cb - 1) & 31; b_msk = 7u;
-            b_dl = S.a_dl[lane]; b_lah = S.a_lah[lane]; b_tl = S.a_tl[lane];
-        }
     };
-    reload_state();
+    reload_fv();
 
     // ring of bitmap rows, filled a block (SGF rows, one bulk copy, one mbarrier) at a time
     const int n_blocks = classified ? (n_frames + SGF - 1) / SGF : 0;
@@ -411,7 +404,7 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
         }
     };
 
-    // bitmap words of one frame: this lane's XU words, and the 3-bin hysteresis window of burst `lane`
+    // bitmap words of one frame: this lane's XU words, and the 3-bin hysteresis window of its burst
     struct FrameRegs { uint32_t xu[WPL]; uint32_t bx0, bx1, bu0, bu1; };
     const uint32_t ring_a = smem_u32(ring), ring_end_a = ring_a + (uint32_t)RROWS * row_bytes;
     const uint32_t my_off = (uint32_t)(lane * WPL) * 4u, x_off = (uint32_t)W * 4u;
@@ -446,19 +439,8 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
         for (int k = 0; k < WPL; k++) acc |= cur.xu[k] & fv[k];
         const uint32_t x3 = __funnelshift_r(cur.bx0, cur.bx1, b_sh) & b_msk;
         const uint32_t u3 = __funnelshift_r(cur.bu0, cur.bu1, b_sh) & b_msk;
-        const bool hit = x3 != 0u;                            // update_bursts (:458-469), decided by an X bit
-        bool ev = acc != 0u || (!hit && (u3 != 0u || f >= b_dl)) || f > b_tl;
-        if (n_act > 32) {                                     // bursts beyond the lane-resident 32
-#pragma unroll 1
-            for (int i = 32 + lane; i < n_act; i += 32) {
-                const uint32_t *XU = ring + (size_t)(f % RROWS) * RW;
-                const int cb = S.a_cb[i];
-                const int w0 = (cb - 1) >> 5, sh = (cb - 1) & 31, w1 = min(w0 + 1, W - 1);
-                if (__funnelshift_r(XU[W + w0], XU[W + w1], sh) & 7u) { S.a_dl[i] = f + PF; S.a_lah[i] = f; }
-                else if ((__funnelshift_r(XU[w0], XU[w1], sh) & 7u) != 0u || f >= S.a_dl[i]) ev = true;
-                if (f > S.a_tl[i]) ev = true;
-            }
-        }
+        bool hit = x3 != 0u;                                  // update_bursts (:458-469), decided by an X bit
+        const bool ev = acc != 0u || (!hit && (u3 != 0u || f >= b_dl)) || f > b_tl;
         if (!__any_sync(FULL, ev)) {
             // ---- nothing happens on this frame
             if (hit) { b_dl = f + PF; b_lah = f; }
@@ -468,17 +450,9 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
             // ================= event frame f: the reference's steps, exactly
             st_events++;
             ST_TICK(cy_scan);
-            // "simple": every hysteresis test of this frame is decided by an X bit and every burst
-            // lives in a lane -- update_bursts happens in registers and no baseline value is needed
-            // unless there are candidate peaks
             const bool cand_any = __any_sync(FULL, acc != 0u);
-            const bool simple = n_act <= 32 && !__any_sync(FULL, (!hit && u3 != 0u) || f > b_tl);
-            int any_done = 0;
-            if (simple) {
-                if (hit) { b_dl = f + PF; b_lah = f; }
-                any_done = __any_sync(FULL, !hit && f >= b_dl);
-            }
-            if (have) { S.a_dl[lane] = b_dl; S.a_lah[lane] = b_lah; }
+            const bool unc_any = __any_sync(FULL, !hit && u3 != 0u);
+            if (__any_sync(FULL, f > b_tl)) { bail = 3; break; }   // a burst may exceed max_burst_len (:498-517)
             // words with a possible unmasked crossing; get their magnitudes (and, while no baseline
             // update is pending, baselines) moving before anything else
             const float *row = mag + (size_t)f * N;
@@ -519,38 +493,26 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
                     }
             }
             ST_TICK(cy_e1);
-            if (cand_any || !simple) {                        // baseline values are about to be used
+            if (cand_any || unc_any) {                        // baseline values are about to be used
                 if (qs >= 0) { issue(qs, f, 0); qs = -1; }
                 if (!wait_all()) { bail = 2; break; }
             }
             ST_TICK(cy_wait);
             const uint64_t idx = index0 + (uint64_t)f * (uint64_t)N;
             __syncwarp();
-            if (!simple) {
-                // update_bursts incl. the tests an X bit does not decide; which bursts end
-                const uint32_t *XU = ring + (size_t)(f % RROWS) * RW;
-                int too_long = 0;
-#pragma unroll 1
-                for (int i = lane; i < n_act; i += 32) {
-                    const int cb = S.a_cb[i];
-                    const int w0 = (cb - 1) >> 5, sh = (cb - 1) & 31, w1 = min(w0 + 1, W - 1);
-                    bool h = (__funnelshift_r(XU[W + w0], XU[W + w1], sh) & 7u) != 0u;
-                    if (!h) {
-                        uint32_t q = __funnelshift_r(XU[w0], XU[w1], sh) & 7u;
-                        while (q) {
-                            const int b = cb - 1 + __ffs(q) - 1;
-                            q &= q - 1;
-                            const float bs = __ldcg(base_g + b);
-                            if (bs > 0.0f && row[b] / bs > thr) h = true;
-                        }
-                    }
-                    if (h) { S.a_lah[i] = f; S.a_dl[i] = f + PF; }
-                    else if (f >= S.a_dl[i]) any_done = 1;
-                    if (f > S.a_tl[i]) too_long = 1;
+            // update_bursts: the tests an X bit did not decide
+            if (unc_any && !hit) {
+                uint32_t q = u3;
+                while (q) {
+                    const int b = r_cb - 1 + __ffs(q) - 1;
+                    q &= q - 1;
+                    const float bs = __ldcg(base_g + b);
+                    if (bs > 0.0f && row[b] / bs > thr) hit = true;
                 }
-                if (__any_sync(FULL, too_long)) { bail = 3; break; }   // a burst may exceed max_burst_len (:498-517)
-                any_done = __any_sync(FULL, any_done);
             }
+            if (hit) { b_dl = f + PF; b_lah = f; }
+            const bool done = !hit && f >= b_dl;              // (a lane without a burst has no deadline)
+            const uint32_t dmask = __ballot_sync(FULL, done);
             // peaks: exact crossings & mask of the previous frame & search range (:522-548).  Up to SPF
             // words stay in registers (lane = bin inside the word); more go through shared memory.
             const bool fast = n_cw <= SPF;
@@ -588,163 +550,124 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
             if (n_cand > SMAXC) { bail = 4; break; }
             __syncwarp();
             ST_TICK(cy_e2);
-            if (any_done) {
-                // delete_gone_bursts (:490-518): gone records and survivors keep the list order
-                int kept = 0, n_del = 0;
-#pragma unroll 1
-                for (int i0 = 0; i0 < n_act; i0 += 32) {
-                    const int i = i0 + lane;
-                    const bool hv = i < n_act;
-                    unsigned long long id = 0, start = 0, la = 0;
-                    int cb = 0, dl = 0, lah = NONE, tl = 0;
-                    float rel = 0.0f, bsc = 0.0f;
-                    if (hv) {
-                        id = S.a_id[i]; start = S.a_start[i]; la = S.a_last[i];
-                        cb = S.a_cb[i]; rel = S.a_rel[i]; bsc = S.a_base[i];
-                        dl = S.a_dl[i]; lah = S.a_lah[i]; tl = S.a_tl[i];
+            bool mask_changed = false;
+            if (dmask) {
+                // delete_gone_bursts (:490-518): gone records in list order = ascending id
+                int rank_d = 0;
+                if (dmask & (dmask - 1)) {                    // several at once: rank by id
+                    for (uint32_t m = dmask; m; m &= m - 1) {
+                        const int src = __ffs(m) - 1;
+                        const unsigned long long oid = ((unsigned long long)__shfl_sync(FULL, (unsigned)(r_id >> 32), src) << 32) |
+                                                       (unsigned long long)__shfl_sync(FULL, (unsigned)r_id, src);
+                        rank_d += oid < r_id ? 1 : 0;
                     }
-                    const bool done = hv && f >= dl;
-                    const uint32_t dm = __ballot_sync(FULL, done), km = __ballot_sync(FULL, hv && !done);
-                    const uint32_t below = (1u << lane) - 1u;
-                    if (done) {
-                        const int dpos = n_del + __popc(dm & below);
-                        const uint32_t slot_g = n_gone + (uint32_t)dpos;
-                        if (slot_g < gone_cap) {
-                            GoneBurst g;
-                            g.id = id; g.start = start; g.stop = idx;
-                            g.last_active = lah == NONE ? la : index0 + (uint64_t)lah * (uint64_t)N;
-                            g.center_bin = cb; g.peak_rel = rel; g.base_at_create = bsc; g.pad = 0;
-                            gone[slot_g] = g;
-                        } else {
-                            overflow = 1;
-                        }
-                        S.cw[dpos] = cb;                       // (the word list is consumed: reuse it for the deleted bins)
-                    }
-                    overflow = __any_sync(FULL, overflow) ? 1u : 0u;
-                    __syncwarp();
-                    if (hv && !done) {
-                        const int pos = kept + __popc(km & below);
-                        S.a_id[pos] = id; S.a_start[pos] = start; S.a_last[pos] = la;
-                        S.a_cb[pos] = cb; S.a_rel[pos] = rel; S.a_base[pos] = bsc;
-                        S.a_dl[pos] = dl; S.a_lah[pos] = lah; S.a_tl[pos] = tl;
-                    }
-                    n_del += __popc(dm);
-                    kept += __popc(km);
-                    __syncwarp();
                 }
-                n_gone += (uint32_t)n_del;
-                n_act = kept;
+                if (done) {
+                    const uint32_t slot_g = n_gone + (uint32_t)rank_d;
+                    if (slot_g < gone_cap) {
+                        GoneBurst g;
+                        g.id = r_id; g.start = r_start; g.stop = idx;
+                        g.last_active = b_lah == NONE ? r_last0 : index0 + (uint64_t)b_lah * (uint64_t)N;
+                        g.center_bin = r_cb; g.peak_rel = r_rel; g.base_at_create = r_base; g.pad = 0;
+                        gone[slot_g] = g;
+                    } else {
+                        overflow = 1;
+                    }
+                    r_have = false;
+                    b_dl = 0x3fffffff; b_lah = NONE; b_tl = 0x3fffffff; b_msk = 0; b_o0 = 0; b_o1 = 0; b_sh = 0;
+                }
+                overflow = __any_sync(FULL, overflow) ? 1u : 0u;
+                n_gone += (uint32_t)__popc(dmask);
+                n_act -= __popc(dmask);
+                have_mask &= ~dmask;
                 // update_burst_mask (:482-486): free the deleted ranges, then re-cover what the
                 // survivors next to them still mask
-                if (n_del <= 4) {
-#pragma unroll 1
-                    for (int d = 0; d < n_del; d++) mask_bins(max(S.cw[d] - c.half_bw, 0), min(S.cw[d] + c.half_bw, N - 1), true);
-#pragma unroll 1
-                    for (int i0 = 0; i0 < n_act; i0 += 32) {
-                        bool near = false;
-                        if (i0 + lane < n_act)
-                            for (int d = 0; d < n_del; d++) near = near || abs(S.a_cb[i0 + lane] - S.cw[d]) <= 2 * c.half_bw;
-                        uint32_t nm = __ballot_sync(FULL, near);
-                        while (nm) {
-                            const int cbi = S.a_cb[i0 + __ffs(nm) - 1];
-                            nm &= nm - 1;
-                            mask_bins(max(cbi - c.half_bw, 0), min(cbi + c.half_bw, N - 1), false);
-                        }
-                    }
-                } else {
-#pragma unroll 1
-                    for (int w = lane; w < W; w += 32) S.fvs[w] = S.valid[w];
-                    __syncwarp();
-#pragma unroll 1
-                    for (int i = 0; i < n_act; i++) mask_bins(max(S.a_cb[i] - c.half_bw, 0), min(S.a_cb[i] + c.half_bw, N - 1), false);
+                for (uint32_t m = dmask; m; m &= m - 1) mask_burst(__shfl_sync(FULL, r_cb, __ffs(m) - 1), true);
+                for (uint32_t m = dmask; m; m &= m - 1) {
+                    const int cbd = __shfl_sync(FULL, r_cb, __ffs(m) - 1);
+                    for (uint32_t nm = __ballot_sync(FULL, r_have && abs(r_cb - cbd) <= 2 * c.half_bw); nm; nm &= nm - 1)
+                        mask_burst(__shfl_sync(FULL, r_cb, __ffs(nm) - 1), false);
                 }
+                mask_changed = true;
             }
             ST_TICK(cy_e3);
-            if (n_cand > 0 && fast) {
-                // create_new_bursts (:556-591): strongest remaining peak first, ties by bin; the
-                // candidates never leave the registers
-#pragma unroll 1
-                for (;;) {
-                    uint32_t key = 0;
-                    int kb = 0x7fffffff;
-#pragma unroll
-                    for (int j = 0; j < SPF; j++) {
-                        const uint32_t kj = exj[j] ? __float_as_uint(relj[j]) : 0u;   // rel > thr > 0: bit order = value order
-                        const int bj = (wj[j] << 5) + lane;
-                        if (kj > key || (kj != 0u && kj == key && bj < kb)) { key = kj; kb = bj; }
-                    }
-                    const uint32_t m = __reduce_max_sync(FULL, key);
-                    if (m == 0u) break;
-                    const int bin = __reduce_min_sync(FULL, key == m ? kb : 0x7fffffff);
-                    float bcl = 0.0f;
-#pragma unroll
-                    for (int j = 0; j < SPF; j++) bcl = wj[j] == (bin >> 5) ? bsj[j] : bcl;
-                    const float bc = __shfl_sync(FULL, bcl, bin & 31);
-                    if (lane == 0) {
-                        const unsigned long long start = idx - (unsigned long long)c.pre_len;
-                        S.a_id[n_act] = next_id;
-                        S.a_start[n_act] = start;
-                        S.a_last[n_act] = start;
-                        S.a_cb[n_act] = bin; S.a_rel[n_act] = __uint_as_float(m); S.a_base[n_act] = bc;
-                        S.a_dl[n_act] = f + PF0; S.a_lah[n_act] = NONE; S.a_tl[n_act] = f + TLF;
-                    }
-                    n_act++;
-                    next_id += 10ull;
-                    mask_bins(max(bin - c.half_bw, 0), min(bin + c.half_bw, N - 1), false);
-#pragma unroll
-                    for (int j = 0; j < SPF; j++) {
-                        const int bj = (wj[j] << 5) + lane;
-                        if (bj >= bin - c.half_bw && bj <= bin + c.half_bw) exj[j] = false;
-                    }
-                    if (n_act > SACT - 64) break;
-                }
-                if (n_act > SACT - 64) { bail = 5; break; }
-            } else if (n_cand > 0) {
-                // the same through the shared-memory candidate list (many words)
+            if (n_cand > 0) {
+                // create_new_bursts (:556-591): strongest remaining peak first, ties by bin.  Up to SPF
+                // words: the candidates never leave the registers; else a list in shared memory.
                 const int nc = n_cand;
 #pragma unroll 1
                 for (;;) {
-                    ArgMax best{-1.0f, 0x7fffffff};
-                    int bslot = -1;
-                    for (int i = lane; i < nc; i += 32) {
-                        const int bin = S.cbin[i];
-                        if (bin >= 0) {
-                            const ArgMax cur2{S.crel[i], bin};
-                            const ArgMax nb = argmax_pick(best, cur2);
-                            if (nb.i != best.i) bslot = i;
-                            best = nb;
+                    int bin;
+                    float rel_w, bc;
+                    if (fast) {
+                        uint32_t key = 0;
+                        int kb = 0x7fffffff;
+#pragma unroll
+                        for (int j = 0; j < SPF; j++) {
+                            const uint32_t kj = exj[j] ? __float_as_uint(relj[j]) : 0u;   // rel > thr > 0: bit order = value order
+                            const int bj = (wj[j] << 5) + lane;
+                            if (kj > key || (kj != 0u && kj == key && bj < kb)) { key = kj; kb = bj; }
                         }
+                        const uint32_t m = __reduce_max_sync(FULL, key);
+                        if (m == 0u) break;
+                        bin = __reduce_min_sync(FULL, key == m ? kb : 0x7fffffff);
+                        float bcl = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < SPF; j++) bcl = wj[j] == (bin >> 5) ? bsj[j] : bcl;
+                        bc = __shfl_sync(FULL, bcl, bin & 31);
+                        rel_w = __uint_as_float(m);
+#pragma unroll
+                        for (int j = 0; j < SPF; j++) {
+                            const int bj = (wj[j] << 5) + lane;
+                            if (bj >= bin - c.half_bw && bj <= bin + c.half_bw) exj[j] = false;
+                        }
+                    } else {
+                        ArgMax best{-1.0f, 0x7fffffff};
+                        int bslot = -1;
+                        for (int i = lane; i < nc; i += 32) {
+                            const int cbn = S.cbin[i];
+                            if (cbn >= 0) {
+                                const ArgMax cur2{S.crel[i], cbn};
+                                const ArgMax nb = argmax_pick(best, cur2);
+                                if (nb.i != best.i) bslot = i;
+                                best = nb;
+                            }
+                        }
+                        const ArgMax wbest = warp_argmax(best);
+                        if (wbest.v < 0.0f) break;
+                        bin = wbest.i;
+                        rel_w = wbest.v;
+                        const unsigned owner = __ballot_sync(FULL, best.i == bin && bslot >= 0);
+                        bc = __shfl_sync(FULL, bslot >= 0 ? S.cbase[bslot] : 0.0f, __ffs(owner) - 1);
+                        for (int i = lane; i < nc; i += 32) {
+                            const int bb = S.cbin[i];
+                            if (bb >= bin - c.half_bw && bb <= bin + c.half_bw) S.cbin[i] = -1;
+                        }
+                        __syncwarp();
                     }
-                    const ArgMax wbest = warp_argmax(best);
-                    if (wbest.v < 0.0f) break;
-                    const int bin = wbest.i;
-                    const unsigned owner = __ballot_sync(FULL, best.i == bin && bslot >= 0);
-                    const int src = __ffs(owner) - 1;
-                    const float bc = __shfl_sync(FULL, bslot >= 0 ? S.cbase[bslot] : 0.0f, src);
-                    if (lane == 0) {
-                        const unsigned long long start = idx - (unsigned long long)c.pre_len;
-                        S.a_id[n_act] = next_id;
-                        S.a_start[n_act] = start;
-                        S.a_last[n_act] = start;
-                        S.a_cb[n_act] = bin; S.a_rel[n_act] = wbest.v; S.a_base[n_act] = bc;
-                        S.a_dl[n_act] = f + PF0; S.a_lah[n_act] = NONE; S.a_tl[n_act] = f + TLF;
+                    if (have_mask == FULL) { bail = 5; break; }          // a 33rd concurrent burst
+                    const int slot = __ffs(~have_mask) - 1;
+                    if (lane == slot) {
+                        r_have = true;
+                        r_id = next_id;
+                        r_start = idx - (unsigned long long)c.pre_len;
+                        r_last0 = r_start;
+                        r_cb = bin; r_rel = rel_w; r_base = bc;
+                        b_dl = f + PF0; b_lah = NONE; b_tl = f + TLF;
+                        set_window();
                     }
+                    have_mask |= 1u << slot;
                     n_act++;
                     next_id += 10ull;
-                    mask_bins(max(bin - c.half_bw, 0), min(bin + c.half_bw, N - 1), false);
-                    for (int i = lane; i < nc; i += 32) {
-                        const int bb = S.cbin[i];
-                        if (bb >= bin - c.half_bw && bb <= bin + c.half_bw) S.cbin[i] = -1;
-                    }
-                    __syncwarp();
-                    if (n_act > SACT - 64) break;
+                    mask_burst(bin, false);
                 }
-                if (n_act > SACT - 64) { bail = 5; break; }
+                if (bail) break;
+                mask_changed = true;
             }
             if (c.max_bursts > 0 && n_act > c.max_bursts) { bail = 6; break; }      // squelch (:593-631)
             if (sq > 0) sq--;                                 // :628-631
             if (n_act == 0) quiet_frames(f, f + 1);
-            reload_state();
+            if (mask_changed) reload_fv();
             ST_TICK(cy_e4);
         }
         f++;
@@ -753,8 +676,6 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     }
     // ---- wrap up
     if (!bail) {
-        if (have) { S.a_dl[lane] = b_dl; S.a_lah[lane] = b_lah; }   // hits since the last event
-        __syncwarp();
         if (qs >= 0) { issue(qs, n_frames, 0); qs = -1; }
         if (!wait_all()) bail = 2;
     }
@@ -765,13 +686,20 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     // bulk copies still in flight (a bailed launch) must land before the shared memory is released
     for (; blk_landed < blk_issued; blk_landed++) mbar_wait(&bars[blk_landed % RB], (uint32_t)((blk_landed / RB) & 1));
     if (!bail) {
-        for (int i = lane; i < n_act; i += 32) {
+        // the list of active bursts, in the reference's order (creation order = ascending id)
+        int rank_a = 0;
+        for (uint32_t m = have_mask; m; m &= m - 1) {
+            const int src = __ffs(m) - 1;
+            const unsigned long long oid = ((unsigned long long)__shfl_sync(FULL, (unsigned)(r_id >> 32), src) << 32) |
+                                           (unsigned long long)__shfl_sync(FULL, (unsigned)r_id, src);
+            rank_a += (r_have && oid < r_id) ? 1 : 0;
+        }
+        if (r_have) {
             ActBurst b;
-            const int lah = S.a_lah[i];
-            b.id = S.a_id[i]; b.start = S.a_start[i];
-            b.last_active = lah == NONE ? S.a_last[i] : index0 + (uint64_t)lah * (uint64_t)N;
-            b.center_bin = S.a_cb[i]; b.peak_rel = S.a_rel[i]; b.base_at_create = S.a_base[i]; b.pad = 0;
-            gs->act[i] = b;
+            b.id = r_id; b.start = r_start;
+            b.last_active = b_lah == NONE ? r_last0 : index0 + (uint64_t)b_lah * (uint64_t)N;
+            b.center_bin = r_cb; b.peak_rel = r_rel; b.base_at_create = r_base; b.pad = 0;
+            gs->act[rank_a] = b;
         }
         if (lane == 0) {
             gs->hist_idx = hist_idx; gs->primed = primed; gs->n_act = n_act; gs->squelch_count = sq;
