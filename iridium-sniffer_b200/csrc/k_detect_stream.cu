@@ -35,6 +35,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "ir_device.cuh"
 #include "ir_internal.h"
 
@@ -433,6 +435,37 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
 #pragma unroll 1
     while (f < n_frames && !bail) {
         if ((f & (SGF - 1)) == 0) ring_advance(f, f);         // frame f's block has landed; older blocks are refilled
+        // Two frames at a time while nothing happens: their instruction streams are independent
+        // (but for the deadline of frame f+1, which a hit on frame f moves), so the warp overlaps
+        // them.  Any event in the pair: commit frame f if it is uneventful and fall through to the
+        // one-frame path at the event frame.
+        if ((f & (SGF - 1)) != SGF - 1 && f + 1 < n_frames) {
+            FrameRegs c1;
+            load_frame(cur, ra);
+            load_frame(c1, ra + row_bytes);                   // same block: no wrap, landed
+            uint32_t a0 = 0, a1 = 0;
+#pragma unroll
+            for (int k = 0; k < WPL; k++) { a0 |= cur.xu[k] & fv[k]; a1 |= c1.xu[k] & fv[k]; }
+            const bool h0 = (__funnelshift_r(cur.bx0, cur.bx1, b_sh) & b_msk) != 0u;
+            const bool h1 = (__funnelshift_r(c1.bx0, c1.bx1, b_sh) & b_msk) != 0u;
+            const bool q0 = (__funnelshift_r(cur.bu0, cur.bu1, b_sh) & b_msk) != 0u;
+            const bool q1 = (__funnelshift_r(c1.bu0, c1.bu1, b_sh) & b_msk) != 0u;
+            const int dl1 = h0 ? f + PF : b_dl;
+            const bool e0 = a0 != 0u || (!h0 && (q0 || f >= b_dl)) || f > b_tl;
+            const bool e1 = a1 != 0u || (!h1 && (q1 || f + 1 >= dl1)) || f + 1 > b_tl;
+            const uint32_t em = __ballot_sync(FULL, e0) ? 1u : (__ballot_sync(FULL, e1) ? 2u : 0u);
+            if (em != 1u) {                                   // frame f is uneventful
+                if (h0) { b_dl = f + PF; b_lah = f; }
+                const int adv = em == 0u ? 2 : 1;
+                if (em == 0u && h1) { b_dl = f + 1 + PF; b_lah = f + 1; }
+                sq = max(sq - adv, 0);                        // :628-631
+                if (n_act == 0) quiet_frames(f, f + adv);
+                f += adv;
+                ra += row_bytes * (uint32_t)adv;
+                if (ra == ring_end_a) ra = ring_a;
+                if (em == 0u) continue;
+            }
+        }
         load_frame(cur, ra);
         uint32_t acc = 0;
 #pragma unroll
@@ -755,7 +788,13 @@ static cudaError_t launch_stream_t(const DetConfig &c, DetState *state, float *b
                                    const uint32_t *xu, const float *ref, int n_frames, GoneBurst *gone,
                                    uint32_t gone_cap, StreamCtl *ctl, unsigned epoch, cudaStream_t st) {
     constexpr int RB = BPT >= 8 ? 4 : 8;
-    const size_t smem = ((sizeof(StShared) + 127) / 128) * 128 + (size_t)RB * SGF * (size_t)(c.N / 16) * sizeof(uint32_t);
+    size_t smem = ((sizeof(StShared) + 127) / 128) * 128 + (size_t)RB * SGF * (size_t)(c.N / 16) * sizeof(uint32_t);
+    // IR_SCAN_EXCLUSIVE_SM=1: ask for all of the SM's shared memory so that no other kernel's CTAs are
+    // co-scheduled on the cluster's SMs (measured: no effect on the leader's pace, so off by default)
+    {
+        const char *env = getenv("IR_SCAN_EXCLUSIVE_SM");
+        if (env && *env == '1') smem = std::max<size_t>(smem, (size_t)227 * 1024);
+    }
     cudaError_t e = cudaFuncSetAttribute(k_detect_scan_stream<BPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k_detect_scan_stream<BPT><<<SCL, SNT, smem, st>>>(c, state, base, hist, mag, xu, ref, n_frames, gone, gone_cap, ctl, epoch);
