@@ -80,7 +80,7 @@ struct StreamCtl {
     int bailed;                                         // last launch gave up: restore + fallback must run
     int reason;                                         // why (1 primed priming launch, 2 guard band, 3 too-long burst,
                                                         //  4 peak list, 5/7 burst table, 6 squelch, 8 primed in mid-launch)
-    unsigned long long stats[16];                       // 0 launches kept, 1 bailed, 2 commands, 3 event frames,
+    unsigned long long stats[24];                       // 0 launches kept, 1 bailed, 2 commands, 3 event frames,
                                                         // 4 words resolved exactly, 5 waits for the workers, 6 frame of last bail,
                                                         // 7 ns inside the kernel, 8-11 leader cycles: ring wait, bitmap pass,
                                                         // wait for workers, event body

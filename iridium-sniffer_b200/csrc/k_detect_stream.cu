@@ -89,6 +89,30 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
+// mbarrier / bulk-copy helpers by 32-bit shared address (kept in registers: the generic-to-shared
+// conversion would otherwise be rematerialised, S2R and all, at every use)
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_1d_a(uint32_t dst, const void *src_gmem, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src_gmem), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(SWT) : "memory"); }
 
 __device__ __forceinline__ uint32_t st_range_bits(int w, int lo, int hi) {
@@ -273,7 +297,7 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     unsigned long long t_glob0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_glob0));
     // per-phase cycle counters of the leader, compiled in only with -DIR_SCAN_TIMING
-    unsigned long long cy_scan = 0, cy_wait = 0, cy_e1 = 0, cy_e2 = 0, cy_e3 = 0, cy_e4 = 0;
+    unsigned long long cy_scan = 0, cy_wait = 0, cy_e1 = 0, cy_e2 = 0, cy_e3 = 0, cy_e4 = 0, cy_ring = 0, n_trips = 0, cy_p1 = 0, cy_p2 = 0, cy_p3 = 0;
     long long tk = clock64();
 #ifdef IR_SCAN_TIMING
 #define ST_TICK(acc) do { const long long _t = clock64(); acc += (unsigned long long)(_t - tk); tk = _t; } while (0)
@@ -359,19 +383,21 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     const int n_blocks = classified ? (n_frames + SGF - 1) / SGF : 0;
     int blk_issued = 0, blk_landed = 0;
     // rows up to frame `upto` are in shared memory; blocks wholly before frame `fcur` may be refilled
+    const uint32_t ring_a = opaque_u32(smem_u32(ring)), bars_a = opaque_u32(smem_u32(bars));
+    const uint32_t ring_end_a = ring_a + (uint32_t)RROWS * row_bytes;
     auto ring_advance = [&](int fcur, int upto) {
         __syncwarp();
         while (blk_issued < n_blocks && (blk_issued < RB || (blk_issued - RB + 1) * SGF <= fcur)) {
             if (lane == 0) {
                 const int r0 = blk_issued * SGF, nr = min(SGF, n_frames - r0);
-                uint64_t *bar = &bars[blk_issued % RB];
-                mbar_expect_tx(bar, row_bytes * (uint32_t)nr);
-                tma_load_1d(ring + (size_t)(r0 % RROWS) * RW, xu + (size_t)r0 * RW, row_bytes * (uint32_t)nr, bar);
+                const uint32_t bar = bars_a + 8u * (uint32_t)(blk_issued % RB);
+                mbar_expect_tx_a(bar, row_bytes * (uint32_t)nr);
+                tma_load_1d_a(ring_a + (uint32_t)(r0 % RROWS) * row_bytes, xu + (size_t)r0 * RW, row_bytes * (uint32_t)nr, bar);
             }
             blk_issued++;
         }
         while (blk_landed <= upto / SGF) {
-            mbar_wait(&bars[blk_landed % RB], (uint32_t)((blk_landed / RB) & 1));
+            mbar_wait_a(bars_a + 8u * (uint32_t)(blk_landed % RB), (uint32_t)((blk_landed / RB) & 1));
             blk_landed++;
         }
     };
@@ -408,7 +434,6 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
 
     // bitmap words of one frame: this lane's XU words, and the 3-bin hysteresis window of its burst
     struct FrameRegs { uint32_t xu[WPL]; uint32_t bx0, bx1, bu0, bu1; };
-    const uint32_t ring_a = smem_u32(ring), ring_end_a = ring_a + (uint32_t)RROWS * row_bytes;
     const uint32_t my_off = (uint32_t)(lane * WPL) * 4u, x_off = (uint32_t)W * 4u;
     auto load_frame = [&](FrameRegs &r, uint32_t ra) {        // ra = shared address of the frame's row
 #pragma unroll
@@ -434,12 +459,16 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     // double buffer than for one shared-memory latency per frame)
 #pragma unroll 1
     while (f < n_frames && !bail) {
-        if ((f & (SGF - 1)) == 0) ring_advance(f, f);         // frame f's block has landed; older blocks are refilled
-        // Two frames at a time while nothing happens: their instruction streams are independent
-        // (but for the deadline of frame f+1, which a hit on frame f moves), so the warp overlaps
-        // them.  Any event in the pair: commit frame f if it is uneventful and fall through to the
-        // one-frame path at the event frame.
-        if ((f & (SGF - 1)) != SGF - 1 && f + 1 < n_frames) {
+        n_trips++;
+        // ---- (A) uneventful frames, two at a time, in a small loop of their own: their instruction
+        // streams are independent (but for the deadline of frame f+1, which a hit on frame f
+        // moves), so the warp overlaps them.  An event in the pair: commit frame f if it is
+        // uneventful, leave the loop and take the one-frame path (B) at the event frame.
+        ST_TICK(cy_scan);
+#pragma unroll 1
+        for (;;) {
+            if ((f & (SGF - 1)) == 0) ring_advance(f, f);     // frame f's block has landed; older blocks are refilled
+            if ((f & (SGF - 1)) == SGF - 1 || f + 1 >= n_frames) break;
             FrameRegs c1;
             load_frame(cur, ra);
             load_frame(c1, ra + row_bytes);                   // same block: no wrap, landed
@@ -454,18 +483,20 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
             const bool e0 = a0 != 0u || (!h0 && (q0 || f >= b_dl)) || f > b_tl;
             const bool e1 = a1 != 0u || (!h1 && (q1 || f + 1 >= dl1)) || f + 1 > b_tl;
             const uint32_t em = __ballot_sync(FULL, e0) ? 1u : (__ballot_sync(FULL, e1) ? 2u : 0u);
-            if (em != 1u) {                                   // frame f is uneventful
-                if (h0) { b_dl = f + PF; b_lah = f; }
-                const int adv = em == 0u ? 2 : 1;
-                if (em == 0u && h1) { b_dl = f + 1 + PF; b_lah = f + 1; }
-                sq = max(sq - adv, 0);                        // :628-631
-                if (n_act == 0) quiet_frames(f, f + adv);
-                f += adv;
-                ra += row_bytes * (uint32_t)adv;
-                if (ra == ring_end_a) ra = ring_a;
-                if (em == 0u) continue;
-            }
+            if (em == 1u) break;                              // frame f is an event
+            if (h0) { b_dl = f + PF; b_lah = f; }
+            const int adv = em == 0u ? 2 : 1;
+            if (em == 0u && h1) { b_dl = f + 1 + PF; b_lah = f + 1; }
+            sq = max(sq - adv, 0);                            // :628-631
+            if (n_act == 0) quiet_frames(f, f + adv);
+            f += adv;
+            ra += row_bytes * (uint32_t)adv;
+            if (ra == ring_end_a) ra = ring_a;
+            if (em != 0u || f >= n_frames) break;
         }
+        ST_TICK(cy_p1);
+        if (f >= n_frames || bail) break;
+        // ---- (B) one frame, any case
         load_frame(cur, ra);
         uint32_t acc = 0;
 #pragma unroll
@@ -717,7 +748,7 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
         while (ld_vol32(&ctl->done[lane]) < n_cmd - 1) __nanosleep(32);     // every real command is finished
     __syncwarp();
     // bulk copies still in flight (a bailed launch) must land before the shared memory is released
-    for (; blk_landed < blk_issued; blk_landed++) mbar_wait(&bars[blk_landed % RB], (uint32_t)((blk_landed / RB) & 1));
+    for (; blk_landed < blk_issued; blk_landed++) mbar_wait_a(bars_a + 8u * (uint32_t)(blk_landed % RB), (uint32_t)((blk_landed / RB) & 1));
     if (!bail) {
         // the list of active bursts, in the reference's order (creation order = ascending id)
         int rank_a = 0;
@@ -748,7 +779,8 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_glob1));
         ctl->stats[7] += t_glob1 - t_glob0;
         ctl->stats[8] += cy_scan; ctl->stats[9] += cy_e1; ctl->stats[10] += cy_wait; ctl->stats[11] += cy_e2;
-        ctl->stats[12] += cy_e3; ctl->stats[13] += cy_e4;
+        ctl->stats[12] += cy_e3; ctl->stats[13] += cy_e4; ctl->stats[14] += cy_ring; ctl->stats[15] += n_trips;
+        ctl->stats[1 + 16] += cy_p1; ctl->stats[2 + 16] += cy_p2; ctl->stats[3 + 16] += cy_p3;
     }
 }
 

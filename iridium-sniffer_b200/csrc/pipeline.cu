@@ -160,7 +160,7 @@ struct ir_pipeline {
     DevBuf<StreamCtl> d_ctl;
     unsigned scan_epoch = 1;
     int scan_mode = 0;                       // 0 = streaming (default where supported), 1 = cluster / single (IR_SCAN)
-    uint64_t scan_stats[16] = {0};
+    uint64_t scan_stats[24] = {0};
     // burst list: pinned host memory mapped into the device; the scan kernel stores the (few,
     // 56-byte) records straight into it, the host reads them after the chunk's event
     GoneBurst *h_gone = nullptr, *d_gone = nullptr;
@@ -765,6 +765,9 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
         fprintf(stderr, "stream scan: kernel %.3f ms; leader Mcycles (IR_SCAN_TIMING builds): frames %.2f list+prefetch %.2f worker wait %.2f hyst+peaks %.2f delete %.2f create+reload %.2f\n",
                 p->scan_stats[7] * 1e-6, p->scan_stats[8] * 1e-6, p->scan_stats[9] * 1e-6, p->scan_stats[10] * 1e-6,
                 p->scan_stats[11] * 1e-6, p->scan_stats[12] * 1e-6, p->scan_stats[13] * 1e-6);
+        fprintf(stderr, "stream scan: ring refill+wait %.2f Mcycles, loop trips %llu; pair path: loads+logic %.2f votes %.2f commit %.2f\n",
+                p->scan_stats[14] * 1e-6, (unsigned long long)p->scan_stats[15], p->scan_stats[17] * 1e-6,
+                p->scan_stats[18] * 1e-6, p->scan_stats[19] * 1e-6);
     }
     if (getenv("IR_SCAN_DEBUG") && p->scan_mode != 0) {
         fprintf(stderr, "scan cycles leader: p1 %llu waitA %llu p2 %llu waitB %llu p3 %llu waitC %llu batches %llu qbatches %llu\n",
