@@ -635,6 +635,7 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     }
     // chunking: copies (host input only) overlap the detector kernels of earlier chunks
     size_t chunk = p->cfg.h2d_chunk > 0 ? (size_t)p->cfg.h2d_chunk : ((size_t)16 << 20);
+    if (const char *env = getenv("IR_CHUNK_MI")) { const long v = atol(env); if (v > 0 && v <= 1024) chunk = (size_t)v << 20; }
     chunk = std::max<size_t>(chunk / N, 1) * N;
     // chunk boundaries: full chunks, then the last stretch in halves (8, 4, 2, 1, 1 Mi samples for
     // the default): what runs after the last copy / the last scan launch -- one wave of
