@@ -144,3 +144,50 @@ def test_many_launches_bursts_across_launch_boundaries(pl, port, synth, mode):
             os.environ.pop("IR_SCAN", None)
         else:
             os.environ["IR_SCAN"] = old
+
+
+def test_full_size_recording_stream_equals_cluster_and_truth(pl, synth):
+    """BASELINE config 2 at full size (60 s, 600 M samples, ~6500 bursts; generated on the GPU like
+    bench.py does): too long for the CPU oracle, so the checks are size-independent properties --
+    the streaming state machine and the cluster kernel (itself pinned to the oracle above) must emit
+    the same burst list field for field, no launch may bail, burst ids must be distinct multiples of 10
+    with (almost) none missing, and >= 99 % of the demodulated frames must carry exactly the
+    bits that were planted."""
+    import sys
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import bench
+    dev = torch.device("cuda", 0)
+    iq, truth = bench.make_recording_gpu(torch, synth, 2, 60.0, 100.0, dev)
+    n = iq.shape[0]
+    keys = ("id", "start", "stop", "last_active", "center_bin", "magnitude", "noise", "num_samples")
+    out = {}
+    old = os.environ.get("IR_SCAN")
+    try:
+        for mode in ("stream", "cluster"):
+            if mode == "stream":
+                os.environ.pop("IR_SCAN", None)
+            else:
+                os.environ["IR_SCAN"] = mode
+            p = pl.Pipeline(sample_rate=10_000_000, start_time_ns=10**18)
+            res = p.run_device_ptr(iq.data_ptr(), n, "cf32")
+            out[mode] = ([tuple(b[k] for k in keys) for b in res.bursts],
+                         [(f["id"], f["bits"].tobytes()) for f in res.frames], p.scan_stats(), res)
+            p.close()
+    finally:
+        if old is None:
+            os.environ.pop("IR_SCAN", None)
+        else:
+            os.environ["IR_SCAN"] = old
+    sb, sf, ss, res = out["stream"]
+    cb, cf, _, _ = out["cluster"]
+    assert ss["streaming"] and ss["launches_bailed"] == 0 and ss["launches_kept"] >= 30, ss
+    assert len(sb) > 6000 and sb == cb
+    assert sf == cf
+    ids = sorted(b[0] for b in sb)
+    assert all(i % 10 == 0 for i in ids) and len(set(ids)) == len(ids) and ids[-1] < 10 * (len(ids) + 64)
+    tset = set(truth)
+    good = sum("".join(map(str, f["bits"])) in tset for f in res.frames)
+    assert good >= 0.99 * len(res.frames) and len(res.frames) > 5500
