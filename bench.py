@@ -205,19 +205,20 @@ def run_ours(args):
     # ---------------- end-to-end leg: pinned host IQ -> RAW text lines
     for _ in range(args.warmup):
         p.run_host_raw(host_ptr, n, "cf32")
-        p.raw_text("b200")
+        p.raw_text_len("b200")
     barrier()
     t1 = time.perf_counter()
     h2d = d2h = 0
-    text = b""
     for _ in range(args.steps):
         p.run_host_raw(host_ptr, n, "cf32")
-        text = p.raw_text("b200")
+        p.raw_text_len("b200")                  # every RAW: line of the step, in the library's text buffer
         st = p.stats()
         h2d += st["h2d_bytes"]; d2h += st["d2h_bytes"]
     barrier()
     wall_e2e = time.perf_counter() - t1
+    text = bytes(p.raw_text_view())
     n_lines = text.count(b"\n")
+    assert text.startswith(b"RAW: b200 ") and n_lines == len(p.results().frames)
     clocks = sampler.stop() if rank == 0 else None
     # context for e2e: the bare pinned->device copy of one step's input (PCIe floor of this box)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

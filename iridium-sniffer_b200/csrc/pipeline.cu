@@ -667,6 +667,7 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     p->raw_rest.clear(); p->raw_off.clear(); p->raw_t0 = 0;
     if (ir_pipeline_reset(p)) return -1;
     if (p->scan_mode == 0) CK(cudaMemsetAsync(p->d_ctl.p, 0, sizeof(StreamCtl), p->st_scan));
+    cudaEvent_t ev_first_copy = nullptr, ev_last_copy = nullptr;
     cudaEvent_t ev_begin = p->ev();
     CK(cudaEventRecord(ev_begin, p->st_scan));          // after the state reset
     CK(cudaStreamWaitEvent(p->st_fft, ev_begin, 0));
@@ -679,6 +680,8 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
             CK(cudaEventRecord(e, p->st_copy));
             CK(cudaStreamWaitEvent(p->st_fft, e, 0));
             p->res.h2d_bytes += m * bps;
+            ev_last_copy = e;
+            if (!ev_first_copy) ev_first_copy = e;
         }
         const int64_t f0 = (int64_t)(off / N);
         const int64_t f1 = std::min<int64_t>((int64_t)((off + m) / N), n_frames);
@@ -734,8 +737,9 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
             if (launch_wave(p, done, hi, iq_dev, n, fmt)) return -1;
             done = hi;
         }
-        // assemble earlier waves while this one runs
-        while (assembled + 1 < p->waves.size()) {
+        // assemble the earlier waves that have finished (never wait here: the slicer of a wave
+        // takes ~1 ms and the next chunk's bursts should be launched as soon as they are known)
+        while (assembled + 1 < p->waves.size() && cudaEventQuery(p->waves[assembled].e_done) == cudaSuccess) {
             if (assemble_wave(p, p->waves[assembled])) return -1;
             assembled++;
         }
@@ -792,6 +796,9 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
         p->res.ms_demod += span(w.e2, w.e3);
     }
     p->res.ms_total = span(ev_begin, e_end);
+    if (getenv("IR_SCAN_DEBUG") && ev_last_copy)
+        fprintf(stderr, "run_host: first copy done at %.3f ms, last copy done at %.3f ms, end of device work at %.3f ms (%zu chunks)\n",
+                span(ev_begin, ev_first_copy), span(ev_begin, ev_last_copy), p->res.ms_total, p->chunks.size());
     p->res.alg_bytes = p->alg;
     p->res.n_bursts = p->bursts.size(); p->res.bursts = p->bursts.data();
     p->res.n_frames = p->frames.size(); p->res.frames = p->frames.data();

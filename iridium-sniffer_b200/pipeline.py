@@ -253,6 +253,32 @@ class Pipeline:
             raise RuntimeError("ir_pipeline_format_raw_all failed: " + self.L.ir_last_error().decode())
         return self._txt.raw[:n]
 
+    def raw_text_len(self, file_info: str = "T", t0: int = 0) -> int:
+        """Bare C call of the batched sink into a buffer kept by this object (what bench.py times);
+        returns the number of bytes.  `raw_text_view()` exposes them without another copy."""
+        fi = file_info.encode()
+        if getattr(self, "_txt_cap", 0) == 0:
+            need = self.L.ir_pipeline_format_raw_all(self.h, fi, t0, None, 0)
+            if need < 0:
+                raise RuntimeError("ir_pipeline_format_raw_all failed")
+            self._txt_cap = max(int(need) * 2, 1 << 20)
+            self._txt = C.create_string_buffer(self._txt_cap)
+        n = self.L.ir_pipeline_format_raw_all(self.h, fi, t0, self._txt, self._txt_cap)
+        if n < 0:                                     # grown since the buffer was sized: size it again
+            need = self.L.ir_pipeline_format_raw_all(self.h, fi, t0, None, 0)
+            if need < 0:
+                raise RuntimeError("ir_pipeline_format_raw_all failed: " + self.L.ir_last_error().decode())
+            self._txt_cap = int(need) * 2
+            self._txt = C.create_string_buffer(self._txt_cap)
+            n = self.L.ir_pipeline_format_raw_all(self.h, fi, t0, self._txt, self._txt_cap)
+            if n < 0:
+                raise RuntimeError("ir_pipeline_format_raw_all failed: " + self.L.ir_last_error().decode())
+        self._txt_len = int(n)
+        return int(n)
+
+    def raw_text_view(self) -> memoryview:
+        return memoryview(self._txt)[:getattr(self, "_txt_len", 0)]
+
     def scan_stats(self) -> dict:
         """Counters of the detector state machine over the last run (ir_pipeline_scan_stats)."""
         a = (C.c_uint64 * 8)()
