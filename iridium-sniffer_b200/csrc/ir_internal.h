@@ -72,6 +72,14 @@ struct DetState {
     ActBurst act[IR_MAX_ACTIVE];
 };
 
+// where a streaming launch's snapshot lives (taken before it, restored by the fallback if it bails)
+struct ScanSnapshot {
+    const float *hist = nullptr;
+    const float *base = nullptr;
+    const DetState *state = nullptr;
+    size_t n_hist = 0;
+};
+
 // control block of the streaming state machine (k_detect_stream.cu), device memory
 struct StreamCtl {
     unsigned long long cmd[IR_STREAM_MAX_FRAMES + 8];   // leader -> workers: ranges of quiet frames
@@ -157,19 +165,20 @@ cudaError_t launch_detect_scan_cluster(const DetConfig &c, DetState *state, floa
 // the same, but a no-op unless *run_if != 0 (device flag; the fallback of the streaming scan)
 cudaError_t launch_detect_scan_cluster_if(const DetConfig &c, DetState *state, float *base, float *hist,
                                           const float *mag, int64_t n_frames, GoneBurst *gone,
-                                          uint32_t gone_cap, const int *run_if, cudaStream_t st);
+                                          uint32_t gone_cap, const int *run_if, const ScanSnapshot &snap,
+                                          cudaStream_t st);
 // k_detect_stream.cu: bitmaps against a reference baseline on all SMs + a one-warp state machine
 // with baseline workers (see the file header).  Caller snapshots / restores around it.
 bool stream_scan_supported(const DetConfig &c);
+// bitmaps of n_frames frames (may be 0) + the snapshot copies (hist/base/state -> their *_snap), one launch
 cudaError_t launch_detect_classify(const float *mag, const float *base, float thr, int N, int n_frames,
-                                   uint32_t *xu, float *ref_out, int sm_count, cudaStream_t st);
+                                   uint32_t *xu, float *ref_out, const float *hist, float *hist_snap,
+                                   size_t n_hist, float *base_snap, const DetState *state, DetState *state_snap,
+                                   int sm_count, cudaStream_t st);
 cudaError_t launch_detect_scan_stream(const DetConfig &c, DetState *state, float *base, float *hist,
                                       const float *mag, const uint32_t *xu, const float *ref, int n_frames,
                                       GoneBurst *gone, uint32_t gone_cap, StreamCtl *ctl, unsigned epoch,
                                       cudaStream_t st);
-cudaError_t launch_scan_restore(const StreamCtl *ctl, float *hist, const float *hist_snap, size_t n_hist,
-                                float *base, const float *base_snap, int N, DetState *gs,
-                                const DetState *gs_snap, int sm_count, cudaStream_t st);
 // picks the cluster kernel for N >= 2048 unless IR_SCAN=single is set in the environment
 cudaError_t launch_detect_scan_auto(const DetConfig &c, DetState *state, float *base, float *hist,
                                     const float *mag, int64_t n_frames, GoneBurst *gone,

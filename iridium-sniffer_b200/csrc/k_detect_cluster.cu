@@ -141,9 +141,23 @@ template <int BPT>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CT, 1)
 k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict__ base_g,
                       float *__restrict__ hist, const float *__restrict__ mag, int64_t n_frames,
-                      GoneBurst *__restrict__ gone, uint32_t gone_cap, int force_dense, const int *run_if) {
+                      GoneBurst *__restrict__ gone, uint32_t gone_cap, int force_dense, const int *run_if,
+                      ScanSnapshot snap) {
     if (run_if != nullptr && *run_if == 0) return;            // uniform over the cluster: nobody reaches a barrier
     cg::cluster_group cluster = cg::this_cluster();
+    if (run_if != nullptr && snap.hist != nullptr) {
+        // fallback of a bailed streaming launch: history, baseline and state back to the snapshot first
+        const size_t stride = (size_t)CL * CT, t = (size_t)cluster.block_rank() * CT + threadIdx.x;
+        const float4 *s4 = reinterpret_cast<const float4 *>(snap.hist);
+        float4 *d4 = reinterpret_cast<float4 *>(hist);
+        for (size_t i = t; i < snap.n_hist / 4; i += stride) d4[i] = s4[i];
+        for (size_t i = t; i < (size_t)c.N; i += stride) base_g[i] = snap.base[i];
+        const uint32_t *gsrc = reinterpret_cast<const uint32_t *>(snap.state);
+        uint32_t *gdst = reinterpret_cast<uint32_t *>(gs);
+        for (size_t i = t; i < sizeof(DetState) / 4; i += stride) gdst[i] = gsrc[i];
+        __threadfence();
+        cluster.sync();
+    }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ClShared &S = *reinterpret_cast<ClShared *>(smem_raw);
     ClShared &LS = *cluster.map_shared_rank(&S, 0);           // the leader's copy (DSMEM)
@@ -1076,25 +1090,26 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
 template <int BPT>
 static cudaError_t launch_cluster_t(const DetConfig &c, DetState *state, float *base, float *hist,
                                     const float *mag, int64_t n_frames, GoneBurst *gone,
-                                    uint32_t gone_cap, const int *run_if, cudaStream_t st) {
+                                    uint32_t gone_cap, const int *run_if, const ScanSnapshot &snap, cudaStream_t st) {
     const size_t smem = ((sizeof(ClShared) + 127) / 128) * 128;
     cudaError_t e = cudaFuncSetAttribute(k_detect_scan_cluster<BPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const char *env = getenv("IR_SCAN");
     const int force_dense = env && strcmp(env, "cluster_dense") == 0;      // cross-check path of the tests
-    k_detect_scan_cluster<BPT><<<CL, CT, smem, st>>>(c, state, base, hist, mag, n_frames, gone, gone_cap, force_dense, run_if);
+    k_detect_scan_cluster<BPT><<<CL, CT, smem, st>>>(c, state, base, hist, mag, n_frames, gone, gone_cap, force_dense, run_if, snap);
     return cudaGetLastError();
 }
 
 cudaError_t launch_detect_scan_cluster_if(const DetConfig &c, DetState *state, float *base, float *hist,
                                           const float *mag, int64_t n_frames, GoneBurst *gone,
-                                          uint32_t gone_cap, const int *run_if, cudaStream_t st) {
+                                          uint32_t gone_cap, const int *run_if, const ScanSnapshot &snap,
+                                          cudaStream_t st) {
     if (n_frames <= 0) return cudaSuccess;
     switch (c.N / (CL * CT)) {
-    case 1: return launch_cluster_t<1>(c, state, base, hist, mag, n_frames, gone, gone_cap, run_if, st);
-    case 2: return launch_cluster_t<2>(c, state, base, hist, mag, n_frames, gone, gone_cap, run_if, st);
-    case 4: return launch_cluster_t<4>(c, state, base, hist, mag, n_frames, gone, gone_cap, run_if, st);
-    case 8: return launch_cluster_t<8>(c, state, base, hist, mag, n_frames, gone, gone_cap, run_if, st);
+    case 1: return launch_cluster_t<1>(c, state, base, hist, mag, n_frames, gone, gone_cap, run_if, snap, st);
+    case 2: return launch_cluster_t<2>(c, state, base, hist, mag, n_frames, gone, gone_cap, run_if, snap, st);
+    case 4: return launch_cluster_t<4>(c, state, base, hist, mag, n_frames, gone, gone_cap, run_if, snap, st);
+    case 8: return launch_cluster_t<8>(c, state, base, hist, mag, n_frames, gone, gone_cap, run_if, snap, st);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -1102,7 +1117,7 @@ cudaError_t launch_detect_scan_cluster_if(const DetConfig &c, DetState *state, f
 cudaError_t launch_detect_scan_cluster(const DetConfig &c, DetState *state, float *base, float *hist,
                                        const float *mag, int64_t n_frames, GoneBurst *gone,
                                        uint32_t gone_cap, cudaStream_t st) {
-    return launch_detect_scan_cluster_if(c, state, base, hist, mag, n_frames, gone, gone_cap, nullptr, st);
+    return launch_detect_scan_cluster_if(c, state, base, hist, mag, n_frames, gone, gone_cap, nullptr, ScanSnapshot{}, st);
 }
 
 cudaError_t launch_detect_scan_auto(const DetConfig &c, DetState *state, float *base, float *hist,

@@ -134,7 +134,22 @@ __device__ __forceinline__ unsigned long long pack_cmd(unsigned epoch, int s, in
 // One warp = 1024 consecutive bins (32 bitmap words) of a run of frames.
 __global__ void __launch_bounds__(128)
 k_detect_classify(const float *__restrict__ mag, const float *base_g, float thr, int N, int n_frames,
-                  int frames_per_warp, uint32_t *__restrict__ xu, float *__restrict__ ref_out) {
+                  int frames_per_warp, uint32_t *__restrict__ xu, float *__restrict__ ref_out, int classify_blocks,
+                  const float *__restrict__ hist, float *__restrict__ hist_snap, size_t n_hist,
+                  float *__restrict__ base_snap, const DetState *__restrict__ state, DetState *__restrict__ state_snap) {
+    if ((int)blockIdx.x >= classify_blocks) {
+        // the rest of the grid takes the snapshot a bailed launch is undone from
+        const size_t nb = gridDim.x - classify_blocks;
+        const size_t stride = nb * blockDim.x, t = (size_t)(blockIdx.x - classify_blocks) * blockDim.x + threadIdx.x;
+        const float4 *s4 = reinterpret_cast<const float4 *>(hist);
+        float4 *d4 = reinterpret_cast<float4 *>(hist_snap);
+        for (size_t i = t; i < n_hist / 4; i += stride) d4[i] = s4[i];
+        for (size_t i = t; i < (size_t)N; i += stride) base_snap[i] = *reinterpret_cast<const volatile float *>(base_g + i);
+        const uint32_t *gsrc = reinterpret_cast<const uint32_t *>(state);
+        uint32_t *gdst = reinterpret_cast<uint32_t *>(state_snap);
+        for (size_t i = t; i < sizeof(DetState) / 4; i += stride) gdst[i] = gsrc[i];
+        return;
+    }
     const int lane = threadIdx.x & 31;
     const int gw = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int ncol = N >> 10;
@@ -784,34 +799,25 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     }
 }
 
-// Undo a bailed launch: history, baseline and state back to the snapshot taken before it.
-__global__ void k_scan_restore(const StreamCtl *ctl, float *hist, const float *hist_snap, size_t n_hist,
-                               float *base, const float *base_snap, int N, DetState *gs, const DetState *gs_snap) {
-    if (!ctl->bailed) return;
-    const size_t stride = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const float4 *s4 = reinterpret_cast<const float4 *>(hist_snap);
-    float4 *d4 = reinterpret_cast<float4 *>(hist);
-    for (size_t i = t; i < n_hist / 4; i += stride) d4[i] = s4[i];
-    for (size_t i = t; i < (size_t)N; i += stride) base[i] = base_snap[i];
-    const uint32_t *gsrc = reinterpret_cast<const uint32_t *>(gs_snap);
-    uint32_t *gdst = reinterpret_cast<uint32_t *>(gs);
-    for (size_t i = t; i < sizeof(DetState) / 4; i += stride) gdst[i] = gsrc[i];
-}
-
 size_t stream_ctl_bytes() { return sizeof(StreamCtl); }
 
 cudaError_t launch_detect_classify(const float *mag, const float *base, float thr, int N, int n_frames,
-                                   uint32_t *xu, float *ref_out, int sm_count, cudaStream_t st) {
-    if (n_frames <= 0) return cudaSuccess;
+                                   uint32_t *xu, float *ref_out, const float *hist, float *hist_snap,
+                                   size_t n_hist, float *base_snap, const DetState *state, DetState *state_snap,
+                                   int sm_count, cudaStream_t st) {
     const int ncol = N >> 10;
-    // enough warps for every SM, not so many that the per-warp threshold setup dominates
-    int parts = (sm_count * 16 + ncol - 1) / ncol;
-    int fpw = (n_frames + parts - 1) / parts;
-    if (fpw < 8) fpw = 8;
-    parts = (n_frames + fpw - 1) / fpw;
-    const int warps = parts * ncol;
-    const int blocks = (warps + 3) / 4;
-    k_detect_classify<<<blocks, 128, 0, st>>>(mag, base, thr, N, n_frames, fpw, xu, ref_out);
+    int blocks = 0, fpw = 8;
+    if (n_frames > 0) {
+        // enough warps for every SM, not so many that the per-warp threshold setup dominates
+        int parts = (sm_count * 16 + ncol - 1) / ncol;
+        fpw = (n_frames + parts - 1) / parts;
+        if (fpw < 8) fpw = 8;
+        parts = (n_frames + fpw - 1) / fpw;
+        blocks = (parts * ncol + 3) / 4;
+    }
+    const int copy_blocks = sm_count * 2;
+    k_detect_classify<<<blocks + copy_blocks, 128, 0, st>>>(mag, base, thr, N, n_frames, fpw, xu, ref_out, blocks, hist,
+                                                            hist_snap, n_hist, base_snap, state, state_snap);
     return cudaGetLastError();
 }
 
@@ -852,13 +858,6 @@ cudaError_t launch_detect_scan_stream(const DetConfig &c, DetState *state, float
     case 8: return launch_stream_t<8>(c, state, base, hist, mag, xu, ref, n_frames, gone, gone_cap, ctl, epoch, st);
     default: return cudaErrorInvalidValue;
     }
-}
-
-cudaError_t launch_scan_restore(const StreamCtl *ctl, float *hist, const float *hist_snap, size_t n_hist, float *base,
-                                const float *base_snap, int N, DetState *gs, const DetState *gs_snap, int sm_count,
-                                cudaStream_t st) {
-    k_scan_restore<<<sm_count * 2, 256, 0, st>>>(ctl, hist, hist_snap, n_hist, base, base_snap, N, gs, gs_snap);
-    return cudaGetLastError();
 }
 
 }  // namespace ir

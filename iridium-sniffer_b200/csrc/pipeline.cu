@@ -159,6 +159,8 @@ struct ir_pipeline {
     DevBuf<DetState> d_state_snap;
     DevBuf<StreamCtl> d_ctl;
     unsigned scan_epoch = 1;
+    bool scan_dbg = false;                   // IR_SCAN_DEBUG: events between the operations of every launch
+    std::vector<cudaEvent_t> scan_dbg_ev;
     int scan_mode = 0;                       // 0 = streaming (default where supported), 1 = cluster / single (IR_SCAN)
     uint64_t scan_stats[24] = {0};
     // burst list: pinned host memory mapped into the device; the scan kernel stores the (few,
@@ -564,33 +566,38 @@ static int assemble_wave(ir_pipeline *p, const Wave &w) {
     return 0;
 }
 
+static float span(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+
 // Frames [f0, f1) of the run through the streaming state machine, on st_scan.  The run starts
 // from a reset detector, so the first hist_size frames are the priming launch (every frame quiet,
 // no bitmaps); after that each launch is: bitmaps against the current baseline, snapshot, state
-// machine, and -- both no-ops unless the launch bailed -- restore + the cluster kernel.
+// machine, and -- a no-op unless the launch bailed -- the cluster kernel, which first restores the snapshot.
 static int scan_stream_range(ir_pipeline *p, int64_t f0, int64_t f1) {
     const DetConfig &dc = p->dc;
     const int N = dc.N;
     cudaStream_t st = p->st_scan;
     const size_t n_hist = (size_t)N * dc.hist_size;
+    const bool dbg = p->scan_dbg;
     for (int64_t a = f0; a < f1;) {
         const bool priming = a < dc.hist_size;
         const int64_t b = priming ? std::min<int64_t>(f1, dc.hist_size) : std::min<int64_t>(f1, a + IR_STREAM_MAX_FRAMES);
         const int nf = (int)(b - a);
         const float *mag = p->d_mag.p + a * N;
-        if (!priming) {
-            CK(launch_detect_classify(mag, p->d_base.p, dc.thr, N, nf, p->d_xu.p, p->d_ref.p, p->sm_count, st));
-            p->res.kernel_launches++;
-        }
-        CK(cudaMemcpyAsync(p->d_hist_snap.p, p->d_hist.p, n_hist * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        CK(cudaMemcpyAsync(p->d_base_snap.p, p->d_base.p, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        CK(cudaMemcpyAsync(p->d_state_snap.p, p->d_state.p, sizeof(DetState), cudaMemcpyDeviceToDevice, st));
+        cudaEvent_t e[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        if (dbg) { for (auto &x : e) x = p->ev(); CK(cudaEventRecord(e[0], st)); }
+        // one launch: bitmaps against the current baseline (none for the priming launch) + the snapshot
+        CK(launch_detect_classify(mag, p->d_base.p, dc.thr, N, priming ? 0 : nf, p->d_xu.p, p->d_ref.p, p->d_hist.p,
+                                  p->d_hist_snap.p, n_hist, p->d_base_snap.p, p->d_state.p, p->d_state_snap.p,
+                                  p->sm_count, st));
+        if (dbg) { CK(cudaEventRecord(e[1], st)); CK(cudaEventRecord(e[2], st)); }
         CK(launch_detect_scan_stream(dc, p->d_state.p, p->d_base.p, p->d_hist.p, mag, priming ? nullptr : p->d_xu.p,
                                      p->d_ref.p, nf, p->d_gone, p->gone_cap, p->d_ctl.p, p->scan_epoch++, st));
-        CK(launch_scan_restore(p->d_ctl.p, p->d_hist.p, p->d_hist_snap.p, n_hist, p->d_base.p, p->d_base_snap.p, N,
-                               p->d_state.p, p->d_state_snap.p, p->sm_count, st));
+        if (dbg) CK(cudaEventRecord(e[3], st));
+        ScanSnapshot snap;
+        snap.hist = p->d_hist_snap.p; snap.base = p->d_base_snap.p; snap.state = p->d_state_snap.p; snap.n_hist = n_hist;
         CK(launch_detect_scan_cluster_if(dc, p->d_state.p, p->d_base.p, p->d_hist.p, mag, nf, p->d_gone, p->gone_cap,
-                                         &p->d_ctl.p->bailed, st));
+                                         &p->d_ctl.p->bailed, snap, st));
+        if (dbg) { CK(cudaEventRecord(e[4], st)); for (auto x : e) p->scan_dbg_ev.push_back(x); }
         p->res.kernel_launches += 3;
         a = b;
     }
@@ -665,6 +672,8 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     p->bursts.clear(); p->h_bp.clear(); p->frame_ptr.clear(); p->dec_ptr.clear();
     p->frames.clear(); p->bits.clear(); p->llr.clear();
     p->raw_rest.clear(); p->raw_off.clear(); p->raw_t0 = 0;
+    p->scan_dbg = getenv("IR_SCAN_DEBUG") != nullptr;
+    p->scan_dbg_ev.clear();
     if (ir_pipeline_reset(p)) return -1;
     if (p->scan_mode == 0) CK(cudaMemsetAsync(p->d_ctl.p, 0, sizeof(StreamCtl), p->st_scan));
     cudaEvent_t ev_first_copy = nullptr, ev_last_copy = nullptr;
@@ -759,6 +768,13 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
         CK(cudaMemcpy(p->scan_stats, p->d_ctl.p->stats, sizeof(p->scan_stats), cudaMemcpyDeviceToHost));
     else
         memset(p->scan_stats, 0, sizeof(p->scan_stats));
+    if (p->scan_dbg && p->scan_mode == 0 && !p->scan_dbg_ev.empty()) {
+        double t[4] = {0, 0, 0, 0};
+        for (size_t i = 0; i + 4 < p->scan_dbg_ev.size() + 1; i += 5)
+            for (int k = 0; k < 4; k++) t[k] += span(p->scan_dbg_ev[i + k], p->scan_dbg_ev[i + k + 1]);
+        fprintf(stderr, "stream scan launches: %zu; ms in classify+snapshot %.3f, (-) %.3f, state machine %.3f, fallback (no-op) %.3f\n",
+                p->scan_dbg_ev.size() / 5, t[0], t[1], t[2], t[3]);
+    }
     if (getenv("IR_SCAN_DEBUG") && p->scan_mode == 0) {
         int reason = 0;
         cudaMemcpy(&reason, &p->d_ctl.p->reason, sizeof(int), cudaMemcpyDeviceToHost);
@@ -783,7 +799,6 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
         fprintf(stderr, "scan owner(rank3) p1 split: setup %llu chunks %llu ship %llu\n", hs.dbg[20], hs.dbg[21], hs.dbg[22]);
     }
     // ---- timings: CUDA events on the launching streams
-    auto span = [&](cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; };
     p->res.ms_detect_fft = 0; p->res.ms_detect_scan = 0;
     p->res.ms_downmix_fir = 0; p->res.ms_downmix_chain = 0; p->res.ms_demod = 0;
     for (auto &c : p->chunks) {
