@@ -72,12 +72,12 @@ struct DetState {
     ActBurst act[IR_MAX_ACTIVE];
 };
 
-// where a streaming launch's snapshot lives (taken before it, restored by the fallback if it bails)
+// what a bailed streaming launch is undone from: the history values its baseline updates overwrote
+// (one row per quiet frame, in order), the baseline at its start, and how many rows (in the control block)
 struct ScanSnapshot {
-    const float *hist = nullptr;
+    const float *undo = nullptr;
     const float *base = nullptr;
-    const DetState *state = nullptr;
-    size_t n_hist = 0;
+    const struct StreamCtl *ctl = nullptr;
 };
 
 // control block of the streaming state machine (k_detect_stream.cu), device memory
@@ -86,6 +86,7 @@ struct StreamCtl {
     unsigned int done[IR_STREAM_CL];                    // workers -> leader: commands finished per CTA
     unsigned int guard_bad;                             // a baseline left the band the bitmaps were made for
     int bailed;                                         // last launch gave up: restore + fallback must run
+    int undo_frames;                                    // rows of the undo log the last launch wrote
     int reason;                                         // why (1 primed priming launch, 2 guard band, 3 too-long burst,
                                                         //  4 peak list, 5/7 burst table, 6 squelch, 8 primed in mid-launch)
     unsigned long long stats[24];                       // 0 launches kept, 1 bailed, 2 commands, 3 event frames,
@@ -170,15 +171,12 @@ cudaError_t launch_detect_scan_cluster_if(const DetConfig &c, DetState *state, f
 // k_detect_stream.cu: bitmaps against a reference baseline on all SMs + a one-warp state machine
 // with baseline workers (see the file header).  Caller snapshots / restores around it.
 bool stream_scan_supported(const DetConfig &c);
-// bitmaps of n_frames frames (may be 0) + the snapshot copies (hist/base/state -> their *_snap), one launch
 cudaError_t launch_detect_classify(const float *mag, const float *base, float thr, int N, int n_frames,
-                                   uint32_t *xu, float *ref_out, const float *hist, float *hist_snap,
-                                   size_t n_hist, float *base_snap, const DetState *state, DetState *state_snap,
-                                   int sm_count, cudaStream_t st);
+                                   uint32_t *xu, float *ref_out, int sm_count, cudaStream_t st);
 cudaError_t launch_detect_scan_stream(const DetConfig &c, DetState *state, float *base, float *hist,
                                       const float *mag, const uint32_t *xu, const float *ref, int n_frames,
                                       GoneBurst *gone, uint32_t gone_cap, StreamCtl *ctl, unsigned epoch,
-                                      cudaStream_t st);
+                                      float *undo, float *base_snap, cudaStream_t st);
 // picks the cluster kernel for N >= 2048 unless IR_SCAN=single is set in the environment
 cudaError_t launch_detect_scan_auto(const DetConfig &c, DetState *state, float *base, float *hist,
                                     const float *mag, int64_t n_frames, GoneBurst *gone,

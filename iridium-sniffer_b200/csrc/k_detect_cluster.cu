@@ -145,16 +145,16 @@ k_detect_scan_cluster(DetConfig c, DetState *__restrict__ gs, float *__restrict_
                       ScanSnapshot snap) {
     if (run_if != nullptr && *run_if == 0) return;            // uniform over the cluster: nobody reaches a barrier
     cg::cluster_group cluster = cg::this_cluster();
-    if (run_if != nullptr && snap.hist != nullptr) {
-        // fallback of a bailed streaming launch: history, baseline and state back to the snapshot first
+    if (run_if != nullptr && snap.undo != nullptr) {
+        // fallback of a bailed streaming launch: first put back what its baseline updates overwrote
+        // (latest first, so that a history row written twice ends with its oldest value) and the
+        // baseline it started from; the state block was never touched by it
         const size_t stride = (size_t)CL * CT, t = (size_t)cluster.block_rank() * CT + threadIdx.x;
-        const float4 *s4 = reinterpret_cast<const float4 *>(snap.hist);
-        float4 *d4 = reinterpret_cast<float4 *>(hist);
-        for (size_t i = t; i < snap.n_hist / 4; i += stride) d4[i] = s4[i];
-        for (size_t i = t; i < (size_t)c.N; i += stride) base_g[i] = snap.base[i];
-        const uint32_t *gsrc = reinterpret_cast<const uint32_t *>(snap.state);
-        uint32_t *gdst = reinterpret_cast<uint32_t *>(gs);
-        for (size_t i = t; i < sizeof(DetState) / 4; i += stride) gdst[i] = gsrc[i];
+        const int nq = snap.ctl->undo_frames, h0 = gs->hist_idx, H = c.hist_size;
+        for (size_t bin = t; bin < (size_t)c.N; bin += stride) {
+            for (int q = nq - 1; q >= 0; q--) hist[(size_t)((h0 + q) % H) * c.N + bin] = snap.undo[(size_t)q * c.N + bin];
+            base_g[bin] = snap.base[bin];
+        }
         __threadfence();
         cluster.sync();
     }

@@ -134,22 +134,7 @@ __device__ __forceinline__ unsigned long long pack_cmd(unsigned epoch, int s, in
 // One warp = 1024 consecutive bins (32 bitmap words) of a run of frames.
 __global__ void __launch_bounds__(128)
 k_detect_classify(const float *__restrict__ mag, const float *base_g, float thr, int N, int n_frames,
-                  int frames_per_warp, uint32_t *__restrict__ xu, float *__restrict__ ref_out, int classify_blocks,
-                  const float *__restrict__ hist, float *__restrict__ hist_snap, size_t n_hist,
-                  float *__restrict__ base_snap, const DetState *__restrict__ state, DetState *__restrict__ state_snap) {
-    if ((int)blockIdx.x >= classify_blocks) {
-        // the rest of the grid takes the snapshot a bailed launch is undone from
-        const size_t nb = gridDim.x - classify_blocks;
-        const size_t stride = nb * blockDim.x, t = (size_t)(blockIdx.x - classify_blocks) * blockDim.x + threadIdx.x;
-        const float4 *s4 = reinterpret_cast<const float4 *>(hist);
-        float4 *d4 = reinterpret_cast<float4 *>(hist_snap);
-        for (size_t i = t; i < n_hist / 4; i += stride) d4[i] = s4[i];
-        for (size_t i = t; i < (size_t)N; i += stride) base_snap[i] = *reinterpret_cast<const volatile float *>(base_g + i);
-        const uint32_t *gsrc = reinterpret_cast<const uint32_t *>(state);
-        uint32_t *gdst = reinterpret_cast<uint32_t *>(state_snap);
-        for (size_t i = t; i < sizeof(DetState) / 4; i += stride) gdst[i] = gsrc[i];
-        return;
-    }
+                  int frames_per_warp, uint32_t *__restrict__ xu, float *__restrict__ ref_out) {
     const int lane = threadIdx.x & 31;
     const int gw = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int ncol = N >> 10;
@@ -198,7 +183,8 @@ __global__ void __cluster_dims__(SCL, 1, 1) __launch_bounds__(SNT, 1)
 k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, float *hist,
                      const float *__restrict__ mag, const uint32_t *__restrict__ xu,
                      const float *__restrict__ ref, int n_frames, GoneBurst *__restrict__ gone,
-                     uint32_t gone_cap, StreamCtl *ctl, unsigned epoch) {
+                     uint32_t gone_cap, StreamCtl *ctl, unsigned epoch, float *__restrict__ undo,
+                     float *__restrict__ base_snap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     StShared &S = *reinterpret_cast<StShared *>(smem_raw);
     const int rank = (int)blockIdx.x;
@@ -217,6 +203,7 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
         for (int u = 0; u < BPT; u++) {
             const int bin = bin0 + u * SWT + wt;
             base[u] = base_g[bin];
+            base_snap[bin] = base[u];                         // what a bailed launch is undone to
             glo[u] = 0.0f; ghi[u] = 0.0f;
             if (classified) {
                 const float r = ref[bin];
@@ -227,6 +214,7 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
         }
         int hist_idx = gs->hist_idx, primed = gs->primed;
         unsigned my = 0;
+        float *ulog = undo + bin0 + wt;                       // undo log: the history value every update overwrites
         for (;;) {
             if (wt == 0) {
                 unsigned long long v;
@@ -267,9 +255,11 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
                             const float t = base[u] - ov[g][u];            // simd_avx2.c:221-236: two roundings
                             base[u] = t + mv[g][u];
                             h[u * SWT] = mv[g][u];
+                            ulog[u * SWT] = ov[g][u];
                             if (classified) bad |= !(base[u] >= glo[u] && base[u] <= ghi[u]);
                         }
                         if (++hist_idx == H) { primed = 1; hist_idx = 0; }
+                        ulog += N;
                     }
                 }
             }
@@ -418,9 +408,11 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     };
     if (!classified && primed) bail = 1;                      // a priming launch on a primed detector
 
+    int undo_frames = 0;                                      // quiet frames handed to the workers so far
     auto issue = [&](int s, int e, int ex) {
         if (lane == 0) *reinterpret_cast<volatile unsigned long long *>(&ctl->cmd[n_cmd]) = pack_cmd(epoch, s, e, ex);
         n_cmd++;
+        undo_frames += e - s;
     };
     // the baseline the workers hold is published and inside the guard band
     auto wait_all = [&]() -> bool {
@@ -788,6 +780,7 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     }
     if (lane == 0) {
         ctl->bailed = bail ? 1 : 0;
+        ctl->undo_frames = undo_frames;
         if (bail) { ctl->reason = bail; ctl->stats[1] += 1; ctl->stats[6] = (unsigned long long)f; } else ctl->stats[0] += 1;
         ctl->stats[2] += n_cmd; ctl->stats[3] += st_events; ctl->stats[4] += st_exact; ctl->stats[5] += st_waits;
         unsigned long long t_glob1;
@@ -802,29 +795,23 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
 size_t stream_ctl_bytes() { return sizeof(StreamCtl); }
 
 cudaError_t launch_detect_classify(const float *mag, const float *base, float thr, int N, int n_frames,
-                                   uint32_t *xu, float *ref_out, const float *hist, float *hist_snap,
-                                   size_t n_hist, float *base_snap, const DetState *state, DetState *state_snap,
-                                   int sm_count, cudaStream_t st) {
+                                   uint32_t *xu, float *ref_out, int sm_count, cudaStream_t st) {
+    if (n_frames <= 0) return cudaSuccess;
     const int ncol = N >> 10;
-    int blocks = 0, fpw = 8;
-    if (n_frames > 0) {
-        // enough warps for every SM, not so many that the per-warp threshold setup dominates
-        int parts = (sm_count * 16 + ncol - 1) / ncol;
-        fpw = (n_frames + parts - 1) / parts;
-        if (fpw < 8) fpw = 8;
-        parts = (n_frames + fpw - 1) / fpw;
-        blocks = (parts * ncol + 3) / 4;
-    }
-    const int copy_blocks = sm_count * 2;
-    k_detect_classify<<<blocks + copy_blocks, 128, 0, st>>>(mag, base, thr, N, n_frames, fpw, xu, ref_out, blocks, hist,
-                                                            hist_snap, n_hist, base_snap, state, state_snap);
+    // enough warps for every SM, not so many that the per-warp threshold setup dominates
+    int parts = (sm_count * 16 + ncol - 1) / ncol;
+    int fpw = (n_frames + parts - 1) / parts;
+    if (fpw < 8) fpw = 8;
+    parts = (n_frames + fpw - 1) / fpw;
+    const int blocks = (parts * ncol + 3) / 4;
+    k_detect_classify<<<blocks, 128, 0, st>>>(mag, base, thr, N, n_frames, fpw, xu, ref_out);
     return cudaGetLastError();
 }
 
 template <int BPT>
 static cudaError_t launch_stream_t(const DetConfig &c, DetState *state, float *base, float *hist, const float *mag,
                                    const uint32_t *xu, const float *ref, int n_frames, GoneBurst *gone,
-                                   uint32_t gone_cap, StreamCtl *ctl, unsigned epoch, cudaStream_t st) {
+                                   uint32_t gone_cap, StreamCtl *ctl, unsigned epoch, float *undo, float *base_snap, cudaStream_t st) {
     constexpr int RB = BPT >= 8 ? 4 : 8;
     size_t smem = ((sizeof(StShared) + 127) / 128) * 128 + (size_t)RB * SGF * (size_t)(c.N / 16) * sizeof(uint32_t);
     // IR_SCAN_EXCLUSIVE_SM=1: ask for all of the SM's shared memory so that no other kernel's CTAs are
@@ -835,7 +822,7 @@ static cudaError_t launch_stream_t(const DetConfig &c, DetState *state, float *b
     }
     cudaError_t e = cudaFuncSetAttribute(k_detect_scan_stream<BPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_detect_scan_stream<BPT><<<SCL, SNT, smem, st>>>(c, state, base, hist, mag, xu, ref, n_frames, gone, gone_cap, ctl, epoch);
+    k_detect_scan_stream<BPT><<<SCL, SNT, smem, st>>>(c, state, base, hist, mag, xu, ref, n_frames, gone, gone_cap, ctl, epoch, undo, base_snap);
     return cudaGetLastError();
 }
 
@@ -849,13 +836,14 @@ bool stream_scan_supported(const DetConfig &c) {
 // The snapshot / restore / fallback around it is the caller's (pipeline.cu).
 cudaError_t launch_detect_scan_stream(const DetConfig &c, DetState *state, float *base, float *hist, const float *mag,
                                       const uint32_t *xu, const float *ref, int n_frames, GoneBurst *gone,
-                                      uint32_t gone_cap, StreamCtl *ctl, unsigned epoch, cudaStream_t st) {
+                                      uint32_t gone_cap, StreamCtl *ctl, unsigned epoch, float *undo, float *base_snap,
+                                      cudaStream_t st) {
     if (n_frames <= 0) return cudaSuccess;
     if (n_frames > IR_STREAM_MAX_FRAMES) return cudaErrorInvalidValue;
     switch (c.N / (SCL * SWT)) {
-    case 2: return launch_stream_t<2>(c, state, base, hist, mag, xu, ref, n_frames, gone, gone_cap, ctl, epoch, st);
-    case 4: return launch_stream_t<4>(c, state, base, hist, mag, xu, ref, n_frames, gone, gone_cap, ctl, epoch, st);
-    case 8: return launch_stream_t<8>(c, state, base, hist, mag, xu, ref, n_frames, gone, gone_cap, ctl, epoch, st);
+    case 2: return launch_stream_t<2>(c, state, base, hist, mag, xu, ref, n_frames, gone, gone_cap, ctl, epoch, undo, base_snap, st);
+    case 4: return launch_stream_t<4>(c, state, base, hist, mag, xu, ref, n_frames, gone, gone_cap, ctl, epoch, undo, base_snap, st);
+    case 8: return launch_stream_t<8>(c, state, base, hist, mag, xu, ref, n_frames, gone, gone_cap, ctl, epoch, undo, base_snap, st);
     default: return cudaErrorInvalidValue;
     }
 }

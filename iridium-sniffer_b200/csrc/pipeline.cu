@@ -155,8 +155,7 @@ struct ir_pipeline {
     // streaming state machine (k_detect_stream.cu): bitmaps of one launch, the reference baseline
     // they were made against, the snapshot a bailed launch is undone from, the control block
     DevBuf<uint32_t> d_xu;
-    DevBuf<float> d_ref, d_hist_snap, d_base_snap;
-    DevBuf<DetState> d_state_snap;
+    DevBuf<float> d_ref, d_undo, d_base_snap;
     DevBuf<StreamCtl> d_ctl;
     unsigned scan_epoch = 1;
     bool scan_dbg = false;                   // IR_SCAN_DEBUG: events between the operations of every launch
@@ -270,8 +269,8 @@ extern "C" ir_pipeline_t *ir_pipeline_create(const ir_config_t *cfg) {
         if (p->scan_mode == 0) {
             const size_t W2 = (size_t)p->dc.N / 16;
             if (p->d_xu.ensure((size_t)IR_STREAM_MAX_FRAMES * W2) || p->d_ref.ensure(p->dc.N) ||
-                p->d_hist_snap.ensure((size_t)p->dc.N * p->dc.hist_size) || p->d_base_snap.ensure(p->dc.N) ||
-                p->d_state_snap.ensure(1) || p->d_ctl.ensure(1))
+                p->d_undo.ensure((size_t)p->dc.N * IR_STREAM_MAX_FRAMES) || p->d_base_snap.ensure(p->dc.N) ||
+                p->d_ctl.ensure(1))
                 return fail(g_err);
             if (cudaMemset(p->d_ctl.p, 0, sizeof(StreamCtl)) != cudaSuccess) return fail("control block init failed");
         }
@@ -288,8 +287,8 @@ extern "C" void ir_pipeline_destroy(ir_pipeline_t *p) {
     p->d_window.release(); p->d_tw_det.release(); p->d_tw12.release(); p->d_tw11.release();
     p->d_sync_dl.release(); p->d_sync_ul.release(); p->d_iq.release(); p->d_mag.release();
     p->d_base.release(); p->d_hist.release(); p->d_state.release();
-    p->d_xu.release(); p->d_ref.release(); p->d_hist_snap.release(); p->d_base_snap.release();
-    p->d_state_snap.release(); p->d_ctl.release();
+    p->d_xu.release(); p->d_ref.release(); p->d_undo.release(); p->d_base_snap.release();
+    p->d_ctl.release();
     p->dev_arena.release(); p->pin_arena.release();
     if (p->h_gone) cudaFreeHost(p->h_gone);
     if (p->h_hdr) cudaFreeHost(p->h_hdr);
@@ -576,7 +575,6 @@ static int scan_stream_range(ir_pipeline *p, int64_t f0, int64_t f1) {
     const DetConfig &dc = p->dc;
     const int N = dc.N;
     cudaStream_t st = p->st_scan;
-    const size_t n_hist = (size_t)N * dc.hist_size;
     const bool dbg = p->scan_dbg;
     for (int64_t a = f0; a < f1;) {
         const bool priming = a < dc.hist_size;
@@ -585,20 +583,22 @@ static int scan_stream_range(ir_pipeline *p, int64_t f0, int64_t f1) {
         const float *mag = p->d_mag.p + a * N;
         cudaEvent_t e[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
         if (dbg) { for (auto &x : e) x = p->ev(); CK(cudaEventRecord(e[0], st)); }
-        // one launch: bitmaps against the current baseline (none for the priming launch) + the snapshot
-        CK(launch_detect_classify(mag, p->d_base.p, dc.thr, N, priming ? 0 : nf, p->d_xu.p, p->d_ref.p, p->d_hist.p,
-                                  p->d_hist_snap.p, n_hist, p->d_base_snap.p, p->d_state.p, p->d_state_snap.p,
-                                  p->sm_count, st));
+        // bitmaps against the current baseline (none for the priming launch)
+        if (!priming) {
+            CK(launch_detect_classify(mag, p->d_base.p, dc.thr, N, nf, p->d_xu.p, p->d_ref.p, p->sm_count, st));
+            p->res.kernel_launches++;
+        }
         if (dbg) { CK(cudaEventRecord(e[1], st)); CK(cudaEventRecord(e[2], st)); }
         CK(launch_detect_scan_stream(dc, p->d_state.p, p->d_base.p, p->d_hist.p, mag, priming ? nullptr : p->d_xu.p,
-                                     p->d_ref.p, nf, p->d_gone, p->gone_cap, p->d_ctl.p, p->scan_epoch++, st));
+                                     p->d_ref.p, nf, p->d_gone, p->gone_cap, p->d_ctl.p, p->scan_epoch++, p->d_undo.p,
+                                     p->d_base_snap.p, st));
         if (dbg) CK(cudaEventRecord(e[3], st));
         ScanSnapshot snap;
-        snap.hist = p->d_hist_snap.p; snap.base = p->d_base_snap.p; snap.state = p->d_state_snap.p; snap.n_hist = n_hist;
+        snap.undo = p->d_undo.p; snap.base = p->d_base_snap.p; snap.ctl = p->d_ctl.p;
         CK(launch_detect_scan_cluster_if(dc, p->d_state.p, p->d_base.p, p->d_hist.p, mag, nf, p->d_gone, p->gone_cap,
                                          &p->d_ctl.p->bailed, snap, st));
         if (dbg) { CK(cudaEventRecord(e[4], st)); for (auto x : e) p->scan_dbg_ev.push_back(x); }
-        p->res.kernel_launches += 3;
+        p->res.kernel_launches += 2;
         a = b;
     }
     return 0;

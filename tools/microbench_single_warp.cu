@@ -49,6 +49,28 @@ __global__ void k_lds_vote(unsigned *out, int iters, long long *cyc) {
     out[threadIdx.x] = acc_all;
     if (threadIdx.x == 0) *cyc = t1 - t0;
 }
+__global__ void k_sysmem_store(unsigned long long *host_mapped, unsigned long long *dev, int iters, long long *cyc) {
+    long long t0 = clock64();
+    for (int i = 0; i < iters; i++) {
+        if (threadIdx.x == (i & 31)) {
+            unsigned long long *g = host_mapped + (size_t)(i & 1023) * 7;
+#pragma unroll
+            for (int k = 0; k < 7; k++) g[k] = (unsigned long long)i + k;
+        }
+        __syncwarp();
+    }
+    long long t1 = clock64();
+    for (int i = 0; i < iters; i++) {
+        if (threadIdx.x == (i & 31)) {
+            unsigned long long *g = dev + (size_t)(i & 1023) * 7;
+#pragma unroll
+            for (int k = 0; k < 7; k++) g[k] = (unsigned long long)i + k;
+        }
+        __syncwarp();
+    }
+    long long t2 = clock64();
+    if (threadIdx.x == 0) { cyc[0] = t1 - t0; cyc[1] = t2 - t1; }
+}
 int main() {
     unsigned *out; long long *cyc, h;
     cudaMalloc(&out, 4096); cudaMalloc(&cyc, 8);
@@ -60,6 +82,15 @@ int main() {
         if (rep) printf("8 independent chains: %.2f cycles per instruction (64 per iteration)\n", (double)h / iters / 64);
         k_lds_vote<<<1, 32>>>(out, iters, cyc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
         if (rep) printf("2x LDS.128 + 8 LOP3 + vote + branch loop: %.1f cycles per iteration\n", (double)h / iters);
+    }
+    {
+        unsigned long long *hm, *dm, *dev; long long *c2, hc[2];
+        cudaHostAlloc((void **)&hm, 1024 * 7 * 8, cudaHostAllocMapped);
+        cudaHostGetDevicePointer((void **)&dm, hm, 0);
+        cudaMalloc(&dev, 1024 * 7 * 8); cudaMalloc(&c2, 16);
+        for (int rep = 0; rep < 2; rep++) { k_sysmem_store<<<1, 32>>>(dm, dev, 20000, c2); cudaMemcpy(hc, c2, 16, cudaMemcpyDeviceToHost); }
+        printf("one lane, 7 x 8-byte stores per iteration: mapped host memory %.1f cycles, device memory %.1f cycles\n",
+               (double)hc[0] / 20000, (double)hc[1] / 20000);
     }
     return 0;
 }
