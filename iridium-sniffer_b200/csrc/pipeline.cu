@@ -154,8 +154,10 @@ struct ir_pipeline {
     DevBuf<DetState> d_state;
     // streaming state machine (k_detect_stream.cu): bitmaps of one launch, the reference baseline
     // they were made against, the snapshot a bailed launch is undone from, the control block
-    DevBuf<uint32_t> d_xu;
-    DevBuf<float> d_ref, d_undo, d_base_snap;
+    DevBuf<uint32_t> d_xu[2];                // double-buffered: the bitmap pass of launch k+1 overlaps launch k
+    DevBuf<float> d_ref[2], d_undo, d_base_snap;
+    cudaStream_t st_cls = nullptr;           // bitmap passes
+    std::vector<cudaEvent_t> ev_scan_done;   // per state-machine launch of the current run
     DevBuf<StreamCtl> d_ctl;
     unsigned scan_epoch = 1;
     bool scan_dbg = false;                   // IR_SCAN_DEBUG: events between the operations of every launch
@@ -268,7 +270,9 @@ extern "C" ir_pipeline_t *ir_pipeline_create(const ir_config_t *cfg) {
         p->scan_mode = (env && *env && strcmp(env, "stream") != 0) || !stream_scan_supported(p->dc) ? 1 : 0;
         if (p->scan_mode == 0) {
             const size_t W2 = (size_t)p->dc.N / 16;
-            if (p->d_xu.ensure((size_t)IR_STREAM_MAX_FRAMES * W2) || p->d_ref.ensure(p->dc.N) ||
+            if (p->d_xu[0].ensure((size_t)IR_STREAM_MAX_FRAMES * W2) || p->d_xu[1].ensure((size_t)IR_STREAM_MAX_FRAMES * W2) ||
+                p->d_ref[0].ensure(p->dc.N) || p->d_ref[1].ensure(p->dc.N) ||
+                cudaStreamCreateWithFlags(&p->st_cls, cudaStreamNonBlocking) != cudaSuccess ||
                 p->d_undo.ensure((size_t)p->dc.N * IR_STREAM_MAX_FRAMES) || p->d_base_snap.ensure(p->dc.N) ||
                 p->d_ctl.ensure(1))
                 return fail(g_err);
@@ -287,7 +291,9 @@ extern "C" void ir_pipeline_destroy(ir_pipeline_t *p) {
     p->d_window.release(); p->d_tw_det.release(); p->d_tw12.release(); p->d_tw11.release();
     p->d_sync_dl.release(); p->d_sync_ul.release(); p->d_iq.release(); p->d_mag.release();
     p->d_base.release(); p->d_hist.release(); p->d_state.release();
-    p->d_xu.release(); p->d_ref.release(); p->d_undo.release(); p->d_base_snap.release();
+    p->d_xu[0].release(); p->d_xu[1].release(); p->d_ref[0].release(); p->d_ref[1].release();
+    p->d_undo.release(); p->d_base_snap.release();
+    if (p->st_cls) cudaStreamDestroy(p->st_cls);
     p->d_ctl.release();
     p->dev_arena.release(); p->pin_arena.release();
     if (p->h_gone) cudaFreeHost(p->h_gone);
@@ -571,7 +577,7 @@ static float span(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsed
 // from a reset detector, so the first hist_size frames are the priming launch (every frame quiet,
 // no bitmaps); after that each launch is: bitmaps against the current baseline, snapshot, state
 // machine, and -- a no-op unless the launch bailed -- the cluster kernel, which first restores the snapshot.
-static int scan_stream_range(ir_pipeline *p, int64_t f0, int64_t f1) {
+static int scan_stream_range(ir_pipeline *p, int64_t f0, int64_t f1, cudaEvent_t fft_done) {
     const DetConfig &dc = p->dc;
     const int N = dc.N;
     cudaStream_t st = p->st_scan;
@@ -583,20 +589,37 @@ static int scan_stream_range(ir_pipeline *p, int64_t f0, int64_t f1) {
         const float *mag = p->d_mag.p + a * N;
         cudaEvent_t e[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
         if (dbg) { for (auto &x : e) x = p->ev(); CK(cudaEventRecord(e[0], st)); }
-        // bitmaps against the current baseline (none for the priming launch)
+        // Bitmaps of this launch, on their own stream.  They are made against the baseline as it
+        // stands when the pass runs -- any recent value is as good as another inside the guard band,
+        // and the workers check theirs against exactly the reference the pass recorded -- so the pass
+        // of launch k only waits for launch k-2 (its buffers are free, the detector is primed) and
+        // overlaps launch k-1; right after priming it has to wait for the priming launch itself.
+        const size_t k = p->ev_scan_done.size();
+        const int buf = (int)(k & 1);
         if (!priming) {
-            CK(launch_detect_classify(mag, p->d_base.p, dc.thr, N, nf, p->d_xu.p, p->d_ref.p, p->sm_count, st));
+            const bool after_priming = k == 0 || a <= dc.hist_size;
+            if (k >= 1) CK(cudaStreamWaitEvent(p->st_cls, p->ev_scan_done[after_priming || k < 2 ? k - 1 : k - 2], 0));
+            CK(cudaStreamWaitEvent(p->st_cls, fft_done, 0));
+            CK(launch_detect_classify(mag, p->d_base.p, dc.thr, N, nf, p->d_xu[buf].p, p->d_ref[buf].p, p->sm_count, p->st_cls));
             p->res.kernel_launches++;
+            cudaEvent_t ec = p->ev();
+            CK(cudaEventRecord(ec, p->st_cls));
+            CK(cudaStreamWaitEvent(st, ec, 0));
         }
         if (dbg) { CK(cudaEventRecord(e[1], st)); CK(cudaEventRecord(e[2], st)); }
-        CK(launch_detect_scan_stream(dc, p->d_state.p, p->d_base.p, p->d_hist.p, mag, priming ? nullptr : p->d_xu.p,
-                                     p->d_ref.p, nf, p->d_gone, p->gone_cap, p->d_ctl.p, p->scan_epoch++, p->d_undo.p,
+        CK(launch_detect_scan_stream(dc, p->d_state.p, p->d_base.p, p->d_hist.p, mag, priming ? nullptr : p->d_xu[buf].p,
+                                     p->d_ref[buf].p, nf, p->d_gone, p->gone_cap, p->d_ctl.p, p->scan_epoch++, p->d_undo.p,
                                      p->d_base_snap.p, st));
         if (dbg) CK(cudaEventRecord(e[3], st));
         ScanSnapshot snap;
         snap.undo = p->d_undo.p; snap.base = p->d_base_snap.p; snap.ctl = p->d_ctl.p;
         CK(launch_detect_scan_cluster_if(dc, p->d_state.p, p->d_base.p, p->d_hist.p, mag, nf, p->d_gone, p->gone_cap,
                                          &p->d_ctl.p->bailed, snap, st));
+        {
+            cudaEvent_t ed = p->ev();
+            CK(cudaEventRecord(ed, st));
+            p->ev_scan_done.push_back(ed);
+        }
         if (dbg) { CK(cudaEventRecord(e[4], st)); for (auto x : e) p->scan_dbg_ev.push_back(x); }
         p->res.kernel_launches += 2;
         a = b;
@@ -674,6 +697,7 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     p->raw_rest.clear(); p->raw_off.clear(); p->raw_t0 = 0;
     p->scan_dbg = getenv("IR_SCAN_DEBUG") != nullptr;
     p->scan_dbg_ev.clear();
+    p->ev_scan_done.clear();
     if (ir_pipeline_reset(p)) return -1;
     if (p->scan_mode == 0) CK(cudaMemsetAsync(p->d_ctl.p, 0, sizeof(StreamCtl), p->st_scan));
     cudaEvent_t ev_first_copy = nullptr, ev_last_copy = nullptr;
@@ -713,7 +737,7 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
                                        p->d_gone, p->gone_cap, p->st_scan));
             p->res.kernel_launches++;
         } else if (f1 > f0) {
-            if (scan_stream_range(p, f0, f1)) return -1;
+            if (scan_stream_range(p, f0, f1, c.fft.b)) return -1;
         }
         CK(cudaEventRecord(c.scan.b, p->st_scan));
         CK(cudaMemcpyAsync(p->h_hdr + p->chunks.size() * kHdrBytes, p->d_state.p, kHdrBytes, cudaMemcpyDeviceToHost,
