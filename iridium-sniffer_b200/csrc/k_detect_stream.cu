@@ -13,25 +13,27 @@
 //      (LO, HI = IR_GUARD_LO, IR_GUARD_HI) and writes two bitmaps per frame (N/32 words each) --
 //      1/16 of the magnitude bytes.
 //
-//  k_detect_scan_stream (one 8-CTA cluster):
+//  k_detect_scan_stream (one 8-CTA cluster, 1 + 64 warps):
 //      * leader = one warp.  Walks the frames in order reading only the bitmaps (streamed into a
-//        shared-memory ring by TMA bulk copies, several frames ahead).  A frame on which no
-//        unmasked bit is set, no burst ends and every hysteresis test is decided by an X bit
-//        costs ~100 cycles.  Otherwise ("event") the leader runs the reference's steps for that
+//        shared-memory ring by TMA bulk copies, eight rows per mbarrier, ~7 blocks ahead).  Up to
+//        32 active bursts live in lane registers.  A frame on which no unmasked bit is set, no
+//        burst ends and every hysteresis test is decided by an X bit costs ~170 cycles (two such
+//        frames per trip).  Otherwise ("event") the leader runs the reference's steps for that
 //        frame exactly: IEEE divide against the true baseline for the few bins concerned, peaks
-//        sorted strongest first, deletions in list order, mask, creations.
-//      * workers = the other 4096 threads of the cluster, one to four bins each, baseline in
-//        registers.  The leader hands them ranges of quiet frames; they apply the reference's
-//        update (two roundings per bin, in frame order), keep the 512-row history, publish the
-//        baseline, and check that it stays inside the guard band the bitmaps were made for.
+//        strongest first, deletions in list (= id) order, mask, creations.
+//      * workers = 8 x 256 threads, two to eight bins each, baseline in registers.  The leader
+//        hands them ranges of quiet frames through a command ring in global memory; they apply
+//        the reference's update (two roundings per bin, in frame order), keep the 512-row
+//        history and an undo log of what they overwrite in it, publish the baseline, and check
+//        that it stays inside the guard band the bitmaps were made for.
 //      The leader waits for the workers only when it needs baseline values: at the first event
 //      after a quiet run.
 //
-//  Anything unusual -- guard band violated, squelch, a burst exceeding max_burst_len (forced
-//  baseline update), the history priming in mid-launch, table overflow -- makes the leader bail:
-//  the launch's effects are undone from a snapshot and the frames are redone by the cluster
-//  kernel of k_detect_cluster.cu, which handles every case.  Both produce the reference's result
-//  bit for bit; tests compare all variants with the CPU oracle.
+//  Anything unusual -- guard band violated, squelch, a burst that may exceed max_burst_len (forced
+//  baseline update), the history priming in mid-launch, a 33rd concurrent burst -- makes the
+//  leader bail: the state block is left untouched, the fallback launch (the cluster kernel of
+//  k_detect_cluster.cu, which handles every case) replays the undo log and redoes the frames.
+//  Both produce the reference's result bit for bit; tests compare all variants with the CPU oracle.
 #include <stdlib.h>
 #include <string.h>
 
