@@ -169,6 +169,12 @@ int ir_format_raw(char *dst, size_t cap, const char *file_info, uint64_t t0,
 long ir_pipeline_format_raw_all(ir_pipeline_t *p, const char *file_info, uint64_t t0, char *dst,
                                 size_t cap);
 
+/* How ir_pipeline_run_* cuts a block of n samples into pieces (end offsets into `ends`, returns their
+ * number or -1): full chunks of `chunk` samples (rounded down to whole detector frames), then the last
+ * chunk in halves down to 1 Mi samples, so that little work is left after the last copy.  Pure host
+ * arithmetic, exported for tests and for callers that want to align their reads with it. */
+long ir_plan_chunks(size_t n_samples, size_t chunk, size_t fft_size, size_t *ends, size_t cap);
+
 /* Pinned host allocations for callers that want full-rate H2D. */
 void *ir_host_alloc(size_t bytes);
 void ir_host_free(void *p);

@@ -667,20 +667,12 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     size_t chunk = p->cfg.h2d_chunk > 0 ? (size_t)p->cfg.h2d_chunk : ((size_t)16 << 20);
     if (const char *env = getenv("IR_CHUNK_MI")) { const long v = atol(env); if (v > 0 && v <= 1024) chunk = (size_t)v << 20; }
     chunk = std::max<size_t>(chunk / N, 1) * N;
-    // chunk boundaries: full chunks, then the last stretch in halves (8, 4, 2, 1, 1 Mi samples for
-    // the default): what runs after the last copy / the last scan launch -- one wave of
-    // FIR + chain + demod, the result copies, the RAW text -- shrinks with the last chunk
-    std::vector<size_t> bounds;
+    // chunk boundaries: full chunks, then the last stretch in halves (ir_plan_chunks)
+    std::vector<size_t> bounds((n / std::max<size_t>(chunk, 1)) + 64);
     {
-        size_t off = 0;
-        const size_t min_piece = std::max<size_t>(((size_t)1 << 20) / N, 1) * N;
-        while (off < n) {
-            size_t m = std::min(chunk, n - off);
-            if (n - off <= chunk)                              // inside the last chunk
-                while (m > min_piece && m / 2 >= min_piece && (n - off) - m < m) m = std::max<size_t>(m / 2 / N, 1) * N;
-            off += m;
-            bounds.push_back(off);
-        }
+        const long nb = ir_plan_chunks(n, chunk, (size_t)N, bounds.data(), bounds.size());
+        if (nb < 0) { set_err("chunk plan does not fit"); return -1; }
+        bounds.resize((size_t)nb);
         if (bounds.empty()) bounds.push_back(0);
     }
     const size_t n_chunks = bounds.size();
@@ -860,6 +852,27 @@ extern "C" int ir_pipeline_results(ir_pipeline_t *p, ir_results_t *out) {
     if (!p || !out) return -1;
     *out = p->res;
     return 0;
+}
+
+// End offsets of the pieces a block of n samples is processed in: full chunks, then the last stretch
+// in halves (8, 4, 2, 1, 1 Mi samples for the default 16 Mi): what runs after the last copy / the last
+// state-machine launch -- one wave of FIR + chain + demod, the result copies, the RAW text -- shrinks
+// with the last piece.  Every piece but the last is a whole number of detector frames.
+extern "C" long ir_plan_chunks(size_t n, size_t chunk, size_t fft_size, size_t *ends, size_t cap) {
+    if (!ends || fft_size == 0 || chunk == 0) return -1;
+    const size_t N = fft_size;
+    chunk = std::max<size_t>(chunk / N, 1) * N;
+    const size_t min_piece = std::max<size_t>(((size_t)1 << 20) / N, 1) * N;
+    size_t off = 0, k = 0;
+    while (off < n) {
+        size_t m = std::min(chunk, n - off);
+        if (n - off <= chunk)                                  // inside the last chunk
+            while (m > min_piece && m / 2 >= min_piece && (n - off) - m < m) m = std::max<size_t>(m / 2 / N, 1) * N;
+        off += m;
+        if (k >= cap) return -1;
+        ends[k++] = off;
+    }
+    return (long)k;
 }
 
 extern "C" int ir_pipeline_scan_stats(ir_pipeline_t *p, uint64_t *out, int n) {

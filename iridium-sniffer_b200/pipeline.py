@@ -106,6 +106,8 @@ def load_library() -> C.CDLL:
     L.ir_host_alloc.restype = C.c_void_p
     L.ir_host_alloc.argtypes = [C.c_size_t]
     L.ir_host_free.argtypes = [C.c_void_p]
+    L.ir_plan_chunks.restype = C.c_long
+    L.ir_plan_chunks.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t), C.c_size_t]
     L.ir_pipeline_scan_stats.restype = C.c_int
     L.ir_pipeline_scan_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
     _lib = L
@@ -117,7 +119,7 @@ EXPORTED_SYMBOLS = [
     "ir_pipeline_reset", "ir_pipeline_run_host", "ir_pipeline_run_device", "ir_pipeline_results",
     "ir_pipeline_copy_mag", "ir_pipeline_copy_frame_samples", "ir_pipeline_copy_decimated",
     "ir_pipeline_copy_burst_samples", "ir_format_raw", "ir_pipeline_format_raw_all", "ir_host_alloc",
-    "ir_host_free", "ir_pipeline_scan_stats",
+    "ir_host_free", "ir_pipeline_scan_stats", "ir_plan_chunks",
 ]
 
 
