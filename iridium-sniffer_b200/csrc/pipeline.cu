@@ -827,6 +827,20 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
         p->res.ms_demod += span(w.e2, w.e3);
     }
     p->res.ms_total = span(ev_begin, e_end);
+    if (getenv("IR_CHUNK_DEBUG")) {
+        for (size_t ci = 0; ci < p->chunks.size(); ci++) {
+            const Chunk &c = p->chunks[ci];
+            fprintf(stderr, "chunk %2zu end %10zu: fft %.3f..%.3f ms, scan %.3f..%.3f ms, header on host %.3f ms\n", ci, c.end,
+                    span(ev_begin, c.fft.a), span(ev_begin, c.fft.b), span(ev_begin, c.scan.a), span(ev_begin, c.scan.b),
+                    span(ev_begin, c.e_hdr));
+        }
+        for (size_t wi = 0; wi < p->waves.size(); wi++) {
+            const Wave &w = p->waves[wi];
+            fprintf(stderr, "wave %2zu (%4zu bursts): fir %.3f..%.3f chain ..%.3f demod %.3f..%.3f results %.3f ms\n", wi, w.nb,
+                    span(ev_begin, w.e0), span(ev_begin, w.e1), span(ev_begin, w.e1b), span(ev_begin, w.e2),
+                    span(ev_begin, w.e3), span(ev_begin, w.e_done));
+        }
+    }
     if (getenv("IR_SCAN_DEBUG") && ev_last_copy)
         fprintf(stderr, "run_host: first copy done at %.3f ms, last copy done at %.3f ms, end of device work at %.3f ms (%zu chunks)\n",
                 span(ev_begin, ev_first_copy), span(ev_begin, ev_last_copy), p->res.ms_total, p->chunks.size());
