@@ -300,7 +300,7 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
     uint32_t overflow = gs->overflow;
     int bail = 0;
     unsigned n_cmd = 0, n_waited = 0;
-    unsigned long long st_events = 0, st_exact = 0, st_waits = 0;
+    unsigned long long st_events = 0, st_exact = 0, st_waits = 0, st_mini = 0;
     unsigned long long t_glob0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_glob0));
     // per-phase cycle counters of the leader, compiled in only with -DIR_SCAN_TIMING
@@ -441,6 +441,45 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
         }
     };
 
+    // delete_gone_bursts (:490-518) for the lanes in dmask on frame fr: gone records in list order
+    // (= ascending id), lanes freed, update_burst_mask (:482-486) by freeing the deleted ranges and
+    // re-covering what the survivors next to them still mask.  (The caller reloads fv.)
+    auto delete_done = [&](uint32_t dmask, bool done, int fr) {
+        int rank_d = 0;
+        if (dmask & (dmask - 1)) {                            // several at once: rank by id
+            for (uint32_t m = dmask; m; m &= m - 1) {
+                const int src = __ffs(m) - 1;
+                const unsigned long long oid = ((unsigned long long)__shfl_sync(FULL, (unsigned)(r_id >> 32), src) << 32) |
+                                               (unsigned long long)__shfl_sync(FULL, (unsigned)r_id, src);
+                rank_d += oid < r_id ? 1 : 0;
+            }
+        }
+        if (done) {
+            const uint32_t slot_g = n_gone + (uint32_t)rank_d;
+            if (slot_g < gone_cap) {
+                GoneBurst g;
+                g.id = r_id; g.start = r_start; g.stop = index0 + (uint64_t)fr * (uint64_t)N;
+                g.last_active = b_lah == NONE ? r_last0 : index0 + (uint64_t)b_lah * (uint64_t)N;
+                g.center_bin = r_cb; g.peak_rel = r_rel; g.base_at_create = r_base; g.pad = 0;
+                gone[slot_g] = g;
+            } else {
+                overflow = 1;
+            }
+            r_have = false;
+            b_dl = 0x3fffffff; b_lah = NONE; b_tl = 0x3fffffff; b_msk = 0; b_o0 = 0; b_o1 = 0; b_sh = 0;
+        }
+        overflow = __any_sync(FULL, overflow) ? 1u : 0u;
+        n_gone += (uint32_t)__popc(dmask);
+        n_act -= __popc(dmask);
+        have_mask &= ~dmask;
+        for (uint32_t m = dmask; m; m &= m - 1) mask_burst(__shfl_sync(FULL, r_cb, __ffs(m) - 1), true);
+        for (uint32_t m = dmask; m; m &= m - 1) {
+            const int cbd = __shfl_sync(FULL, r_cb, __ffs(m) - 1);
+            for (uint32_t nm = __ballot_sync(FULL, r_have && abs(r_cb - cbd) <= 2 * c.half_bw); nm; nm &= nm - 1)
+                mask_burst(__shfl_sync(FULL, r_cb, __ffs(nm) - 1), false);
+        }
+    };
+
     // bitmap words of one frame: this lane's XU words, and the 3-bin hysteresis window of its burst
     struct FrameRegs { uint32_t xu[WPL]; uint32_t bx0, bx1, bu0, bu1; };
     const uint32_t my_off = (uint32_t)(lane * WPL) * 4u, x_off = (uint32_t)W * 4u;
@@ -492,7 +531,24 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
             const bool e0 = a0 != 0u || (!h0 && (q0 || f >= b_dl)) || f > b_tl;
             const bool e1 = a1 != 0u || (!h1 && (q1 || f + 1 >= dl1)) || f + 1 > b_tl;
             const uint32_t em = __ballot_sync(FULL, e0) ? 1u : (__ballot_sync(FULL, e1) ? 2u : 0u);
-            if (em == 1u) break;                              // frame f is an event
+            if (em == 1u) {                                   // frame f is an event
+                // the commonest one -- bursts reaching their deadline, nothing else -- is handled right
+                // here: no baseline value is needed and no peak can appear
+                const bool d0 = !h0 && f >= b_dl;
+                if (__any_sync(FULL, a0 != 0u || (!h0 && q0) || f > b_tl)) break;
+                st_events++;
+                st_mini++;
+                if (h0) { b_dl = f + PF; b_lah = f; }
+                delete_done(__ballot_sync(FULL, d0), d0, f);
+                reload_fv();
+                if (sq > 0) sq--;                             // :628-631
+                if (n_act == 0) quiet_frames(f, f + 1);
+                f += 1;
+                ra += row_bytes;
+                if (ra == ring_end_a) ra = ring_a;
+                if (f >= n_frames) break;
+                continue;
+            }
             if (h0) { b_dl = f + PF; b_lah = f; }
             const int adv = em == 0u ? 2 : 1;
             if (em == 0u && h1) { b_dl = f + 1 + PF; b_lah = f + 1; }
@@ -501,7 +557,7 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
             f += adv;
             ra += row_bytes * (uint32_t)adv;
             if (ra == ring_end_a) ra = ring_a;
-            if (em != 0u || f >= n_frames) break;
+            if (f >= n_frames) break;                         // (an event on frame f+1 is met again as frame f of the next trip)
         }
         ST_TICK(cy_p1);
         if (f >= n_frames || bail) break;
@@ -625,42 +681,7 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
             ST_TICK(cy_e2);
             bool mask_changed = false;
             if (dmask) {
-                // delete_gone_bursts (:490-518): gone records in list order = ascending id
-                int rank_d = 0;
-                if (dmask & (dmask - 1)) {                    // several at once: rank by id
-                    for (uint32_t m = dmask; m; m &= m - 1) {
-                        const int src = __ffs(m) - 1;
-                        const unsigned long long oid = ((unsigned long long)__shfl_sync(FULL, (unsigned)(r_id >> 32), src) << 32) |
-                                                       (unsigned long long)__shfl_sync(FULL, (unsigned)r_id, src);
-                        rank_d += oid < r_id ? 1 : 0;
-                    }
-                }
-                if (done) {
-                    const uint32_t slot_g = n_gone + (uint32_t)rank_d;
-                    if (slot_g < gone_cap) {
-                        GoneBurst g;
-                        g.id = r_id; g.start = r_start; g.stop = idx;
-                        g.last_active = b_lah == NONE ? r_last0 : index0 + (uint64_t)b_lah * (uint64_t)N;
-                        g.center_bin = r_cb; g.peak_rel = r_rel; g.base_at_create = r_base; g.pad = 0;
-                        gone[slot_g] = g;
-                    } else {
-                        overflow = 1;
-                    }
-                    r_have = false;
-                    b_dl = 0x3fffffff; b_lah = NONE; b_tl = 0x3fffffff; b_msk = 0; b_o0 = 0; b_o1 = 0; b_sh = 0;
-                }
-                overflow = __any_sync(FULL, overflow) ? 1u : 0u;
-                n_gone += (uint32_t)__popc(dmask);
-                n_act -= __popc(dmask);
-                have_mask &= ~dmask;
-                // update_burst_mask (:482-486): free the deleted ranges, then re-cover what the
-                // survivors next to them still mask
-                for (uint32_t m = dmask; m; m &= m - 1) mask_burst(__shfl_sync(FULL, r_cb, __ffs(m) - 1), true);
-                for (uint32_t m = dmask; m; m &= m - 1) {
-                    const int cbd = __shfl_sync(FULL, r_cb, __ffs(m) - 1);
-                    for (uint32_t nm = __ballot_sync(FULL, r_have && abs(r_cb - cbd) <= 2 * c.half_bw); nm; nm &= nm - 1)
-                        mask_burst(__shfl_sync(FULL, r_cb, __ffs(nm) - 1), false);
-                }
+                delete_done(dmask, done, f);
                 mask_changed = true;
             }
             ST_TICK(cy_e3);
@@ -790,6 +811,7 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
         ctl->stats[7] += t_glob1 - t_glob0;
         ctl->stats[8] += cy_scan; ctl->stats[9] += cy_e1; ctl->stats[10] += cy_wait; ctl->stats[11] += cy_e2;
         ctl->stats[12] += cy_e3; ctl->stats[13] += cy_e4; ctl->stats[14] += cy_ring; ctl->stats[15] += n_trips;
+        ctl->stats[16] += st_mini;
         ctl->stats[1 + 16] += cy_p1; ctl->stats[2 + 16] += cy_p2; ctl->stats[3 + 16] += cy_p3;
     }
 }

@@ -802,6 +802,7 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
         fprintf(stderr, "stream scan: kernel %.3f ms; leader Mcycles (IR_SCAN_TIMING builds): frames %.2f list+prefetch %.2f worker wait %.2f hyst+peaks %.2f delete %.2f create+reload %.2f\n",
                 p->scan_stats[7] * 1e-6, p->scan_stats[8] * 1e-6, p->scan_stats[9] * 1e-6, p->scan_stats[10] * 1e-6,
                 p->scan_stats[11] * 1e-6, p->scan_stats[12] * 1e-6, p->scan_stats[13] * 1e-6);
+        fprintf(stderr, "stream scan: deadline-only events handled in the fast loop %llu\n", (unsigned long long)p->scan_stats[16]);
         fprintf(stderr, "stream scan: ring refill+wait %.2f Mcycles, loop trips %llu; pair path: loads+logic %.2f votes %.2f commit %.2f\n",
                 p->scan_stats[14] * 1e-6, (unsigned long long)p->scan_stats[15], p->scan_stats[17] * 1e-6,
                 p->scan_stats[18] * 1e-6, p->scan_stats[19] * 1e-6);
