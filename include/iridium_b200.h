@@ -58,7 +58,7 @@ typedef struct {
                                    (burst_detect.c:755-759) */
     uint64_t max_samples;       /* capacity of the resident IQ buffer; 0 = size of first feed */
     int32_t h2d_chunk;          /* samples per pinned->device copy in ir_pipeline_run_host;
-                                   0 = 16 Mi */
+                                   0 = 32 Mi */
     int32_t reserved[7];
 } ir_config_t;
 

@@ -336,6 +336,22 @@ static float2 *rot_alloc(ir_pipeline *p, size_t count) {
     return r;
 }
 
+// Small parameter blocks go pinned host -> device through a kernel that reads the pinned memory
+// directly (UVA), NOT through cudaMemcpyAsync: the H2D copy engine's queue holds the bulk IQ copies of
+// the whole run, and a parameter copy queued behind them would hold the burst kernels back until the
+// last sample has arrived (measured: with 32 Mi-sample chunks every FIR started after the last copy).
+__global__ void k_fetch_words(const uint32_t *__restrict__ src_pinned, uint32_t *__restrict__ dst, size_t n_words) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src_pinned[i];
+}
+static cudaError_t fetch_to_device(void *dst, const void *src_pinned, size_t bytes, cudaStream_t st) {
+    const size_t n_words = (bytes + 3) / 4;                    // (arena blocks are 256-byte multiples)
+    if (n_words == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)std::min<size_t>((n_words + 255) / 256, 64);
+    k_fetch_words<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint32_t *>(src_pinned), reinterpret_cast<uint32_t *>(dst), n_words);
+    return cudaGetLastError();
+}
+
 // Bursts [b0, b1) of the gone list: host bookkeeping (burst_data_t equivalents, decimation
 // geometry), then FIR + chain + demod + result copies enqueued on st_burst.  Does not wait.
 static int launch_wave(ir_pipeline *p, size_t b0, size_t b1, const void *iq_dev, size_t n, int fmt) {
@@ -444,11 +460,11 @@ static int launch_wave(ir_pipeline *p, size_t b0, size_t b1, const void *iq_dev,
             h_incr[j] = rt.incr; h_ptrs[j] = rt.d; h_lens[j] = rt.len;
             j++;
         }
-        CK(cudaMemcpyAsync(d_incr, h_incr, k * sizeof(float2), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d_ptrs, h_ptrs, k * sizeof(float2 *), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d_lens, h_lens, k * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(fetch_to_device(d_incr, h_incr, k * sizeof(float2), st));
+        CK(fetch_to_device(d_ptrs, h_ptrs, k * sizeof(float2 *), st));
+        CK(fetch_to_device(d_lens, h_lens, k * sizeof(int), st));
         CK(launch_rot_tables(d_incr, d_ptrs, d_lens, (int)k, st));
-        p->res.kernel_launches++;
+        p->res.kernel_launches += 4;                           // 3 parameter fetches + the tables
     }
     for (size_t i = b0; i < b1; i++) {
         auto it = p->rot.find(p->h_gone[i].center_bin);
@@ -474,8 +490,8 @@ static int launch_wave(ir_pipeline *p, size_t b0, size_t b1, const void *iq_dev,
         p->frame_ptr[i] = w.d_frames + (i - b0) * (size_t)IR_MAX_FRAME;
         p->dec_ptr[i] = w.d_dec + p->h_bp[i].dec_off;
     }
-    CK(cudaMemcpyAsync(w.d_bp, w.h_bp, nb * sizeof(BurstParam), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(w.d_tile_start, w.h_tile_start, (nb + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(fetch_to_device(w.d_bp, w.h_bp, nb * sizeof(BurstParam), st));
+    CK(fetch_to_device(w.d_tile_start, w.h_tile_start, (nb + 1) * sizeof(int), st));
     p->res.h2d_bytes += nb * sizeof(BurstParam) + (nb + 1) * sizeof(int);
     CK(cudaEventRecord(w.e0, st));
     CK(launch_fir(fmt, p->dec, iq_dev, (int64_t)n, R, w.d_bp, w.d_tile_start, (int)nb, n_tiles, w.d_dec, st));
@@ -491,7 +507,7 @@ static int launch_wave(ir_pipeline *p, size_t b0, size_t b1, const void *iq_dev,
     CK(cudaEventRecord(w.e2, sd));
     CK(launch_demod(w.d_co, (int)nb, w.d_frames, p->cfg.use_gardner, w.d_do, w.d_bits, w.d_llr, sd));
     CK(cudaEventRecord(w.e3, sd));
-    p->res.kernel_launches += (n_tiles > 0 ? 1 : 0) + 2;
+    p->res.kernel_launches += (n_tiles > 0 ? 1 : 0) + 2 + 2;   // FIR, chain, demod + 2 parameter fetches
     CK(cudaMemcpyAsync(w.h_co, w.d_co, nb * sizeof(ChainOut), cudaMemcpyDeviceToHost, sd));
     CK(cudaMemcpyAsync(w.h_do, w.d_do, nb * sizeof(DemodOut), cudaMemcpyDeviceToHost, sd));
     CK(cudaMemcpyAsync(w.h_bits, w.d_bits, nb * nsym2, cudaMemcpyDeviceToHost, sd));
@@ -664,7 +680,7 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
         iq_dev = p->d_iq.p;
     }
     // chunking: copies (host input only) overlap the detector kernels of earlier chunks
-    size_t chunk = p->cfg.h2d_chunk > 0 ? (size_t)p->cfg.h2d_chunk : ((size_t)16 << 20);
+    size_t chunk = p->cfg.h2d_chunk > 0 ? (size_t)p->cfg.h2d_chunk : ((size_t)32 << 20);
     if (const char *env = getenv("IR_CHUNK_MI")) { const long v = atol(env); if (v > 0 && v <= 1024) chunk = (size_t)v << 20; }
     chunk = std::max<size_t>(chunk / N, 1) * N;
     // chunk boundaries: full chunks, then the last stretch in halves (ir_plan_chunks)
@@ -870,7 +886,7 @@ extern "C" int ir_pipeline_results(ir_pipeline_t *p, ir_results_t *out) {
 }
 
 // End offsets of the pieces a block of n samples is processed in: full chunks, then the last stretch
-// in halves (8, 4, 2, 1, 1 Mi samples for the default 16 Mi): what runs after the last copy / the last
+// in halves (16, 8, 4, 2, 1, 1 Mi samples for the default 32 Mi): what runs after the last copy / the last
 // state-machine launch -- one wave of FIR + chain + demod, the result copies, the RAW text -- shrinks
 // with the last piece.  Every piece but the last is a whole number of detector frames.
 extern "C" long ir_plan_chunks(size_t n, size_t chunk, size_t fft_size, size_t *ends, size_t cap) {

@@ -54,7 +54,7 @@ def _plan(L, n, chunk, N):
     return [int(ends[i]) for i in range(k)]
 
 
-def test_chunk_plan_default_halves_the_last_chunk():
+def test_chunk_plan_halves_the_last_chunk():
     _, L = _lib()
     N, Mi = 8192, 1 << 20
     e = _plan(L, 600_000_000, 16 * Mi, N)
