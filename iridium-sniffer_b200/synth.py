@@ -219,3 +219,23 @@ def make_dense_recording(seed: int = 1234, sample_rate: int = 10_000_000) -> Rec
             sig[s0:s0 + m] += (amp * hi_wave[:m] * np.exp(1j * (2 * math.pi * f / fs * k + ph))).astype(np.complex64)
             truth.append(PlantedBurst(s0, f, amp, snr, bits, 179))
     return Recording(sig, "cf32", fs, 1_622_000_000.0, truth)
+
+
+def make_tone_recording(seed: int, n_tones: int, dur_s: float, t0_s: float, total_s: float = 0.62,
+                        snr_db: float = 20.0, sample_rate: int = 10_000_000, sigma: float = 0.01) -> np.ndarray:
+    """Noise + n_tones unmodulated carriers switched on together for dur_s seconds from t0_s: the
+    detector edge cases (more carriers than max_bursts -> squelch, burst_detect.c:593-631; one long
+    carrier -> a burst exceeding max_burst_len and the forced baseline update of :498-517)."""
+    rng = np.random.default_rng(seed)
+    fs = sample_rate
+    n = int(total_s * fs)
+    x = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * sigma).astype(np.complex64)
+    k = np.arange(int(dur_s * fs))
+    s0 = int(t0_s * fs)
+    amp = sigma * 10 ** (snr_db / 20)
+    for i in range(n_tones):
+        f = -4.7e6 + i * (9.4e6 / max(n_tones - 1, 1)) if n_tones > 1 else 1.0e6
+        if abs(f) < 60e3:
+            f += 120e3
+        x[s0:s0 + len(k)] += (amp * np.exp(2j * np.pi * (f / fs) * k + 1j * rng.uniform(0, 6.28))).astype(np.complex64)
+    return x

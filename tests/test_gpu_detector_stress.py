@@ -78,19 +78,8 @@ def test_dense_672_bursts(pl, port, dense, mode):
 
 
 def _tones(seed, n_tones, dur_s, t0_s, total_s=0.62, snr_db=20.0):
-    rng = np.random.default_rng(seed)
-    fs = 10_000_000
-    n = int(total_s * fs)
-    x = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 0.01).astype(np.complex64)
-    k = np.arange(int(dur_s * fs))
-    s0 = int(t0_s * fs)
-    amp = 0.01 * 10 ** (snr_db / 20)
-    for i in range(n_tones):
-        f = -4.7e6 + i * (9.4e6 / max(n_tones - 1, 1)) if n_tones > 1 else 1.0e6
-        if abs(f) < 60e3:
-            f += 120e3
-        x[s0:s0 + len(k)] += (amp * np.exp(2j * np.pi * (f / fs) * k + 1j * rng.uniform(0, 6.28))).astype(np.complex64)
-    return x
+    synth = importlib.import_module("iridium-sniffer_b200.synth")
+    return synth.make_tone_recording(seed, n_tones, dur_s, t0_s, total_s=total_s, snr_db=snr_db)
 
 
 @pytest.mark.parametrize("mode", MODES)
