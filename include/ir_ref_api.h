@@ -16,9 +16,13 @@
  *     NULL; its callers do not check -- with this library they crash early instead of silently
  *     computing on the CPU).
  *   - burst_config_t.use_gpu is ignored (always GPU).
- *   - the three *_thread functions are not exported: they only shuttle items between the
- *     reference's queues (blocking_queue.h) and these calls; INTEGRATION.md has the 3x10-line
- *     glue a maintainer keeps in main.c's tree.
+ *   - burst_detector_thread / burst_downmix_thread (burst_detect.h:97, burst_downmix.h:76) are
+ *     exported too.  They shuttle items between main.c's queues (samples_queue, burst_queue,
+ *     frame_queue; blocking_queue.h) and these calls, so the library refers to those queues, to
+ *     blocking_queue_take/put/add and to stat_n_detected / stat_n_dropped as WEAK symbols: linked
+ *     into the reference's program they bind to main.c's definitions, stand-alone they are null and
+ *     the thread functions return at once.  (qpsk_demod_thread is declared by the reference but
+ *     never defined, qpsk_demod.h:45.)
  *   - qpsk_demod reads `use_gardner` (main.c:143) exactly like the reference; the library
  *     carries a weak definition (=1) so it also loads stand-alone.
  * C99 only (float complex); C++ callers use include/iridium_b200.h instead.
@@ -79,6 +83,7 @@ uint64_t burst_detector_total_count(burst_detector_t *det);                     
 float burst_detector_noise_floor(burst_detector_t *det);                         /* :88 */
 float burst_detector_peak_signal(burst_detector_t *det);                         /* :91 */
 void burst_detector_destroy(burst_detector_t *det);                              /* :94 */
+void *burst_detector_thread(void *arg);      /* :97; arg = burst_detector_t*, destroyed on exit */
 
 typedef enum { DIR_UNDEF = 0, DIR_DOWNLINK = 1, DIR_UPLINK = 2 } ir_direction_t; /* burst_downmix.h:32-36 */
 
@@ -108,6 +113,7 @@ burst_downmix_t *burst_downmix_create(downmix_config_t *config);                
 int burst_downmix_process(burst_downmix_t *dm, burst_data_t *burst,
                           downmix_frame_t **frames_out);                         /* :69 */
 void burst_downmix_destroy(burst_downmix_t *dm);                                 /* :73 */
+void *burst_downmix_thread(void *arg);       /* :76; arg = burst_downmix_t*, destroyed on exit */
 
 typedef struct {                 /* qpsk_demod.h:24-38 */
     uint64_t id;

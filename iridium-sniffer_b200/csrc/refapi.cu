@@ -18,6 +18,9 @@
 using namespace ir;
 
 // ---- layouts of include/ir_ref_api.h (float complex == two floats)
+// the host program's statistics counter (main.c:181, atomic_ulong); weak: null when loaded stand-alone
+extern "C" { extern unsigned long stat_n_detected __attribute__((weak)); }
+
 extern "C" {
 typedef struct { uint64_t id, start, stop, last_active; int center_bin; float magnitude, noise; } burst_info_t;
 typedef struct {
@@ -312,6 +315,7 @@ static void detector_feed(_burst_detector *d, const void *host, size_t n, bool i
         bd->sample_rate = dc.sample_rate; bd->fft_size = dc.N;
         bd->start_time_ns = d->start_time_ns;
         bd->num_samples = ns; bd->samples = smp;
+        if (&stat_n_detected) __atomic_fetch_add(&stat_n_detected, 1ul, __ATOMIC_SEQ_CST);   // burst_detect.c:739
         cb(bd, user);
         d->n_tagged++;
     }
@@ -537,4 +541,88 @@ extern "C" int qpsk_demod(downmix_frame_t *in, demod_frame_t **out) {
     }
     *out = f;
     return 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// Thread functions (burst_detect.c:927-960, burst_downmix.c:801-828).  They only move items between
+// the host program's queues (main.c:176-178, blocking_queue.h) and the calls above, so the library
+// refers to those queues, the queue functions and the two statistics counters as WEAK symbols: linked
+// into the reference's program they bind to main.c's definitions; loaded stand-alone (tests, bench.py)
+// they stay null and the thread functions return at once with a message.
+extern "C" {
+struct Blocking_Queue;                                                  // opaque here: the host program's type
+extern struct Blocking_Queue samples_queue __attribute__((weak));       // main.c:176
+extern struct Blocking_Queue burst_queue __attribute__((weak));         // main.c:177
+extern struct Blocking_Queue frame_queue __attribute__((weak));         // main.c:178
+int blocking_queue_take(struct Blocking_Queue *bq, void *element) __attribute__((weak));   // blocking_queue.h:215
+int blocking_queue_put(struct Blocking_Queue *bq, void *element) __attribute__((weak));    // :194
+int blocking_queue_add(struct Blocking_Queue *bq, void *element) __attribute__((weak));    // :184
+extern unsigned long stat_n_dropped __attribute__((weak));              // atomic_ulong, main.c:185
+}
+#define IR_BQ_FULL 2                                                    // blocking_queue.h:124
+
+struct ir_sample_buf {                                                  // sample_buf_t, sdr.h:13-17
+    unsigned num;
+    int format;                                                         // 0 = int8 pairs, 1 = float pairs
+    int8_t samples[1];
+};
+
+static bool host_queues_present() {
+    return &samples_queue && &burst_queue && &frame_queue && blocking_queue_take && blocking_queue_put &&
+           blocking_queue_add;
+}
+
+static void burst_to_queue(burst_data_t *burst, void *user) {          // burst_detect.c:929-937
+    if (blocking_queue_put((struct Blocking_Queue *)user, burst) != 0) {
+        free(burst->samples);
+        free(burst);
+        if (&stat_n_dropped) __atomic_fetch_add(&stat_n_dropped, 1ul, __ATOMIC_SEQ_CST);
+    }
+}
+
+extern "C" void *burst_detector_thread(void *arg) {                     // burst_detect.c:941-960
+    _burst_detector *det = (_burst_detector *)arg;
+    if (!host_queues_present()) {
+        fprintf(stderr, "burst_detector_thread: the host program's queues (samples_queue, burst_queue, blocking_queue_*) are not linked in\n");
+        return nullptr;
+    }
+    for (;;) {
+        ir_sample_buf *samples = nullptr;
+        if (blocking_queue_take(&samples_queue, &samples) != 0) break;
+        if (det) {
+            if (samples->format == 1)
+                burst_detector_feed_cf32(det, (const float *)samples->samples, samples->num, burst_to_queue, &burst_queue);
+            else
+                burst_detector_feed(det, samples->samples, samples->num, burst_to_queue, &burst_queue);
+        }
+        free(samples);
+    }
+    burst_detector_destroy(det);
+    return nullptr;
+}
+
+extern "C" void *burst_downmix_thread(void *arg) {                      // burst_downmix.c:801-828
+    _burst_downmix *dm = (_burst_downmix *)arg;
+    if (!host_queues_present()) {
+        fprintf(stderr, "burst_downmix_thread: the host program's queues (burst_queue, frame_queue, blocking_queue_*) are not linked in\n");
+        return nullptr;
+    }
+    for (;;) {
+        burst_data_t *burst = nullptr;
+        if (blocking_queue_take(&burst_queue, &burst) != 0) break;
+        downmix_frame_t *frames = nullptr;
+        const int n_frames = dm ? burst_downmix_process(dm, burst, &frames) : 0;
+        if (n_frames > 0 && frames) {
+            if (blocking_queue_add(&frame_queue, frames) == IR_BQ_FULL) {   // live capture: drop, never block
+                free(frames->samples);
+                free(frames);
+            }
+        } else {
+            free(frames);
+        }
+        free(burst->samples);
+        free(burst);
+    }
+    burst_downmix_destroy(dm);
+    return nullptr;
 }
