@@ -47,3 +47,39 @@ int ref_frame_decode(const uint8_t *bits, const float *llr, int n_bits, orc_fram
     }
     return o->ret;
 }
+
+/* ---- ida_decode() (ida_decode.c compiled unmodified), flattened the same way ---- */
+#include "ida_decode.h"
+
+typedef struct {
+    int32_t ret;
+    int32_t ft, lcw_ok, lcw_ft, lcw_code, ec_lcw;
+    uint32_t lcw3_val;
+    int32_t da_ctr, da_len, cont, payload_len, crc_ok, fixederrs, bch_len;
+    uint16_t stored_crc, computed_crc;
+    uint8_t payload[32];
+    uint8_t bch_stream[256];
+} orc_ida_t;
+
+int ref_ida_decode(const uint8_t *bits, const float *llr, int n_bits, int direction, orc_ida_t *o) {
+    static int ready;
+    if (!ready) { frame_decode_init(); ida_decode_init(); ready = 1; }
+    demod_frame_t f;
+    static ida_burst_t b;
+    memset(&f, 0, sizeof(f));
+    memset(o, 0, sizeof(*o));
+    f.bits = (uint8_t *)bits;
+    f.llr = (float *)llr;
+    f.n_bits = n_bits;
+    f.direction = (ir_direction_t)direction;
+    o->ret = ida_decode(&f, &b);
+    if (!o->ret) return 0;
+    o->ft = b.lcw.ft; o->lcw_ok = b.lcw.lcw_ok; o->lcw_ft = b.lcw.lcw_ft; o->lcw_code = b.lcw.lcw_code;
+    o->ec_lcw = b.lcw.ec_lcw; o->lcw3_val = b.lcw.lcw3_val;
+    o->da_ctr = b.da_ctr; o->da_len = b.da_len; o->cont = b.cont; o->payload_len = b.payload_len;
+    o->crc_ok = b.crc_ok; o->fixederrs = b.fixederrs; o->bch_len = b.bch_len;
+    o->stored_crc = b.stored_crc; o->computed_crc = b.computed_crc;
+    memcpy(o->payload, b.payload, sizeof(o->payload));
+    memcpy(o->bch_stream, b.bch_stream, sizeof(o->bch_stream));
+    return 1;
+}

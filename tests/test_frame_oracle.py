@@ -167,3 +167,137 @@ def test_truncated_and_garbage(libs):
             bits[:24] = ACCESS_DL
         hits += _both(libs, bits, rng.uniform(0, 1, n)).ret
     assert hits < 30                                             # random payloads (almost) never pass three parity-checked blocks
+
+
+# ================================================================= IDA bursts (ida_decode.c:543-662)
+class FlatIda(C.Structure):
+    _fields_ = [("ret", C.c_int32), ("ft", C.c_int32), ("lcw_ok", C.c_int32), ("lcw_ft", C.c_int32),
+                ("lcw_code", C.c_int32), ("ec_lcw", C.c_int32), ("lcw3_val", C.c_uint32), ("da_ctr", C.c_int32),
+                ("da_len", C.c_int32), ("cont", C.c_int32), ("payload_len", C.c_int32), ("crc_ok", C.c_int32),
+                ("fixederrs", C.c_int32), ("bch_len", C.c_int32), ("stored_crc", C.c_uint16),
+                ("computed_crc", C.c_uint16), ("payload", C.c_uint8 * 32), ("bch_stream", C.c_uint8 * 256)]
+
+
+LCW_FROM = [40, 39, 36, 35, 32, 31, 28, 27, 24, 23, 20, 19, 16, 15, 12, 11, 8, 7, 4, 3,
+            41, 38, 37, 34, 33, 30, 29, 26, 25, 22, 21, 18, 17, 14, 13, 10, 9, 6, 5, 2,
+            1, 46, 45, 44, 43, 42]                               # ida_decode.c:54-60
+
+
+@pytest.fixture(scope="module")
+def ida_libs(libs):
+    port, ref = C.CDLL(PORT_SO), C.CDLL(REF_SO)
+    for f in (port.orc_ida_decode, ref.ref_ida_decode):
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(FlatIda)]
+    return port.orc_ida_decode, ref.ref_ida_decode
+
+
+def _both_ida(ida_libs, bits, llr, direction=1):
+    bits = np.ascontiguousarray(bits, np.uint8)
+    out = []
+    for fn in ida_libs:
+        o = FlatIda()
+        lp = None if llr is None else np.ascontiguousarray(llr, np.float32).ctypes.data_as(C.c_void_p)
+        fn(bits.ctypes.data_as(C.c_void_p), lp, len(bits), direction, C.byref(o))
+        out.append(o)
+    a, b = out
+    assert bytes(a) == bytes(b), ([(k, getattr(a, k), getattr(b, k)) for k, _ in FlatIda._fields_[:16] if getattr(a, k) != getattr(b, k)])
+    return a
+
+
+def _crc(data):
+    crc = 0xFFFF
+    for byte in data:
+        crc ^= byte << 8
+        for _ in range(8):
+            crc = ((crc << 1) ^ 0x1021) & 0xFFFF if crc & 0x8000 else (crc << 1) & 0xFFFF
+    return crc
+
+
+def _cw20(d20):
+    d = int("".join(map(str, d20)), 2)
+    return [int(c) for c in format((d << 11) | _rem(3545, d << 11), "031b")]
+
+
+def _interleave_n(h1, h2, ns):
+    out = [0] * (2 * ns)
+    for k, s in enumerate(range(ns - 1, 0, -2)):
+        out[2 * s], out[2 * s + 1] = h1[2 * k], h1[2 * k + 1]
+    for k, s in enumerate(range(ns - 2, -1, -2)):
+        out[2 * s], out[2 * s + 1] = h2[2 * k], h2[2 * k + 1]
+    return out
+
+
+def make_ida(rng, da_len, ft=2, extra_words=0, good_crc=True):
+    # link control word: three short BCH code words, permuted and dibit-swapped on the air
+    l2d, l3d = int(rng.integers(0, 64)), int(rng.integers(0, 1 << 21))
+    v1 = (ft << 4) | _rem(29, ft << 4)
+    v2 = (l2d << 8) | _rem(465, l2d << 8)                      # 14 bits; only the top 13 are sent (the last is taken as 0)
+    v3 = (l3d << 5) | _rem(41, l3d << 5)
+    lcw_bits = _bits(v1, 7) + _bits(v2 >> 1, 13) + _bits(v3, 26)
+    lcw = [0] * 46
+    for i, src in enumerate(LCW_FROM):
+        lcw[(src - 1) ^ 1] = lcw_bits[i]
+    # payload stream: 20 header bits, 160 payload bits, CRC, padding to whole 20-bit words
+    hdr = [int(b) for b in rng.integers(0, 2, 20)]
+    hdr[3] = int(rng.integers(0, 2))
+    hdr[5:8] = _bits(int(rng.integers(0, 8)), 3)
+    hdr[11:16] = _bits(da_len, 5)
+    hdr[17:20] = [0, 0, 0]
+    pay = [int(b) for b in rng.integers(0, 2, 160)]
+    head = hdr + [0] * 12 + pay
+    crc = _crc(bytes(int("".join(map(str, head[i:i + 8])), 2) for i in range(0, 192, 8)))
+    if not good_crc:
+        crc ^= 0x0400
+    stream = hdr + pay + _bits(crc, 16) + [int(b) for b in rng.integers(0, 2, 4 + 20 * extra_words)]
+    words = [_cw20(stream[i:i + 20]) for i in range(0, len(stream), 20)]
+    assert len(words) == 10 + extra_words
+    body = []
+    while len(words) >= 4:                                     # full blocks: the words are read 4th, 2nd, 3rd, 1st
+        a, b, c, d = words[:4]
+        words = words[4:]
+        comb = d + b + c + a
+        body += _interleave_n(comb[:62], comb[62:], 62)
+    if words:                                                  # partial block of two words: halves swapped, first bits dropped
+        assert len(words) == 2
+        h2 = [int(rng.integers(0, 2))] + words[0]
+        h1 = [int(rng.integers(0, 2))] + words[1]
+        body += _interleave_n(h1, h2, 32)
+    return list(ACCESS_DL) + lcw + body
+
+
+def test_ida_clean_and_crc(ida_libs):
+    rng = np.random.default_rng(11)
+    for da_len in (0, 1, 7, 20):
+        for extra in (0, 4):
+            o = _both_ida(ida_libs, make_ida(rng, da_len, extra_words=extra), None, direction=1 + da_len % 2)
+            assert o.ret == 1 and o.ft == 2 and o.da_len == da_len and o.bch_len == 200 + 20 * extra
+            if da_len > 0 and extra == 0:
+                assert o.crc_ok == 1 and o.computed_crc == 0
+    o = _both_ida(ida_libs, make_ida(rng, 12, good_crc=False), None)
+    assert o.ret == 1 and o.crc_ok == 0
+    assert _both_ida(ida_libs, make_ida(rng, 5, ft=3), None).ret == 0        # not an IDA frame type
+    assert _both_ida(ida_libs, make_ida(rng, 5), None, direction=0).ret == 0  # direction undefined
+    assert _both_ida(ida_libs, make_ida(rng, 21), None).ret == 0             # da_len > 20
+
+
+def test_ida_bit_errors_and_truncation(ida_libs):
+    rng = np.random.default_rng(12)
+    ok = 0
+    for trial in range(500):
+        bits = np.array(make_ida(rng, int(rng.integers(0, 21)), extra_words=4 * int(rng.integers(0, 2))), np.uint8)
+        llr = rng.uniform(0.2, 1.0, len(bits)).astype(np.float32)
+        n_err = int(rng.integers(0, 16))
+        pos = rng.choice(np.arange(24, len(bits)), n_err, replace=False)
+        bits[pos] ^= 1
+        llr[pos] = rng.uniform(0.0, 0.25, n_err)
+        if trial % 4 == 0:
+            llr = np.round(llr * 8) / 8
+        n = len(bits)
+        if trial % 6 == 0:
+            n = 24 + 46 + 4 * int(rng.integers(0, (len(bits) - 70) // 4 + 1))   # cut on a 4-bit boundary (even symbol counts)
+        ok += _both_ida(ida_libs, bits[:n], (llr[:n] if trial % 5 else None)).ret
+    assert ok > 200
+    for _ in range(200):                                                     # random bits: both must refuse alike
+        n = 24 + 46 + 4 * int(rng.integers(31, 120))
+        _both_ida(ida_libs, rng.integers(0, 2, n).astype(np.uint8), rng.uniform(0, 1, n))
