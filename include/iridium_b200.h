@@ -169,6 +169,49 @@ int ir_format_raw(char *dst, size_t cap, const char *file_info, uint64_t t0,
 long ir_pipeline_format_raw_all(ir_pipeline_t *p, const char *file_info, uint64_t t0, char *dst,
                                 size_t cap);
 
+/* ---- next row of the path: what frame_consumer_thread does with each frame ---- */
+
+/* frame_type_t (frame_decode.h:20-24). */
+enum { IR_FRAME_UNKNOWN = 0, IR_FRAME_IRA = 1, IR_FRAME_IBC = 2 };
+
+/* Outcome of frame_decode() (frame_decode.c:414-598) AND ida_decode() (ida_decode.c:543-662) on one
+ * demodulated frame -- main.c:320-350 calls both on every frame.  The first half mirrors
+ * decoded_frame_t's ira_data_t / ibc_data_t (frame_decode.h:26-58; timestamp and frequency are the
+ * ir_frame_t's), the second ida_burst_t + lcw_t (ida_decode.h:19-56) without the fields copied from the
+ * frame and without lcw_header (text, ida_decode.c:398-541: stays with the host). */
+typedef struct ir_frame_class {
+    int32_t frame_type;         /* IR_FRAME_*; != 0 <=> frame_decode() returned 1 */
+    int32_t sat_id, beam_id;    /* IRA and IBC */
+    double lat, lon;            /* IRA */
+    int32_t alt;
+    int32_t pos_xyz[3];
+    int32_t n_pages;
+    uint32_t tmsi[12];
+    int32_t msc_id[12];
+    int32_t timeslot, sv_blocking, bc_type;   /* IBC */
+    uint32_t iri_time;
+    int32_t ida_ok;             /* != 0 <=> ida_decode() returned 1 */
+    int32_t lcw_ft, lcw_code, ec_lcw;
+    uint32_t lcw3_val;
+    int32_t da_ctr, da_len, cont, payload_len, crc_ok, fixederrs, bch_len;
+    uint16_t stored_crc, computed_crc;
+    uint8_t payload[32];
+    uint8_t bch_stream[256];
+} ir_frame_class_t;
+
+/* Classify n_frames demodulated frames on the GPU (one launch): frames[i].n_bits / .direction /
+ * .bits_offset select the frame's bits and LLRs in the two arrays (host memory, n_bits_total
+ * elements each; llr may be NULL = hard decisions only, like a demod_frame_t without llr).
+ * Replaces the per-frame frame_decode() + ida_decode() calls of main.c:320-350.  Returns 0, or -1
+ * (ir_last_error()); there is no CPU path. */
+int ir_classify_frames(int device, const ir_frame_t *frames, size_t n_frames, const uint8_t *bits,
+                       const float *llr, size_t n_bits_total, ir_frame_class_t *out);
+
+/* The same over the frames of the pipeline's last run, reading bits and LLRs where the demod kernel
+ * left them in device memory (no copy of the bit arrays back up).  out[i] belongs to
+ * ir_results_t.frames[i].  Returns the number of frames classified, or -1. */
+long ir_pipeline_classify(ir_pipeline_t *p, ir_frame_class_t *out, size_t cap);
+
 /* How ir_pipeline_run_* cuts a block of n samples into pieces (end offsets into `ends`, returns their
  * number or -1): full chunks of `chunk` samples (rounded down to whole detector frames), then the last
  * chunk in halves down to 1 Mi samples, so that little work is left after the last copy.  Pure host

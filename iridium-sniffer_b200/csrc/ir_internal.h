@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 
+
 #define IR_MAX_ACTIVE 1024      // device-side cap on simultaneously tracked bursts
 #define IR_SCAN_THREADS 1024
 #define IR_STREAM_CL 8          // CTAs of the streaming state machine's cluster
@@ -28,6 +29,8 @@
 #define IR_CORR_N 2048
 #define IR_SYNC_SEARCH 840
 #define IR_SYNC_LEN 271
+
+struct ir_frame_class;     // include/iridium_b200.h
 
 namespace ir {
 
@@ -196,5 +199,16 @@ cudaError_t launch_chain(const BurstParam *bp, int n_bursts, const float2 *dec, 
 // k_demod.cu
 cudaError_t launch_demod(const ChainOut *co, int n_bursts, const float2 *frames, int use_gardner,
                          DemodOut *out, uint8_t *bits, float *llr, cudaStream_t st);
+// k_classify.cu: frame classification (frame_decode() + ida_decode() per frame), one warp per frame
+struct FrameSrc {
+    const uint8_t *bits;     // one byte per bit, device memory
+    const float *llr;        // may be null
+    int32_t n_bits;
+    int32_t direction;
+};
+// syndrome tables of the five BCH codes, built once per process and uploaded once per device
+cudaError_t classify_tables(int device, const void **d_tables);
+cudaError_t launch_classify(const void *d_tables, const FrameSrc *src, int n_frames,
+                            ::ir_frame_class *out, cudaStream_t st);
 
 }  // namespace ir

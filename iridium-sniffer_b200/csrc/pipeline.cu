@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "../../include/iridium_b200.h"
+#include "frame_classify.cuh"
 #include "ir_device.cuh"
 #include "ir_internal.h"
 
@@ -187,6 +188,9 @@ struct ir_pipeline {
     std::vector<ir_frame_t> frames;
     std::vector<uint8_t> bits;
     std::vector<float> llr;
+    std::vector<FrameSrc> frame_src;                              // per frame: where k_demod left its bits / LLRs (device)
+    DevBuf<FrameSrc> d_frame_src;
+    DevBuf<ir_frame_class_t> d_class;
     // RAW: lines formatted while the run is still in flight (everything after the file_info field,
     // with t0 = frame_output.c:144-158's rule), so that the batched sink is a copy
     std::string raw_rest;
@@ -293,6 +297,7 @@ extern "C" void ir_pipeline_destroy(ir_pipeline_t *p) {
     p->d_base.release(); p->d_hist.release(); p->d_state.release();
     p->d_xu[0].release(); p->d_xu[1].release(); p->d_ref[0].release(); p->d_ref[1].release();
     p->d_undo.release(); p->d_base_snap.release();
+    p->d_frame_src.release(); p->d_class.release();
     if (p->st_cls) cudaStreamDestroy(p->st_cls);
     p->d_ctl.release();
     p->dev_arena.release(); p->pin_arena.release();
@@ -575,6 +580,7 @@ static int assemble_wave(ir_pipeline *p, const Wave &w) {
         p->bits.insert(p->bits.end(), br, br + f.n_bits);
         p->llr.insert(p->llr.end(), lr, lr + f.n_bits);
         p->frames.push_back(f);
+        p->frame_src.push_back(FrameSrc{w.d_bits + (i - w.b0) * nsym2, w.d_llr + (i - w.b0) * nsym2, f.n_bits, f.direction});
         p->alg += 8ull * (uint64_t)c.frame_len + (uint64_t)f.n_bits;
         {   // its RAW: line, while the GPU is busy with later waves
             if (p->frames.size() == 1) p->raw_t0 = (f.timestamp / 1000000000ULL) * 1000000000ULL;
@@ -701,7 +707,7 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     if (p->dev_arena.begin((size_t)64 << 20) || p->pin_arena.begin((size_t)8 << 20)) return -1;
     p->waves.clear(); p->chunks.clear();
     p->bursts.clear(); p->h_bp.clear(); p->frame_ptr.clear(); p->dec_ptr.clear();
-    p->frames.clear(); p->bits.clear(); p->llr.clear();
+    p->frames.clear(); p->bits.clear(); p->llr.clear(); p->frame_src.clear();
     p->raw_rest.clear(); p->raw_off.clear(); p->raw_t0 = 0;
     p->scan_dbg = getenv("IR_SCAN_DEBUG") != nullptr;
     p->scan_dbg_ev.clear();
@@ -1007,6 +1013,67 @@ extern "C" long ir_pipeline_format_raw_all(ir_pipeline_t *p, const char *file_in
         pos += (size_t)n;
     }
     return (long)pos;
+}
+
+// ---- frame classification: frame_decode() + ida_decode() of main.c:320-350, batched
+static int classify_finish(ir_frame_class_t *out, size_t n) {
+    for (size_t i = 0; i < n; i++) fc_geo(&out[i]);     // three doubles per IRA frame, with the C library like the reference
+    return 0;
+}
+
+extern "C" long ir_pipeline_classify(ir_pipeline_t *p, ir_frame_class_t *out, size_t cap) {
+    if (!p || (!out && cap)) { set_err("ir_pipeline_classify: null argument"); return -1; }
+    const size_t n = p->frames.size();
+    if (n > cap) { set_err("ir_pipeline_classify: output array too small"); return -1; }
+    if (n == 0) return 0;
+    CK(cudaSetDevice(p->dev));
+    const void *d_tab = nullptr;
+    CK(classify_tables(p->dev, &d_tab));
+    if (p->d_frame_src.ensure(n) || p->d_class.ensure(n)) return -1;
+    CK(cudaMemcpyAsync(p->d_frame_src.p, p->frame_src.data(), n * sizeof(FrameSrc), cudaMemcpyHostToDevice, p->st_burst));
+    CK(launch_classify(d_tab, p->d_frame_src.p, (int)n, p->d_class.p, p->st_burst));
+    CK(cudaMemcpyAsync(out, p->d_class.p, n * sizeof(ir_frame_class_t), cudaMemcpyDeviceToHost, p->st_burst));
+    CK(cudaStreamSynchronize(p->st_burst));
+    p->res.kernel_launches++;
+    classify_finish(out, n);
+    return (long)n;
+}
+
+extern "C" int ir_classify_frames(int device, const ir_frame_t *frames, size_t n_frames, const uint8_t *bits,
+                                  const float *llr, size_t n_bits_total, ir_frame_class_t *out) {
+    if (n_frames == 0) return 0;
+    if (!frames || !bits || !out) { set_err("ir_classify_frames: null argument"); return -1; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        set_err(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)");
+        return -1;
+    }
+    if (device < 0 || device >= ndev) { set_err("device ordinal out of range"); return -1; }
+    CK(cudaSetDevice(device));
+    const void *d_tab = nullptr;
+    CK(classify_tables(device, &d_tab));
+    DevBuf<uint8_t> d_bits;
+    DevBuf<float> d_llr;
+    DevBuf<FrameSrc> d_src;
+    DevBuf<ir_frame_class_t> d_out;
+    struct Guard { DevBuf<uint8_t> &a; DevBuf<float> &b; DevBuf<FrameSrc> &c; DevBuf<ir_frame_class_t> &d;
+                   ~Guard() { a.release(); b.release(); c.release(); d.release(); } } guard{d_bits, d_llr, d_src, d_out};
+    std::vector<FrameSrc> src(n_frames);
+    if (d_bits.ensure(n_bits_total + 1) || (llr && d_llr.ensure(n_bits_total + 1)) || d_src.ensure(n_frames) || d_out.ensure(n_frames))
+        return -1;
+    for (size_t i = 0; i < n_frames; i++) {
+        const ir_frame_t &f = frames[i];
+        if (f.n_bits < 0 || (size_t)f.bits_offset + (size_t)f.n_bits > n_bits_total) { set_err("ir_classify_frames: frame outside the bit array"); return -1; }
+        src[i] = FrameSrc{d_bits.p + f.bits_offset, llr ? d_llr.p + f.bits_offset : nullptr, f.n_bits, f.direction};
+    }
+    CK(cudaMemcpy(d_bits.p, bits, n_bits_total, cudaMemcpyHostToDevice));
+    if (llr) CK(cudaMemcpy(d_llr.p, llr, n_bits_total * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_src.p, src.data(), n_frames * sizeof(FrameSrc), cudaMemcpyHostToDevice));
+    CK(launch_classify(d_tab, d_src.p, (int)n_frames, d_out.p, 0));
+    CK(cudaMemcpy(out, d_out.p, n_frames * sizeof(ir_frame_class_t), cudaMemcpyDeviceToHost));
+    classify_finish(out, n_frames);
+    return 0;
 }
 
 extern "C" void *ir_host_alloc(size_t bytes) {

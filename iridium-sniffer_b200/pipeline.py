@@ -50,6 +50,18 @@ class Burst(C.Structure):
                 ("dm_direction", C.c_int32), ("dec_len", C.c_int32)]
 
 
+class FrameClass(C.Structure):
+    """ir_frame_class_t: frame_decode() + ida_decode() outcome of one frame"""
+    _fields_ = [("frame_type", C.c_int32), ("sat_id", C.c_int32), ("beam_id", C.c_int32), ("lat", C.c_double),
+                ("lon", C.c_double), ("alt", C.c_int32), ("pos_xyz", C.c_int32 * 3), ("n_pages", C.c_int32),
+                ("tmsi", C.c_uint32 * 12), ("msc_id", C.c_int32 * 12), ("timeslot", C.c_int32),
+                ("sv_blocking", C.c_int32), ("bc_type", C.c_int32), ("iri_time", C.c_uint32), ("ida_ok", C.c_int32),
+                ("lcw_ft", C.c_int32), ("lcw_code", C.c_int32), ("ec_lcw", C.c_int32), ("lcw3_val", C.c_uint32),
+                ("da_ctr", C.c_int32), ("da_len", C.c_int32), ("cont", C.c_int32), ("payload_len", C.c_int32),
+                ("crc_ok", C.c_int32), ("fixederrs", C.c_int32), ("bch_len", C.c_int32), ("stored_crc", C.c_uint16),
+                ("computed_crc", C.c_uint16), ("payload", C.c_uint8 * 32), ("bch_stream", C.c_uint8 * 256)]
+
+
 class Results(C.Structure):
     _fields_ = [("n_bursts", C.c_size_t), ("bursts", C.POINTER(Burst)),
                 ("n_frames", C.c_size_t), ("frames", C.POINTER(Frame)),
@@ -110,8 +122,39 @@ def load_library() -> C.CDLL:
     L.ir_plan_chunks.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t), C.c_size_t]
     L.ir_pipeline_scan_stats.restype = C.c_int
     L.ir_pipeline_scan_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
+    L.ir_classify_frames.restype = C.c_int
+    L.ir_classify_frames.argtypes = [C.c_int, C.POINTER(Frame), C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
+                                     C.POINTER(FrameClass)]
+    L.ir_pipeline_classify.restype = C.c_long
+    L.ir_pipeline_classify.argtypes = [C.c_void_p, C.POINTER(FrameClass), C.c_size_t]
     _lib = L
     return L
+
+
+def classify_frames(cases, device: int = 0):
+    """ir_classify_frames over [(bits uint8[n], llr float32[n] or None, direction)]: one launch for all of them.
+    Either every case carries LLRs or none does (the C call takes one llr array or NULL)."""
+    L = load_library()
+    n = len(cases)
+    with_llr = n > 0 and cases[0][1] is not None
+    if any((c[1] is not None) != with_llr for c in cases):
+        raise ValueError("mixed LLR / no-LLR cases: call once per kind")
+    frames = (Frame * max(n, 1))()
+    off = 0
+    for i, (bits, llr, direction) in enumerate(cases):
+        frames[i].n_bits, frames[i].direction, frames[i].bits_offset = len(bits), direction, off
+        off += len(bits)
+    allb = np.concatenate([np.asarray(c[0], np.uint8) for c in cases]) if n else np.zeros(0, np.uint8)
+    allb = np.ascontiguousarray(np.append(allb, np.uint8(0)))
+    alll = None
+    if with_llr:
+        alll = np.ascontiguousarray(np.append(np.concatenate([np.asarray(c[1], np.float32) for c in cases]), np.float32(0)))
+    out = (FrameClass * max(n, 1))()
+    rc = L.ir_classify_frames(device, frames, n, allb.ctypes.data_as(C.c_void_p),
+                              alll.ctypes.data_as(C.c_void_p) if with_llr else None, off, out)
+    if rc != 0:
+        raise RuntimeError("ir_classify_frames failed: " + L.ir_last_error().decode())
+    return [out[i] for i in range(n)]
 
 
 EXPORTED_SYMBOLS = [
@@ -119,7 +162,7 @@ EXPORTED_SYMBOLS = [
     "ir_pipeline_reset", "ir_pipeline_run_host", "ir_pipeline_run_device", "ir_pipeline_results",
     "ir_pipeline_copy_mag", "ir_pipeline_copy_frame_samples", "ir_pipeline_copy_decimated",
     "ir_pipeline_copy_burst_samples", "ir_format_raw", "ir_pipeline_format_raw_all", "ir_host_alloc",
-    "ir_host_free", "ir_pipeline_scan_stats", "ir_plan_chunks",
+    "ir_host_free", "ir_pipeline_scan_stats", "ir_plan_chunks", "ir_classify_frames", "ir_pipeline_classify",
 ]
 
 
@@ -280,6 +323,18 @@ class Pipeline:
 
     def raw_text_view(self) -> memoryview:
         return memoryview(self._txt)[:getattr(self, "_txt_len", 0)]
+
+    def classify(self) -> list:
+        """frame_decode() + ida_decode() outcome of every frame of the last run (one launch, bits / LLRs read
+        where the demod kernel left them)"""
+        r = Results()
+        self._check(self.L.ir_pipeline_results(self.h, C.byref(r)), "ir_pipeline_results")
+        n = int(r.n_frames)
+        out = (FrameClass * max(n, 1))()
+        got = self.L.ir_pipeline_classify(self.h, out, n)
+        if got < 0:
+            raise RuntimeError("ir_pipeline_classify failed: " + self.L.ir_last_error().decode())
+        return [out[i] for i in range(got)]
 
     def scan_stats(self) -> dict:
         """Counters of the detector state machine over the last run (ir_pipeline_scan_stats)."""

@@ -57,12 +57,24 @@ def expected_bits(symbols: Sequence[int]) -> str:
     return "".join(out)
 
 
+def symbols_for_bits(bits: Sequence[int], uplink: bool = False) -> List[int]:
+    """Payload symbols whose DQPSK bits (after the unique word) are `bits`: the inverse of expected_bits()."""
+    inv = {d: k for k, d in enumerate(_DQPSK)}
+    old = (UW_UL if uplink else UW_DL)[-1]
+    out = []
+    for i in range(0, len(bits) - 1, 2):
+        old = (old + inv[(int(bits[i]) << 1) | int(bits[i + 1])]) % 4
+        out.append(old)
+    return out
+
+
 def burst_waveform(rng: np.random.Generator, up: int, n_payload: int = 179,
-                   uplink: bool = False):
-    """One burst at the capture rate (250 kHz * up).  Returns (waveform, bit string)."""
+                   uplink: bool = False, payload_bits: Optional[Sequence[int]] = None):
+    """One burst at the capture rate (250 kHz * up).  Returns (waveform, bit string).  payload_bits: the bits
+    the demodulator should print after the 24 access-code bits (default: random symbols)."""
     from scipy.signal import resample_poly
 
-    pay = rng.integers(0, 4, n_payload)
+    pay = rng.integers(0, 4, n_payload) if payload_bits is None else symbols_for_bits(payload_bits, uplink)
     if uplink:
         pre = [2 if i % 2 == 0 else 0 for i in range(16)]
         uw = UW_UL
@@ -112,13 +124,15 @@ def make_recording(seed: int, sample_rate: int = 10_000_000, duration_s: float =
                    channels: Optional[Sequence[float]] = None,
                    starts_s: Optional[Sequence[float]] = None,
                    n_payload: int = 179, uplink_fraction: float = 0.0,
-                   waveform_pool: int = 0) -> Recording:
+                   waveform_pool: int = 0,
+                   frame_bits: Optional[Sequence[Sequence[int]]] = None) -> Recording:
     """Noise + planted bursts.  All randomness from numpy default_rng(seed).
 
     channels: candidate centre offsets in Hz (default: 41.667 kHz raster inside
     +-(fs/2-200 kHz), |f|>=60 kHz).  starts_s: explicit burst start times; default
     spreads bursts uniformly after the 512-frame quiet lead-in and keeps same-channel
-    reuse >= 27 ms apart (SURVEY.md 8d constraints).
+    reuse >= 27 ms apart (SURVEY.md 8d constraints).  frame_bits: whole frames as bit arrays (24 access-code
+    bits first, e.g. from tests/frame_gen.py); burst k carries frame_bits[k % len] instead of random symbols.
     """
     rng = np.random.default_rng(seed)
     fs = int(sample_rate)
@@ -143,6 +157,8 @@ def make_recording(seed: int, sample_rate: int = 10_000_000, duration_s: float =
         for _ in range(waveform_pool):
             pool.append(burst_waveform(rng, up, n_payload, False))
 
+    if frame_bits:
+        n_payload = max((len(fb) - 24) // 2 for fb in frame_bits)
     blen = (16 + 12 + n_payload) * 10 * up + 81 * up
     if starts_s is None:
         lo, hi = lead, duration_s - blen / fs - 0.03
@@ -161,7 +177,11 @@ def make_recording(seed: int, sample_rate: int = 10_000_000, duration_s: float =
             continue
         last_use[ch] = float(t0)
         ul = bool(rng.random() < uplink_fraction)
-        if pool and not ul:
+        if frame_bits:
+            fb = [int(b) for b in frame_bits[len(truth) % len(frame_bits)]]
+            ul = "".join(map(str, fb[:24])) == ACCESS_UL
+            hi_wave, bits = burst_waveform(rng, up, 0, ul, payload_bits=fb[24:])
+        elif pool and not ul:
             hi_wave, bits = pool[int(rng.integers(0, len(pool)))]
         else:
             hi_wave, bits = burst_waveform(rng, up, n_payload, ul)
@@ -176,7 +196,7 @@ def make_recording(seed: int, sample_rate: int = 10_000_000, duration_s: float =
         k = np.arange(m, dtype=np.float64)
         rot = np.exp(1j * (2 * math.pi * f / fs * k + ph))
         sig[s0:s0 + m] += (amp * hi_wave[:m] * rot).astype(np.complex64)
-        truth.append(PlantedBurst(s0, f, amp, snr, bits, n_payload, ul))
+        truth.append(PlantedBurst(s0, f, amp, snr, bits, (len(bits) - 24) // 2, ul))
 
     if fmt == "cf32":
         iq = sig

@@ -1,0 +1,73 @@
+"""ctypes mirror of ir_frame_class_t (include/iridium_b200.h) and of the flattened structs of the frame oracle /
+reference glue (oracle/ir_frame_oracle.c, oracle/ref_frame_glue.c), plus the field-for-field comparison the
+classification tests share."""
+import ctypes as C
+
+import numpy as np
+
+
+class FrameClass(C.Structure):
+    _fields_ = [("frame_type", C.c_int32), ("sat_id", C.c_int32), ("beam_id", C.c_int32), ("lat", C.c_double),
+                ("lon", C.c_double), ("alt", C.c_int32), ("pos_xyz", C.c_int32 * 3), ("n_pages", C.c_int32),
+                ("tmsi", C.c_uint32 * 12), ("msc_id", C.c_int32 * 12), ("timeslot", C.c_int32),
+                ("sv_blocking", C.c_int32), ("bc_type", C.c_int32), ("iri_time", C.c_uint32), ("ida_ok", C.c_int32),
+                ("lcw_ft", C.c_int32), ("lcw_code", C.c_int32), ("ec_lcw", C.c_int32), ("lcw3_val", C.c_uint32),
+                ("da_ctr", C.c_int32), ("da_len", C.c_int32), ("cont", C.c_int32), ("payload_len", C.c_int32),
+                ("crc_ok", C.c_int32), ("fixederrs", C.c_int32), ("bch_len", C.c_int32), ("stored_crc", C.c_uint16),
+                ("computed_crc", C.c_uint16), ("payload", C.c_uint8 * 32), ("bch_stream", C.c_uint8 * 256)]
+
+
+class Flat(C.Structure):
+    _fields_ = [("ret", C.c_int32), ("type", C.c_int32), ("sat_id", C.c_int32), ("beam_id", C.c_int32),
+                ("lat", C.c_double), ("lon", C.c_double), ("alt", C.c_int32), ("pos_xyz", C.c_int32 * 3),
+                ("n_pages", C.c_int32), ("tmsi", C.c_uint32 * 12), ("msc_id", C.c_int32 * 12),
+                ("timeslot", C.c_int32), ("sv_blocking", C.c_int32), ("bc_type", C.c_int32), ("iri_time", C.c_uint32)]
+
+
+class FlatIda(C.Structure):
+    _fields_ = [("ret", C.c_int32), ("ft", C.c_int32), ("lcw_ok", C.c_int32), ("lcw_ft", C.c_int32),
+                ("lcw_code", C.c_int32), ("ec_lcw", C.c_int32), ("lcw3_val", C.c_uint32), ("da_ctr", C.c_int32),
+                ("da_len", C.c_int32), ("cont", C.c_int32), ("payload_len", C.c_int32), ("crc_ok", C.c_int32),
+                ("fixederrs", C.c_int32), ("bch_len", C.c_int32), ("stored_crc", C.c_uint16),
+                ("computed_crc", C.c_uint16), ("payload", C.c_uint8 * 32), ("bch_stream", C.c_uint8 * 256)]
+
+
+def bind_checker(lib, prefix):
+    """(bits, llr, direction) -> (Flat, FlatIda) from orc_* (oracle port) or ref_* (the reference itself)"""
+    fdec, idec = getattr(lib, prefix + "frame_decode"), getattr(lib, prefix + "ida_decode")
+    fdec.restype = idec.restype = C.c_int
+    fdec.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Flat)]
+    idec.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(FlatIda)]
+
+    def run(bits, llr, direction):
+        bits = np.ascontiguousarray(bits, np.uint8)
+        lp = None if llr is None else np.ascontiguousarray(llr, np.float32).ctypes.data_as(C.c_void_p)
+        a, b = Flat(), FlatIda()
+        fdec(bits.ctypes.data_as(C.c_void_p), lp, len(bits), C.byref(a))
+        idec(bits.ctypes.data_as(C.c_void_p), lp, len(bits), direction, C.byref(b))
+        return a, b
+    return run
+
+
+_FRAME_FIELDS = ["sat_id", "beam_id", "lat", "lon", "alt", "n_pages", "timeslot", "sv_blocking", "bc_type", "iri_time"]
+_IDA_FIELDS = ["lcw_ft", "lcw_code", "ec_lcw", "lcw3_val", "da_ctr", "da_len", "cont", "payload_len", "crc_ok",
+               "fixederrs", "bch_len", "stored_crc", "computed_crc"]
+
+
+def assert_same(got, flat, ida, where=""):
+    """got: FrameClass from the product's code; flat / ida: what frame_decode() / ida_decode() said"""
+    assert got.frame_type == (flat.type if flat.ret else 0), (where, "type", got.frame_type, flat.ret, flat.type)
+    if flat.ret:
+        for k in _FRAME_FIELDS:
+            assert getattr(got, k) == getattr(flat, k), (where, k, getattr(got, k), getattr(flat, k))
+        for k in ("pos_xyz", "tmsi", "msc_id"):
+            assert list(getattr(got, k)) == list(getattr(flat, k)), (where, k)
+    assert got.ida_ok == ida.ret, (where, "ida", got.ida_ok, ida.ret)
+    if ida.ret:
+        for k in _IDA_FIELDS:
+            assert getattr(got, k) == getattr(ida, k), (where, k, getattr(got, k), getattr(ida, k))
+        assert bytes(got.payload) == bytes(ida.payload), (where, "payload")
+        assert bytes(got.bch_stream) == bytes(ida.bch_stream), (where, "bch_stream")
+    else:
+        # a refused frame leaves the IDA half untouched (zero)
+        assert got.bch_len == 0 and got.payload_len == 0, where

@@ -10,13 +10,15 @@ import os
 import numpy as np
 import pytest
 
+import importlib.util
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_spec = importlib.util.spec_from_file_location("frame_gen", os.path.join(os.path.dirname(__file__), "frame_gen.py"))
+fg = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(fg)
+ACCESS_DL, ACCESS_UL, make_ira, make_ibc, make_ida = fg.ACCESS_DL, fg.ACCESS_UL, fg.make_ira, fg.make_ibc, fg.make_ida
 PORT_SO = os.path.join(ROOT, "oracle", "libir_frame_oracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_frame.so")
-
-ACCESS_DL = [0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 1, 1, 0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 1, 1]      # frame_decode.c:51-53
-ACCESS_UL = [1, 1, 0, 0, 1, 1, 0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 1, 1, 1, 1, 1, 1, 0, 0]      # :54-56
-
 
 class Flat(C.Structure):
     _fields_ = [("ret", C.c_int32), ("type", C.c_int32), ("sat_id", C.c_int32), ("beam_id", C.c_int32),
@@ -53,71 +55,6 @@ def _both(libs, bits, llr):
     assert bytes(a) == bytes(b), ({k: getattr(a, k) for k, _ in Flat._fields_ if not hasattr(getattr(a, k), "_length_")},
                                   {k: getattr(b, k) for k, _ in Flat._fields_ if not hasattr(getattr(b, k), "_length_")})
     return a
-
-
-# ---------------------------------------------------------------- a frame generator (test-side only)
-def _rem(poly, v):
-    deg = poly.bit_length() - 1
-    while v >> deg:
-        v ^= poly << (v.bit_length() - 1 - deg)
-    return v
-
-
-def _block(data21):
-    """21 data bits -> 32-bit block: systematic BCH(31,21) with generator 1207, then overall even parity"""
-    d = int("".join(map(str, data21)), 2)
-    code = (d << 10) | _rem(1207, d << 10)
-    bits = [int(c) for c in format(code, "031b")]
-    return bits + [sum(bits) & 1]
-
-
-def _interleave2(b1, b2):
-    out = [0] * 64
-    for k in range(16):
-        for blk, s in ((b1, 31 - 2 * k), (b2, 30 - 2 * k)):
-            out[2 * s], out[2 * s + 1] = blk[2 * k], blk[2 * k + 1]
-    return out
-
-
-def _interleave3(b1, b2, b3):
-    out = [0] * 96
-    for k in range(16):
-        for blk, s in ((b1, 47 - 3 * k), (b2, 46 - 3 * k), (b3, 45 - 3 * k)):
-            out[2 * s], out[2 * s + 1] = blk[2 * k], blk[2 * k + 1]
-    return out
-
-
-def _bits(v, n):
-    return [int(c) for c in format(v & ((1 << n) - 1), "0%db" % n)]
-
-
-def make_ira(rng, n_pages):
-    x, y, z = (int(v) for v in rng.integers(-2048, 2048, 3))
-    s12 = lambda v: [1 if v < 0 else 0] + _bits(v + 2048 if v < 0 else v, 11)
-    stream = _bits(int(rng.integers(0, 128)), 7) + _bits(int(rng.integers(0, 64)), 6) + s12(x) + s12(y) + s12(z)
-    stream += [int(b) for b in rng.integers(0, 2, 63 - len(stream))]
-    for _ in range(n_pages):
-        stream += _bits(int(rng.integers(0, 2**32)), 32) + [int(b) for b in rng.integers(0, 2, 10)]
-    stream += [1] * 42                                           # terminator page
-    blocks = [_block(stream[i:i + 21]) for i in range(0, len(stream), 21)]
-    assert len(blocks) % 2 == 1
-    body = _interleave3(*blocks[:3])
-    for i in range(3, len(blocks), 2):
-        body += _interleave2(blocks[i], blocks[i + 1])
-    return list(ACCESS_DL) + body
-
-
-def make_ibc(rng, n_pairs, bc_type):
-    hv = {0: 0, 1: 29, 2: 39, 3: 58}[bc_type]                    # the 6-bit multiples of the BCH(7,3) generator 29
-    stream = _bits(int(rng.integers(0, 128)), 7) + _bits(int(rng.integers(0, 64)), 6) + [int(b) for b in rng.integers(0, 2, 29)]
-    if n_pairs > 1:
-        stream += _bits(int(rng.integers(0, 3)), 6) + [int(b) for b in rng.integers(0, 2, 36)]
-    stream += [int(b) for b in rng.integers(0, 2, 42 * max(0, n_pairs - 2))]
-    blocks = [_block(stream[i:i + 21]) for i in range(0, 42 * n_pairs, 21)]
-    body = _bits(hv, 6)
-    for i in range(0, len(blocks), 2):
-        body += _interleave2(blocks[i], blocks[i + 1])
-    return list(ACCESS_DL if rng.integers(0, 2) else ACCESS_UL) + body
 
 
 def test_clean_frames(libs):
@@ -178,11 +115,6 @@ class FlatIda(C.Structure):
                 ("computed_crc", C.c_uint16), ("payload", C.c_uint8 * 32), ("bch_stream", C.c_uint8 * 256)]
 
 
-LCW_FROM = [40, 39, 36, 35, 32, 31, 28, 27, 24, 23, 20, 19, 16, 15, 12, 11, 8, 7, 4, 3,
-            41, 38, 37, 34, 33, 30, 29, 26, 25, 22, 21, 18, 17, 14, 13, 10, 9, 6, 5, 2,
-            1, 46, 45, 44, 43, 42]                               # ida_decode.c:54-60
-
-
 @pytest.fixture(scope="module")
 def ida_libs(libs):
     port, ref = C.CDLL(PORT_SO), C.CDLL(REF_SO)
@@ -203,67 +135,6 @@ def _both_ida(ida_libs, bits, llr, direction=1):
     a, b = out
     assert bytes(a) == bytes(b), ([(k, getattr(a, k), getattr(b, k)) for k, _ in FlatIda._fields_[:16] if getattr(a, k) != getattr(b, k)])
     return a
-
-
-def _crc(data):
-    crc = 0xFFFF
-    for byte in data:
-        crc ^= byte << 8
-        for _ in range(8):
-            crc = ((crc << 1) ^ 0x1021) & 0xFFFF if crc & 0x8000 else (crc << 1) & 0xFFFF
-    return crc
-
-
-def _cw20(d20):
-    d = int("".join(map(str, d20)), 2)
-    return [int(c) for c in format((d << 11) | _rem(3545, d << 11), "031b")]
-
-
-def _interleave_n(h1, h2, ns):
-    out = [0] * (2 * ns)
-    for k, s in enumerate(range(ns - 1, 0, -2)):
-        out[2 * s], out[2 * s + 1] = h1[2 * k], h1[2 * k + 1]
-    for k, s in enumerate(range(ns - 2, -1, -2)):
-        out[2 * s], out[2 * s + 1] = h2[2 * k], h2[2 * k + 1]
-    return out
-
-
-def make_ida(rng, da_len, ft=2, extra_words=0, good_crc=True):
-    # link control word: three short BCH code words, permuted and dibit-swapped on the air
-    l2d, l3d = int(rng.integers(0, 64)), int(rng.integers(0, 1 << 21))
-    v1 = (ft << 4) | _rem(29, ft << 4)
-    v2 = (l2d << 8) | _rem(465, l2d << 8)                      # 14 bits; only the top 13 are sent (the last is taken as 0)
-    v3 = (l3d << 5) | _rem(41, l3d << 5)
-    lcw_bits = _bits(v1, 7) + _bits(v2 >> 1, 13) + _bits(v3, 26)
-    lcw = [0] * 46
-    for i, src in enumerate(LCW_FROM):
-        lcw[(src - 1) ^ 1] = lcw_bits[i]
-    # payload stream: 20 header bits, 160 payload bits, CRC, padding to whole 20-bit words
-    hdr = [int(b) for b in rng.integers(0, 2, 20)]
-    hdr[3] = int(rng.integers(0, 2))
-    hdr[5:8] = _bits(int(rng.integers(0, 8)), 3)
-    hdr[11:16] = _bits(da_len, 5)
-    hdr[17:20] = [0, 0, 0]
-    pay = [int(b) for b in rng.integers(0, 2, 160)]
-    head = hdr + [0] * 12 + pay
-    crc = _crc(bytes(int("".join(map(str, head[i:i + 8])), 2) for i in range(0, 192, 8)))
-    if not good_crc:
-        crc ^= 0x0400
-    stream = hdr + pay + _bits(crc, 16) + [int(b) for b in rng.integers(0, 2, 4 + 20 * extra_words)]
-    words = [_cw20(stream[i:i + 20]) for i in range(0, len(stream), 20)]
-    assert len(words) == 10 + extra_words
-    body = []
-    while len(words) >= 4:                                     # full blocks: the words are read 4th, 2nd, 3rd, 1st
-        a, b, c, d = words[:4]
-        words = words[4:]
-        comb = d + b + c + a
-        body += _interleave_n(comb[:62], comb[62:], 62)
-    if words:                                                  # partial block of two words: halves swapped, first bits dropped
-        assert len(words) == 2
-        h2 = [int(rng.integers(0, 2))] + words[0]
-        h1 = [int(rng.integers(0, 2))] + words[1]
-        body += _interleave_n(h1, h2, 32)
-    return list(ACCESS_DL) + lcw + body
 
 
 def test_ida_clean_and_crc(ida_libs):
