@@ -1,5 +1,5 @@
 /*
- * ir_frame_oracle.c -- TEST INFRASTRUCTURE ONLY (groundwork for SURVEY.md section 8f rank 3).
+ * ir_frame_oracle.c -- TEST INFRASTRUCTURE ONLY.
  *
  * CPU restatement of the reference's frame classifiers: access code, IBC header BCH(7,3),
  * de-interleaving, BCH(31,21) + parity with Chase decoding on the LLRs, IRA / IBC field extraction
@@ -7,8 +7,8 @@
  * de-interleave, BCH(31,20)/Chase, header fields, CRC (ida_decode.c:33-396, 543-662).  Nothing in the
  * product imports it; tests/test_frame_oracle.py pins it to the reference's own frame_decode() and
  * ida_decode() compiled unmodified (oracle/_ref/libref_frame.so) on generated IRA / IBC / IDA frames with
- * and without bit errors.  No CUDA kernel consumes it yet: parity for this row is "oracle
- * pinned, device path not built".
+ * and without bit errors.  It is the checker of k_classify_frames (tests/test_zz_gpu_classify.py) and of that
+ * kernel's arithmetic compiled for the host (tests/test_frame_classify_host.py).
  *
  * Representation differs from the reference on purpose (it is what a bit-parallel device kernel would
  * use): a de-interleaved 32-bit block is one word, first bit in bit 31, so the 31-bit codeword is

@@ -3,7 +3,8 @@ oracle/ir_frame_oracle.c against the reference's own frame_decode() (frame_decod
 into oracle/_ref/libref_frame.so) on generated IRA / IBC frames -- clean, with correctable errors, with
 errors only the Chase step can repair (incl. tied reliabilities), with too many errors, truncated, and on
 random bits.  Every field of the flattened decoded_frame_t must agree, lat/lon included (same libm calls).
-No device path exists for this row yet; nothing in the product uses these files."""
+The device kernel of this row (k_classify_frames) is checked against this oracle in
+tests/test_zz_gpu_classify.py; nothing in the product uses these files."""
 import ctypes as C
 import os
 
