@@ -212,6 +212,23 @@ int ir_classify_frames(int device, const ir_frame_t *frames, size_t n_frames, co
  * ir_results_t.frames[i].  Returns the number of frames classified, or -1. */
 long ir_pipeline_classify(ir_pipeline_t *p, ir_frame_class_t *out, size_t cap);
 
+/* The reference's --parsed sink.  ir_format_lcw: the "LCW(...)" header ida_decode() leaves in
+ * ida_burst_t.lcw_header (ida_decode.c:398-541; 110 columns + one space).  ir_format_ida: the whole
+ * "IDA: ..." line of frame_output_print_ida() (frame_output.c:203-357) for a frame whose class has
+ * ida_ok set; t0 as for ir_format_raw.  Return the length, or -1 (not an IDA frame / buffer too small).
+ * Host text formatting, byte-identical to the reference for bch_len <= 256 (beyond that the reference
+ * prints past its own bch_stream array; this prints the 256 bits it holds). */
+int ir_format_lcw(char *dst, size_t cap, const ir_frame_class_t *cls);
+int ir_format_ida(char *dst, size_t cap, uint64_t t0, const ir_frame_t *frame,
+                  const ir_frame_class_t *cls);
+
+/* All output lines of the last run the way `--parsed` prints them (main.c:328-331): the IDA line for a
+ * frame ida_decode() accepted, its RAW line otherwise.  cls = what ir_pipeline_classify returned for this
+ * run (n_cls entries), or NULL to classify here.  dst == NULL returns the size needed.  Returns bytes
+ * written, or -1. */
+long ir_pipeline_format_parsed_all(ir_pipeline_t *p, const char *file_info, uint64_t t0,
+                                   const ir_frame_class_t *cls, size_t n_cls, char *dst, size_t cap);
+
 /* How ir_pipeline_run_* cuts a block of n samples into pieces (end offsets into `ends`, returns their
  * number or -1): full chunks of `chunk` samples (rounded down to whole detector frames), then the last
  * chunk in halves down to 1 Mi samples, so that little work is left after the last copy.  Pure host

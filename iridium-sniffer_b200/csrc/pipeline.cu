@@ -1076,6 +1076,35 @@ extern "C" int ir_classify_frames(int device, const ir_frame_t *frames, size_t n
     return 0;
 }
 
+// `--parsed` output of the whole run (main.c:328-331): the IDA line where ida_decode() accepted the frame, the RAW line otherwise
+extern "C" long ir_pipeline_format_parsed_all(ir_pipeline_t *p, const char *file_info, uint64_t t0, const ir_frame_class_t *cls,
+                                              size_t n_cls, char *dst, size_t cap) {
+    if (!p) return -1;
+    const size_t n = p->frames.size();
+    const size_t head = 512 + (file_info ? strlen(file_info) : 0);   // an IDA line is < 450 characters
+    if (!dst) return (long)(n * head + p->bits.size() + 64);
+    if (n == 0) return 0;
+    std::vector<ir_frame_class_t> own;
+    if (!cls) {
+        own.resize(n);
+        if (ir_pipeline_classify(p, own.data(), n) < 0) return -1;
+        cls = own.data();
+        n_cls = n;
+    }
+    if (n_cls != n) { set_err("ir_pipeline_format_parsed_all: class array does not match the last run"); return -1; }
+    if (t0 == 0) t0 = (p->frames[0].timestamp / 1000000000ULL) * 1000000000ULL;
+    size_t pos = 0;
+    for (size_t i = 0; i < n; i++) {
+        const ir_frame_t &f = p->frames[i];
+        if (pos + head + (size_t)f.n_bits + 2 > cap) { set_err("ir_pipeline_format_parsed_all: buffer too small"); return -1; }
+        const int k = cls[i].ida_ok ? ir_format_ida(dst + pos, cap - pos, t0, &f, &cls[i])
+                                    : ir_format_raw(dst + pos, cap - pos, file_info, t0, &f, p->bits.data() + f.bits_offset);
+        if (k < 0) { set_err("ir_pipeline_format_parsed_all: formatting failed"); return -1; }
+        pos += (size_t)k;
+    }
+    return (long)pos;
+}
+
 extern "C" void *ir_host_alloc(size_t bytes) {
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;

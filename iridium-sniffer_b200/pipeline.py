@@ -127,6 +127,13 @@ def load_library() -> C.CDLL:
                                      C.POINTER(FrameClass)]
     L.ir_pipeline_classify.restype = C.c_long
     L.ir_pipeline_classify.argtypes = [C.c_void_p, C.POINTER(FrameClass), C.c_size_t]
+    L.ir_format_lcw.restype = C.c_int
+    L.ir_format_lcw.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p]
+    L.ir_format_ida.restype = C.c_int
+    L.ir_format_ida.argtypes = [C.c_char_p, C.c_size_t, C.c_uint64, C.POINTER(Frame), C.c_void_p]
+    L.ir_pipeline_format_parsed_all.restype = C.c_long
+    L.ir_pipeline_format_parsed_all.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_void_p, C.c_size_t, C.c_char_p,
+                                                C.c_size_t]
     _lib = L
     return L
 
@@ -163,6 +170,7 @@ EXPORTED_SYMBOLS = [
     "ir_pipeline_copy_mag", "ir_pipeline_copy_frame_samples", "ir_pipeline_copy_decimated",
     "ir_pipeline_copy_burst_samples", "ir_format_raw", "ir_pipeline_format_raw_all", "ir_host_alloc",
     "ir_host_free", "ir_pipeline_scan_stats", "ir_plan_chunks", "ir_classify_frames", "ir_pipeline_classify",
+    "ir_format_lcw", "ir_format_ida", "ir_pipeline_format_parsed_all",
 ]
 
 
@@ -335,6 +343,18 @@ class Pipeline:
         if got < 0:
             raise RuntimeError("ir_pipeline_classify failed: " + self.L.ir_last_error().decode())
         return [out[i] for i in range(got)]
+
+    def parsed_text(self, file_info: str = "T", t0: int = 0) -> bytes:
+        """The run's output the way `--parsed` prints it: IDA lines where ida_decode() accepts, RAW lines otherwise
+        (classification on the GPU inside the call)."""
+        need = self.L.ir_pipeline_format_parsed_all(self.h, file_info.encode(), t0, None, 0, None, 0)
+        if need < 0:
+            raise RuntimeError("ir_pipeline_format_parsed_all failed: " + self.L.ir_last_error().decode())
+        buf = C.create_string_buffer(int(need) + 1)
+        n = self.L.ir_pipeline_format_parsed_all(self.h, file_info.encode(), t0, None, 0, buf, len(buf))
+        if n < 0:
+            raise RuntimeError("ir_pipeline_format_parsed_all failed: " + self.L.ir_last_error().decode())
+        return buf.raw[:n]
 
     def scan_stats(self) -> dict:
         """Counters of the detector state machine over the last run (ir_pipeline_scan_stats)."""

@@ -83,3 +83,69 @@ int ref_ida_decode(const uint8_t *bits, const float *llr, int n_bits, int direct
     memcpy(o->bch_stream, b.bch_stream, sizeof(o->bch_stream));
     return 1;
 }
+
+/* ---- the reference's --parsed sink: ida_decode() + frame_output_print_ida() (frame_output.c compiled
+ * unmodified), with stdout captured into the caller's buffer.  frame_output.c keeps its time origin in a
+ * static that the first printed line sets (frame_output.c:144-158): ref_print_prime() prints one throw-away
+ * line so that the origin is a known whole second for everything printed afterwards in this process. ---- */
+#include <stdio.h>
+#include <unistd.h>
+
+#include "frame_output.h"
+
+int diagnostic_mode, parsed_mode, acars_enabled;      /* main.c's globals that frame_output.c refers to */
+
+static int capture_begin(FILE **tmp) {
+    fflush(stdout);
+    const int saved = dup(1);
+    *tmp = tmpfile();
+    if (saved < 0 || !*tmp) return -1;
+    dup2(fileno(*tmp), 1);
+    return saved;
+}
+static int capture_end(int saved, FILE *tmp, char *out, int cap) {
+    fflush(stdout);
+    dup2(saved, 1);
+    close(saved);
+    rewind(tmp);
+    const int n = (int)fread(out, 1, cap > 0 ? cap - 1 : 0, tmp);
+    fclose(tmp);
+    if (cap > 0) out[n] = 0;
+    return n;
+}
+
+void ref_print_prime(uint64_t timestamp_ns) {
+    static ida_burst_t b;
+    char sink[512];
+    FILE *tmp;
+    memset(&b, 0, sizeof(b));
+    b.timestamp = timestamp_ns;
+    const int saved = capture_begin(&tmp);
+    if (saved < 0) return;
+    frame_output_print_ida(&b);
+    capture_end(saved, tmp, sink, sizeof(sink));
+}
+
+/* returns the length of the IDA line (0 if ida_decode() refuses the frame); lcw_header gets ida_burst_t.lcw_header */
+int ref_print_ida(const uint8_t *bits, const float *llr, int n_bits, int direction, uint64_t timestamp,
+                  double center_frequency, float magnitude, float noise, float level, int confidence,
+                  int n_payload_symbols, char *out, int cap, char *lcw_header) {
+    static int ready;
+    if (!ready) { frame_decode_init(); ida_decode_init(); ready = 1; }
+    demod_frame_t f;
+    static ida_burst_t b;
+    memset(&f, 0, sizeof(f));
+    f.bits = (uint8_t *)bits; f.llr = (float *)llr; f.n_bits = n_bits;
+    f.direction = (ir_direction_t)direction;
+    f.timestamp = timestamp; f.center_frequency = center_frequency;
+    f.magnitude = magnitude; f.noise = noise; f.level = level; f.confidence = confidence;
+    f.n_payload_symbols = n_payload_symbols; f.n_symbols = n_payload_symbols + 12;
+    if (cap > 0) out[0] = 0;
+    if (!ida_decode(&f, &b)) return 0;
+    if (lcw_header) memcpy(lcw_header, b.lcw_header, sizeof(b.lcw_header));
+    FILE *tmp;
+    const int saved = capture_begin(&tmp);
+    if (saved < 0) return -1;
+    frame_output_print_ida(&b);
+    return capture_end(saved, tmp, out, cap);
+}

@@ -101,9 +101,15 @@ def _interleave_n(h1, h2, ns):
     return out
 
 
-def make_ida(rng, da_len, ft=2, extra_words=0, good_crc=True):
+def make_ida(rng, da_len, ft=2, extra_words=0, good_crc=True, lcw_ft=None, lcw_code=None, lcw3=None):
     # link control word: three short BCH code words, permuted and dibit-swapped on the air
     l2d, l3d = int(rng.integers(0, 64)), int(rng.integers(0, 1 << 21))
+    if lcw_ft is not None:
+        l2d = (l2d & 0x0f) | (lcw_ft << 4)
+    if lcw_code is not None:
+        l2d = (l2d & 0x30) | lcw_code
+    if lcw3 is not None:
+        l3d = lcw3
     v1 = (ft << 4) | _rem(29, ft << 4)
     v2 = (l2d << 8) | _rem(465, l2d << 8)                      # 14 bits; only the top 13 are sent (the last is taken as 0)
     v3 = (l3d << 5) | _rem(41, l3d << 5)

@@ -96,6 +96,37 @@ def test_pipeline_classifies_planted_frames_from_device_memory(pl, checkers, syn
     assert seen["ira"] >= 3 and seen["ibc"] >= 2 and seen["ida"] >= 6, seen
 
 
+def test_parsed_output_of_a_run(pl, checkers, synth):
+    """ir_pipeline_format_parsed_all (classification on the GPU + the host line formatter) against lines put
+    together from the oracle's classification: IDA line where ida_decode() accepts, RAW line otherwise
+    (main.c:328-331).  The formatter itself is pinned to the reference's text on the CPU (test_parsed_output.py)."""
+    L = pl.load_library()
+    rec, _ = fg.planted_recordings(synth)[1]
+    p = pl.Pipeline(sample_rate=rec.sample_rate, center_frequency=rec.center_freq)
+    res = p.run_host(rec.iq, rec.fmt)
+    text = p.parsed_text("T").decode()
+    cls = p.classify()
+    raw = res.raw_lines("T")
+    t0 = (res.frames[0]["timestamp"] // 1_000_000_000) * 1_000_000_000
+    want = []
+    n_ida = 0
+    for i, f in enumerate(res.frames):
+        _, chk = checkers[0]
+        _, ida = chk(f["bits"], f["llr"], f["direction"])
+        assert cls[i].ida_ok == ida.ret
+        if ida.ret:
+            buf = C.create_string_buffer(2048)
+            assert L.ir_format_ida(buf, len(buf), t0, C.byref(res._cframes[i]), C.byref(cls[i])) > 0
+            want.append(buf.value.decode())
+            n_ida += 1
+        else:
+            want.append(raw[i] if raw[i].endswith("\n") else raw[i] + "\n")
+    assert n_ida >= 6
+    assert text == "".join(want)
+    assert text.count("IDA: p-") == n_ida and "CRC:OK" in text and "CRC:no" in text
+    p.close()
+
+
 def test_classify_refuses_bad_arguments(pl):
     L = pl.load_library()
     fr = (pl.Frame * 1)()
