@@ -133,4 +133,96 @@ typedef struct {                 /* qpsk_demod.h:24-38 */
 
 int qpsk_demod(downmix_frame_t *in, demod_frame_t **out);                        /* qpsk_demod.h:42 */
 
+/* ---- next row: frame_decode.h / ida_decode.h, so that frame_decode.c and ida_decode.c
+ * can leave the build as well.  frame_decode() and ida_decode() classify their one frame on the GPU
+ * (k_classify_frames); the reassembly and the bit helpers are host bookkeeping, restated. ---- */
+typedef enum { FRAME_UNKNOWN = 0, FRAME_IRA, FRAME_IBC } frame_type_t;           /* frame_decode.h:20-24 */
+
+typedef struct {                 /* frame_decode.h:26-38 */
+    int sat_id;
+    int beam_id;
+    double lat, lon;
+    int alt;
+    int pos_xyz[3];
+    int n_pages;
+    struct { uint32_t tmsi; int msc_id; } pages[12];
+} ira_data_t;
+
+typedef struct {                 /* frame_decode.h:40-47 */
+    int sat_id;
+    int beam_id;
+    int timeslot;
+    int sv_blocking;
+    int bc_type;
+    uint32_t iri_time;
+} ibc_data_t;
+
+typedef struct {                 /* frame_decode.h:49-57 */
+    frame_type_t type;
+    uint64_t timestamp;
+    double frequency;
+    union { ira_data_t ira; ibc_data_t ibc; };
+} decoded_frame_t;
+
+void frame_decode_init(void);                                                    /* frame_decode.h:60 (no-op here) */
+int frame_decode(const demod_frame_t *frame, decoded_frame_t *out);              /* :63 */
+uint32_t gf2_remainder(uint32_t poly, uint32_t val);                             /* :66-68 */
+uint32_t bits_to_uint(const uint8_t *bits, int n);
+void uint_to_bits(uint32_t val, uint8_t *bits, int n);
+int bch_31_21_correct(uint32_t syndrome, uint32_t *locator);                     /* :72 */
+
+typedef struct {                 /* ida_decode.h:19-26 */
+    int ft;
+    int lcw_ok;
+    int lcw_ft;
+    int lcw_code;
+    uint32_t lcw3_val;
+    int ec_lcw;
+} lcw_t;
+
+typedef struct {                 /* ida_decode.h:29-56 */
+    uint64_t timestamp;
+    double frequency;
+    ir_direction_t direction;
+    float magnitude;
+    float noise;
+    float level;
+    int confidence;
+    int n_symbols;
+    int da_ctr;
+    int da_len;
+    int cont;
+    uint8_t payload[32];
+    int payload_len;
+    int crc_ok;
+    uint16_t stored_crc;
+    uint16_t computed_crc;
+    int fixederrs;
+    uint8_t bch_stream[256];
+    int bch_len;
+    lcw_t lcw;
+    char lcw_header[128];
+} ida_burst_t;
+
+typedef struct {                 /* ida_decode.h:59-67 */
+    int active;
+    ir_direction_t direction;
+    double frequency;
+    uint64_t last_timestamp;
+    int last_ctr;
+    uint8_t data[256];
+    int data_len;
+} ida_reassembly_t;
+
+#define IDA_MAX_REASSEMBLY 16
+typedef struct { ida_reassembly_t slots[IDA_MAX_REASSEMBLY]; } ida_context_t;   /* ida_decode.h:72-74 */
+
+typedef void (*ida_message_cb)(const uint8_t *data, int len, uint64_t timestamp, double frequency,
+                               ir_direction_t direction, float magnitude, void *user);   /* :77-80 */
+
+void ida_decode_init(void);                                                      /* ida_decode.h:83 (no-op here) */
+int ida_decode(const demod_frame_t *frame, ida_burst_t *burst);                  /* :87 */
+int ida_reassemble(ida_context_t *ctx, const ida_burst_t *burst, ida_message_cb cb, void *user);   /* :91 */
+void ida_reassemble_flush(ida_context_t *ctx, uint64_t now_ns);                  /* :95 */
+
 #endif

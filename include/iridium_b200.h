@@ -229,6 +229,13 @@ int ir_format_ida(char *dst, size_t cap, uint64_t t0, const ir_frame_t *frame,
 long ir_pipeline_format_parsed_all(ir_pipeline_t *p, const char *file_info, uint64_t t0,
                                    const ir_frame_class_t *cls, size_t n_cls, char *dst, size_t cap);
 
+/* ir_frame_t + ir_frame_class_t -> the reference's own structs, exactly as frame_decode() / ida_decode() leave
+ * them: decoded_frame_t (frame_decode.h:49-57) and ida_burst_t (ida_decode.h:29-56, lcw_header included); the
+ * pointers are void here so that this header needs no reference types (include/ir_ref_api.h declares them).
+ * ir_fill_ida_burst returns 0 and a zeroed struct when ida_ok is not set, like ida_decode(). */
+void ir_fill_decoded_frame(const ir_frame_t *frame, const ir_frame_class_t *cls, void *decoded_frame_out);
+int ir_fill_ida_burst(const ir_frame_t *frame, const ir_frame_class_t *cls, void *ida_burst_out);
+
 /* How ir_pipeline_run_* cuts a block of n samples into pieces (end offsets into `ends`, returns their
  * number or -1): full chunks of `chunk` samples (rounded down to whole detector frames), then the last
  * chunk in halves down to 1 Mi samples, so that little work is left after the last copy.  Pure host

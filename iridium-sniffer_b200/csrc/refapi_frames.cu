@@ -1,0 +1,175 @@
+// refapi_frames.cu -- the reference's per-frame interface of the next row (include/ir_ref_api.h):
+// frame_decode() / ida_decode() with the reference's struct layouts, each call classifying its one frame
+// on the GPU (k_classify_frames through ir_classify_frames; no CPU path), and the pieces of frame_decode.c /
+// ida_decode.c that are host bookkeeping by nature: the public bit helpers (frame_decode.h:66-73) and the
+// IDA multi-burst reassembly (ida_decode.c:669-748).  With these a maintainer can drop frame_decode.c and
+// ida_decode.c from the build and link the library instead.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "frame_classify.cuh"
+
+extern "C" {
+
+// ---- layouts of include/ir_ref_api.h
+typedef struct {
+    uint64_t id, timestamp; double center_frequency; int direction; float magnitude, noise;
+    int confidence; float level; int n_symbols, n_payload_symbols; uint8_t *bits; float *llr; int n_bits;
+} demod_frame_t;
+typedef struct { int sat_id, beam_id; double lat, lon; int alt; int pos_xyz[3]; int n_pages; struct { uint32_t tmsi; int msc_id; } pages[12]; } ira_data_t;
+typedef struct { int sat_id, beam_id, timeslot, sv_blocking, bc_type; uint32_t iri_time; } ibc_data_t;
+typedef struct { int type; uint64_t timestamp; double frequency; union { ira_data_t ira; ibc_data_t ibc; }; } decoded_frame_t;
+typedef struct { int ft, lcw_ok, lcw_ft, lcw_code; uint32_t lcw3_val; int ec_lcw; } lcw_t;
+typedef struct {
+    uint64_t timestamp; double frequency; int direction; float magnitude, noise, level; int confidence, n_symbols,
+        da_ctr, da_len, cont; uint8_t payload[32]; int payload_len, crc_ok; uint16_t stored_crc, computed_crc;
+    int fixederrs; uint8_t bch_stream[256]; int bch_len; lcw_t lcw; char lcw_header[128];
+} ida_burst_t;
+typedef struct { int active, direction; double frequency; uint64_t last_timestamp; int last_ctr; uint8_t data[256]; int data_len; } ida_reassembly_t;
+typedef struct { ida_reassembly_t slots[16]; } ida_context_t;
+typedef void (*ida_message_cb)(const uint8_t *data, int len, uint64_t timestamp, double frequency, int direction,
+                               float magnitude, void *user);
+
+// ---- ir_frame_class_t -> the reference's structs (exactly what frame_decode() / ida_decode() leave behind)
+void ir_fill_decoded_frame(const ir_frame_t *f, const ir_frame_class_t *c, void *decoded_frame_out) {
+    decoded_frame_t *out = (decoded_frame_t *)decoded_frame_out;
+    memset(out, 0, sizeof(*out));
+    out->type = c->frame_type;
+    out->timestamp = f->timestamp;
+    out->frequency = f->center_frequency;
+    if (c->frame_type == IR_FRAME_IRA) {
+        ira_data_t &a = out->ira;
+        a.sat_id = c->sat_id; a.beam_id = c->beam_id; a.lat = c->lat; a.lon = c->lon; a.alt = c->alt;
+        for (int i = 0; i < 3; i++) a.pos_xyz[i] = c->pos_xyz[i];
+        a.n_pages = c->n_pages;
+        for (int i = 0; i < c->n_pages && i < 12; i++) { a.pages[i].tmsi = c->tmsi[i]; a.pages[i].msc_id = c->msc_id[i]; }
+    } else if (c->frame_type == IR_FRAME_IBC) {
+        ibc_data_t &b = out->ibc;
+        b.sat_id = c->sat_id; b.beam_id = c->beam_id; b.timeslot = c->timeslot; b.sv_blocking = c->sv_blocking;
+        b.bc_type = c->bc_type; b.iri_time = c->iri_time;
+    }
+}
+
+int ir_fill_ida_burst(const ir_frame_t *f, const ir_frame_class_t *c, void *ida_burst_out) {
+    ida_burst_t *out = (ida_burst_t *)ida_burst_out;
+    memset(out, 0, sizeof(*out));
+    if (!c->ida_ok) return 0;
+    out->timestamp = f->timestamp; out->frequency = f->center_frequency; out->direction = f->direction;
+    out->magnitude = f->magnitude; out->noise = f->noise; out->level = f->level; out->confidence = f->confidence;
+    out->n_symbols = f->n_payload_symbols;                                    // ida_decode.c:644
+    out->da_ctr = c->da_ctr; out->da_len = c->da_len; out->cont = c->cont;
+    out->payload_len = c->payload_len; out->crc_ok = c->crc_ok;
+    out->stored_crc = c->stored_crc; out->computed_crc = c->computed_crc; out->fixederrs = c->fixederrs;
+    memcpy(out->payload, c->payload, (size_t)(c->payload_len < 32 ? c->payload_len : 32));
+    out->bch_len = c->bch_len;
+    memcpy(out->bch_stream, c->bch_stream, (size_t)(c->bch_len < 256 ? c->bch_len : 256));
+    out->lcw.ft = 2; out->lcw.lcw_ok = 1; out->lcw.lcw_ft = c->lcw_ft; out->lcw.lcw_code = c->lcw_code;
+    out->lcw.lcw3_val = c->lcw3_val; out->lcw.ec_lcw = c->ec_lcw;
+    ir_format_lcw(out->lcw_header, sizeof(out->lcw_header), c);
+    return 1;
+}
+
+// ---- frame_decode.h:60-73, ida_decode.h:84-89
+void frame_decode_init(void) {}          // tables live on the device, built at the first call
+void ida_decode_init(void) {}
+
+static int classify_one(const demod_frame_t *frame, ir_frame_t *f, ir_frame_class_t *c) {
+    memset(f, 0, sizeof(*f));
+    f->id = frame->id; f->timestamp = frame->timestamp; f->center_frequency = frame->center_frequency;
+    f->direction = frame->direction; f->magnitude = frame->magnitude; f->noise = frame->noise;
+    f->confidence = frame->confidence; f->level = frame->level; f->n_symbols = frame->n_symbols;
+    f->n_payload_symbols = frame->n_payload_symbols; f->n_bits = frame->n_bits; f->bits_offset = 0;
+    if (frame->n_bits <= 0 || !frame->bits) { memset(c, 0, sizeof(*c)); return 0; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (ir_classify_frames(dev, f, 1, frame->bits, frame->llr, (size_t)frame->n_bits, c) != 0) {
+        fprintf(stderr, "iridium_b200: frame classification failed: %s\n", ir_last_error());
+        memset(c, 0, sizeof(*c));
+        return -1;
+    }
+    return 0;
+}
+
+int frame_decode(const demod_frame_t *frame, decoded_frame_t *out) {           // frame_decode.c:414-598
+    ir_frame_t f;
+    ir_frame_class_t c;
+    classify_one(frame, &f, &c);
+    ir_fill_decoded_frame(&f, &c, out);
+    return c.frame_type != IR_FRAME_UNKNOWN;
+}
+
+int ida_decode(const demod_frame_t *frame, ida_burst_t *burst) {               // ida_decode.c:543-665
+    ir_frame_t f;
+    ir_frame_class_t c;
+    classify_one(frame, &f, &c);
+    return ir_fill_ida_burst(&f, &c, burst);
+}
+
+uint32_t gf2_remainder(uint32_t poly, uint32_t val) {                          // frame_decode.c:82-92
+    if (poly == 0) return val;
+    return ir::fc_rem(poly, ir::fc_top_bit(poly), val);
+}
+uint32_t bits_to_uint(const uint8_t *bits, int n) { return ir::fc_take(bits, n); }
+void uint_to_bits(uint32_t val, uint8_t *bits, int n) {
+    for (int i = 0; i < n; i++) bits[i] = (uint8_t)((val >> (n - 1 - i)) & 1u);
+}
+int bch_31_21_correct(uint32_t syndrome, uint32_t *locator) {                  // frame_decode.c:136-145
+    static ir::FcSyn tab[1024];
+    static bool ready = false;
+    if (!ready) { ir::fc_fill(tab, 1024, 1207, 10, 31, 2); ready = true; }
+    if (syndrome == 0) { *locator = 0; return 0; }
+    if (syndrome < 1024 && tab[syndrome].errs >= 0) { *locator = tab[syndrome].mask; return tab[syndrome].errs; }
+    return -1;
+}
+
+// ---- IDA multi-burst reassembly (ida_decode.c:669-748): host bookkeeping over CRC-clean bursts.  A message is
+// a run of bursts on one channel (same direction, within 260 Hz, at most 280 ms apart) whose 3-bit counters
+// follow each other, opened by counter 0 and closed by the first burst without the continuation flag.
+static const uint64_t kGapNs = 280000000ULL;
+
+static bool continues(const ida_reassembly_t &s, const ida_burst_t &b) {
+    return s.active && s.direction == b.direction && !(fabs(s.frequency - b.frequency) > 260.0) &&
+           b.timestamp >= s.last_timestamp && b.timestamp - s.last_timestamp <= kGapNs && (s.last_ctr + 1) % 8 == b.da_ctr;
+}
+
+int ida_reassemble(ida_context_t *ctx, const ida_burst_t *burst, ida_message_cb cb, void *user) {
+    const ida_burst_t &b = *burst;
+    if (!b.crc_ok || b.da_len == 0) return 0;
+    for (ida_reassembly_t &s : ctx->slots) {
+        if (!continues(s, b)) continue;
+        if (s.data_len + b.da_len <= (int)sizeof(s.data)) {       // a fragment that does not fit is skipped, the message goes on
+            memcpy(s.data + s.data_len, b.payload, (size_t)b.da_len);
+            s.data_len += b.da_len;
+        }
+        s.last_timestamp = b.timestamp;
+        s.last_ctr = b.da_ctr;
+        if (b.cont) return 0;
+        cb(s.data, s.data_len, b.timestamp, s.frequency, s.direction, b.magnitude, user);
+        s.active = 0;
+        return 1;
+    }
+    if (b.da_ctr != 0) return 0;                                  // a fragment without its beginning
+    if (!b.cont) {                                                // the whole message in one burst
+        cb(b.payload, b.da_len, b.timestamp, b.frequency, b.direction, b.magnitude, user);
+        return 1;
+    }
+    // a new message: the first free slot, else the one that has waited longest (first among equals)
+    ida_reassembly_t *s = nullptr;
+    for (ida_reassembly_t &t : ctx->slots) {
+        if (!t.active) { s = &t; break; }
+        if (!s || t.last_timestamp < s->last_timestamp) s = &t;
+    }
+    s->active = 1; s->direction = b.direction; s->frequency = b.frequency;
+    s->last_timestamp = b.timestamp; s->last_ctr = b.da_ctr;
+    memcpy(s->data, b.payload, (size_t)b.da_len);
+    s->data_len = b.da_len;
+    return 0;
+}
+
+void ida_reassemble_flush(ida_context_t *ctx, uint64_t now_ns) {
+    for (ida_reassembly_t &s : ctx->slots)
+        if (s.active && now_ns > s.last_timestamp + kGapNs) s.active = 0;
+}
+
+}  // extern "C"

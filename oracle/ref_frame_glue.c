@@ -149,3 +149,36 @@ int ref_print_ida(const uint8_t *bits, const float *llr, int n_bits, int directi
     frame_output_print_ida(&b);
     return capture_end(saved, tmp, out, cap);
 }
+
+/* ---- the reference's structs as they come out of frame_decode() / ida_decode(), byte for byte ---- */
+static void fill_frame(demod_frame_t *f, const uint8_t *bits, const float *llr, int n_bits, int direction,
+                       uint64_t timestamp, double center_frequency, float magnitude, float noise, float level,
+                       int confidence, int n_payload_symbols) {
+    memset(f, 0, sizeof(*f));
+    f->bits = (uint8_t *)bits; f->llr = (float *)llr; f->n_bits = n_bits;
+    f->direction = (ir_direction_t)direction;
+    f->timestamp = timestamp; f->center_frequency = center_frequency;
+    f->magnitude = magnitude; f->noise = noise; f->level = level; f->confidence = confidence;
+    f->n_payload_symbols = n_payload_symbols; f->n_symbols = n_payload_symbols + 12;
+}
+int ref_sizeof_decoded_frame(void) { return (int)sizeof(decoded_frame_t); }
+int ref_sizeof_ida_burst(void) { return (int)sizeof(ida_burst_t); }
+int ref_sizeof_ida_context(void) { return (int)sizeof(ida_context_t); }
+int ref_frame_decode_raw(const uint8_t *bits, const float *llr, int n_bits, int direction, uint64_t timestamp,
+                         double center_frequency, float magnitude, float noise, float level, int confidence,
+                         int n_payload_symbols, void *out) {
+    static int ready;
+    if (!ready) { frame_decode_init(); ida_decode_init(); ready = 1; }
+    demod_frame_t f;
+    fill_frame(&f, bits, llr, n_bits, direction, timestamp, center_frequency, magnitude, noise, level, confidence, n_payload_symbols);
+    return frame_decode(&f, (decoded_frame_t *)out);
+}
+int ref_ida_decode_raw(const uint8_t *bits, const float *llr, int n_bits, int direction, uint64_t timestamp,
+                       double center_frequency, float magnitude, float noise, float level, int confidence,
+                       int n_payload_symbols, void *out) {
+    static int ready;
+    if (!ready) { frame_decode_init(); ida_decode_init(); ready = 1; }
+    demod_frame_t f;
+    fill_frame(&f, bits, llr, n_bits, direction, timestamp, center_frequency, magnitude, noise, level, confidence, n_payload_symbols);
+    return ida_decode(&f, (ida_burst_t *)out);
+}

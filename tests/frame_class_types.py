@@ -71,3 +71,30 @@ def assert_same(got, flat, ida, where=""):
     else:
         # a refused frame leaves the IDA half untouched (zero)
         assert got.bch_len == 0 and got.payload_len == 0, where
+
+
+# ---- the reference's own structs (frame_decode.h, ida_decode.h), for tests that drive its functions directly
+class Lcw(C.Structure):                    # ida_decode.h:19-26
+    _fields_ = [("ft", C.c_int), ("lcw_ok", C.c_int), ("lcw_ft", C.c_int), ("lcw_code", C.c_int),
+                ("lcw3_val", C.c_uint32), ("ec_lcw", C.c_int)]
+
+
+class IdaBurst(C.Structure):               # ida_decode.h:29-56
+    _fields_ = [("timestamp", C.c_uint64), ("frequency", C.c_double), ("direction", C.c_int), ("magnitude", C.c_float),
+                ("noise", C.c_float), ("level", C.c_float), ("confidence", C.c_int), ("n_symbols", C.c_int),
+                ("da_ctr", C.c_int), ("da_len", C.c_int), ("cont", C.c_int), ("payload", C.c_uint8 * 32),
+                ("payload_len", C.c_int), ("crc_ok", C.c_int), ("stored_crc", C.c_uint16), ("computed_crc", C.c_uint16),
+                ("fixederrs", C.c_int), ("bch_stream", C.c_uint8 * 256), ("bch_len", C.c_int), ("lcw", Lcw),
+                ("lcw_header", C.c_char * 128)]
+
+
+class IdaSlot(C.Structure):                # ida_decode.h:59-67
+    _fields_ = [("active", C.c_int), ("direction", C.c_int), ("frequency", C.c_double), ("last_timestamp", C.c_uint64),
+                ("last_ctr", C.c_int), ("data", C.c_uint8 * 256), ("data_len", C.c_int)]
+
+
+class IdaContext(C.Structure):             # ida_decode.h:72-74
+    _fields_ = [("slots", IdaSlot * 16)]
+
+
+IDA_CB = C.CFUNCTYPE(None, C.POINTER(C.c_uint8), C.c_int, C.c_uint64, C.c_double, C.c_int, C.c_float, C.c_void_p)

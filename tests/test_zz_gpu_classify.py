@@ -127,6 +127,45 @@ def test_parsed_output_of_a_run(pl, checkers, synth):
     p.close()
 
 
+def test_reference_named_entry_points(pl):
+    """frame_decode() / ida_decode() of include/ir_ref_api.h, one frame per call the way main.c:320-350 calls
+    them, against the reference's own functions: the returned structs byte for byte."""
+    from oracle import bindings as ob
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref/libref_frame.so did not travel with the snapshot")
+    ref, L = C.CDLL(REF_SO), pl.load_library()
+    raw_args = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_float, C.c_float, C.c_float, C.c_int,
+                C.c_int, C.c_void_p]
+    ref.ref_frame_decode_raw.argtypes = raw_args
+    ref.ref_ida_decode_raw.argtypes = raw_args
+    L.frame_decode.argtypes = [C.POINTER(ob.RefDemodFrame), C.c_void_p]
+    L.ida_decode.argtypes = [C.POINTER(ob.RefDemodFrame), C.c_void_p]
+    nd, nb = ref.ref_sizeof_decoded_frame(), ref.ref_sizeof_ida_burst()
+    rng = np.random.default_rng(9)
+    L.frame_decode_init()
+    L.ida_decode_init()
+    hits = 0
+    for bits, llr, direction in fg.corpus(77, 300):
+        ts, freq = int(rng.integers(1, 2**62)), float(rng.uniform(1.616e9, 1.6265e9))
+        mag, noise, level = (float(np.float32(v)) for v in (rng.uniform(5, 60), rng.uniform(-130, -90), rng.uniform(0, 2)))
+        conf, npay = int(rng.integers(0, 101)), len(bits) // 2 - 12
+        lp = None if llr is None else llr.ctypes.data_as(C.c_void_p)
+        want_d, want_b = C.create_string_buffer(nd), C.create_string_buffer(nb)
+        r1 = ref.ref_frame_decode_raw(bits.ctypes.data_as(C.c_void_p), lp, len(bits), direction, ts, freq, mag, noise, level, conf, npay, want_d)
+        r2 = ref.ref_ida_decode_raw(bits.ctypes.data_as(C.c_void_p), lp, len(bits), direction, ts, freq, mag, noise, level, conf, npay, want_b)
+        f = ob.RefDemodFrame()
+        f.timestamp, f.center_frequency, f.direction, f.magnitude, f.noise, f.level = ts, freq, direction, mag, noise, level
+        f.confidence, f.n_payload_symbols, f.n_symbols, f.n_bits = conf, npay, npay + 12, len(bits)
+        f.bits = bits.ctypes.data_as(C.POINTER(C.c_uint8))
+        f.llr = None if llr is None else llr.ctypes.data_as(C.POINTER(C.c_float))
+        got_d, got_b = C.create_string_buffer(b"\x55" * nd, nd), C.create_string_buffer(b"\x55" * nb, nb)
+        assert L.frame_decode(C.byref(f), got_d) == r1
+        assert L.ida_decode(C.byref(f), got_b) == r2
+        assert got_d.raw == want_d.raw and got_b.raw == want_b.raw
+        hits += r1 + r2
+    assert hits > 100
+
+
 def test_classify_refuses_bad_arguments(pl):
     L = pl.load_library()
     fr = (pl.Frame * 1)()
