@@ -1,0 +1,180 @@
+"""SURVEY.md 8f rank 3 on the GPU: k_classify_frames through the C ABI (ir_classify_frames,
+ir_pipeline_classify) against the oracle port and -- when oracle/_ref/libref_frame.so travelled with the
+snapshot -- the reference's own frame_decode() / ida_decode(), every field, bit for bit.
+
+NOTE (round 1): this kernel was written after the round's GPU minutes were spent; its arithmetic is pinned on
+the CPU (tests/test_frame_classify_host.py compiles the same header for the host), but these tests had not yet
+run on a B200 when they were committed.  Its runner (tests/test_zz_gpu_classify.py) sorts last so that a failure here cannot hide the results of
+the path's own parity tests under `pytest -x`.
+
+This file is not collected by name; tests/test_zz_gpu_classify.py runs each case in a child process, so that
+even a crash in here stays an ordinary test failure of that one case."""
+import ctypes as C
+import importlib
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+PORT_SO = os.path.join(ROOT, "oracle", "libir_frame_oracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_frame.so")
+
+
+def _load(name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(HERE, name + ".py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+fg = _load("frame_gen")
+fc = _load("frame_class_types")
+
+
+@pytest.fixture(scope="module")
+def pl():
+    return importlib.import_module("iridium-sniffer_b200.pipeline")
+
+
+@pytest.fixture(scope="module")
+def checkers():
+    from oracle import bindings as ob
+    if not os.path.exists(PORT_SO):
+        ob.build(port=True, ref=False)
+    libs = [("port", fc.bind_checker(C.CDLL(PORT_SO), "orc_"))]
+    if os.path.exists(REF_SO):
+        libs.append(("reference", fc.bind_checker(C.CDLL(REF_SO), "ref_")))
+    return libs
+
+
+def _as_fc(o):
+    """pipeline.FrameClass -> tests' mirror (same layout), so that assert_same applies"""
+    return fc.FrameClass.from_buffer_copy(bytes(o))
+
+
+def test_generated_frames_one_launch(pl, checkers):
+    assert C.sizeof(pl.FrameClass) == C.sizeof(fc.FrameClass)
+    cases = fg.corpus(202, 3000)
+    with_llr = [c for c in cases if c[1] is not None]
+    without = [c for c in cases if c[1] is None]
+    decoded = 0
+    for group in (with_llr, without):
+        got = pl.classify_frames(group)
+        assert len(got) == len(group)
+        for o, (bits, llr, direction) in zip(got, group):
+            o = _as_fc(o)
+            for name, chk in checkers:
+                fc.assert_same(o, *chk(bits, llr, direction), where=name)
+            decoded += (o.frame_type != 0) + o.ida_ok
+    assert decoded > 800
+    assert pl.classify_frames([]) == []
+
+
+def test_pipeline_classifies_planted_frames_from_device_memory(pl, checkers, synth):
+    seen = {"ira": 0, "ibc": 0, "ida": 0}
+    for rec, frames in fg.planted_recordings(synth):
+        p = pl.Pipeline(sample_rate=rec.sample_rate, center_frequency=rec.center_freq)
+        res = p.run_host(rec.iq, rec.fmt)
+        got = p.classify()
+        assert len(got) == len(res.frames)
+        # the same frames handed over as host arrays must give the same answer as the device-resident ones
+        again = pl.classify_frames([(f["bits"], f["llr"], f["direction"]) for f in res.frames])
+        planted = {t.bits for t in rec.truth}
+        for o, o2, f in zip(got, again, res.frames):
+            assert bytes(o) == bytes(o2)
+            o = _as_fc(o)
+            for name, chk in checkers:
+                fc.assert_same(o, *chk(f["bits"], f["llr"], f["direction"]), where=name)
+            if "".join(map(str, f["bits"])) in planted:
+                assert o.frame_type != 0 or o.ida_ok == 1
+                seen["ira"] += o.frame_type == 1
+                seen["ibc"] += o.frame_type == 2
+                seen["ida"] += o.ida_ok
+        p.close()
+    assert seen["ira"] >= 3 and seen["ibc"] >= 2 and seen["ida"] >= 6, seen
+
+
+def test_parsed_output_of_a_run(pl, checkers, synth):
+    """ir_pipeline_format_parsed_all (classification on the GPU + the host line formatter) against lines put
+    together from the oracle's classification: IDA line where ida_decode() accepts, RAW line otherwise
+    (main.c:328-331).  The formatter itself is pinned to the reference's text on the CPU (test_parsed_output.py)."""
+    L = pl.load_library()
+    rec, _ = fg.planted_recordings(synth)[1]
+    p = pl.Pipeline(sample_rate=rec.sample_rate, center_frequency=rec.center_freq)
+    res = p.run_host(rec.iq, rec.fmt)
+    text = p.parsed_text("T").decode()
+    cls = p.classify()
+    raw = res.raw_lines("T")
+    t0 = (res.frames[0]["timestamp"] // 1_000_000_000) * 1_000_000_000
+    want = []
+    n_ida = 0
+    for i, f in enumerate(res.frames):
+        _, chk = checkers[0]
+        _, ida = chk(f["bits"], f["llr"], f["direction"])
+        assert cls[i].ida_ok == ida.ret
+        if ida.ret:
+            buf = C.create_string_buffer(2048)
+            assert L.ir_format_ida(buf, len(buf), t0, C.byref(res._cframes[i]), C.byref(cls[i])) > 0
+            want.append(buf.value.decode())
+            n_ida += 1
+        else:
+            want.append(raw[i] if raw[i].endswith("\n") else raw[i] + "\n")
+    assert n_ida >= 6
+    assert text == "".join(want)
+    assert text.count("IDA: p-") == n_ida and "CRC:OK" in text and "CRC:no" in text
+    p.close()
+
+
+def test_reference_named_entry_points(pl):
+    """frame_decode() / ida_decode() of include/ir_ref_api.h, one frame per call the way main.c:320-350 calls
+    them, against the reference's own functions: the returned structs byte for byte."""
+    from oracle import bindings as ob
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref/libref_frame.so did not travel with the snapshot")
+    ref, L = C.CDLL(REF_SO), pl.load_library()
+    raw_args = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_float, C.c_float, C.c_float, C.c_int,
+                C.c_int, C.c_void_p]
+    ref.ref_frame_decode_raw.argtypes = raw_args
+    ref.ref_ida_decode_raw.argtypes = raw_args
+    L.frame_decode.argtypes = [C.POINTER(ob.RefDemodFrame), C.c_void_p]
+    L.ida_decode.argtypes = [C.POINTER(ob.RefDemodFrame), C.c_void_p]
+    nd, nb = ref.ref_sizeof_decoded_frame(), ref.ref_sizeof_ida_burst()
+    rng = np.random.default_rng(9)
+    L.frame_decode_init()
+    L.ida_decode_init()
+    hits = 0
+    for bits, llr, direction in fg.corpus(77, 300):
+        ts, freq = int(rng.integers(1, 2**62)), float(rng.uniform(1.616e9, 1.6265e9))
+        mag, noise, level = (float(np.float32(v)) for v in (rng.uniform(5, 60), rng.uniform(-130, -90), rng.uniform(0, 2)))
+        conf, npay = int(rng.integers(0, 101)), len(bits) // 2 - 12
+        lp = None if llr is None else llr.ctypes.data_as(C.c_void_p)
+        want_d, want_b = C.create_string_buffer(nd), C.create_string_buffer(nb)
+        r1 = ref.ref_frame_decode_raw(bits.ctypes.data_as(C.c_void_p), lp, len(bits), direction, ts, freq, mag, noise, level, conf, npay, want_d)
+        r2 = ref.ref_ida_decode_raw(bits.ctypes.data_as(C.c_void_p), lp, len(bits), direction, ts, freq, mag, noise, level, conf, npay, want_b)
+        f = ob.RefDemodFrame()
+        f.timestamp, f.center_frequency, f.direction, f.magnitude, f.noise, f.level = ts, freq, direction, mag, noise, level
+        f.confidence, f.n_payload_symbols, f.n_symbols, f.n_bits = conf, npay, npay + 12, len(bits)
+        f.bits = bits.ctypes.data_as(C.POINTER(C.c_uint8))
+        f.llr = None if llr is None else llr.ctypes.data_as(C.POINTER(C.c_float))
+        got_d, got_b = C.create_string_buffer(b"\x55" * nd, nd), C.create_string_buffer(b"\x55" * nb, nb)
+        assert L.frame_decode(C.byref(f), got_d) == r1
+        assert L.ida_decode(C.byref(f), got_b) == r2
+        assert got_d.raw == want_d.raw and got_b.raw == want_b.raw
+        hits += r1 + r2
+    assert hits > 100
+
+
+def test_classify_refuses_bad_arguments(pl):
+    L = pl.load_library()
+    fr = (pl.Frame * 1)()
+    fr[0].n_bits, fr[0].bits_offset = 100, 50
+    bits = np.zeros(100, np.uint8)
+    out = (pl.FrameClass * 1)()
+    assert L.ir_classify_frames(0, fr, 1, bits.ctypes.data_as(C.c_void_p), None, 100, out) == -1   # frame outside the array
+    assert b"outside" in L.ir_last_error()
+    assert L.ir_classify_frames(99, fr, 1, bits.ctypes.data_as(C.c_void_p), None, 100, out) == -1  # no such device
