@@ -140,7 +140,7 @@ extern "C" int ir_format_ida(char *dst, size_t cap, uint64_t t0, const ir_frame_
         if (c->da_len > 0) {
             bool rest_zero = true;
             for (int i = c->da_len + 1; i < 20; i++) rest_zero = rest_zero && c->payload[i] == 0;
-            if (rest_zero) shown = c->da_len;
+            if (rest_zero) shown = c->da_len < 32 ? c->da_len : 32;      // (da_len <= 20 from the classifier; never read past payload[])
         }
         s += " [";
         for (int i = 0; i < shown; i++) {

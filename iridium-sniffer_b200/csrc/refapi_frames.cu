@@ -61,9 +61,9 @@ int ir_fill_ida_burst(const ir_frame_t *f, const ir_frame_class_t *c, void *ida_
     out->da_ctr = c->da_ctr; out->da_len = c->da_len; out->cont = c->cont;
     out->payload_len = c->payload_len; out->crc_ok = c->crc_ok;
     out->stored_crc = c->stored_crc; out->computed_crc = c->computed_crc; out->fixederrs = c->fixederrs;
-    memcpy(out->payload, c->payload, (size_t)(c->payload_len < 32 ? c->payload_len : 32));
+    memcpy(out->payload, c->payload, (size_t)(c->payload_len < 0 ? 0 : c->payload_len < 32 ? c->payload_len : 32));
     out->bch_len = c->bch_len;
-    memcpy(out->bch_stream, c->bch_stream, (size_t)(c->bch_len < 256 ? c->bch_len : 256));
+    memcpy(out->bch_stream, c->bch_stream, (size_t)(c->bch_len < 0 ? 0 : c->bch_len < 256 ? c->bch_len : 256));
     out->lcw.ft = 2; out->lcw.lcw_ok = 1; out->lcw.lcw_ft = c->lcw_ft; out->lcw.lcw_code = c->lcw_code;
     out->lcw.lcw3_val = c->lcw3_val; out->lcw.ec_lcw = c->ec_lcw;
     ir_format_lcw(out->lcw_header, sizeof(out->lcw_header), c);

@@ -168,3 +168,19 @@ def test_parsed_run_equals_the_reference_program(shim, product, port, synth, tmp
             line = port.format_raw("x", BASE_NS, fr) + "\n"
         got.append(line.rstrip("\n").split(" ", 3)[3])
     assert sorted(got) == want
+
+
+def test_formatter_survives_records_no_classifier_would_produce(product):
+    """garbage in a class record (negative or huge lengths, codes out of range) must not crash or overrun"""
+    pl, L = product
+    f = pl.Frame()
+    f.timestamp = BASE_NS + 1
+    buf = C.create_string_buffer(4096)
+    for bch_len, da_len, lcw_ft, lcw_code in ((-5, 3, 0, 0), (100000, 20, 7, 99), (19, 0, -1, -1), (256, 31, 2, 3), (200, 100, 1, 1)):
+        c = fc.FrameClass()
+        c.ida_ok, c.bch_len, c.da_len, c.lcw_ft, c.lcw_code, c.lcw3_val = 1, bch_len, da_len, lcw_ft, lcw_code, 0xFFFFFFFF
+        n = L.ir_format_ida(buf, len(buf), BASE_NS, C.byref(f), C.byref(c))
+        assert 0 < n < 1000 and buf.value.decode().startswith("IDA: p-1700000000 ") and buf.value.endswith(b"\n")
+    c = fc.FrameClass()
+    assert L.ir_format_ida(buf, len(buf), BASE_NS, C.byref(f), C.byref(c)) == -1      # not an IDA frame
+    assert L.ir_format_lcw(buf, len(buf), C.byref(c)) == -1
