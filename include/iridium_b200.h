@@ -212,6 +212,10 @@ int ir_classify_frames(int device, const ir_frame_t *frames, size_t n_frames, co
  * ir_results_t.frames[i].  Returns the number of frames classified, or -1. */
 long ir_pipeline_classify(ir_pipeline_t *p, ir_frame_class_t *out, size_t cap);
 
+/* Device time (ms, CUDA events on the launching stream) of the classification kernel in the last
+ * ir_pipeline_classify call; -1 without a pipeline. */
+float ir_pipeline_last_classify_ms(ir_pipeline_t *p);
+
 /* The reference's --parsed sink.  ir_format_lcw: the "LCW(...)" header ida_decode() leaves in
  * ida_burst_t.lcw_header (ida_decode.c:398-541; 110 columns + one space).  ir_format_ida: the whole
  * "IDA: ..." line of frame_output_print_ida() (frame_output.c:203-357) for a frame whose class has

@@ -191,6 +191,8 @@ struct ir_pipeline {
     std::vector<FrameSrc> frame_src;                              // per frame: where k_demod left its bits / LLRs (device)
     DevBuf<FrameSrc> d_frame_src;
     DevBuf<ir_frame_class_t> d_class;
+    float ms_classify = 0.0f;                                     // device time of the last k_classify_frames launch
+    cudaEvent_t ev_cls[2] = {nullptr, nullptr};
     // RAW: lines formatted while the run is still in flight (everything after the file_info field,
     // with t0 = frame_output.c:144-158's rule), so that the batched sink is a copy
     std::string raw_rest;
@@ -298,6 +300,7 @@ extern "C" void ir_pipeline_destroy(ir_pipeline_t *p) {
     p->d_xu[0].release(); p->d_xu[1].release(); p->d_ref[0].release(); p->d_ref[1].release();
     p->d_undo.release(); p->d_base_snap.release();
     p->d_frame_src.release(); p->d_class.release();
+    for (auto e : p->ev_cls) if (e) cudaEventDestroy(e);
     if (p->st_cls) cudaStreamDestroy(p->st_cls);
     p->d_ctl.release();
     p->dev_arena.release(); p->pin_arena.release();
@@ -1031,13 +1034,21 @@ extern "C" long ir_pipeline_classify(ir_pipeline_t *p, ir_frame_class_t *out, si
     CK(classify_tables(p->dev, &d_tab));
     if (p->d_frame_src.ensure(n) || p->d_class.ensure(n)) return -1;
     CK(cudaMemcpyAsync(p->d_frame_src.p, p->frame_src.data(), n * sizeof(FrameSrc), cudaMemcpyHostToDevice, p->st_burst));
+    for (auto &e : p->ev_cls)
+        if (!e) CK(cudaEventCreate(&e));
+    cudaEvent_t e0 = p->ev_cls[0], e1 = p->ev_cls[1];
+    CK(cudaEventRecord(e0, p->st_burst));
     CK(launch_classify(d_tab, p->d_frame_src.p, (int)n, p->d_class.p, p->st_burst));
+    CK(cudaEventRecord(e1, p->st_burst));
     CK(cudaMemcpyAsync(out, p->d_class.p, n * sizeof(ir_frame_class_t), cudaMemcpyDeviceToHost, p->st_burst));
     CK(cudaStreamSynchronize(p->st_burst));
+    CK(cudaEventElapsedTime(&p->ms_classify, e0, e1));
     p->res.kernel_launches++;
     classify_finish(out, n);
     return (long)n;
 }
+
+extern "C" float ir_pipeline_last_classify_ms(ir_pipeline_t *p) { return p ? p->ms_classify : -1.0f; }
 
 extern "C" int ir_classify_frames(int device, const ir_frame_t *frames, size_t n_frames, const uint8_t *bits,
                                   const float *llr, size_t n_bits_total, ir_frame_class_t *out) {

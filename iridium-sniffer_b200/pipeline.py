@@ -127,6 +127,8 @@ def load_library() -> C.CDLL:
                                      C.POINTER(FrameClass)]
     L.ir_pipeline_classify.restype = C.c_long
     L.ir_pipeline_classify.argtypes = [C.c_void_p, C.POINTER(FrameClass), C.c_size_t]
+    L.ir_pipeline_last_classify_ms.restype = C.c_float
+    L.ir_pipeline_last_classify_ms.argtypes = [C.c_void_p]
     L.ir_format_lcw.restype = C.c_int
     L.ir_format_lcw.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p]
     L.ir_format_ida.restype = C.c_int
@@ -170,7 +172,8 @@ EXPORTED_SYMBOLS = [
     "ir_pipeline_copy_mag", "ir_pipeline_copy_frame_samples", "ir_pipeline_copy_decimated",
     "ir_pipeline_copy_burst_samples", "ir_format_raw", "ir_pipeline_format_raw_all", "ir_host_alloc",
     "ir_host_free", "ir_pipeline_scan_stats", "ir_plan_chunks", "ir_classify_frames", "ir_pipeline_classify",
-    "ir_format_lcw", "ir_format_ida", "ir_pipeline_format_parsed_all",
+    "ir_format_lcw", "ir_format_ida", "ir_pipeline_format_parsed_all", "ir_pipeline_last_classify_ms",
+    "ir_fill_decoded_frame", "ir_fill_ida_burst",
 ]
 
 
@@ -343,6 +346,9 @@ class Pipeline:
         if got < 0:
             raise RuntimeError("ir_pipeline_classify failed: " + self.L.ir_last_error().decode())
         return [out[i] for i in range(got)]
+
+    def classify_ms(self) -> float:
+        return float(self.L.ir_pipeline_last_classify_ms(self.h))
 
     def parsed_text(self, file_info: str = "T", t0: int = 0) -> bytes:
         """The run's output the way `--parsed` prints it: IDA lines where ida_decode() accepts, RAW lines otherwise
