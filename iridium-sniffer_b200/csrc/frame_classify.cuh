@@ -4,11 +4,12 @@
 // fields, CRC) compute from demod_frame_t.bits / .llr.  The reference calls both on every frame
 // (main.c:320-350), so one pass fills both halves of ir_frame_class_t.
 //
-// Written as __host__ __device__ code on purpose: k_classify.cu runs it one thread per frame on the
+// Written as __host__ __device__ code on purpose: k_classify.cu runs it one warp per frame on the
 // GPU (frames are few and small next to the IQ stream; the work is integer/bit arithmetic on <= 16
 // 32-bit blocks), and tests compile the very same header for the host to compare it with the CPU
-// oracle and with the reference's own functions without a GPU.  The library itself never runs it on
-// the host.
+// oracle and with the reference's own functions without a GPU.  The library itself never classifies a
+// frame on the host (only the public bit helpers of frame_decode.h, host functions by contract, reuse
+// fc_rem / fc_take / fc_fill in refapi_frames.cu).
 //
 // A de-interleaved 32-bit block is one word with its first bit in bit 31: the 31-bit code word is
 // w >> 1, the overall parity bit w & 1, corrections are XOR masks.
@@ -393,10 +394,11 @@ IR_HD int fc_ida(const FcTables &T, const uint8_t *bits, const float *llr, int n
     return 1;
 }
 
-// lat / lon / alt of an IRA frame from its integer position (frame_decode.c:338-347).  Host only: the
-// reference computes them with the C library's double atan2 / sqrt, and the last bit of the device's atan2
-// is not the C library's, so the kernel stops at pos_xyz and the C-ABI wrapper finishes the three numbers.
-inline void fc_geo(ir_frame_class_t *o) {
+// lat / lon / alt of an IRA frame from its integer position (frame_decode.c:338-347), in double like the
+// reference.  alt is exact (products of 12-bit integers and an IEEE square root); lat / lon go through atan2,
+// where the device's double-precision atan2 may differ from the host C library's in the last bits (as two C
+// libraries may from each other): the GPU tests allow 1e-11 degrees on these two fields and nothing elsewhere.
+IR_HD void fc_geo(ir_frame_class_t *o) {
     if (o->frame_type != IR_FRAME_IRA) return;
     const int x = o->pos_xyz[0], y = o->pos_xyz[1], z = o->pos_xyz[2];
     const double xy = sqrt((double)x * x + (double)y * y);
@@ -410,6 +412,7 @@ IR_HD void fc_classify(const FcTables &T, const uint8_t *bits, const float *llr,
     uint8_t *z = reinterpret_cast<uint8_t *>(o);
     for (unsigned i = 0; i < sizeof(*o); i++) z[i] = 0;
     fc_frame(T, bits, llr, n_bits, o);
+    fc_geo(o);
     fc_ida(T, bits, llr, n_bits, direction, o);
 }
 

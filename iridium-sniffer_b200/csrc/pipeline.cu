@@ -1019,11 +1019,6 @@ extern "C" long ir_pipeline_format_raw_all(ir_pipeline_t *p, const char *file_in
 }
 
 // ---- frame classification: frame_decode() + ida_decode() of main.c:320-350, batched
-static int classify_finish(ir_frame_class_t *out, size_t n) {
-    for (size_t i = 0; i < n; i++) fc_geo(&out[i]);     // three doubles per IRA frame, with the C library like the reference
-    return 0;
-}
-
 extern "C" long ir_pipeline_classify(ir_pipeline_t *p, ir_frame_class_t *out, size_t cap) {
     if (!p || (!out && cap)) { set_err("ir_pipeline_classify: null argument"); return -1; }
     const size_t n = p->frames.size();
@@ -1044,7 +1039,6 @@ extern "C" long ir_pipeline_classify(ir_pipeline_t *p, ir_frame_class_t *out, si
     CK(cudaStreamSynchronize(p->st_burst));
     CK(cudaEventElapsedTime(&p->ms_classify, e0, e1));
     p->res.kernel_launches++;
-    classify_finish(out, n);
     return (long)n;
 }
 
@@ -1083,7 +1077,6 @@ extern "C" int ir_classify_frames(int device, const ir_frame_t *frames, size_t n
     CK(cudaMemcpy(d_src.p, src.data(), n_frames * sizeof(FrameSrc), cudaMemcpyHostToDevice));
     CK(launch_classify(d_tab, d_src.p, (int)n_frames, d_out.p, 0));
     CK(cudaMemcpy(out, d_out.p, n_frames * sizeof(ir_frame_class_t), cudaMemcpyDeviceToHost));
-    classify_finish(out, n_frames);
     return 0;
 }
 

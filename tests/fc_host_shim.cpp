@@ -10,7 +10,6 @@ static bool g_ready;
 extern "C" int fc_host_classify(const uint8_t *bits, const float *llr, int n_bits, int direction, ir_frame_class_t *out) {
     if (!g_ready) { ir::fc_build_tables(g_tab); g_ready = true; }
     ir::fc_classify(g_tab, bits, llr, n_bits, direction, out);
-    ir::fc_geo(out);
     return 0;
 }
 extern "C" int fc_host_sizeof(void) { return (int)sizeof(ir_frame_class_t); }

@@ -54,11 +54,16 @@ _IDA_FIELDS = ["lcw_ft", "lcw_code", "ec_lcw", "lcw3_val", "da_ctr", "da_len", "
                "fixederrs", "bch_len", "stored_crc", "computed_crc"]
 
 
-def assert_same(got, flat, ida, where=""):
-    """got: FrameClass from the product's code; flat / ida: what frame_decode() / ida_decode() said"""
+def assert_same(got, flat, ida, where="", geo_tol=0.0):
+    """got: FrameClass from the product's code; flat / ida: what frame_decode() / ida_decode() said.  geo_tol:
+    absolute tolerance in degrees on lat / lon only (0 = bit-exact: host-compiled code shares the reference's C
+    library; 1e-11 for the GPU, whose double atan2 is not the C library's) -- every other field is exact."""
     assert got.frame_type == (flat.type if flat.ret else 0), (where, "type", got.frame_type, flat.ret, flat.type)
     if flat.ret:
         for k in _FRAME_FIELDS:
+            if k in ("lat", "lon") and geo_tol > 0:
+                assert abs(getattr(got, k) - getattr(flat, k)) <= geo_tol, (where, k, getattr(got, k), getattr(flat, k))
+                continue
             assert getattr(got, k) == getattr(flat, k), (where, k, getattr(got, k), getattr(flat, k))
         for k in ("pos_xyz", "tmsi", "msc_id"):
             assert list(getattr(got, k)) == list(getattr(flat, k)), (where, k)

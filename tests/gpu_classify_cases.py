@@ -1,6 +1,7 @@
 """SURVEY.md 8f rank 3 on the GPU: k_classify_frames through the C ABI (ir_classify_frames,
 ir_pipeline_classify) against the oracle port and -- when oracle/_ref/libref_frame.so travelled with the
-snapshot -- the reference's own frame_decode() / ida_decode(), every field, bit for bit.
+snapshot -- the reference's own frame_decode() / ida_decode(): every field bit for bit, except the two
+floating-point ones (lat, lon of an IRA frame: double atan2 on the device), which get 1e-11 degrees.
 
 NOTE (round 1): this kernel was written after the round's GPU minutes were spent; its arithmetic is pinned on
 the CPU (tests/test_frame_classify_host.py compiles the same header for the host), but these tests had not yet
@@ -23,6 +24,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 PORT_SO = os.path.join(ROOT, "oracle", "libir_frame_oracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_frame.so")
+GEO_TOL = 1e-11          # degrees, on lat / lon of IRA frames only (double atan2 on the device vs the C library); all else exact
 
 
 def _load(name):
@@ -69,7 +71,7 @@ def test_generated_frames_one_launch(pl, checkers):
         for o, (bits, llr, direction) in zip(got, group):
             o = _as_fc(o)
             for name, chk in checkers:
-                fc.assert_same(o, *chk(bits, llr, direction), where=name)
+                fc.assert_same(o, *chk(bits, llr, direction), where=name, geo_tol=GEO_TOL)
             decoded += (o.frame_type != 0) + o.ida_ok
     assert decoded > 800
     assert pl.classify_frames([]) == []
@@ -89,7 +91,7 @@ def test_pipeline_classifies_planted_frames_from_device_memory(pl, checkers, syn
             assert bytes(o) == bytes(o2)
             o = _as_fc(o)
             for name, chk in checkers:
-                fc.assert_same(o, *chk(f["bits"], f["llr"], f["direction"]), where=name)
+                fc.assert_same(o, *chk(f["bits"], f["llr"], f["direction"]), where=name, geo_tol=GEO_TOL)
             if "".join(map(str, f["bits"])) in planted:
                 assert o.frame_type != 0 or o.ida_ok == 1
                 seen["ira"] += o.frame_type == 1
@@ -164,7 +166,14 @@ def test_reference_named_entry_points(pl):
         got_d, got_b = C.create_string_buffer(b"\x55" * nd, nd), C.create_string_buffer(b"\x55" * nb, nb)
         assert L.frame_decode(C.byref(f), got_d) == r1
         assert L.ida_decode(C.byref(f), got_b) == r2
-        assert got_d.raw == want_d.raw and got_b.raw == want_b.raw
+        assert got_b.raw == want_b.raw
+        g, w = got_d.raw, want_d.raw
+        if r1 and int.from_bytes(w[:4], "little") == 1:          # IRA: lat, lon are the doubles at bytes 32..48 of decoded_frame_t
+            import struct
+            for a, b in zip(struct.unpack_from("<2d", g, 32), struct.unpack_from("<2d", w, 32)):
+                assert abs(a - b) <= GEO_TOL
+            g, w = g[:32] + g[48:], w[:32] + w[48:]
+        assert g == w
         hits += r1 + r2
     assert hits > 100
 
