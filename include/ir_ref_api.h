@@ -225,4 +225,11 @@ int ida_decode(const demod_frame_t *frame, ida_burst_t *burst);                 
 int ida_reassemble(ida_context_t *ctx, const ida_burst_t *burst, ida_message_cb cb, void *user);   /* :91 */
 void ida_reassemble_flush(ida_context_t *ctx, uint64_t now_ns);                  /* :95 */
 
+/* ---- frame_output.h:20-29: the per-line sinks (one fwrite + fflush per line, like the reference).  They read
+ * main.c's diagnostic_mode / acars_enabled as weak symbols.  frame_output_zmq_* (HAVE_ZMQ builds) are not
+ * provided: keep frame_output.c if ZMQ publishing is wanted. ---- */
+void frame_output_init(const char *file_info);
+void frame_output_print(demod_frame_t *frame);
+void frame_output_print_ida(const ida_burst_t *burst);
+
 #endif

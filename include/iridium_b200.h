@@ -225,6 +225,9 @@ float ir_pipeline_last_classify_ms(ir_pipeline_t *p);
 int ir_format_lcw(char *dst, size_t cap, const ir_frame_class_t *cls);
 int ir_format_ida(char *dst, size_t cap, uint64_t t0, const ir_frame_t *frame,
                   const ir_frame_class_t *cls);
+/* the same with the header text given (what frame_output_print_ida() does with ida_burst_t.lcw_header) */
+int ir_format_ida_hdr(char *dst, size_t cap, uint64_t t0, const ir_frame_t *frame,
+                      const ir_frame_class_t *cls, const char *lcw_header);
 
 /* All output lines of the last run the way `--parsed` prints them (main.c:328-331): the IDA line for a
  * frame ida_decode() accepted, its RAW line otherwise.  cls = what ir_pipeline_classify returned for this

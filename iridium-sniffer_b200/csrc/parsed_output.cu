@@ -113,6 +113,11 @@ extern "C" int ir_format_lcw(char *dst, size_t cap, const ir_frame_class_t *c) {
 }
 
 extern "C" int ir_format_ida(char *dst, size_t cap, uint64_t t0, const ir_frame_t *f, const ir_frame_class_t *c) {
+    return ir_format_ida_hdr(dst, cap, t0, f, c, nullptr);
+}
+
+extern "C" int ir_format_ida_hdr(char *dst, size_t cap, uint64_t t0, const ir_frame_t *f, const ir_frame_class_t *c,
+                                 const char *lcw_text) {
     if (!f || !c || !c->ida_ok) return -1;
     std::string s;
     const double ts_ms = (double)(f->timestamp - t0) / 1000000.0;
@@ -123,7 +128,7 @@ extern "C" int ir_format_ida(char *dst, size_t cap, uint64_t t0, const ir_frame_
     appendf(s, "IDA: p-%llu %014.4f %010d %3d%% %06.2f|%07.2f|%05.2f %3d %s ", (unsigned long long)(t0 / 1000000000ULL), ts_ms,
             fhz, f->confidence, leveldb, (double)f->noise, (double)f->magnitude, syms,
             f->direction == IR_DIR_UPLINK ? "UL" : "DL");
-    s += lcw_header(c);
+    if (lcw_text) s += lcw_text; else s += lcw_header(c);
     const uint8_t *bs = c->bch_stream;
     const int bch_len = c->bch_len < 256 ? c->bch_len : 256;      // what bch_stream holds
     auto bits = [&](int a, int n) { for (int i = a; i < a + n; i++) s += (char)('0' + bs[i]); };

@@ -172,4 +172,64 @@ void ida_reassemble_flush(ida_context_t *ctx, uint64_t now_ns) {
         if (s.active && now_ns > s.last_timestamp + kGapNs) s.active = 0;
 }
 
+// ---- frame_output.h: the per-line sinks under the reference's names (frame_output.c:100-105, 144-357), so
+// that frame_output.c can leave the build as well when ZMQ is not used (frame_output_zmq_* are not provided).
+// One fwrite + fflush per line like the reference; ir_pipeline_format_raw_all / _parsed_all are the batched way.
+extern int diagnostic_mode __attribute__((weak));      // main.c's switches; absent (stand-alone) = 0
+extern int acars_enabled __attribute__((weak));
+
+static const char *g_file_info = nullptr;
+static uint64_t g_t0 = 0;
+static bool g_sink_ready = false;
+static char g_auto_info[64];
+
+static void sink_begin(uint64_t timestamp) {               // frame_output.c:144-158
+    if (g_sink_ready) return;
+    g_t0 = (timestamp / 1000000000ULL) * 1000000000ULL;
+    if (!g_file_info || !g_file_info[0]) {
+        snprintf(g_auto_info, sizeof(g_auto_info), "i-%llu-t1", (unsigned long long)(g_t0 / 1000000000ULL));
+        g_file_info = g_auto_info;
+    }
+    g_sink_ready = true;
+}
+static void sink_write(const char *line, int n) {
+    if (n > 0) { fwrite(line, 1, (size_t)n, stdout); fflush(stdout); }
+}
+
+void frame_output_init(const char *file_info) { g_file_info = file_info; }
+
+void frame_output_print(demod_frame_t *frame) {
+    if ((&diagnostic_mode && diagnostic_mode) || (&acars_enabled && acars_enabled)) return;
+    sink_begin(frame->timestamp);
+    ir_frame_t f;
+    memset(&f, 0, sizeof(f));
+    f.id = frame->id; f.timestamp = frame->timestamp; f.center_frequency = frame->center_frequency;
+    f.magnitude = frame->magnitude; f.noise = frame->noise; f.confidence = frame->confidence; f.level = frame->level;
+    f.n_payload_symbols = frame->n_payload_symbols; f.n_bits = frame->n_bits;
+    static char line[8192];                                // the reference's line buffer size
+    int nb = frame->n_bits;
+    ir_frame_t g = f;
+    if (nb > 8000) g.n_bits = 8000;
+    sink_write(line, ir_format_raw(line, sizeof(line), g_file_info, g_t0, &g, frame->bits));
+}
+
+void frame_output_print_ida(const ida_burst_t *burst) {
+    if (&diagnostic_mode && diagnostic_mode) return;
+    sink_begin(burst->timestamp);
+    ir_frame_t f;
+    memset(&f, 0, sizeof(f));
+    f.timestamp = burst->timestamp; f.center_frequency = burst->frequency; f.direction = burst->direction;
+    f.magnitude = burst->magnitude; f.noise = burst->noise; f.level = burst->level; f.confidence = burst->confidence;
+    f.n_payload_symbols = burst->n_symbols;
+    ir_frame_class_t c;
+    memset(&c, 0, sizeof(c));
+    c.ida_ok = 1;
+    c.da_len = burst->da_len; c.crc_ok = burst->crc_ok; c.stored_crc = burst->stored_crc; c.computed_crc = burst->computed_crc;
+    c.bch_len = burst->bch_len;
+    memcpy(c.payload, burst->payload, sizeof(c.payload));
+    memcpy(c.bch_stream, burst->bch_stream, sizeof(c.bch_stream));
+    static char line[8192];
+    sink_write(line, ir_format_ida_hdr(line, sizeof(line), g_t0, &f, &c, burst->lcw_header));
+}
+
 }  // extern "C"

@@ -204,3 +204,67 @@ def test_bit_helpers(ref, lib):
         ref.uint_to_bits(v, o1.ctypes.data_as(C.c_void_p), n)
         lib.uint_to_bits(v, o2.ctypes.data_as(C.c_void_p), n)
         assert o1.tolist() == o2.tolist() == bits.tolist()
+
+
+_SINK_SCRIPT = r'''
+import ctypes as C, importlib, importlib.util, os, sys, numpy as np
+ROOT, REF_SO, out_dir = sys.argv[1], sys.argv[2], sys.argv[3]
+sys.path.insert(0, ROOT)
+def _load(name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tests", name + ".py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m); return m
+fg, fc = _load("frame_gen"), _load("frame_class_types")
+from oracle import bindings as ob
+ref = C.CDLL(REF_SO)
+lib = importlib.import_module("iridium-sniffer_b200.pipeline").load_library()
+raw_args = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p]
+ref.ref_ida_decode_raw.argtypes = raw_args
+libc = C.CDLL(None)
+FI = None if sys.argv[4] == "auto" else C.c_char_p(sys.argv[4].encode())      # borrowed by both: must stay alive
+rng = np.random.default_rng(3)
+items = []
+t = 1_723_456_789_123_456_789
+for k in range(60):
+    t += int(rng.integers(1, 10**8))
+    da = int(rng.integers(0, 21))
+    bits = np.array(fg.make_ida(rng, da, good_crc=bool(k % 3)), np.uint8) if k % 2 else rng.integers(0, 2, int(rng.integers(0, 400))).astype(np.uint8)
+    f = ob.RefDemodFrame()
+    f.id, f.timestamp, f.center_frequency, f.direction = int(rng.integers(0, 10**10)), t, float(rng.uniform(1.616e9, 1.6265e9)), 1 + k % 2
+    f.magnitude, f.noise, f.level, f.confidence = float(rng.uniform(5, 60)), float(rng.uniform(-130, -90)), float(rng.uniform(0, 2)), int(rng.integers(0, 101))
+    f.n_payload_symbols, f.n_symbols, f.n_bits = len(bits) // 2 - 12, len(bits) // 2, len(bits)
+    f.bits = bits.ctypes.data_as(C.POINTER(C.c_uint8))
+    burst = fc.IdaBurst()
+    ok = ref.ref_ida_decode_raw(bits.ctypes.data_as(C.c_void_p), None, len(bits), f.direction, f.timestamp, f.center_frequency,
+                                f.magnitude, f.noise, f.level, f.confidence, f.n_payload_symbols, C.byref(burst))
+    items.append((f, bits, burst if ok else None))
+for name, L in (("ref", ref), ("lib", lib)):
+    L.frame_output_init.argtypes = [C.c_char_p]
+    L.frame_output_print.argtypes = [C.POINTER(ob.RefDemodFrame)]
+    L.frame_output_print_ida.argtypes = [C.POINTER(fc.IdaBurst)]
+    fd = os.open(os.path.join(out_dir, name + ".txt"), os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+    libc.fflush(None)
+    saved = os.dup(1)
+    os.dup2(fd, 1)
+    L.frame_output_init(FI)
+    for f, bits, burst in items:
+        if burst is not None:
+            L.frame_output_print_ida(C.byref(burst))       # main.c:328-331 with --parsed
+        else:
+            L.frame_output_print(C.byref(f))
+    libc.fflush(None)
+    os.dup2(saved, 1)
+    os.close(fd)
+'''
+
+
+@pytest.mark.parametrize("file_info", ["auto", "rec-17"])
+def test_per_line_sinks_equal_the_references(ref, tmp_path, file_info):
+    """frame_output_init / frame_output_print / frame_output_print_ida under the reference's names: the bytes on
+    stdout for a mixed run of RAW and IDA lines, time origin and automatic file_info included (in a child
+    process: both implementations fix their time origin at the first line they ever print)."""
+    import sys
+    r = subprocess.run([sys.executable, "-c", _SINK_SCRIPT, ROOT, REF_SO, str(tmp_path), file_info], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    a, b = open(tmp_path / "ref.txt", "rb").read(), open(tmp_path / "lib.txt", "rb").read()
+    assert a == b and a.count(b"\n") == 60 and a.count(b"IDA: ") >= 20 and a.count(b"RAW: ") >= 20
+    assert (b"RAW: rec-17 " in a) == (file_info != "auto") and (b"RAW: i-1723456789-t1 " in a) == (file_info == "auto")
