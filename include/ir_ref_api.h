@@ -225,6 +225,9 @@ int ida_decode(const demod_frame_t *frame, ida_burst_t *burst);                 
 int ida_reassemble(ida_context_t *ctx, const ida_burst_t *burst, ida_message_cb cb, void *user);   /* :91 */
 void ida_reassemble_flush(ida_context_t *ctx, uint64_t now_ns);                  /* :95 */
 
+/* simd_kernels.h:105 -- main.c:567 calls it at start-up; with this library there are no CPU kernels to select. */
+void simd_init(int force_generic);
+
 /* ---- frame_output.h:20-29: the per-line sinks (one fwrite + fflush per line, like the reference).  They read
  * main.c's diagnostic_mode / acars_enabled as weak symbols.  frame_output_zmq_* (HAVE_ZMQ builds) are not
  * provided: keep frame_output.c if ZMQ publishing is wanted. ---- */

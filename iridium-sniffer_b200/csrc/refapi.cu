@@ -48,6 +48,13 @@ __attribute__((weak)) int use_gardner = 1;
 __attribute__((weak)) int verbose = 0;
 }
 
+// simd_kernels.h:105: main.c:567 calls it before any DSP to pick the CPU kernels of simd_*.c.  Those files are
+// not part of a build that links this library (every stage runs on the GPU), so there is nothing to select.
+extern "C" void simd_init(int force_generic) {
+    (void)force_generic;
+    fprintf(stderr, "iridium-sniffer: DSP stages run on the GPU (libiridium_b200, sm_100a kernels); no CPU SIMD kernels in this build\n");
+}
+
 #define RCK(expr, ret)                                                                     \
     do {                                                                                   \
         cudaError_t _e = (expr);                                                           \

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared(header):
     txt = open(os.path.join(ROOT, "include", header)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:ir_|gpu_burst_fft_|burst_detector_|burst_downmix_|qpsk_demod|frame_decode|frame_output_|ida_|gf2_remainder|bits_to_uint|uint_to_bits|bch_31_21_correct)\w*)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b((?:ir_|gpu_burst_fft_|burst_detector_|burst_downmix_|qpsk_demod|frame_decode|frame_output_|simd_init|ida_|gf2_remainder|bits_to_uint|uint_to_bits|bch_31_21_correct)\w*)\s*\(", txt)))
 
 
 def test_library_exports_declared_symbols():

@@ -1,5 +1,6 @@
 """Runs the GPU cases of the frame classification row (tests/gpu_classify_cases.py: k_classify_frames through the
-C ABI against the oracle and the reference) one per child process.  They were written after round 1's GPU minutes
+C ABI against the oracle and the reference) and of the linked drop-in program (tests/gpu_dropin_cases.py) one per
+child process.  They were written after round 1's GPU minutes
 were spent and had not run on a B200 when committed; a child process keeps a crash in not-yet-proven code from
 taking the whole pytest run with it, and the name sorts this file last under `pytest -x`."""
 import os
@@ -11,14 +12,16 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CASES = ["test_generated_frames_one_launch", "test_pipeline_classifies_planted_frames_from_device_memory",
-         "test_parsed_output_of_a_run", "test_reference_named_entry_points", "test_classify_refuses_bad_arguments"]
+CASES = ["gpu_classify_cases.py::" + c for c in (
+    "test_generated_frames_one_launch", "test_pipeline_classifies_planted_frames_from_device_memory",
+    "test_parsed_output_of_a_run", "test_reference_named_entry_points", "test_classify_refuses_bad_arguments")]
+CASES.append("gpu_dropin_cases.py::test_reference_main_linked_against_the_library")
 
 
 @pytest.mark.parametrize("case", CASES)
 def test_classification_on_the_gpu(case):
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
-                        os.path.join("tests", "gpu_classify_cases.py") + "::" + case],
+                        os.path.join("tests", case)],
                        cwd=ROOT, capture_output=True, text=True, timeout=900)
     tail = (r.stdout + r.stderr)[-4000:]
     assert r.returncode == 0, tail
