@@ -22,7 +22,7 @@ CASES.append("gpu_dropin_cases.py::test_reference_main_linked_against_the_librar
 def test_classification_on_the_gpu(case):
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
                         os.path.join("tests", case)],
-                       cwd=ROOT, capture_output=True, text=True, timeout=900)
+                       cwd=ROOT, capture_output=True, text=True, timeout=420)
     tail = (r.stdout + r.stderr)[-4000:]
     assert r.returncode == 0, tail
     assert "1 passed" in r.stdout or "skipped" in r.stdout, tail
