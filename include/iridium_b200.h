@@ -249,6 +249,50 @@ int ir_fill_ida_burst(const ir_frame_t *frame, const ir_frame_class_t *cls, void
  * arithmetic, exported for tests and for callers that want to align their reads with it. */
 long ir_plan_chunks(size_t n_samples, size_t chunk, size_t fft_size, size_t *ends, size_t cap);
 
+/* ---- one long stream over several pipelines / GPUs by contiguous time blocks ----
+ * Each block is processed exactly like a separate file handed to the reference: a fresh detector whose first 512
+ * frames build the noise baseline and detect nothing (burst_detect.c:426-428).  So that nothing is lost, block k is
+ * fed from `halo` samples before the range it owns -- 512*N for the baseline, plus the longest burst, its post_len
+ * and 2*pre_len (burst_detect.c:181-213), so that a burst already on the air when detection goes live is over before
+ * the owned range begins -- and `tail` samples past its end, so that a burst starting in the owned range is finished,
+ * declared gone and emitted (emission happens at the end of a feed call, burst_detect.c:839-841; bursts still active
+ * at end of input are never emitted: burst_detector_destroy just frees).  Halo, tail and block length are multiples of
+ * lcm(fft_size, feed_block), so detector frames and feed calls fall on the same samples as in the unsharded run.
+ * No exchange between blocks, no collective: the host merges the frames by time stamp.
+ * What differs from the unsharded run, by construction: burst ids (per block, see ir_merge_blocks), and the noise
+ * baseline a block starts from (its own first 512 frames instead of the last 512 quiet frames), which moves the
+ * magnitude / noise fields by hundredths of a dB and can flip a marginal detection. */
+typedef struct {
+    uint64_t feed_first, feed_end;   /* samples [feed_first, feed_end) of the stream go to the block's pipeline */
+    uint64_t own_first, own_end;     /* the block keeps frames whose time stamp falls on samples [own_first, own_end) */
+} ir_block_t;
+
+#define IR_BLOCK_ID_STRIDE 1000000000ULL   /* merged id = block * stride + the block's own id (`I:%011`) */
+
+/* Samples a block is fed before / after the range it owns (0 on a bad configuration). */
+size_t ir_block_halo(const ir_config_t *cfg);
+size_t ir_block_tail(const ir_config_t *cfg);
+
+/* Cuts [0, n_samples) into at most n_blocks blocks of equal owned length (the last takes the remainder; fewer
+ * blocks come back when n_samples is too short for the owned length to exceed the halo).  Block 0 starts at
+ * sample 0 like the unsharded run.  Returns the number of blocks written, -1 on error. */
+long ir_plan_blocks(const ir_config_t *cfg, size_t n_samples, int n_blocks, ir_block_t *blocks, size_t cap);
+
+/* Absolute index of sample 0 of the following runs of this pipeline (= ir_block_t.feed_first): enters the frame time
+ * stamps only -- (start + origin) / fs like burst_downmix.c:659-660 on the whole stream -- with cfg.start_time_ns
+ * staying the time of the STREAM's sample 0.  Sticky until set again; 0 at creation. */
+int ir_pipeline_set_origin(ir_pipeline_t *p, uint64_t sample_origin);
+
+/* Merge of the blocks' frame lists: keeps from block k the frames whose time stamp lies in its owned range (plus
+ * 1 ms beyond its end, where a frame also reported by block k+1 -- within 1 ms and 200 Hz -- is kept once, the
+ * earlier block's), orders them by time stamp (stable: ties keep block, then frame order) and gives them unique ids.
+ * frames[k] / n_frames[k] = ir_results_t.frames / .n_frames of block k (run with ir_pipeline_set_origin(feed_first)
+ * and the stream's start_time_ns).  out[i] is a copy of the frame with the merged id, bits_offset still into its
+ * own block's bit array; out_block[i] says which block.  Returns the number kept, -1 on error (cap too small). */
+long ir_merge_blocks(const ir_config_t *cfg, uint64_t start_time_ns, const ir_block_t *blocks, int n_blocks,
+                     const ir_frame_t *const *frames, const size_t *n_frames, ir_frame_t *out,
+                     uint32_t *out_block, size_t cap);
+
 /* Pinned host allocations for callers that want full-rate H2D. */
 void *ir_host_alloc(size_t bytes);
 void ir_host_free(void *p);

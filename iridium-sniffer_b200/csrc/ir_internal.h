@@ -150,6 +150,7 @@ struct HostTables {
     std::vector<float2> sync_ul_fft;
 };
 void build_host_tables(HostTables &t, int det_fft_size);
+void set_last_error(const std::string &s);   // what ir_last_error() returns on this thread (pipeline.cu)
 void derive_det_config(DetConfig &c, int sample_rate, int fft_size, int burst_width_hz, float threshold_db);
 std::vector<float2> build_twiddle_image(int L);      // layout of ir_device.cuh
 void host_fft(std::vector<float2> &x, bool inverse);   // same radix-2 DIF, for the templates

@@ -30,6 +30,7 @@ using namespace ir;
 
 static thread_local std::string g_err;
 static void set_err(const std::string &s) { g_err = s; }
+namespace ir { void set_last_error(const std::string &s) { g_err = s; } }
 extern "C" const char *ir_last_error(void) { return g_err.c_str(); }
 
 #define CK(expr)                                                                              \
@@ -203,6 +204,7 @@ struct ir_pipeline {
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     uint64_t start_time_ns = 0;
+    uint64_t sample_origin = 0;                                  // ir_pipeline_set_origin: index of sample 0 in the whole stream
     int64_t n_frames_last = 0;
 
     cudaEvent_t ev() {
@@ -562,7 +564,7 @@ static int assemble_wave(ir_pipeline *p, const Wave &w) {
         ob.demod_ok = 1;
         ir_frame_t f;
         f.id = ob.id;
-        uint64_t ts = p->start_time_ns + (uint64_t)((double)ob.start / fs * 1e9);          // :659-660
+        uint64_t ts = p->start_time_ns + (uint64_t)((double)(ob.start + p->sample_origin) / fs * 1e9);          // :659-660
         ts += delay_ns;
         f.timestamp = ts + (uint64_t)((double)c.start / IR_OUT_RATE * 1e9);               // :783
         double cf = p->h_bp[i].cfreq_coarse;
@@ -913,6 +915,12 @@ extern "C" long ir_plan_chunks(size_t n, size_t chunk, size_t fft_size, size_t *
         ends[k++] = off;
     }
     return (long)k;
+}
+
+extern "C" int ir_pipeline_set_origin(ir_pipeline_t *p, uint64_t sample_origin) {
+    if (!p) { set_err("null pipeline"); return -1; }
+    p->sample_origin = sample_origin;
+    return 0;
 }
 
 extern "C" int ir_pipeline_scan_stats(ir_pipeline_t *p, uint64_t *out, int n) {

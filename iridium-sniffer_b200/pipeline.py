@@ -62,6 +62,14 @@ class FrameClass(C.Structure):
                 ("computed_crc", C.c_uint16), ("payload", C.c_uint8 * 32), ("bch_stream", C.c_uint8 * 256)]
 
 
+class Block(C.Structure):
+    """ir_block_t: one time block of a long stream (feed range and owned range, in samples)"""
+    _fields_ = [("feed_first", C.c_uint64), ("feed_end", C.c_uint64), ("own_first", C.c_uint64), ("own_end", C.c_uint64)]
+
+
+BLOCK_ID_STRIDE = 1_000_000_000
+
+
 class Results(C.Structure):
     _fields_ = [("n_bursts", C.c_size_t), ("bursts", C.POINTER(Burst)),
                 ("n_frames", C.c_size_t), ("frames", C.POINTER(Frame)),
@@ -136,8 +144,85 @@ def load_library() -> C.CDLL:
     L.ir_pipeline_format_parsed_all.restype = C.c_long
     L.ir_pipeline_format_parsed_all.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_void_p, C.c_size_t, C.c_char_p,
                                                 C.c_size_t]
+    L.ir_block_halo.restype = C.c_size_t
+    L.ir_block_halo.argtypes = [C.POINTER(Config)]
+    L.ir_block_tail.restype = C.c_size_t
+    L.ir_block_tail.argtypes = [C.POINTER(Config)]
+    L.ir_plan_blocks.restype = C.c_long
+    L.ir_plan_blocks.argtypes = [C.POINTER(Config), C.c_size_t, C.c_int, C.POINTER(Block), C.c_size_t]
+    L.ir_pipeline_set_origin.restype = C.c_int
+    L.ir_pipeline_set_origin.argtypes = [C.c_void_p, C.c_uint64]
+    L.ir_merge_blocks.restype = C.c_long
+    L.ir_merge_blocks.argtypes = [C.POINTER(Config), C.c_uint64, C.POINTER(Block), C.c_int, C.POINTER(C.POINTER(Frame)),
+                                  C.POINTER(C.c_size_t), C.POINTER(Frame), C.POINTER(C.c_uint32), C.c_size_t]
     _lib = L
     return L
+
+
+def make_config(sample_rate: int = 10_000_000, center_frequency: float = 1_622_000_000.0, device: int = 0,
+                threshold_db: float = 16.0, use_gardner: bool = True, fft_size: int = 0, feed_block: int = 32768,
+                start_time_ns: int = 0, h2d_chunk: int = 0) -> Config:
+    cfg = Config()
+    cfg.abi_version = ABI_VERSION
+    cfg.device = device
+    cfg.center_frequency = center_frequency
+    cfg.sample_rate = sample_rate
+    cfg.fft_size = fft_size
+    cfg.threshold_db = threshold_db
+    cfg.use_gardner = int(use_gardner)
+    cfg.feed_block = feed_block
+    cfg.start_time_ns = start_time_ns
+    cfg.h2d_chunk = h2d_chunk
+    return cfg
+
+
+# ---- one long stream over several pipelines by time blocks: plan and merge, host bookkeeping
+def plan_blocks(cfg: Config, n_samples: int, n_blocks: int) -> List[Block]:
+    L = load_library()
+    out = (Block * max(n_blocks, 1))()
+    k = L.ir_plan_blocks(C.byref(cfg), n_samples, n_blocks, out, max(n_blocks, 1))
+    if k < 0:
+        raise RuntimeError("ir_plan_blocks failed: " + L.ir_last_error().decode())
+    res = []
+    for i in range(k):
+        b = Block()
+        C.memmove(C.byref(b), C.byref(out[i]), C.sizeof(Block))
+        res.append(b)
+    return res
+
+
+def merge_blocks(cfg: Config, start_time_ns: int, blocks: List[Block], frame_lists: List[List[dict]]) -> List[dict]:
+    """ir_merge_blocks over per-block frame lists (dicts with the ir_frame_t fields, as RunResult.frames holds them;
+    other keys -- bits, llr -- ride along).  Returns the kept frames in time order, each a copy with the merged id and
+    a "block" key."""
+    L = load_library()
+    nb = len(blocks)
+    assert len(frame_lists) == nb
+    names = [k for k, _ in Frame._fields_]
+    arrays, ptrs, counts = [], (C.POINTER(Frame) * max(nb, 1))(), (C.c_size_t * max(nb, 1))()
+    for k, fl in enumerate(frame_lists):
+        a = (Frame * max(len(fl), 1))()
+        for i, d in enumerate(fl):
+            for nm in names:
+                if nm in d:
+                    setattr(a[i], nm, d[nm])
+            a[i].bits_offset = i                       # carries the list index through the merge
+        arrays.append(a)
+        ptrs[k] = C.cast(a, C.POINTER(Frame))
+        counts[k] = len(fl)
+    cap = sum(len(fl) for fl in frame_lists)
+    out, out_block = (Frame * max(cap, 1))(), (C.c_uint32 * max(cap, 1))()
+    barr = (Block * max(nb, 1))(*blocks)
+    n = L.ir_merge_blocks(C.byref(cfg), start_time_ns, barr, nb, ptrs, counts, out, out_block, cap)
+    if n < 0:
+        raise RuntimeError("ir_merge_blocks failed: " + L.ir_last_error().decode())
+    res = []
+    for i in range(n):
+        d = dict(frame_lists[out_block[i]][out[i].bits_offset])
+        d["id"] = out[i].id
+        d["block"] = int(out_block[i])
+        res.append(d)
+    return res
 
 
 def classify_frames(cases, device: int = 0):
@@ -174,6 +259,7 @@ EXPORTED_SYMBOLS = [
     "ir_host_free", "ir_pipeline_scan_stats", "ir_plan_chunks", "ir_classify_frames", "ir_pipeline_classify",
     "ir_format_lcw", "ir_format_ida", "ir_pipeline_format_parsed_all", "ir_pipeline_last_classify_ms",
     "ir_fill_decoded_frame", "ir_fill_ida_burst",
+    "ir_block_halo", "ir_block_tail", "ir_plan_blocks", "ir_pipeline_set_origin", "ir_merge_blocks",
 ]
 
 
@@ -229,17 +315,8 @@ class Pipeline:
                  fft_size: int = 0, feed_block: int = 32768, start_time_ns: int = 0,
                  h2d_chunk: int = 0):
         self.L = load_library()
-        cfg = Config()
-        cfg.abi_version = ABI_VERSION
-        cfg.device = device
-        cfg.center_frequency = center_frequency
-        cfg.sample_rate = sample_rate
-        cfg.fft_size = fft_size
-        cfg.threshold_db = threshold_db
-        cfg.use_gardner = int(use_gardner)
-        cfg.feed_block = feed_block
-        cfg.start_time_ns = start_time_ns
-        cfg.h2d_chunk = h2d_chunk
+        cfg = make_config(sample_rate, center_frequency, device, threshold_db, use_gardner, fft_size, feed_block,
+                          start_time_ns, h2d_chunk)
         self.cfg = cfg
         self.h = self.L.ir_pipeline_create(C.byref(cfg))
         if not self.h:
@@ -286,6 +363,20 @@ class Pipeline:
         self._check(self.L.ir_pipeline_run_device(self.h, C.c_void_p(dev_ptr), n_samples,
                                                   FMT_BY_NAME[fmt]), "ir_pipeline_run_device")
         return self.results()
+
+    def set_origin(self, sample_origin: int) -> None:
+        """ir_pipeline_set_origin: absolute index of sample 0 of the following runs (time stamps only)."""
+        self._check(self.L.ir_pipeline_set_origin(self.h, sample_origin), "ir_pipeline_set_origin")
+
+    def run_block(self, iq: np.ndarray, block: Block) -> RunResult:
+        """One time block of the cf32 stream `iq` (the whole stream, host memory): feed range in, frames stamped
+        on the stream's clock out.  The caller merges the blocks' results with merge_blocks()."""
+        a = np.ascontiguousarray(iq[block.feed_first:block.feed_end], np.complex64)
+        self.set_origin(block.feed_first)
+        try:
+            return self.run_host(a, "cf32")
+        finally:
+            self.set_origin(0)
 
     # ---- bare calls (no Python-side result conversion): what bench.py times
     def run_device_raw(self, dev_ptr: int, n_samples: int, fmt: str = "cf32") -> None:
