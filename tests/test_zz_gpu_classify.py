@@ -1,6 +1,6 @@
 """Runs the GPU cases of the frame classification row (tests/gpu_classify_cases.py: k_classify_frames through the
-C ABI against the oracle and the reference) and of the linked drop-in program (tests/gpu_dropin_cases.py) one per
-child process.  They were written after round 1's GPU minutes
+C ABI against the oracle and the reference), of the linked drop-in program (tests/gpu_dropin_cases.py) and of the
+time-block sharding of one stream (tests/gpu_block_cases.py) one per child process.  They were written after round 1's GPU minutes
 were spent and had not run on a B200 when committed; a child process keeps a crash in not-yet-proven code from
 taking the whole pytest run with it, and the name sorts this file last under `pytest -x`."""
 import os
@@ -16,6 +16,7 @@ CASES = ["gpu_classify_cases.py::" + c for c in (
     "test_generated_frames_one_launch", "test_pipeline_classifies_planted_frames_from_device_memory",
     "test_parsed_output_of_a_run", "test_reference_named_entry_points", "test_classify_refuses_bad_arguments")]
 CASES.append("gpu_dropin_cases.py::test_reference_main_linked_against_the_library")
+CASES.append("gpu_block_cases.py::test_time_blocks_through_the_cuda_path")      # time blocks, merged
 
 
 @pytest.mark.parametrize("case", CASES)
