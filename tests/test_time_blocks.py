@@ -201,6 +201,37 @@ def test_sharded_oracle_equals_unsharded(port, synth):
         assert len(near_w) >= 4 and len(near_m) == len(near_w), (len(near_w), len(near_m))
 
 
+def test_sharded_oracle_12mhz_two_blocks(port, synth):
+    """config B geometry (12 MHz -> 16384-pt frames, halo 0.82 s): the plan's sizes hold there too"""
+    pl = _pl()
+    fs = 12_000_000
+    cfg = pl.make_config(sample_rate=fs, center_frequency=1_621_000_000.0)
+    n = int(2.6 * fs)
+    blocks = pl.plan_blocks(cfg, n, 2)
+    assert len(blocks) == 2 and int(blocks[1].feed_first) > 0
+    e = int(blocks[0].own_end) / fs
+    rng = np.random.default_rng(5)
+    starts = sorted(list(rng.uniform(0.75, 2.55, 60)) + [e - 0.010, e - 0.005, e - 0.001, e + 0.001])
+    rec = synth.make_recording(99, sample_rate=fs, duration_s=2.6, starts_s=starts, snr_db=(14.0, 25.0),
+                               center_freq=1_621_000_000.0)
+    kw = dict(center_frequency=1_621_000_000.0, sample_rate=fs)
+    whole, _ = port.run(rec.iq, start_time_ns=T0, **kw)
+    lists = []
+    for b in blocks:
+        ff, fe = int(b.feed_first), int(b.feed_end)
+        t_ff = T0 + int(ff / fs * 1e9)                      # ir_pipeline_set_origin's arithmetic, to the ns
+        lists.append(port.run(rec.iq[ff:fe], start_time_ns=t_ff, **kw)[0])
+    merged = pl.merge_blocks(cfg, T0, blocks, lists)
+    matched, exact, missing, extra, dmag = _compare(whole, merged, blocks, fs)
+    assert len(whole) >= 50 and matched >= len(whole) - 1 and exact == matched and len(extra) <= 1, \
+        (len(whole), matched, exact, len(extra))
+    assert (np.array(dmag)[:, 2] <= 3).all()
+    e_ns = T0 + int(int(blocks[0].own_end) / fs * 1e9)
+    near_w = [w for w in whole if abs(w["timestamp"] - e_ns) < 15_000_000]
+    near_m = [d for d in merged if abs(d["timestamp"] - e_ns) < 15_000_000]
+    assert len(near_w) >= 3 and len(near_m) == len(near_w)
+
+
 # ------------------------------------------------------------------ two gloo ranks, blocks dealt round-robin
 def _free_port():
     s = socket.socket()
