@@ -15,6 +15,8 @@
  *                         signatures and struct layouts (include/ir_ref_api.h).
  *   3. gpu_burst_fft_*    the reference's existing accelerator plug-in ABI
  *                         (opencl/burst_fft.h:35-47), see include/burst_fft.h.
+ * Around layer 1: ir_plan_blocks / ir_merge_blocks / ir_multi_* put one long stream on several
+ * GPUs by contiguous time blocks (host bookkeeping, no collective).
  *
  * There is no CPU fallback anywhere: if no CUDA device / kernel image is usable the
  * create calls return NULL and ir_last_error() says why.
@@ -282,6 +284,8 @@ long ir_plan_blocks(const ir_config_t *cfg, size_t n_samples, int n_blocks, ir_b
  * stamps only -- (start + origin) / fs like burst_downmix.c:659-660 on the whole stream -- with cfg.start_time_ns
  * staying the time of the STREAM's sample 0.  Sticky until set again; 0 at creation. */
 int ir_pipeline_set_origin(ir_pipeline_t *p, uint64_t sample_origin);
+/* Replaces cfg.start_time_ns for the following runs (0 = CLOCK_REALTIME at each run again). */
+int ir_pipeline_set_start_time(ir_pipeline_t *p, uint64_t start_time_ns);
 
 /* Merge of the blocks' frame lists: keeps from block k the frames whose time stamp lies in its owned range (plus
  * 1 ms beyond its end, where a frame also reported by block k+1 -- within 1 ms and 200 Hz -- is kept once, the
@@ -292,6 +296,32 @@ int ir_pipeline_set_origin(ir_pipeline_t *p, uint64_t sample_origin);
 long ir_merge_blocks(const ir_config_t *cfg, uint64_t start_time_ns, const ir_block_t *blocks, int n_blocks,
                      const ir_frame_t *const *frames, const size_t *n_frames, ir_frame_t *out,
                      uint32_t *out_block, size_t cap);
+
+/* The above in one call, for a single process that owns several GPUs (the reference is one process, main.c): one
+ * pipeline and one host thread per device, the stream cut into n_blocks time blocks (0 = one per device) dealt
+ * round-robin to the devices, each device working through its blocks in order, the frame lists merged on the calling
+ * thread.  cfg.device is ignored (devices[] decides), cfg.start_time_ns = 0 is resolved once (CLOCK_REALTIME, like
+ * burst_detect.c:755-759) and shared by all blocks.  Results stay valid until the next run / destroy. */
+typedef struct ir_multi ir_multi_t;
+ir_multi_t *ir_multi_create(const ir_config_t *cfg, const int *devices, int n_devices);
+void ir_multi_destroy(ir_multi_t *m);
+int ir_multi_run_host(ir_multi_t *m, const void *iq, size_t n_samples, int fmt, int n_blocks);
+/* merged frames of the last run; block[i] = the time block frame i came from, bits[block] + frames[i].bits_offset its bits */
+typedef struct {
+    size_t n_frames;
+    const ir_frame_t *frames;
+    const uint32_t *block;
+    size_t n_blocks;
+    const ir_block_t *blocks;
+    const uint8_t *const *bits;      /* per block */
+    const float *const *llr;         /* per block */
+    uint64_t start_time_ns;
+    uint64_t kernel_launches;        /* all blocks */
+    uint64_t samples_fed;            /* sum of the blocks' feed ranges (>= n_samples: halos and tails are read twice) */
+} ir_multi_results_t;
+int ir_multi_results(ir_multi_t *m, ir_multi_results_t *out);
+/* every RAW: line of the merged run, in time order (frame_output.c:160-199); conventions of ir_pipeline_format_raw_all */
+long ir_multi_format_raw_all(ir_multi_t *m, const char *file_info, uint64_t t0, char *dst, size_t cap);
 
 /* Pinned host allocations for callers that want full-rate H2D. */
 void *ir_host_alloc(size_t bytes);

@@ -6,6 +6,10 @@
 #include <algorithm>
 #include <cmath>
 #include <numeric>
+#include <string>
+#include <thread>
+#include <time.h>
+#include <string.h>
 #include <vector>
 
 #include "../../include/iridium_b200.h"
@@ -121,4 +125,144 @@ extern "C" long ir_merge_blocks(const ir_config_t *cfg, uint64_t start_time_ns, 
         out_block[i] = kept[i].block;
     }
     return (long)kept.size();
+}
+
+// ---- one process, several GPUs: a pipeline and a host thread per device, blocks dealt round-robin
+struct ir_multi {
+    ir_config_t cfg;
+    std::vector<int> devices;
+    std::vector<ir_pipeline_t *> pipes;
+    // last run
+    std::vector<ir_block_t> blocks;
+    std::vector<std::vector<ir_frame_t>> frames;       // per block
+    std::vector<std::vector<uint8_t>> bits;
+    std::vector<std::vector<float>> llr;
+    std::vector<const uint8_t *> bits_ptr;
+    std::vector<const float *> llr_ptr;
+    std::vector<ir_frame_t> merged;
+    std::vector<uint32_t> merged_block;
+    uint64_t start_time_ns = 0, launches = 0, fed = 0;
+};
+
+extern "C" void ir_multi_destroy(ir_multi_t *m) {
+    if (!m) return;
+    for (ir_pipeline_t *p : m->pipes)
+        if (p) ir_pipeline_destroy(p);
+    delete m;
+}
+
+extern "C" ir_multi_t *ir_multi_create(const ir_config_t *cfg, const int *devices, int n_devices) {
+    if (!cfg || !devices || n_devices <= 0) { set_err("ir_multi_create: null argument"); return nullptr; }
+    for (int i = 0; i < n_devices; i++)
+        for (int j = 0; j < i; j++)
+            if (devices[i] == devices[j]) { set_err("ir_multi_create: a device is listed twice (one pipeline per GPU)"); return nullptr; }
+    ir_multi_t *m = new ir_multi();
+    m->cfg = *cfg;
+    m->devices.assign(devices, devices + n_devices);
+    for (int i = 0; i < n_devices; i++) {
+        ir_config_t c = *cfg;
+        c.device = devices[i];
+        ir_pipeline_t *p = ir_pipeline_create(&c);              // (sets ir_last_error on failure: no device, no fallback)
+        if (!p) { ir_multi_destroy(m); return nullptr; }
+        m->pipes.push_back(p);
+    }
+    return m;
+}
+
+extern "C" int ir_multi_run_host(ir_multi_t *m, const void *iq, size_t n, int fmt, int n_blocks) {
+    if (!m || (!iq && n)) { set_err("ir_multi_run_host: null argument"); return -1; }
+    if (fmt < 0 || fmt > 2) { set_err("bad sample format"); return -1; }
+    const size_t bps = fmt == IR_FMT_CF32 ? 8 : fmt == IR_FMT_CI16 ? 4 : 2;
+    const int nd = (int)m->pipes.size();
+    if (n_blocks <= 0) n_blocks = nd;
+    m->start_time_ns = m->cfg.start_time_ns;
+    if (!m->start_time_ns) {
+        struct timespec ts;
+        clock_gettime(CLOCK_REALTIME, &ts);                     // burst_detect.c:755-759, once for the whole stream
+        m->start_time_ns = (uint64_t)ts.tv_sec * 1000000000ULL + (uint64_t)ts.tv_nsec;
+    }
+    m->blocks.assign((size_t)n_blocks, ir_block_t{});
+    const long nb = ir_plan_blocks(&m->cfg, n, n_blocks, m->blocks.data(), m->blocks.size());
+    if (nb < 0) return -1;
+    m->blocks.resize((size_t)nb);
+    m->frames.assign((size_t)nb, {}); m->bits.assign((size_t)nb, {}); m->llr.assign((size_t)nb, {});
+    m->merged.clear(); m->merged_block.clear();
+    m->launches = 0; m->fed = 0;
+    std::vector<std::string> errs((size_t)nd);
+    std::vector<uint64_t> launches((size_t)nd, 0);
+    auto work = [&](int d) {
+        ir_pipeline_t *p = m->pipes[(size_t)d];
+        for (long k = d; k < nb; k += nd) {
+            const ir_block_t &b = m->blocks[(size_t)k];
+            ir_results_t r;
+            if (ir_pipeline_set_start_time(p, m->start_time_ns) || ir_pipeline_set_origin(p, b.feed_first) ||
+                ir_pipeline_run_host(p, (const unsigned char *)iq + b.feed_first * bps, (size_t)(b.feed_end - b.feed_first), fmt) ||
+                ir_pipeline_results(p, &r)) {
+                errs[(size_t)d] = std::string("block ") + std::to_string(k) + " on device " + std::to_string(m->devices[(size_t)d]) +
+                                  ": " + ir_last_error();
+                break;
+            }
+            m->frames[(size_t)k].assign(r.frames, r.frames + r.n_frames);
+            m->bits[(size_t)k].assign(r.bits, r.bits + r.n_bits_total);
+            m->llr[(size_t)k].assign(r.llr, r.llr + r.n_bits_total);
+            launches[(size_t)d] += r.kernel_launches;
+        }
+        ir_pipeline_set_origin(p, 0);
+    };
+    std::vector<std::thread> th;
+    for (int d = 1; d < nd; d++) th.emplace_back(work, d);
+    work(0);                                                    // the calling thread takes the first device
+    for (auto &t : th) t.join();
+    for (int d = 0; d < nd; d++)
+        if (!errs[(size_t)d].empty()) { set_last_error("ir_multi_run_host: " + errs[(size_t)d]); return -1; }
+    std::vector<const ir_frame_t *> fl((size_t)nb);
+    std::vector<size_t> nf((size_t)nb);
+    size_t total = 0;
+    m->bits_ptr.resize((size_t)nb); m->llr_ptr.resize((size_t)nb);
+    for (long k = 0; k < nb; k++) {
+        fl[(size_t)k] = m->frames[(size_t)k].data(); nf[(size_t)k] = m->frames[(size_t)k].size(); total += nf[(size_t)k];
+        m->bits_ptr[(size_t)k] = m->bits[(size_t)k].data(); m->llr_ptr[(size_t)k] = m->llr[(size_t)k].data();
+        m->fed += m->blocks[(size_t)k].feed_end - m->blocks[(size_t)k].feed_first;
+    }
+    for (uint64_t l : launches) m->launches += l;
+    m->merged.resize(total + 1); m->merged_block.resize(total + 1);
+    const long kept = ir_merge_blocks(&m->cfg, m->start_time_ns, m->blocks.data(), (int)nb, fl.data(), nf.data(),
+                                      m->merged.data(), m->merged_block.data(), total);
+    if (kept < 0) return -1;
+    m->merged.resize((size_t)kept); m->merged_block.resize((size_t)kept);
+    return 0;
+}
+
+extern "C" int ir_multi_results(ir_multi_t *m, ir_multi_results_t *out) {
+    if (!m || !out) { set_err("ir_multi_results: null argument"); return -1; }
+    out->n_frames = m->merged.size();
+    out->frames = m->merged.data();
+    out->block = m->merged_block.data();
+    out->n_blocks = m->blocks.size();
+    out->blocks = m->blocks.data();
+    out->bits = m->bits_ptr.data();
+    out->llr = m->llr_ptr.data();
+    out->start_time_ns = m->start_time_ns;
+    out->kernel_launches = m->launches;
+    out->samples_fed = m->fed;
+    return 0;
+}
+
+extern "C" long ir_multi_format_raw_all(ir_multi_t *m, const char *file_info, uint64_t t0, char *dst, size_t cap) {
+    if (!m) return -1;
+    const size_t head = 128 + (file_info ? strlen(file_info) : 0);
+    size_t need = 64;
+    for (const ir_frame_t &f : m->merged) need += head + (size_t)f.n_bits + 2;
+    if (!dst) return (long)need;
+    if (m->merged.empty()) return 0;
+    if (t0 == 0) t0 = (m->merged[0].timestamp / 1000000000ULL) * 1000000000ULL;       // frame_output.c:144-158
+    size_t pos = 0;
+    for (size_t i = 0; i < m->merged.size(); i++) {
+        const ir_frame_t &f = m->merged[i];
+        if (pos + head + (size_t)f.n_bits + 2 > cap) { set_err("ir_multi_format_raw_all: buffer too small"); return -1; }
+        const int k = ir_format_raw(dst + pos, cap - pos, file_info, t0, &f, m->bits[m->merged_block[i]].data() + f.bits_offset);
+        if (k < 0) { set_err("ir_multi_format_raw_all: formatting failed"); return -1; }
+        pos += (size_t)k;
+    }
+    return (long)pos;
 }

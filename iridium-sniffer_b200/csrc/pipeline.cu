@@ -923,6 +923,12 @@ extern "C" int ir_pipeline_set_origin(ir_pipeline_t *p, uint64_t sample_origin) 
     return 0;
 }
 
+extern "C" int ir_pipeline_set_start_time(ir_pipeline_t *p, uint64_t start_time_ns) {
+    if (!p) { set_err("null pipeline"); return -1; }
+    p->cfg.start_time_ns = start_time_ns;
+    return 0;
+}
+
 extern "C" int ir_pipeline_scan_stats(ir_pipeline_t *p, uint64_t *out, int n) {
     if (!p || !out) return -1;
     for (int i = 0; i < n && i < 8; i++) out[i] = p->scan_stats[i];

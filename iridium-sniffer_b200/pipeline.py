@@ -70,6 +70,14 @@ class Block(C.Structure):
 BLOCK_ID_STRIDE = 1_000_000_000
 
 
+class MultiResults(C.Structure):
+    """ir_multi_results_t"""
+    _fields_ = [("n_frames", C.c_size_t), ("frames", C.POINTER(Frame)), ("block", C.POINTER(C.c_uint32)),
+                ("n_blocks", C.c_size_t), ("blocks", C.POINTER(Block)), ("bits", C.POINTER(C.POINTER(C.c_uint8))),
+                ("llr", C.POINTER(C.POINTER(C.c_float))), ("start_time_ns", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("samples_fed", C.c_uint64)]
+
+
 class Results(C.Structure):
     _fields_ = [("n_bursts", C.c_size_t), ("bursts", C.POINTER(Burst)),
                 ("n_frames", C.c_size_t), ("frames", C.POINTER(Frame)),
@@ -155,6 +163,17 @@ def load_library() -> C.CDLL:
     L.ir_merge_blocks.restype = C.c_long
     L.ir_merge_blocks.argtypes = [C.POINTER(Config), C.c_uint64, C.POINTER(Block), C.c_int, C.POINTER(C.POINTER(Frame)),
                                   C.POINTER(C.c_size_t), C.POINTER(Frame), C.POINTER(C.c_uint32), C.c_size_t]
+    L.ir_pipeline_set_start_time.restype = C.c_int
+    L.ir_pipeline_set_start_time.argtypes = [C.c_void_p, C.c_uint64]
+    L.ir_multi_create.restype = C.c_void_p
+    L.ir_multi_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_int), C.c_int]
+    L.ir_multi_destroy.argtypes = [C.c_void_p]
+    L.ir_multi_run_host.restype = C.c_int
+    L.ir_multi_run_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+    L.ir_multi_results.restype = C.c_int
+    L.ir_multi_results.argtypes = [C.c_void_p, C.POINTER(MultiResults)]
+    L.ir_multi_format_raw_all.restype = C.c_long
+    L.ir_multi_format_raw_all.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_size_t]
     _lib = L
     return L
 
@@ -260,6 +279,8 @@ EXPORTED_SYMBOLS = [
     "ir_format_lcw", "ir_format_ida", "ir_pipeline_format_parsed_all", "ir_pipeline_last_classify_ms",
     "ir_fill_decoded_frame", "ir_fill_ida_burst",
     "ir_block_halo", "ir_block_tail", "ir_plan_blocks", "ir_pipeline_set_origin", "ir_merge_blocks",
+    "ir_pipeline_set_start_time", "ir_multi_create", "ir_multi_destroy", "ir_multi_run_host", "ir_multi_results",
+    "ir_multi_format_raw_all",
 ]
 
 
@@ -305,6 +326,60 @@ class RunResult:
                 raise RuntimeError("ir_format_raw failed")
             out.append(buf.value.decode())
         return out
+
+
+class Multi:
+    """ir_multi_t: one stream in time blocks over several GPUs of one process (a pipeline and a thread per device)."""
+
+    def __init__(self, devices, **cfg_kw):
+        self.L = load_library()
+        self.cfg = make_config(**cfg_kw)
+        devs = (C.c_int * len(devices))(*devices)
+        self.h = self.L.ir_multi_create(C.byref(self.cfg), devs, len(devices))
+        if not self.h:
+            raise RuntimeError("ir_multi_create failed: " + self.L.ir_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ir_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_host(self, iq: np.ndarray, fmt: str = "cf32", n_blocks: int = 0) -> List[dict]:
+        a, n = Pipeline._as_raw(iq, fmt)
+        if self.L.ir_multi_run_host(self.h, a.ctypes.data_as(C.c_void_p), n, FMT_BY_NAME[fmt], n_blocks) != 0:
+            raise RuntimeError("ir_multi_run_host failed: " + self.L.ir_last_error().decode())
+        return self.frames()
+
+    def results(self) -> MultiResults:
+        r = MultiResults()
+        if self.L.ir_multi_results(self.h, C.byref(r)) != 0:
+            raise RuntimeError("ir_multi_results failed: " + self.L.ir_last_error().decode())
+        return r
+
+    def frames(self) -> List[dict]:
+        r = self.results()
+        out = []
+        for i in range(r.n_frames):
+            f = r.frames[i]
+            d = {k: getattr(f, k) for k, _ in Frame._fields_}
+            d["block"] = int(r.block[i])
+            d["bits"] = np.ctypeslib.as_array(r.bits[d["block"]], (f.bits_offset + f.n_bits,))[f.bits_offset:].copy()
+            out.append(d)
+        return out
+
+    def raw_text(self, file_info: str = "T", t0: int = 0) -> bytes:
+        need = self.L.ir_multi_format_raw_all(self.h, file_info.encode(), t0, None, 0)
+        buf = C.create_string_buffer(max(need, 1))
+        n = self.L.ir_multi_format_raw_all(self.h, file_info.encode(), t0, buf, need)
+        if n < 0:
+            raise RuntimeError("ir_multi_format_raw_all failed: " + self.L.ir_last_error().decode())
+        return buf.raw[:n]
 
 
 class Pipeline:

@@ -76,3 +76,28 @@ def test_time_blocks_through_the_cuda_path():
     want_m = pl.merge_blocks(cfg, T0, blocks, want)
     assert [(d["id"], d["block"], tb._bitstr(d)) for d in merged] == [(d["id"], d["block"], tb._bitstr(d)) for d in want_m]
     p.close()
+
+
+def test_one_process_driver_on_the_gpu():
+    """ir_multi_*: the same three blocks through one C call (one device here, so its thread works through them in
+    order), merged and formatted inside the library == the block-by-block route above"""
+    pl = importlib.import_module("iridium-sniffer_b200.pipeline")
+    synth = importlib.import_module("iridium-sniffer_b200.synth")
+    rec, cfg, blocks = tb._recording(synth)
+    p = pl.Pipeline(sample_rate=rec.sample_rate, start_time_ns=T0)
+    want = pl.merge_blocks(cfg, T0, blocks, [p.run_block(rec.iq, b).frames for b in blocks])
+    p.close()
+    m = pl.Multi([0], sample_rate=rec.sample_rate, start_time_ns=T0)
+    got = m.run_host(rec.iq, "cf32", n_blocks=3)
+    assert [(d["id"], d["timestamp"], d["block"], tb._bitstr(d)) for d in got] == \
+        [(d["id"], d["timestamp"], d["block"], tb._bitstr(d)) for d in want]
+    r = m.results()
+    assert r.n_blocks == 3 and r.kernel_launches > 0 and r.samples_fed > rec.n_samples
+    lines = m.raw_text("T").decode().splitlines()
+    assert len(lines) == len(got) >= 120 and all(l.startswith("RAW: T ") for l in lines)
+    assert all(tb._bitstr(d) == l.split()[-1] for d, l in zip(got, lines))
+    with pytest.raises(RuntimeError):
+        pl.Multi([0, 0], sample_rate=rec.sample_rate)
+    with pytest.raises(RuntimeError):
+        pl.Multi([4096], sample_rate=rec.sample_rate)
+    m.close()

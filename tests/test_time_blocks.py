@@ -280,3 +280,89 @@ def test_two_gloo_ranks_give_the_single_process_merge(port, synth):
         got = list(out["merged"])
     assert got == [(d["id"], d["timestamp"], d["block"], _bitstr(d)) for d in want]
     assert len(got) >= 120
+
+
+# ------------------------------------------------------------------ ir_multi_*: the one-process driver, on stand-in devices
+@pytest.fixture(scope="module")
+def multi_shim(tmp_path_factory):
+    """csrc/blocks.cu compiled for the host over oracle-backed stand-ins of ir_pipeline_* (tests/blocks_host_shim.cpp)"""
+    import subprocess
+    pl = _pl()
+    from oracle import bindings as ob
+    ob.build(port=True, ref=False)
+    out = str(tmp_path_factory.mktemp("blk") / "libblocks_shim.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", os.path.join(ROOT, "tests", "blocks_host_shim.cpp"),
+                    "-I/usr/local/cuda/include", "-o", out, "-L", os.path.dirname(pl.LIB_PATH), "-l:libiridium_b200.so",
+                    "-L", os.path.dirname(ob.PORT_SO), "-l:libir_oracle.so", "-Wl,-rpath," + os.path.dirname(pl.LIB_PATH),
+                    "-Wl,-rpath," + os.path.dirname(ob.PORT_SO), "-lpthread"], check=True)
+    S = C.CDLL(out)
+    S.ir_multi_create.restype = C.c_void_p
+    S.ir_multi_create.argtypes = [C.POINTER(pl.Config), C.POINTER(C.c_int), C.c_int]
+    S.ir_multi_destroy.argtypes = [C.c_void_p]
+    S.ir_multi_run_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+    S.ir_multi_results.argtypes = [C.c_void_p, C.POINTER(pl.MultiResults)]
+    S.ir_multi_format_raw_all.restype = C.c_long
+    S.ir_multi_format_raw_all.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_size_t]
+    return S
+
+
+def test_one_process_driver_on_stand_in_devices(multi_shim, port, synth):
+    pl = _pl()
+    L = pl.load_library()
+    S = multi_shim
+    rec, cfg, blocks = _recording(synth)
+    cfg.start_time_ns = T0
+    cfg.use_gardner = 1
+    want = pl.merge_blocks(cfg, T0, blocks, _oracle_blocks(port, rec, blocks))
+    S.shim_set_devices(4, -1)
+    devs = (C.c_int * 2)(0, 1)
+    m = S.ir_multi_create(C.byref(cfg), devs, 2)
+    assert m
+    iq = np.ascontiguousarray(rec.iq, np.complex64)
+    for n_blocks in (3, 0):                        # 3 blocks over 2 devices (device 0 takes two); 0 = one per device
+        assert S.ir_multi_run_host(m, iq.ctypes.data_as(C.c_void_p), iq.shape[0], pl.FMT_CF32, n_blocks) == 0, L.ir_last_error()
+        r = pl.MultiResults()
+        assert S.ir_multi_results(m, C.byref(r)) == 0
+        assert r.n_blocks == (3 if n_blocks == 3 else 2) and r.start_time_ns == T0 and r.kernel_launches == r.n_blocks
+        assert r.samples_fed == sum(int(r.blocks[k].feed_end - r.blocks[k].feed_first) for k in range(r.n_blocks)) > iq.shape[0]
+        got = []
+        for i in range(r.n_frames):
+            f = r.frames[i]
+            b = int(r.block[i])
+            bits = np.ctypeslib.as_array(r.bits[b], (f.bits_offset + f.n_bits,))[f.bits_offset:]
+            got.append((f.id, f.timestamp, b, "".join(map(str, bits.tolist()))))
+        if n_blocks == 3:
+            assert got == [(d["id"], d["timestamp"], d["block"], _bitstr(d)) for d in want]
+        else:
+            assert len(got) >= len(want) - 2 and {g[2] for g in got} == {0, 1}
+        # the text: every line is ir_format_raw of the merged frame over its own block's bits, in time order
+        need = S.ir_multi_format_raw_all(m, b"T", 0, None, 0)
+        buf = C.create_string_buffer(need)
+        k = S.ir_multi_format_raw_all(m, b"T", 0, buf, need)
+        lines = buf.raw[:k].decode().splitlines()
+        assert len(lines) == r.n_frames and all(l.startswith("RAW: T ") for l in lines)
+        t0 = (r.frames[0].timestamp // 1_000_000_000) * 1_000_000_000
+        one = C.create_string_buffer(4096)
+        for i in (0, r.n_frames // 2, r.n_frames - 1):
+            f = r.frames[i]
+            bits = np.ctypeslib.as_array(r.bits[int(r.block[i])], (f.bits_offset + f.n_bits,))[f.bits_offset:].copy()
+            L.ir_format_raw(one, 4096, b"T", t0, C.byref(f), bits.ctypes.data_as(C.c_void_p))
+            assert one.value.decode().rstrip("\n") == lines[i]
+        assert [l.split()[2] for l in lines] == sorted((l.split()[2] for l in lines), key=float)
+        assert S.ir_multi_format_raw_all(m, b"T", 0, buf, 100) == -1 and b"too small" in L.ir_last_error()
+    # errors: a bad format is refused by the pipeline, the message names the block and the device
+    assert S.ir_multi_run_host(m, iq.ctypes.data_as(C.c_void_p), iq.shape[0], pl.FMT_CI16, 3) == -1
+    assert b"block" in L.ir_last_error() and b"cf32 only" in L.ir_last_error()
+    S.ir_multi_destroy(m)
+    # a device that fails in the middle of its list, on a worker thread: the run fails, the message reaches the caller
+    S.shim_set_devices(4, 1)
+    devs3 = (C.c_int * 2)(0, 1)
+    m = S.ir_multi_create(C.byref(cfg), devs3, 2)
+    quick = np.ascontiguousarray(rec.iq[:24_000_000])
+    assert S.ir_multi_run_host(m, quick.ctypes.data_as(C.c_void_p), quick.shape[0], pl.FMT_CF32, 4) == -1
+    assert b"device 1" in L.ir_last_error() and b"fell off the bus" in L.ir_last_error(), L.ir_last_error()
+    S.ir_multi_destroy(m)
+    # a device that does not exist, a device listed twice
+    S.shim_set_devices(1, -1)
+    assert not S.ir_multi_create(C.byref(cfg), devs, 2) and b"no such device" in L.ir_last_error()
+    assert not S.ir_multi_create(C.byref(cfg), (C.c_int * 2)(0, 0), 2) and b"twice" in L.ir_last_error()

@@ -17,6 +17,7 @@ CASES = ["gpu_classify_cases.py::" + c for c in (
     "test_parsed_output_of_a_run", "test_reference_named_entry_points", "test_classify_refuses_bad_arguments")]
 CASES.append("gpu_dropin_cases.py::test_reference_main_linked_against_the_library")
 CASES.append("gpu_block_cases.py::test_time_blocks_through_the_cuda_path")      # time blocks, merged
+CASES.append("gpu_block_cases.py::test_one_process_driver_on_the_gpu")           # ir_multi_*: the same in one C call
 
 
 @pytest.mark.parametrize("case", CASES)
