@@ -32,7 +32,8 @@ fg = _load("frame_gen")
 
 def _run(binary, path, rec, extra):
     r = subprocess.run([binary, "-f", path, "--format=cf32", "-r", str(rec.sample_rate), "-c", str(int(rec.center_freq)),
-                        "--file-info=T"] + extra, capture_output=True, text=True, timeout=600)
+                        "--file-info=T"] + extra, capture_output=True, text=True, timeout=90)   # (seconds of work; well inside the runner's limit,
+                                                                                  # so that a hang is killed HERE, with the program)
     assert r.returncode == 0, r.stderr[-2000:]
     return [l for l in r.stdout.splitlines() if l.startswith(("RAW:", "IDA:"))]
 

@@ -4,6 +4,7 @@ time-block sharding of one stream (tests/gpu_block_cases.py) one per child proce
 were spent and had not run on a B200 when committed; a child process keeps a crash in not-yet-proven code from
 taking the whole pytest run with it, and the name sorts this file last under `pytest -x`."""
 import os
+import signal
 import subprocess
 import sys
 
@@ -22,9 +23,17 @@ CASES.append("gpu_block_cases.py::test_one_process_driver_on_the_gpu")          
 
 @pytest.mark.parametrize("case", CASES)
 def test_classification_on_the_gpu(case):
-    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
-                        os.path.join("tests", case)],
-                       cwd=ROOT, capture_output=True, text=True, timeout=420)
+    # own session: on a timeout the whole group goes (the case, and any program it started that still holds the GPU)
+    pr = subprocess.Popen([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                           os.path.join("tests", case)], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                          start_new_session=True)
+    try:
+        out, err = pr.communicate(timeout=420)
+    except subprocess.TimeoutExpired:
+        os.killpg(pr.pid, signal.SIGKILL)
+        out, err = pr.communicate()
+        pytest.fail("timed out after 420 s:\n" + (out + err)[-4000:])
+    r = subprocess.CompletedProcess(pr.args, pr.returncode, out, err)
     tail = (r.stdout + r.stderr)[-4000:]
     assert r.returncode == 0, tail
     assert "1 passed" in r.stdout or "skipped" in r.stdout, tail
