@@ -311,6 +311,8 @@ typedef struct {
     size_t n_frames;
     const ir_frame_t *frames;
     const uint32_t *block;
+    const uint32_t *index;           /* frame i is frame index[i] of block[i]'s own list */
+    const ir_frame_class_t *const *classes;   /* per block, parallel to its frame list; NULL unless ir_multi_set_classify */
     size_t n_blocks;
     const ir_block_t *blocks;
     const uint8_t *const *bits;      /* per block */
@@ -320,6 +322,11 @@ typedef struct {
     uint64_t samples_fed;            /* sum of the blocks' feed ranges (>= n_samples: halos and tails are read twice) */
 } ir_multi_results_t;
 int ir_multi_results(ir_multi_t *m, ir_multi_results_t *out);
+/* on != 0: the following runs also classify every frame (ir_pipeline_classify per block, while its bits and LLRs are
+ * still in that GPU's memory) -- what frame_consumer_thread does with `--parsed` (main.c:320-350) */
+int ir_multi_set_classify(ir_multi_t *m, int on);
+/* the `--parsed` text of the merged run: conventions of ir_pipeline_format_parsed_all */
+long ir_multi_format_parsed_all(ir_multi_t *m, const char *file_info, uint64_t t0, char *dst, size_t cap);
 /* every RAW: line of the merged run, in time order (frame_output.c:160-199); conventions of ir_pipeline_format_raw_all */
 long ir_multi_format_raw_all(ir_multi_t *m, const char *file_info, uint64_t t0, char *dst, size_t cap);
 

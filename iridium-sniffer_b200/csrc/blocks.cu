@@ -82,9 +82,9 @@ extern "C" long ir_plan_blocks(const ir_config_t *cfg, size_t n, int n_blocks, i
     return (long)k;
 }
 
-extern "C" long ir_merge_blocks(const ir_config_t *cfg, uint64_t start_time_ns, const ir_block_t *blocks, int n_blocks,
-                                const ir_frame_t *const *frames, const size_t *n_frames, ir_frame_t *out,
-                                uint32_t *out_block, size_t cap) {
+static long merge_impl(const ir_config_t *cfg, uint64_t start_time_ns, const ir_block_t *blocks, int n_blocks,
+                       const ir_frame_t *const *frames, const size_t *n_frames, ir_frame_t *out,
+                       uint32_t *out_block, uint32_t *out_index, size_t cap) {
     if (!cfg || cfg->sample_rate <= 0 || !blocks || !frames || !n_frames || n_blocks < 0 || (cap && (!out || !out_block))) {
         set_err("ir_merge_blocks: null argument");
         return -1;
@@ -123,8 +123,15 @@ extern "C" long ir_merge_blocks(const ir_config_t *cfg, uint64_t start_time_ns, 
         out[i] = frames[kept[i].block][kept[i].index];
         out[i].id = (uint64_t)kept[i].block * IR_BLOCK_ID_STRIDE + out[i].id % IR_BLOCK_ID_STRIDE;
         out_block[i] = kept[i].block;
+        if (out_index) out_index[i] = kept[i].index;
     }
     return (long)kept.size();
+}
+
+extern "C" long ir_merge_blocks(const ir_config_t *cfg, uint64_t start_time_ns, const ir_block_t *blocks, int n_blocks,
+                                const ir_frame_t *const *frames, const size_t *n_frames, ir_frame_t *out,
+                                uint32_t *out_block, size_t cap) {
+    return merge_impl(cfg, start_time_ns, blocks, n_blocks, frames, n_frames, out, out_block, nullptr, cap);
 }
 
 // ---- one process, several GPUs: a pipeline and a host thread per device, blocks dealt round-robin
@@ -140,9 +147,18 @@ struct ir_multi {
     std::vector<const uint8_t *> bits_ptr;
     std::vector<const float *> llr_ptr;
     std::vector<ir_frame_t> merged;
-    std::vector<uint32_t> merged_block;
+    std::vector<uint32_t> merged_block, merged_index;
+    bool classify = false;                             // ir_multi_set_classify: frame_decode() + ida_decode() per frame too
+    std::vector<std::vector<ir_frame_class_t>> cls;    // per block, parallel to frames[k]
+    std::vector<const ir_frame_class_t *> cls_ptr;
     uint64_t start_time_ns = 0, launches = 0, fed = 0;
 };
+
+extern "C" int ir_multi_set_classify(ir_multi_t *m, int on) {
+    if (!m) { set_err("ir_multi_set_classify: null argument"); return -1; }
+    m->classify = on != 0;
+    return 0;
+}
 
 extern "C" void ir_multi_destroy(ir_multi_t *m) {
     if (!m) return;
@@ -185,8 +201,8 @@ extern "C" int ir_multi_run_host(ir_multi_t *m, const void *iq, size_t n, int fm
     const long nb = ir_plan_blocks(&m->cfg, n, n_blocks, m->blocks.data(), m->blocks.size());
     if (nb < 0) return -1;
     m->blocks.resize((size_t)nb);
-    m->frames.assign((size_t)nb, {}); m->bits.assign((size_t)nb, {}); m->llr.assign((size_t)nb, {});
-    m->merged.clear(); m->merged_block.clear();
+    m->frames.assign((size_t)nb, {}); m->bits.assign((size_t)nb, {}); m->llr.assign((size_t)nb, {}); m->cls.assign((size_t)nb, {});
+    m->merged.clear(); m->merged_block.clear(); m->merged_index.clear();
     m->launches = 0; m->fed = 0;
     std::vector<std::string> errs((size_t)nd);
     std::vector<uint64_t> launches((size_t)nd, 0);
@@ -206,6 +222,15 @@ extern "C" int ir_multi_run_host(ir_multi_t *m, const void *iq, size_t n, int fm
             m->bits[(size_t)k].assign(r.bits, r.bits + r.n_bits_total);
             m->llr[(size_t)k].assign(r.llr, r.llr + r.n_bits_total);
             launches[(size_t)d] += r.kernel_launches;
+            if (m->classify && r.n_frames) {            // while the block's bits and LLRs are still in device memory
+                m->cls[(size_t)k].resize(r.n_frames);
+                if (ir_pipeline_classify(p, m->cls[(size_t)k].data(), r.n_frames) < 0) {
+                    errs[(size_t)d] = std::string("classifying block ") + std::to_string(k) + " on device " +
+                                      std::to_string(m->devices[(size_t)d]) + ": " + ir_last_error();
+                    break;
+                }
+                launches[(size_t)d] += 1;
+            }
         }
         ir_pipeline_set_origin(p, 0);
     };
@@ -218,18 +243,19 @@ extern "C" int ir_multi_run_host(ir_multi_t *m, const void *iq, size_t n, int fm
     std::vector<const ir_frame_t *> fl((size_t)nb);
     std::vector<size_t> nf((size_t)nb);
     size_t total = 0;
-    m->bits_ptr.resize((size_t)nb); m->llr_ptr.resize((size_t)nb);
+    m->bits_ptr.resize((size_t)nb); m->llr_ptr.resize((size_t)nb); m->cls_ptr.resize((size_t)nb);
     for (long k = 0; k < nb; k++) {
         fl[(size_t)k] = m->frames[(size_t)k].data(); nf[(size_t)k] = m->frames[(size_t)k].size(); total += nf[(size_t)k];
         m->bits_ptr[(size_t)k] = m->bits[(size_t)k].data(); m->llr_ptr[(size_t)k] = m->llr[(size_t)k].data();
+        m->cls_ptr[(size_t)k] = m->cls[(size_t)k].empty() ? nullptr : m->cls[(size_t)k].data();
         m->fed += m->blocks[(size_t)k].feed_end - m->blocks[(size_t)k].feed_first;
     }
     for (uint64_t l : launches) m->launches += l;
-    m->merged.resize(total + 1); m->merged_block.resize(total + 1);
-    const long kept = ir_merge_blocks(&m->cfg, m->start_time_ns, m->blocks.data(), (int)nb, fl.data(), nf.data(),
-                                      m->merged.data(), m->merged_block.data(), total);
+    m->merged.resize(total + 1); m->merged_block.resize(total + 1); m->merged_index.resize(total + 1);
+    const long kept = merge_impl(&m->cfg, m->start_time_ns, m->blocks.data(), (int)nb, fl.data(), nf.data(),
+                                 m->merged.data(), m->merged_block.data(), m->merged_index.data(), total);
     if (kept < 0) return -1;
-    m->merged.resize((size_t)kept); m->merged_block.resize((size_t)kept);
+    m->merged.resize((size_t)kept); m->merged_block.resize((size_t)kept); m->merged_index.resize((size_t)kept);
     return 0;
 }
 
@@ -238,6 +264,8 @@ extern "C" int ir_multi_results(ir_multi_t *m, ir_multi_results_t *out) {
     out->n_frames = m->merged.size();
     out->frames = m->merged.data();
     out->block = m->merged_block.data();
+    out->index = m->merged_index.data();
+    out->classes = m->classify ? m->cls_ptr.data() : nullptr;
     out->n_blocks = m->blocks.size();
     out->blocks = m->blocks.data();
     out->bits = m->bits_ptr.data();
@@ -262,6 +290,30 @@ extern "C" long ir_multi_format_raw_all(ir_multi_t *m, const char *file_info, ui
         if (pos + head + (size_t)f.n_bits + 2 > cap) { set_err("ir_multi_format_raw_all: buffer too small"); return -1; }
         const int k = ir_format_raw(dst + pos, cap - pos, file_info, t0, &f, m->bits[m->merged_block[i]].data() + f.bits_offset);
         if (k < 0) { set_err("ir_multi_format_raw_all: formatting failed"); return -1; }
+        pos += (size_t)k;
+    }
+    return (long)pos;
+}
+
+// `--parsed` output of the merged run (main.c:328-331): the IDA line where ida_decode() accepted the frame, the RAW line otherwise
+extern "C" long ir_multi_format_parsed_all(ir_multi_t *m, const char *file_info, uint64_t t0, char *dst, size_t cap) {
+    if (!m) return -1;
+    if (!m->classify) { set_err("ir_multi_format_parsed_all: the run was not classified (ir_multi_set_classify)"); return -1; }
+    const size_t head = 512 + (file_info ? strlen(file_info) : 0);
+    size_t need = 64;
+    for (const ir_frame_t &f : m->merged) need += head + (size_t)f.n_bits + 2;
+    if (!dst) return (long)need;
+    if (m->merged.empty()) return 0;
+    if (t0 == 0) t0 = (m->merged[0].timestamp / 1000000000ULL) * 1000000000ULL;
+    size_t pos = 0;
+    for (size_t i = 0; i < m->merged.size(); i++) {
+        const ir_frame_t &f = m->merged[i];
+        const uint32_t b = m->merged_block[i];
+        const ir_frame_class_t &c = m->cls[b][m->merged_index[i]];
+        if (pos + head + (size_t)f.n_bits + 2 > cap) { set_err("ir_multi_format_parsed_all: buffer too small"); return -1; }
+        const int k = c.ida_ok ? ir_format_ida(dst + pos, cap - pos, t0, &f, &c)
+                               : ir_format_raw(dst + pos, cap - pos, file_info, t0, &f, m->bits[b].data() + f.bits_offset);
+        if (k < 0) { set_err("ir_multi_format_parsed_all: formatting failed"); return -1; }
         pos += (size_t)k;
     }
     return (long)pos;

@@ -73,6 +73,7 @@ BLOCK_ID_STRIDE = 1_000_000_000
 class MultiResults(C.Structure):
     """ir_multi_results_t"""
     _fields_ = [("n_frames", C.c_size_t), ("frames", C.POINTER(Frame)), ("block", C.POINTER(C.c_uint32)),
+                ("index", C.POINTER(C.c_uint32)), ("classes", C.POINTER(C.POINTER(FrameClass))),
                 ("n_blocks", C.c_size_t), ("blocks", C.POINTER(Block)), ("bits", C.POINTER(C.POINTER(C.c_uint8))),
                 ("llr", C.POINTER(C.POINTER(C.c_float))), ("start_time_ns", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("samples_fed", C.c_uint64)]
@@ -174,6 +175,10 @@ def load_library() -> C.CDLL:
     L.ir_multi_results.argtypes = [C.c_void_p, C.POINTER(MultiResults)]
     L.ir_multi_format_raw_all.restype = C.c_long
     L.ir_multi_format_raw_all.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_size_t]
+    L.ir_multi_set_classify.restype = C.c_int
+    L.ir_multi_set_classify.argtypes = [C.c_void_p, C.c_int]
+    L.ir_multi_format_parsed_all.restype = C.c_long
+    L.ir_multi_format_parsed_all.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_size_t]
     _lib = L
     return L
 
@@ -280,7 +285,7 @@ EXPORTED_SYMBOLS = [
     "ir_fill_decoded_frame", "ir_fill_ida_burst",
     "ir_block_halo", "ir_block_tail", "ir_plan_blocks", "ir_pipeline_set_origin", "ir_merge_blocks",
     "ir_pipeline_set_start_time", "ir_multi_create", "ir_multi_destroy", "ir_multi_run_host", "ir_multi_results",
-    "ir_multi_format_raw_all",
+    "ir_multi_format_raw_all", "ir_multi_set_classify", "ir_multi_format_parsed_all",
 ]
 
 
@@ -373,13 +378,26 @@ class Multi:
             out.append(d)
         return out
 
-    def raw_text(self, file_info: str = "T", t0: int = 0) -> bytes:
-        need = self.L.ir_multi_format_raw_all(self.h, file_info.encode(), t0, None, 0)
+    def _text(self, fn, what: str, file_info: str, t0: int) -> bytes:
+        need = fn(self.h, file_info.encode(), t0, None, 0)
+        if need < 0:
+            raise RuntimeError(what + " failed: " + self.L.ir_last_error().decode())
         buf = C.create_string_buffer(max(need, 1))
-        n = self.L.ir_multi_format_raw_all(self.h, file_info.encode(), t0, buf, need)
+        n = fn(self.h, file_info.encode(), t0, buf, need)
         if n < 0:
-            raise RuntimeError("ir_multi_format_raw_all failed: " + self.L.ir_last_error().decode())
+            raise RuntimeError(what + " failed: " + self.L.ir_last_error().decode())
         return buf.raw[:n]
+
+    def raw_text(self, file_info: str = "T", t0: int = 0) -> bytes:
+        return self._text(self.L.ir_multi_format_raw_all, "ir_multi_format_raw_all", file_info, t0)
+
+    def set_classify(self, on: bool = True) -> None:
+        if self.L.ir_multi_set_classify(self.h, int(on)) != 0:
+            raise RuntimeError("ir_multi_set_classify failed: " + self.L.ir_last_error().decode())
+
+    def parsed_text(self, file_info: str = "T", t0: int = 0) -> bytes:
+        """the `--parsed` text of the merged run (needs set_classify() before the run)"""
+        return self._text(self.L.ir_multi_format_parsed_all, "ir_multi_format_parsed_all", file_info, t0)
 
 
 class Pipeline:

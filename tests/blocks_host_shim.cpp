@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../iridium-sniffer_b200/csrc/blocks.cu"
+#include "../iridium-sniffer_b200/csrc/frame_classify.cuh"
 #include "../oracle/ir_oracle.h"
 
 static_assert(sizeof(orc_result) == sizeof(ir_frame_t), "orc_result mirrors ir_frame_t field for field");
@@ -65,4 +66,16 @@ extern "C" int ir_pipeline_results(ir_pipeline_t *p, ir_results_t *out) {
     out->n_bits_total = p->run.bits_len;
     out->kernel_launches = 1;
     return 0;
+}
+
+// classification stand-in: the product's own arithmetic (csrc/frame_classify.cuh, pinned to the reference by
+// tests/test_frame_classify_host.py) compiled for the host, over the oracle's bits (no LLRs: no Chase search)
+extern "C" long ir_pipeline_classify(ir_pipeline_t *p, ir_frame_class_t *out, size_t cap) {
+    static const ir::FcTables &tab = *[] { auto *t = new ir::FcTables(); ir::fc_build_tables(*t); return t; }();   // thread-safe
+    if (p->run.n_results > cap) { ir::set_last_error("shim: class array too small"); return -1; }
+    for (size_t i = 0; i < p->run.n_results; i++) {
+        const orc_result &r = p->run.results[i];
+        ir::fc_classify(tab, p->run.bits + r.bits_offset, nullptr, r.n_bits, r.direction, &out[i]);
+    }
+    return (long)p->run.n_results;
 }

@@ -101,3 +101,34 @@ def test_one_process_driver_on_the_gpu():
     with pytest.raises(RuntimeError):
         pl.Multi([4096], sample_rate=rec.sample_rate)
     m.close()
+
+
+def test_one_process_driver_parsed_on_the_gpu():
+    """`--parsed` through ir_multi_*: one block = the single pipeline's text, byte for byte; two blocks = the same lines
+    (ids aside) in time order"""
+    pl = importlib.import_module("iridium-sniffer_b200.pipeline")
+    synth = importlib.import_module("iridium-sniffer_b200.synth")
+    fg = _load("frame_gen")
+    rng = np.random.default_rng(3)
+    duplex = [fg.make_ida(rng, 9), fg.make_ida(rng, 20), fg.make_ida(rng, 0), fg.make_ida(rng, 13, good_crc=False)]
+    rec = synth.make_recording(21, duration_s=1.5, n_bursts=14, snr_db=(22.0, 28.0), frame_bits=duplex)
+    p = pl.Pipeline(sample_rate=rec.sample_rate, start_time_ns=T0)
+    p.run_host(rec.iq)
+    want = p.parsed_text("T").decode()
+    p.close()
+    assert want.count("IDA: p-") >= 8
+    m = pl.Multi([0], sample_rate=rec.sample_rate, start_time_ns=T0)
+    m.set_classify(True)
+    m.run_host(rec.iq, "cf32", n_blocks=1)
+    assert m.parsed_text("T").decode() == want
+    fr = m.run_host(rec.iq, "cf32", n_blocks=2)
+    assert {d["block"] for d in fr} == {0, 1}
+    two = m.parsed_text("T").decode().splitlines()
+    one = want.splitlines()
+    assert len(two) == len(one)
+    # block 0 starts where the stream starts: its lines are the single pipeline's, byte for byte; block 1 has its own
+    # noise baseline (level|noise|snr may move in the last digit), the decoded content from LCW( on is the same
+    n0 = sum(d["block"] == 0 for d in fr)
+    assert n0 >= 2 and all(l in set(one) for d, l in zip(fr, two) if d["block"] == 0)
+    assert [l[l.index("LCW("):] for l in one if l.startswith("IDA:")] == [l[l.index("LCW("):] for l in two if l.startswith("IDA:")]
+    m.close()

@@ -350,6 +350,16 @@ def test_one_process_driver_on_stand_in_devices(multi_shim, port, synth):
             assert one.value.decode().rstrip("\n") == lines[i]
         assert [l.split()[2] for l in lines] == sorted((l.split()[2] for l in lines), key=float)
         assert S.ir_multi_format_raw_all(m, b"T", 0, buf, 100) == -1 and b"too small" in L.ir_last_error()
+    # the Python mirror (pipeline.Multi) over the same handle: what the GPU case will call
+    S.ir_multi_results.restype = C.c_int
+    mm = object.__new__(pl.Multi)
+    mm.L, mm.h, mm.cfg = S, m, cfg
+    S.ir_last_error = L.ir_last_error
+    fr = mm.run_host(rec.iq, "cf32", n_blocks=3)
+    assert [(d["id"], d["timestamp"], d["block"], _bitstr(d)) for d in fr] == [(d["id"], d["timestamp"], d["block"], _bitstr(d)) for d in want]
+    txt = mm.raw_text("T").decode().splitlines()
+    assert len(txt) == len(fr) and all(_bitstr(d) == l.split()[-1] for d, l in zip(fr, txt))
+    mm.h = None
     # errors: a bad format is refused by the pipeline, the message names the block and the device
     assert S.ir_multi_run_host(m, iq.ctypes.data_as(C.c_void_p), iq.shape[0], pl.FMT_CI16, 3) == -1
     assert b"block" in L.ir_last_error() and b"cf32 only" in L.ir_last_error()
@@ -366,3 +376,56 @@ def test_one_process_driver_on_stand_in_devices(multi_shim, port, synth):
     S.shim_set_devices(1, -1)
     assert not S.ir_multi_create(C.byref(cfg), devs, 2) and b"no such device" in L.ir_last_error()
     assert not S.ir_multi_create(C.byref(cfg), (C.c_int * 2)(0, 0), 2) and b"twice" in L.ir_last_error()
+
+
+def test_one_process_driver_parsed_output(multi_shim, port, synth):
+    """`--parsed` through the driver: blocks classified while their results are at hand, IDA line where ida_decode()
+    accepts, RAW line otherwise (main.c:328-331), in time order over the merged stream"""
+    import importlib.util
+    pl = _pl()
+    L = pl.load_library()
+    S = multi_shim
+    spec = importlib.util.spec_from_file_location("frame_gen", os.path.join(ROOT, "tests", "frame_gen.py"))
+    fg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fg)
+    rng = np.random.default_rng(3)
+    duplex = [fg.make_ida(rng, 9), fg.make_ida(rng, 20), fg.make_ida(rng, 0), fg.make_ida(rng, 13, good_crc=False)]
+    rec = synth.make_recording(21, duration_s=1.5, n_bursts=14, snr_db=(22.0, 28.0), frame_bits=duplex)
+    cfg = pl.make_config(sample_rate=rec.sample_rate, start_time_ns=T0)
+    S.shim_set_devices(2, -1)
+    S.ir_multi_set_classify.argtypes = [C.c_void_p, C.c_int]
+    S.ir_multi_format_parsed_all.restype = C.c_long
+    S.ir_multi_format_parsed_all.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_size_t]
+    m = S.ir_multi_create(C.byref(cfg), (C.c_int * 2)(0, 1), 2)
+    iq = np.ascontiguousarray(rec.iq, np.complex64)
+    assert S.ir_multi_run_host(m, iq.ctypes.data_as(C.c_void_p), iq.shape[0], pl.FMT_CF32, 2) == 0
+    assert S.ir_multi_format_parsed_all(m, b"T", 0, None, 0) == -1 and b"not classified" in L.ir_last_error()
+    assert S.ir_multi_set_classify(m, 1) == 0
+    assert S.ir_multi_run_host(m, iq.ctypes.data_as(C.c_void_p), iq.shape[0], pl.FMT_CF32, 2) == 0, L.ir_last_error()
+    r = pl.MultiResults()
+    assert S.ir_multi_results(m, C.byref(r)) == 0 and r.n_blocks == 2 and r.n_frames >= 10
+    assert r.kernel_launches == 4                       # two runs + two classification launches
+    need = S.ir_multi_format_parsed_all(m, b"T", 0, None, 0)
+    buf = C.create_string_buffer(need)
+    k = S.ir_multi_format_parsed_all(m, b"T", 0, buf, need)
+    assert k > 0, L.ir_last_error()
+    lines = buf.raw[:k].decode().splitlines(keepends=True)
+    assert len(lines) == r.n_frames
+    t0 = (r.frames[0].timestamp // 1_000_000_000) * 1_000_000_000
+    one = C.create_string_buffer(4096)
+    n_ida, blocks_seen = 0, set()
+    for i in range(r.n_frames):
+        f, b, idx = r.frames[i], int(r.block[i]), int(r.index[i])
+        cls = r.classes[b][idx]
+        bits = np.ctypeslib.as_array(r.bits[b], (f.bits_offset + f.n_bits,))[f.bits_offset:].copy()
+        if cls.ida_ok:
+            assert L.ir_format_ida(one, 4096, t0, C.byref(f), C.byref(cls)) > 0
+            n_ida += 1
+            blocks_seen.add(b)
+        else:
+            assert L.ir_format_raw(one, 4096, b"T", t0, C.byref(f), bits.ctypes.data_as(C.c_void_p)) > 0
+        assert one.value.decode() == lines[i], (i, one.value.decode(), lines[i])
+    assert n_ida >= 8 and blocks_seen == {0, 1}
+    text = "".join(lines)
+    assert text.count("IDA: p-") == n_ida and "CRC:OK" in text and "CRC:no" in text
+    S.ir_multi_destroy(m)
