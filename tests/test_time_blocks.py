@@ -429,3 +429,74 @@ def test_one_process_driver_parsed_output(multi_shim, port, synth):
     text = "".join(lines)
     assert text.count("IDA: p-") == n_ida and "CRC:OK" in text and "CRC:no" in text
     S.ir_multi_destroy(m)
+
+
+# ------------------------------------------------------------------ properties (hypothesis)
+from hypothesis import given, settings, strategies as st   # noqa: E402
+
+
+@settings(max_examples=200, deadline=None)
+@given(fs=st.sampled_from([2_000_000, 8_000_000, 10_000_000, 12_000_000, 20_000_000]),
+       fft=st.sampled_from([0, 4096, 8192, 16384]), feed=st.sampled_from([0, 8192, 32768, 65536, 10000]),
+       seconds=st.floats(0.01, 400.0), k=st.integers(1, 16), odd=st.integers(0, 40000))
+def test_plan_properties(fs, fft, feed, seconds, k, odd):
+    pl = _pl()
+    L = pl.load_library()
+    cfg = pl.make_config(sample_rate=fs, fft_size=fft, feed_block=feed)
+    n = int(seconds * fs) + odd
+    halo, tail = L.ir_block_halo(cfg), L.ir_block_tail(cfg)
+    N = fft or 1 << int(round(math.log2(fs / 1000.0)))
+    unit = N * (feed or 32768) // math.gcd(N, feed or 32768)
+    assert halo % unit == 0 and tail % unit == 0 and halo >= 512 * N
+    bl = [_tuple(b) for b in pl.plan_blocks(cfg, n, k)]
+    assert 1 <= len(bl) <= k
+    assert bl[0][0] == 0 and bl[0][2] == 0 and bl[-1][1] == n and bl[-1][3] == n
+    for i, (ff, fe, of, oe) in enumerate(bl):
+        assert ff <= of < oe <= fe <= n
+        assert of % unit == 0 and ff % unit == 0
+        assert ff == max(0, of - halo) and fe == min(n, oe + tail)
+        if i:
+            assert of == bl[i - 1][3]
+        if i < len(bl) - 1:
+            assert oe - of > halo and (oe - of) % unit == 0          # never re-reads more than it owns
+    if len(bl) > 1:
+        own = bl[0][3] - bl[0][2]
+        assert all(oe - of == own for _, _, of, oe in bl[:-1]) and bl[-1][3] - bl[-1][2] <= own + unit
+
+
+@settings(max_examples=100, deadline=None)
+@given(data=st.data())
+def test_merge_properties(data):
+    pl = _pl()
+    fs = 10_000_000
+    cfg = pl.make_config(sample_rate=fs)
+    nb = data.draw(st.integers(1, 5))
+    blocks = pl.plan_blocks(cfg, 40 * fs, nb)
+    nb = len(blocks)
+    chans = [1.6200e9 + 41_667.0 * c for c in range(6)]
+    lists = []
+    for k, b in enumerate(blocks):
+        lo, hi = int(b.feed_first) * 100, int(b.feed_end) * 100
+        edges = [int(b.own_first) * 100, int(b.own_end) * 100]
+        ts = data.draw(st.lists(st.one_of(st.integers(lo, hi - 1),
+                                          st.builds(lambda e, d: min(max(e + d, lo), hi - 1), st.sampled_from(edges),
+                                                    st.integers(-3_000_000, 3_000_000))), max_size=12))
+        lists.append([_fr(t, f=data.draw(st.sampled_from(chans)), fid=10 * (i + 1), src=(k, i)) for i, t in enumerate(sorted(ts))])
+    m = pl.merge_blocks(cfg, T0, blocks, lists)
+    ts = [d["timestamp"] for d in m]
+    assert ts == sorted(ts)
+    assert len({d["id"] for d in m}) == len(m) and all(d["id"] // pl.BLOCK_ID_STRIDE == d["block"] for d in m)
+    kept = {d["src"] for d in m}
+    assert len(kept) == len(m)
+    for k, b in enumerate(blocks):
+        o0, o1 = T0 + int(b.own_first) * 100, T0 + int(b.own_end) * 100
+        for d in lists[k]:
+            inside = o0 <= d["timestamp"] < o1
+            t = d["timestamp"]
+            if d["src"] in kept:
+                assert o0 <= t and (t < o1 + 1_000_000 or k == nb - 1)          # only from its own range (+1 ms)
+            elif inside and not (k > 0 and t < o0 + 1_000_000):
+                raise AssertionError(("a frame well inside its block's own range was dropped", k, t - T0))
+            elif inside:                                                         # dropped near the lower edge: a twin was kept
+                assert any(e["block"] == k - 1 and abs(e["timestamp"] - t) < 1_000_000 and
+                           abs(e["center_frequency"] - d["center_frequency"]) < 200 for e in m)
