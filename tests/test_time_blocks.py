@@ -500,3 +500,46 @@ def test_merge_properties(data):
             elif inside:                                                         # dropped near the lower edge: a twin was kept
                 assert any(e["block"] == k - 1 and abs(e["timestamp"] - t) < 1_000_000 and
                            abs(e["center_frequency"] - d["center_frequency"]) < 200 for e in m)
+
+
+# ------------------------------------------------------------------ the GPU cases' own code, dry-run over the stand-ins
+def test_gpu_case_code_runs_over_the_stand_ins(multi_shim, monkeypatch):
+    """tests/gpu_block_cases.py had not run on a B200 when committed; so that at least its own code (calls, result
+    handling, tolerances, the Python mirror it goes through) is not what fails there, its cases run here with
+    pipeline.Pipeline / pipeline.Multi bound to the oracle-backed stand-ins of tests/blocks_host_shim.cpp."""
+    import importlib.util
+    pl = _pl()
+    L = pl.load_library()
+    S = multi_shim
+    S.ir_last_error = L.ir_last_error
+    S.ir_pipeline_create.restype = C.c_void_p
+    S.ir_pipeline_create.argtypes = [C.POINTER(pl.Config)]
+    S.ir_pipeline_destroy.argtypes = [C.c_void_p]
+    S.ir_pipeline_run_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    S.ir_pipeline_results.argtypes = [C.c_void_p, C.POINTER(pl.Results)]
+    S.ir_pipeline_set_origin.argtypes = [C.c_void_p, C.c_uint64]
+    S.ir_format_raw = L.ir_format_raw
+    S.shim_set_devices(1, -1)
+
+    class StandInPipeline(pl.Pipeline):
+        def __init__(self, **kw):
+            self.L = S
+            self.cfg = pl.make_config(**kw)
+            self.h = S.ir_pipeline_create(C.byref(self.cfg))
+            assert self.h
+
+    class StandInMulti(pl.Multi):
+        def __init__(self, devices, **kw):
+            self.L = S
+            self.cfg = pl.make_config(**kw)
+            self.h = S.ir_multi_create(C.byref(self.cfg), (C.c_int * len(devices))(*devices), len(devices))
+            if not self.h:
+                raise RuntimeError("ir_multi_create failed: " + L.ir_last_error().decode())
+
+    monkeypatch.setattr(pl, "Pipeline", StandInPipeline)
+    monkeypatch.setattr(pl, "Multi", StandInMulti)
+    spec = importlib.util.spec_from_file_location("gpu_block_cases", os.path.join(ROOT, "tests", "gpu_block_cases.py"))
+    cases = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cases)
+    cases.test_time_blocks_through_the_cuda_path()
+    cases.test_one_process_driver_on_the_gpu()
