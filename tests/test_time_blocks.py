@@ -283,14 +283,13 @@ def test_two_gloo_ranks_give_the_single_process_merge(port, synth):
 
 
 # ------------------------------------------------------------------ ir_multi_*: the one-process driver, on stand-in devices
-@pytest.fixture(scope="module")
-def multi_shim(tmp_path_factory):
+def build_blocks_shim(outdir):
     """csrc/blocks.cu compiled for the host over oracle-backed stand-ins of ir_pipeline_* (tests/blocks_host_shim.cpp)"""
     import subprocess
     pl = _pl()
     from oracle import bindings as ob
     ob.build(port=True, ref=False)
-    out = str(tmp_path_factory.mktemp("blk") / "libblocks_shim.so")
+    out = os.path.join(str(outdir), "libblocks_shim.so")
     subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", os.path.join(ROOT, "tests", "blocks_host_shim.cpp"),
                     "-I/usr/local/cuda/include", "-o", out, "-L", os.path.dirname(pl.LIB_PATH), "-l:libiridium_b200.so",
                     "-L", os.path.dirname(ob.PORT_SO), "-l:libir_oracle.so", "-Wl,-rpath," + os.path.dirname(pl.LIB_PATH),
@@ -303,7 +302,34 @@ def multi_shim(tmp_path_factory):
     S.ir_multi_results.argtypes = [C.c_void_p, C.POINTER(pl.MultiResults)]
     S.ir_multi_format_raw_all.restype = C.c_long
     S.ir_multi_format_raw_all.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_size_t]
+    S.ir_pipeline_create.restype = C.c_void_p
+    S.ir_pipeline_create.argtypes = [C.POINTER(pl.Config)]
+    S.ir_pipeline_destroy.argtypes = [C.c_void_p]
+    S.ir_pipeline_run_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    S.ir_pipeline_results.argtypes = [C.c_void_p, C.POINTER(pl.Results)]
+    S.ir_pipeline_set_origin.argtypes = [C.c_void_p, C.c_uint64]
+    S.ir_pipeline_classify.restype = C.c_long
+    S.ir_pipeline_classify.argtypes = [C.c_void_p, C.POINTER(pl.FrameClass), C.c_size_t]
+    L = pl.load_library()
+    S.ir_last_error = L.ir_last_error
+    S.ir_format_raw = L.ir_format_raw
     return S
+
+
+def stand_in_pipeline_class(pl, S):
+    """pipeline.Pipeline bound to the stand-ins (oracle-backed; test infrastructure)"""
+    class StandInPipeline(pl.Pipeline):
+        def __init__(self, **kw):
+            self.L = S
+            self.cfg = pl.make_config(**kw)
+            self.h = S.ir_pipeline_create(C.byref(self.cfg))
+            assert self.h
+    return StandInPipeline
+
+
+@pytest.fixture(scope="module")
+def multi_shim(tmp_path_factory):
+    return build_blocks_shim(tmp_path_factory.mktemp("blk"))
 
 
 def test_one_process_driver_on_stand_in_devices(multi_shim, port, synth):
@@ -511,22 +537,8 @@ def test_gpu_case_code_runs_over_the_stand_ins(multi_shim, monkeypatch):
     pl = _pl()
     L = pl.load_library()
     S = multi_shim
-    S.ir_last_error = L.ir_last_error
-    S.ir_pipeline_create.restype = C.c_void_p
-    S.ir_pipeline_create.argtypes = [C.POINTER(pl.Config)]
-    S.ir_pipeline_destroy.argtypes = [C.c_void_p]
-    S.ir_pipeline_run_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
-    S.ir_pipeline_results.argtypes = [C.c_void_p, C.POINTER(pl.Results)]
-    S.ir_pipeline_set_origin.argtypes = [C.c_void_p, C.c_uint64]
-    S.ir_format_raw = L.ir_format_raw
     S.shim_set_devices(1, -1)
-
-    class StandInPipeline(pl.Pipeline):
-        def __init__(self, **kw):
-            self.L = S
-            self.cfg = pl.make_config(**kw)
-            self.h = S.ir_pipeline_create(C.byref(self.cfg))
-            assert self.h
+    StandInPipeline = stand_in_pipeline_class(pl, S)
 
     class StandInMulti(pl.Multi):
         def __init__(self, devices, **kw):
