@@ -79,3 +79,24 @@ extern "C" long ir_pipeline_classify(ir_pipeline_t *p, ir_frame_class_t *out, si
     }
     return (long)p->run.n_results;
 }
+
+// ir_pipeline_format_parsed_all over the stand-in (same rule as the library's: IDA line where ida_decode() accepted,
+// RAW line otherwise; main.c:328-331) -- only so that the GPU cases' own code can be dry-run on the CPU
+extern "C" long ir_pipeline_format_parsed_all(ir_pipeline_t *p, const char *file_info, uint64_t t0, const ir_frame_class_t *cls,
+                                              size_t n_cls, char *dst, size_t cap) {
+    const size_t n = p->run.n_results;
+    if (!dst) return (long)(n * 1024 + p->run.bits_len + 64);
+    std::vector<ir_frame_class_t> own;
+    if (!cls) { own.resize(n + 1); if (ir_pipeline_classify(p, own.data(), n) < 0) return -1; cls = own.data(); n_cls = n; }
+    if (n_cls != n) return -1;
+    const ir_frame_t *fr = (const ir_frame_t *)p->run.results;
+    if (n && t0 == 0) t0 = (fr[0].timestamp / 1000000000ULL) * 1000000000ULL;
+    size_t pos = 0;
+    for (size_t i = 0; i < n; i++) {
+        const int k = cls[i].ida_ok ? ir_format_ida(dst + pos, cap - pos, t0, &fr[i], &cls[i])
+                                    : ir_format_raw(dst + pos, cap - pos, file_info, t0, &fr[i], p->run.bits + fr[i].bits_offset);
+        if (k < 0) return -1;
+        pos += (size_t)k;
+    }
+    return (long)pos;
+}

@@ -71,3 +71,24 @@ def test_dry_run_pipeline_classifies_planted_frames(host_classifier, monkeypatch
     chk = cases.fc.bind_checker(C.CDLL(cases.PORT_SO), "orc_")
     libs = [("port", lambda bits, llr, direction: chk(bits, None, direction))]
     cases.test_pipeline_classifies_planted_frames_from_device_memory(pl, libs, synth)
+
+
+def test_dry_run_parsed_output_of_a_run(host_classifier, monkeypatch, tmp_path, synth):
+    pl, _ = host_classifier
+    tb = _load("test_time_blocks")
+    S = tb.build_blocks_shim(tmp_path)
+    S.shim_set_devices(1, -1)
+    cases = _load("gpu_classify_cases")
+    monkeypatch.setattr(pl, "Pipeline", tb.stand_in_pipeline_class(pl, S))
+    chk = cases.fc.bind_checker(C.CDLL(cases.PORT_SO), "orc_")
+    cases.test_parsed_output_of_a_run(pl, [("port", lambda bits, llr, direction: chk(bits, None, direction))], synth)
+
+
+def test_dry_run_dropin_comparison_code(monkeypatch, tmp_path, synth):
+    """tests/gpu_dropin_cases.py compares the linked drop-in program with the reference program; here the reference
+    program stands on both sides, which runs the case's own parsing / sorting / tolerance code on real output"""
+    cases = _load("gpu_dropin_cases")
+    if not os.path.exists(cases.REF_BIN):
+        pytest.skip("oracle/_ref/iridium-sniffer not built")
+    monkeypatch.setattr(cases, "NEW_BIN", cases.REF_BIN)
+    cases.test_reference_main_linked_against_the_library(synth, tmp_path)

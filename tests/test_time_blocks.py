@@ -310,6 +310,8 @@ def build_blocks_shim(outdir):
     S.ir_pipeline_set_origin.argtypes = [C.c_void_p, C.c_uint64]
     S.ir_pipeline_classify.restype = C.c_long
     S.ir_pipeline_classify.argtypes = [C.c_void_p, C.POINTER(pl.FrameClass), C.c_size_t]
+    S.ir_pipeline_format_parsed_all.restype = C.c_long
+    S.ir_pipeline_format_parsed_all.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]
     L = pl.load_library()
     S.ir_last_error = L.ir_last_error
     S.ir_format_raw = L.ir_format_raw
