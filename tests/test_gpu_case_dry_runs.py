@@ -92,3 +92,18 @@ def test_dry_run_dropin_comparison_code(monkeypatch, tmp_path, synth):
         pytest.skip("oracle/_ref/iridium-sniffer not built")
     monkeypatch.setattr(cases, "NEW_BIN", cases.REF_BIN)
     cases.test_reference_main_linked_against_the_library(synth, tmp_path)
+
+
+def test_dry_run_reference_named_entry_points(host_classifier, monkeypatch, tmp_path):
+    """frame_decode() / ida_decode() of csrc/refapi_frames.cu compiled for the host (tests/refapi_frames_host_shim.cpp),
+    through the GPU case's own comparison with the reference's structs, byte for byte"""
+    pl, _ = host_classifier
+    cases = _load("gpu_classify_cases")
+    out = str(tmp_path / "librf_shim.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-x", "c++",
+                    os.path.join(HERE, "refapi_frames_host_shim.cpp"), "-o", out, "-L", os.path.dirname(pl.LIB_PATH),
+                    "-l:libiridium_b200.so", "-Wl,-rpath," + os.path.dirname(pl.LIB_PATH)], check=True)
+    S = C.CDLL(out)
+    monkeypatch.setattr(pl, "load_library", lambda: S)
+    monkeypatch.setattr(cases, "GEO_TOL", 0.0)          # host-compiled: the C library's atan2 on both sides
+    cases.test_reference_named_entry_points(pl)
