@@ -1,4 +1,4 @@
-"""The GPU cases of tests/gpu_classify_cases.py and tests/gpu_dropin_cases.py in ONE process, most valuable first,
+"""The GPU cases of tests/gpu_classify_cases.py, tests/gpu_dropin_cases.py and tests/gpu_block_cases.py in ONE process, most valuable first,
 each result appended to gpurun_out/quick_gpu_cases.log as soon as it is known (for a GPU call of a few seconds).
     python tools/quick_gpu_cases.py"""
 import ctypes as C
@@ -94,4 +94,8 @@ step("dropin_simplex_raw", lambda: dropin(0, []))
 step("dropin_duplex_raw", lambda: dropin(1, []))
 step("dropin_simplex_parsed", lambda: dropin(0, ["--parsed"]))
 step("generated_frames_one_launch", lambda: gc.test_generated_frames_one_launch(pl, checkers))
+gb = _load("gpu_block_cases")              # one stream in time blocks, ir_multi_*
+step("time_blocks_through_the_cuda_path", gb.test_time_blocks_through_the_cuda_path)
+step("one_process_driver", gb.test_one_process_driver_on_the_gpu)
+step("one_process_driver_parsed", gb.test_one_process_driver_parsed_on_the_gpu)
 say("done")
