@@ -310,6 +310,9 @@ def build_blocks_shim(outdir):
     S.ir_pipeline_set_origin.argtypes = [C.c_void_p, C.c_uint64]
     S.ir_pipeline_classify.restype = C.c_long
     S.ir_pipeline_classify.argtypes = [C.c_void_p, C.POINTER(pl.FrameClass), C.c_size_t]
+    S.ir_multi_set_classify.argtypes = [C.c_void_p, C.c_int]
+    S.ir_multi_format_parsed_all.restype = C.c_long
+    S.ir_multi_format_parsed_all.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_size_t]
     S.ir_pipeline_format_parsed_all.restype = C.c_long
     S.ir_pipeline_format_parsed_all.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]
     L = pl.load_library()
@@ -557,3 +560,4 @@ def test_gpu_case_code_runs_over_the_stand_ins(multi_shim, monkeypatch):
     spec.loader.exec_module(cases)
     cases.test_time_blocks_through_the_cuda_path()
     cases.test_one_process_driver_on_the_gpu()
+    cases.test_one_process_driver_parsed_on_the_gpu()
