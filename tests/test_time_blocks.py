@@ -106,8 +106,17 @@ def test_merge_rules():
 
 
 # ------------------------------------------------------------------ against the oracle
+_CACHE = {}
+
+
 def _recording(synth):
     """3.6 s at 10 MHz, ~150 bursts, some planted right across the two block boundaries of a 3-block plan"""
+    if "rec" not in _CACHE:
+        _CACHE["rec"] = _make_recording(synth)
+    return _CACHE["rec"]
+
+
+def _make_recording(synth):
     fs = 10_000_000
     pl = _pl()
     cfg = pl.make_config(sample_rate=fs)
@@ -123,6 +132,13 @@ def _recording(synth):
 
 
 def _oracle_blocks(port, rec, blocks, which=None):
+    key = ("orc", id(rec), None if which is None else tuple(sorted(which)))
+    if key not in _CACHE:
+        _CACHE[key] = _run_oracle_blocks(port, rec, blocks, which)
+    return [[dict(d) for d in fl] for fl in _CACHE[key]]
+
+
+def _run_oracle_blocks(port, rec, blocks, which=None):
     lists = []
     for k, b in enumerate(blocks):
         if which is not None and k not in which:
