@@ -306,6 +306,11 @@ typedef struct ir_multi ir_multi_t;
 ir_multi_t *ir_multi_create(const ir_config_t *cfg, const int *devices, int n_devices);
 void ir_multi_destroy(ir_multi_t *m);
 int ir_multi_run_host(ir_multi_t *m, const void *iq, size_t n_samples, int fmt, int n_blocks);
+/* n_streams INDEPENDENT streams (BASELINE config 5: e.g. one recording or receiver per GPU): stream s goes to device
+ * s % n_devices, each device working through its streams in order; no halo, no merge.  The result lists the streams
+ * one after the other, each in its pipeline's own frame order; `block` = the stream's index, ids = stream *
+ * IR_BLOCK_ID_STRIDE + id.  All streams share cfg (rate, centre frequency, start time). */
+int ir_multi_run_streams_host(ir_multi_t *m, const void *const *iq, const size_t *n_samples, int n_streams, int fmt);
 /* merged frames of the last run; block[i] = the time block frame i came from, bits[block] + frames[i].bits_offset its bits */
 typedef struct {
     size_t n_frames;

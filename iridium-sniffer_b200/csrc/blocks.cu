@@ -318,3 +318,69 @@ extern "C" long ir_multi_format_parsed_all(ir_multi_t *m, const char *file_info,
     }
     return (long)pos;
 }
+
+// Independent streams (BASELINE config 5: one recording per GPU, nothing shared): stream s on device s % n_devices, each
+// device working through its streams in order.  No halo, no merge -- the result lists the streams one after the other,
+// each in its pipeline's own order, `block` = the stream's index, ids = stream * IR_BLOCK_ID_STRIDE + id.
+extern "C" int ir_multi_run_streams_host(ir_multi_t *m, const void *const *iq, const size_t *n_samples, int n_streams, int fmt) {
+    if (!m || !iq || !n_samples || n_streams <= 0) { set_err("ir_multi_run_streams_host: null argument"); return -1; }
+    if (fmt < 0 || fmt > 2) { set_err("bad sample format"); return -1; }
+    const int nd = (int)m->pipes.size();
+    const size_t ns = (size_t)n_streams;
+    m->start_time_ns = m->cfg.start_time_ns;
+    if (!m->start_time_ns) {
+        struct timespec ts;
+        clock_gettime(CLOCK_REALTIME, &ts);
+        m->start_time_ns = (uint64_t)ts.tv_sec * 1000000000ULL + (uint64_t)ts.tv_nsec;
+    }
+    m->blocks.assign(ns, ir_block_t{});
+    for (size_t k = 0; k < ns; k++) { m->blocks[k].feed_end = n_samples[k]; m->blocks[k].own_end = n_samples[k]; }
+    m->frames.assign(ns, {}); m->bits.assign(ns, {}); m->llr.assign(ns, {}); m->cls.assign(ns, {});
+    m->merged.clear(); m->merged_block.clear(); m->merged_index.clear();
+    m->launches = 0; m->fed = 0;
+    std::vector<std::string> errs((size_t)nd);
+    std::vector<uint64_t> launches((size_t)nd, 0);
+    auto work = [&](int d) {
+        ir_pipeline_t *p = m->pipes[(size_t)d];
+        for (size_t k = (size_t)d; k < ns; k += (size_t)nd) {
+            ir_results_t r;
+            if (ir_pipeline_set_start_time(p, m->start_time_ns) || ir_pipeline_set_origin(p, 0) ||
+                ir_pipeline_run_host(p, iq[k], n_samples[k], fmt) || ir_pipeline_results(p, &r)) {
+                errs[(size_t)d] = std::string("stream ") + std::to_string(k) + " on device " + std::to_string(m->devices[(size_t)d]) +
+                                  ": " + ir_last_error();
+                break;
+            }
+            m->frames[k].assign(r.frames, r.frames + r.n_frames);
+            m->bits[k].assign(r.bits, r.bits + r.n_bits_total);
+            m->llr[k].assign(r.llr, r.llr + r.n_bits_total);
+            launches[(size_t)d] += r.kernel_launches;
+            if (m->classify && r.n_frames) {
+                m->cls[k].resize(r.n_frames);
+                if (ir_pipeline_classify(p, m->cls[k].data(), r.n_frames) < 0) {
+                    errs[(size_t)d] = std::string("classifying stream ") + std::to_string(k) + ": " + ir_last_error();
+                    break;
+                }
+                launches[(size_t)d] += 1;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int d = 1; d < nd; d++) th.emplace_back(work, d);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int d = 0; d < nd; d++)
+        if (!errs[(size_t)d].empty()) { set_last_error("ir_multi_run_streams_host: " + errs[(size_t)d]); return -1; }
+    m->bits_ptr.resize(ns); m->llr_ptr.resize(ns); m->cls_ptr.resize(ns);
+    for (size_t k = 0; k < ns; k++) {
+        m->bits_ptr[k] = m->bits[k].data(); m->llr_ptr[k] = m->llr[k].data();
+        m->cls_ptr[k] = m->cls[k].empty() ? nullptr : m->cls[k].data();
+        m->fed += n_samples[k];
+        for (size_t i = 0; i < m->frames[k].size(); i++) {
+            ir_frame_t f = m->frames[k][i];
+            f.id = (uint64_t)k * IR_BLOCK_ID_STRIDE + f.id % IR_BLOCK_ID_STRIDE;
+            m->merged.push_back(f); m->merged_block.push_back((uint32_t)k); m->merged_index.push_back((uint32_t)i);
+        }
+    }
+    for (uint64_t l : launches) m->launches += l;
+    return 0;
+}

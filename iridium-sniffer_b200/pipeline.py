@@ -175,6 +175,8 @@ def load_library() -> C.CDLL:
     L.ir_multi_results.argtypes = [C.c_void_p, C.POINTER(MultiResults)]
     L.ir_multi_format_raw_all.restype = C.c_long
     L.ir_multi_format_raw_all.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_size_t]
+    L.ir_multi_run_streams_host.restype = C.c_int
+    L.ir_multi_run_streams_host.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_int, C.c_int]
     L.ir_multi_set_classify.restype = C.c_int
     L.ir_multi_set_classify.argtypes = [C.c_void_p, C.c_int]
     L.ir_multi_format_parsed_all.restype = C.c_long
@@ -285,7 +287,7 @@ EXPORTED_SYMBOLS = [
     "ir_fill_decoded_frame", "ir_fill_ida_burst",
     "ir_block_halo", "ir_block_tail", "ir_plan_blocks", "ir_pipeline_set_origin", "ir_merge_blocks",
     "ir_pipeline_set_start_time", "ir_multi_create", "ir_multi_destroy", "ir_multi_run_host", "ir_multi_results",
-    "ir_multi_format_raw_all", "ir_multi_set_classify", "ir_multi_format_parsed_all",
+    "ir_multi_format_raw_all", "ir_multi_set_classify", "ir_multi_format_parsed_all", "ir_multi_run_streams_host",
 ]
 
 
@@ -359,6 +361,16 @@ class Multi:
         a, n = Pipeline._as_raw(iq, fmt)
         if self.L.ir_multi_run_host(self.h, a.ctypes.data_as(C.c_void_p), n, FMT_BY_NAME[fmt], n_blocks) != 0:
             raise RuntimeError("ir_multi_run_host failed: " + self.L.ir_last_error().decode())
+        return self.frames()
+
+    def run_streams_host(self, streams, fmt: str = "cf32") -> List[dict]:
+        """independent streams (one numpy array each), stream s on device s % n_devices; frames of all of them back,
+        `block` = the stream's index"""
+        arrs = [Pipeline._as_raw(a, fmt) for a in streams]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a, _ in arrs])
+        ns = (C.c_size_t * len(arrs))(*[n for _, n in arrs])
+        if self.L.ir_multi_run_streams_host(self.h, ptrs, ns, len(arrs), FMT_BY_NAME[fmt]) != 0:
+            raise RuntimeError("ir_multi_run_streams_host failed: " + self.L.ir_last_error().decode())
         return self.frames()
 
     def results(self) -> MultiResults:

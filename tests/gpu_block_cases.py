@@ -135,3 +135,25 @@ def test_one_process_driver_parsed_on_the_gpu():
     assert n0 >= 2 and all(l in set(one) for d, l in zip(fr, two) if d["block"] == 0)
     assert [l[l.index("LCW("):] for l in one if l.startswith("IDA:")] == [l[l.index("LCW("):] for l in two if l.startswith("IDA:")]
     m.close()
+
+
+def test_one_process_driver_independent_streams_on_the_gpu():
+    """BASELINE config 5 through ir_multi_run_streams_host: each stream's frames == that stream through a pipeline of
+    its own (one device here: the streams run one after the other on it)"""
+    pl = importlib.import_module("iridium-sniffer_b200.pipeline")
+    synth = importlib.import_module("iridium-sniffer_b200.synth")
+    recs = [synth.make_recording(40 + s, duration_s=0.62 + 0.05 * s, n_bursts=4 + s, snr_db=(15.0, 22.0)) for s in range(3)]
+    want = []
+    for r in recs:
+        p = pl.Pipeline(sample_rate=r.sample_rate, start_time_ns=T0)
+        want.append(p.run_host(r.iq).frames)
+        p.close()
+    m = pl.Multi([0], sample_rate=recs[0].sample_rate, start_time_ns=T0)
+    got = m.run_streams_host([r.iq for r in recs])
+    flat = [(s, d) for s, fl in enumerate(want) for d in fl]
+    assert len(got) == len(flat) >= 9
+    for g, (s, w) in zip(got, flat):
+        assert g["block"] == s and g["id"] == s * pl.BLOCK_ID_STRIDE + w["id"] and g["timestamp"] == w["timestamp"]
+        assert tb._bitstr(g) == tb._bitstr(w)
+    assert len(m.raw_text("T").decode().splitlines()) == len(got)
+    m.close()

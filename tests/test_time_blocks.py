@@ -326,6 +326,7 @@ def build_blocks_shim(outdir):
     S.ir_pipeline_set_origin.argtypes = [C.c_void_p, C.c_uint64]
     S.ir_pipeline_classify.restype = C.c_long
     S.ir_pipeline_classify.argtypes = [C.c_void_p, C.POINTER(pl.FrameClass), C.c_size_t]
+    S.ir_multi_run_streams_host.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_int, C.c_int]
     S.ir_multi_set_classify.argtypes = [C.c_void_p, C.c_int]
     S.ir_multi_format_parsed_all.restype = C.c_long
     S.ir_multi_format_parsed_all.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_size_t]
@@ -577,3 +578,32 @@ def test_gpu_case_code_runs_over_the_stand_ins(multi_shim, monkeypatch):
     cases.test_time_blocks_through_the_cuda_path()
     cases.test_one_process_driver_on_the_gpu()
     cases.test_one_process_driver_parsed_on_the_gpu()
+    cases.test_one_process_driver_independent_streams_on_the_gpu()
+
+
+def test_one_process_driver_independent_streams(multi_shim, port, synth):
+    """config 5 in one process: three recordings over two stand-in devices == each recording on its own"""
+    pl = _pl()
+    L = pl.load_library()
+    S = multi_shim
+    S.ir_multi_run_streams_host.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_int, C.c_int]
+    recs = [synth.make_recording(40 + s, duration_s=0.62 + 0.05 * s, n_bursts=4 + s, snr_db=(15.0, 22.0)) for s in range(3)]
+    want = [port.run(r.iq, start_time_ns=T0)[0] for r in recs]
+    S.shim_set_devices(2, -1)
+    cfg = pl.make_config(sample_rate=recs[0].sample_rate, start_time_ns=T0)
+    h = S.ir_multi_create(C.byref(cfg), (C.c_int * 2)(0, 1), 2)
+    mm = object.__new__(pl.Multi)
+    mm.L, mm.h, mm.cfg = S, h, cfg
+    got = mm.run_streams_host([r.iq for r in recs])
+    flat = [(s, d) for s, fl in enumerate(want) for d in fl]
+    assert len(got) == len(flat) >= 9
+    for g, (s, w) in zip(got, flat):
+        assert g["block"] == s and g["id"] == s * pl.BLOCK_ID_STRIDE + w["id"] and g["timestamp"] == w["timestamp"]
+        assert _bitstr(g) == _bitstr(w)
+    lines = mm.raw_text("T").decode().splitlines()
+    assert len(lines) == len(got) and all(_bitstr(g) == l.split()[-1] for g, l in zip(got, lines))
+    r = mm.results()
+    assert r.n_blocks == 3 and r.samples_fed == sum(x.n_samples for x in recs) and r.kernel_launches == 3
+    assert S.ir_multi_run_streams_host(h, None, None, 0, 0) == -1
+    mm.h = None
+    S.ir_multi_destroy(h)

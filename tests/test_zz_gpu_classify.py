@@ -20,6 +20,7 @@ CASES.append("gpu_dropin_cases.py::test_reference_main_linked_against_the_librar
 CASES.append("gpu_block_cases.py::test_time_blocks_through_the_cuda_path")      # time blocks, merged
 CASES.append("gpu_block_cases.py::test_one_process_driver_on_the_gpu")           # ir_multi_*: the same in one C call
 CASES.append("gpu_block_cases.py::test_one_process_driver_parsed_on_the_gpu")    # ... with classification / --parsed text
+CASES.append("gpu_block_cases.py::test_one_process_driver_independent_streams_on_the_gpu")   # config 5 in one process
 
 
 @pytest.mark.parametrize("case", CASES)

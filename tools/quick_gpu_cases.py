@@ -98,4 +98,5 @@ gb = _load("gpu_block_cases")              # one stream in time b
 step("time_blocks_through_the_cuda_path", gb.test_time_blocks_through_the_cuda_path)
 step("one_process_driver", gb.test_one_process_driver_on_the_gpu)
 step("one_process_driver_parsed", gb.test_one_process_driver_parsed_on_the_gpu)
+step("one_process_driver_independent_streams", gb.test_one_process_driver_independent_streams_on_the_gpu)
 say("done")
