@@ -12,6 +12,9 @@
 #define IR_SCAN_THREADS 1024
 #define IR_STREAM_CL 8          // CTAs of the streaming state machine's cluster
 #define IR_STREAM_MAX_FRAMES 4096   // frames per launch of the streaming state machine
+#define IR_SEG_MAX_FRAMES 16384     // frames per chunk of the segmented state machine (k_detect_seg.cu)
+#define IR_SEG_LEN 128              // frames per segment (one warp each); multiple of 32
+#define IR_SEG_ROUNDS 10            // rounds enqueued per chunk (a chunk without a fixed point by then falls back)
 // guard band of the bitmaps: valid while every baseline stays inside [LO, HI] x its reference value.
 // LO also sets how often pure noise lands in the uncertain band (e^(-23.1*LO) per bin and frame at 16 dB).
 #define IR_GUARD_LO 0.65f
@@ -98,6 +101,36 @@ struct StreamCtl {
                                                         // wait for workers, event body
 };
 
+// ---- segmented state machine (k_detect_seg.cu)
+struct SegBurst {                  // an active burst at a segment cut; times in frames of the chunk
+    unsigned long long id;         // real id, or (1<<63 | segment<<32 | ordinal) for a burst created in this chunk
+    unsigned long long start, last0;
+    int cb;
+    float rel, base;
+    int dl, lah, tl;               // deletion deadline, frame of the latest hit (or NONE), last frame it cannot be too long
+};
+struct SegState { int n_act; int pad[3]; SegBurst b[32]; };
+struct SegGone { GoneBurst g; int seg, ord; };
+struct SegCtl {
+    int finished, converged, changed, round, cur, round_bail, hard_bail, F, S, nq, n_slots, sq0, hist_idx0;
+    int bailed;                    // the chunk was not kept: the fallback must run
+    int reason;                    // why (1 not primed, 2 guard band, 3 too-long burst, 4 peak list, 5/7 burst table, 6 squelch,
+                                   //  9 missing snapshot, 10 gone pool, 11 snapshot slots, 12 no fixed point)
+    unsigned int guard_bad, pool_count, n_gone0;
+    unsigned long long index0, next_id0;
+    unsigned long long stats[8];   // 0 chunks kept, 1 chunks bailed, 2 rounds, 3 event frames (all rounds), 4 snapshots, 5 quiet frames
+};
+struct SegBuffers {                // device memory of the segmented scan, owned by the pipeline
+    SegCtl *ctl = nullptr;
+    SegState *stA = nullptr, *stB = nullptr;
+    uint32_t *qw = nullptr, *valid = nullptr;
+    int *wpre = nullptr, *qlist = nullptr, *slotv = nullptr, *fslot = nullptr, *ncreate = nullptr, *ngone = nullptr;
+    SegGone *pool = nullptr;
+    uint32_t pool_cap = 0;
+    float *snap = nullptr, *bfinal = nullptr;
+    int slot_cap = 0, frames_cap = 0;
+};
+
 // ------------------------------------------------------------------ downmix
 struct BurstParam {                // one per emitted burst, built on the host
     int64_t start;                 // first sample of the extract (after ring clamp)
@@ -176,7 +209,16 @@ cudaError_t launch_detect_scan_cluster_if(const DetConfig &c, DetState *state, f
 // with baseline workers (see the file header).  Caller snapshots / restores around it.
 bool stream_scan_supported(const DetConfig &c);
 cudaError_t launch_detect_classify(const float *mag, const float *base, float thr, int N, int n_frames,
-                                   uint32_t *xu, float *ref_out, int sm_count, cudaStream_t st);
+                                   uint32_t *xu, float *ref_out, int sm_count, cudaStream_t st,
+                                   unsigned char *rowany = nullptr);
+// k_detect_seg.cu: the same state machine cut into segments walked concurrently, exact by fixed point
+bool seg_scan_supported(const DetConfig &c);
+cudaError_t launch_detect_seg_prime(const DetConfig &c, DetState *state, float *base, float *hist, const float *mag,
+                                    int n_frames, cudaStream_t st);
+size_t seg_walk_smem(const DetConfig &c);
+cudaError_t launch_detect_scan_seg(const DetConfig &c, DetState *state, float *base, float *hist, const float *mag,
+                                   const uint32_t *xu, const unsigned char *rowany, const float *ref, int n_frames,
+                                   GoneBurst *gone, uint32_t gone_cap, const SegBuffers &b, int *n_launches, cudaStream_t st);
 cudaError_t launch_detect_scan_stream(const DetConfig &c, DetState *state, float *base, float *hist,
                                       const float *mag, const uint32_t *xu, const float *ref, int n_frames,
                                       GoneBurst *gone, uint32_t gone_cap, StreamCtl *ctl, unsigned epoch,

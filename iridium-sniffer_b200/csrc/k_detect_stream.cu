@@ -136,7 +136,8 @@ __device__ __forceinline__ unsigned long long pack_cmd(unsigned epoch, int s, in
 // One warp = 1024 consecutive bins (32 bitmap words) of a run of frames.
 __global__ void __launch_bounds__(128)
 k_detect_classify(const float *__restrict__ mag, const float *base_g, float thr, int N, int n_frames,
-                  int frames_per_warp, uint32_t *__restrict__ xu, float *__restrict__ ref_out) {
+                  int frames_per_warp, uint32_t *__restrict__ xu, float *__restrict__ ref_out,
+                  unsigned char *__restrict__ rowany) {
     const int lane = threadIdx.x & 31;
     const int gw = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int ncol = N >> 10;
@@ -151,7 +152,7 @@ k_detect_classify(const float *__restrict__ mag, const float *base_g, float thr,
     for (int j = 0; j < 32; j++) {
         const int bin = (col << 10) + (j << 5) + lane;
         const float r = *reinterpret_cast<const volatile float *>(base_g + bin);
-        if (part == 0) ref_out[bin] = r;
+        if (part == 0 && ref_out != nullptr) ref_out[bin] = r;
         if (r > 0.0f) {
             thi[j] = thr * (r * IR_GUARD_HI) * 1.0001f;
             tlo[j] = thr * (r * IR_GUARD_LO) * 0.9999f;
@@ -175,6 +176,8 @@ k_detect_classify(const float *__restrict__ mag, const float *base_g, float thr,
         uint32_t *o = xu + (size_t)f * (2 * W) + (col << 5) + lane;
         o[0] = uw;                                             // row = [XU][X]
         o[W] = xw;
+        // (segmented scan) does the row have any bit at all?  cleared by the caller; everybody stores 1
+        if (rowany != nullptr && __any_sync(FULL, uw != 0u) && lane == 0) rowany[f] = 1;
     }
 }
 
@@ -819,8 +822,12 @@ k_detect_scan_stream(DetConfig c, DetState *__restrict__ gs, float *base_g, floa
 size_t stream_ctl_bytes() { return sizeof(StreamCtl); }
 
 cudaError_t launch_detect_classify(const float *mag, const float *base, float thr, int N, int n_frames,
-                                   uint32_t *xu, float *ref_out, int sm_count, cudaStream_t st) {
+                                   uint32_t *xu, float *ref_out, int sm_count, cudaStream_t st, unsigned char *rowany) {
     if (n_frames <= 0) return cudaSuccess;
+    if (rowany != nullptr) {
+        cudaError_t e = cudaMemsetAsync(rowany, 0, (size_t)n_frames, st);
+        if (e != cudaSuccess) return e;
+    }
     const int ncol = N >> 10;
     // enough warps for every SM, not so many that the per-warp threshold setup dominates
     int parts = (sm_count * 16 + ncol - 1) / ncol;
@@ -828,7 +835,7 @@ cudaError_t launch_detect_classify(const float *mag, const float *base, float th
     if (fpw < 8) fpw = 8;
     parts = (n_frames + fpw - 1) / fpw;
     const int blocks = (parts * ncol + 3) / 4;
-    k_detect_classify<<<blocks, 128, 0, st>>>(mag, base, thr, N, n_frames, fpw, xu, ref_out);
+    k_detect_classify<<<blocks, 128, 0, st>>>(mag, base, thr, N, n_frames, fpw, xu, ref_out, rowany);
     return cudaGetLastError();
 }
 

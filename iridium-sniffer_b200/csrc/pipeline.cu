@@ -164,7 +164,12 @@ struct ir_pipeline {
     unsigned scan_epoch = 1;
     bool scan_dbg = false;                   // IR_SCAN_DEBUG: events between the operations of every launch
     std::vector<cudaEvent_t> scan_dbg_ev;
-    int scan_mode = 0;                       // 0 = streaming (default where supported), 1 = cluster / single (IR_SCAN)
+    int scan_mode = 0;                       // 0 = streaming, 1 = cluster / single, 2 = segmented (default where supported); IR_SCAN
+    // segmented state machine (k_detect_seg.cu)
+    SegBuffers seg;
+    DevBuf<unsigned char> d_rowany[2], d_seg_raw;
+    DevBuf<float> d_seg_snap;
+    size_t seg_frames_cap = 0;
     uint64_t scan_stats[24] = {0};
     // burst list: pinned host memory mapped into the device; the scan kernel stores the (few,
     // 56-byte) records straight into it, the host reads them after the chunk's event
@@ -275,7 +280,13 @@ extern "C" ir_pipeline_t *ir_pipeline_create(const ir_config_t *cfg) {
         return fail(g_err);
     {
         const char *env = getenv("IR_SCAN");
-        p->scan_mode = (env && *env && strcmp(env, "stream") != 0) || !stream_scan_supported(p->dc) ? 1 : 0;
+        if (!env || !*env || strcmp(env, "seg") == 0) p->scan_mode = seg_scan_supported(p->dc) ? 2 : (stream_scan_supported(p->dc) ? 0 : 1);
+        else p->scan_mode = strcmp(env, "stream") == 0 && stream_scan_supported(p->dc) ? 0 : 1;
+        if (p->scan_mode == 2) {
+            if (p->d_ref[0].ensure(p->dc.N) || p->d_ref[1].ensure(p->dc.N) ||
+                cudaStreamCreateWithFlags(&p->st_cls, cudaStreamNonBlocking) != cudaSuccess)
+                return fail(g_err);
+        }
         if (p->scan_mode == 0) {
             const size_t W2 = (size_t)p->dc.N / 16;
             if (p->d_xu[0].ensure((size_t)IR_STREAM_MAX_FRAMES * W2) || p->d_xu[1].ensure((size_t)IR_STREAM_MAX_FRAMES * W2) ||
@@ -301,6 +312,7 @@ extern "C" void ir_pipeline_destroy(ir_pipeline_t *p) {
     p->d_base.release(); p->d_hist.release(); p->d_state.release();
     p->d_xu[0].release(); p->d_xu[1].release(); p->d_ref[0].release(); p->d_ref[1].release();
     p->d_undo.release(); p->d_base_snap.release();
+    p->d_rowany[0].release(); p->d_rowany[1].release(); p->d_seg_raw.release(); p->d_seg_snap.release();
     p->d_frame_src.release(); p->d_class.release();
     for (auto e : p->ev_cls) if (e) cudaEventDestroy(e);
     if (p->st_cls) cudaStreamDestroy(p->st_cls);
@@ -654,6 +666,85 @@ static int scan_stream_range(ir_pipeline *p, int64_t f0, int64_t f1, cudaEvent_t
     return 0;
 }
 
+// Device memory of the segmented state machine for chunks of up to `fc` frames.
+static int seg_ensure(ir_pipeline *p, size_t fc) {
+    fc = std::min<size_t>(std::max<size_t>(fc, IR_SEG_LEN), IR_SEG_MAX_FRAMES);
+    fc = (fc + IR_SEG_LEN - 1) / IR_SEG_LEN * IR_SEG_LEN;
+    if (fc <= p->seg_frames_cap) return 0;
+    const size_t N = (size_t)p->dc.N, S = fc / IR_SEG_LEN;
+    const uint32_t pool_cap = (uint32_t)std::max<size_t>(4096, fc * 4);
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_ctl = carve(sizeof(SegCtl)), o_a = carve((S + 1) * sizeof(SegState)), o_b = carve((S + 1) * sizeof(SegState)),
+                 o_qw = carve((fc / 32 + 2) * 4), o_valid = carve(N / 32 * 4), o_wpre = carve((fc / 32 + 4) * 4),
+                 o_ql = carve((fc + 2) * 4), o_sv = carve((fc + 4) * 4), o_fs = carve((fc + 2) * 4), o_nc = carve((S + 2) * 4),
+                 o_ng = carve((S + 2) * 4), o_pool = carve((size_t)pool_cap * sizeof(SegGone)), o_bf = carve(N * 4);
+    if (p->d_seg_raw.ensure(off) || p->d_seg_snap.ensure((fc + 1) * N) || p->d_rowany[0].ensure(fc) || p->d_rowany[1].ensure(fc) ||
+        p->d_xu[0].ensure(fc * (N / 16)) || p->d_xu[1].ensure(fc * (N / 16)))
+        return -1;
+    CK(cudaMemset(p->d_seg_raw.p, 0, off));
+    unsigned char *b = p->d_seg_raw.p;
+    SegBuffers &g = p->seg;
+    g.ctl = (SegCtl *)(b + o_ctl); g.stA = (SegState *)(b + o_a); g.stB = (SegState *)(b + o_b);
+    g.qw = (uint32_t *)(b + o_qw); g.valid = (uint32_t *)(b + o_valid); g.wpre = (int *)(b + o_wpre);
+    g.qlist = (int *)(b + o_ql); g.slotv = (int *)(b + o_sv); g.fslot = (int *)(b + o_fs);
+    g.ncreate = (int *)(b + o_nc); g.ngone = (int *)(b + o_ng); g.pool = (SegGone *)(b + o_pool); g.pool_cap = pool_cap;
+    g.bfinal = (float *)(b + o_bf);
+    g.snap = p->d_seg_snap.p; g.slot_cap = (int)fc + 1; g.frames_cap = (int)fc;
+    p->seg_frames_cap = fc;
+    return 0;
+}
+
+// Frames [f0, f1) of the run through the segmented state machine, on st_scan.  The first hist_size frames
+// of a run prime the detector (k_seg_prime).  After that every chunk of <= IR_SEG_MAX_FRAMES frames is:
+// bitmaps against the baseline as it stood two chunks ago (a copy taken in stream order, so the pass of
+// chunk k+1 overlaps chunk k and nobody reads a baseline that is being written), the rounds of
+// k_detect_seg.cu, and -- a no-op unless the chunk bailed -- the cluster kernel.
+static int scan_seg_range(ir_pipeline *p, int64_t f0, int64_t f1, cudaEvent_t fft_done) {
+    const DetConfig &dc = p->dc;
+    const int N = dc.N;
+    cudaStream_t st = p->st_scan;
+    for (int64_t a = f0; a < f1;) {
+        const bool priming = a < dc.hist_size;
+        const int64_t b = priming ? std::min<int64_t>(f1, dc.hist_size) : std::min<int64_t>(f1, a + (int64_t)p->seg_frames_cap);
+        const int nf = (int)(b - a);
+        const float *mag = p->d_mag.p + a * N;
+        const size_t k = p->ev_scan_done.size();
+        if (priming) {
+            CK(launch_detect_seg_prime(dc, p->d_state.p, p->d_base.p, p->d_hist.p, mag, nf, st));
+            p->res.kernel_launches += 2;
+            if (b >= dc.hist_size) {       // primed: both reference buffers start from this baseline
+                CK(cudaMemcpyAsync(p->d_ref[0].p, p->d_base.p, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+                CK(cudaMemcpyAsync(p->d_ref[1].p, p->d_base.p, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+            }
+        } else {
+            const int buf = (int)(k & 1);
+            if (k >= 2) CK(cudaStreamWaitEvent(p->st_cls, p->ev_scan_done[k - 2], 0));
+            else if (k >= 1) CK(cudaStreamWaitEvent(p->st_cls, p->ev_scan_done[0], 0));
+            CK(cudaStreamWaitEvent(p->st_cls, fft_done, 0));
+            CK(launch_detect_classify(mag, p->d_ref[buf].p, dc.thr, N, nf, p->d_xu[buf].p, nullptr, p->sm_count, p->st_cls,
+                                      p->d_rowany[buf].p));
+            p->res.kernel_launches++;
+            cudaEvent_t ec = p->ev();
+            CK(cudaEventRecord(ec, p->st_cls));
+            CK(cudaStreamWaitEvent(st, ec, 0));
+            int nl = 0;
+            CK(launch_detect_scan_seg(dc, p->d_state.p, p->d_base.p, p->d_hist.p, mag, p->d_xu[buf].p, p->d_rowany[buf].p,
+                                      p->d_ref[buf].p, nf, p->d_gone, p->gone_cap, p->seg, &nl, st));
+            CK(launch_detect_scan_cluster_if(dc, p->d_state.p, p->d_base.p, p->d_hist.p, mag, nf, p->d_gone, p->gone_cap,
+                                             &p->seg.ctl->bailed, ScanSnapshot{}, st));
+            p->res.kernel_launches += nl + 1;
+            // the baseline the bitmaps of chunk k+2 are made against
+            CK(cudaMemcpyAsync(p->d_ref[buf].p, p->d_base.p, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+        }
+        cudaEvent_t ed = p->ev();
+        CK(cudaEventRecord(ed, st));
+        p->ev_scan_done.push_back(ed);
+        a = b;
+    }
+    return 0;
+}
+
 // Whole path over one block.  Every chunk's copy / FFT / scan is enqueued up front; the host then
 // follows the detector chunk by chunk and launches the downmix + demod of the bursts each chunk
 // emitted (a "wave") on a fourth stream, so that only the last wave runs after the detector is
@@ -693,7 +784,11 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     // chunking: copies (host input only) overlap the detector kernels of earlier chunks
     size_t chunk = p->cfg.h2d_chunk > 0 ? (size_t)p->cfg.h2d_chunk : ((size_t)32 << 20);
     if (const char *env = getenv("IR_CHUNK_MI")) { const long v = atol(env); if (v > 0 && v <= 1024) chunk = (size_t)v << 20; }
+    // device-resident input in segmented mode: nothing to overlap with copies, so the chunks are as long as
+    // one pass of the segmented state machine takes (more segments side by side per round)
+    if (!host_iq && p->scan_mode == 2 && p->cfg.h2d_chunk == 0 && !getenv("IR_CHUNK_MI")) chunk = (size_t)IR_SEG_MAX_FRAMES * N;
     chunk = std::max<size_t>(chunk / N, 1) * N;
+    if (p->scan_mode == 2 && seg_ensure(p, std::min<size_t>(chunk / N, (size_t)std::max<int64_t>(n_frames, 1)))) return -1;
     // chunk boundaries: full chunks, then the last stretch in halves (ir_plan_chunks)
     std::vector<size_t> bounds((n / std::max<size_t>(chunk, 1)) + 64);
     {
@@ -719,6 +814,7 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     p->ev_scan_done.clear();
     if (ir_pipeline_reset(p)) return -1;
     if (p->scan_mode == 0) CK(cudaMemsetAsync(p->d_ctl.p, 0, sizeof(StreamCtl), p->st_scan));
+    if (p->scan_mode == 2) CK(cudaMemsetAsync(p->seg.ctl, 0, sizeof(SegCtl), p->st_scan));
     cudaEvent_t ev_first_copy = nullptr, ev_last_copy = nullptr;
     cudaEvent_t ev_begin = p->ev();
     CK(cudaEventRecord(ev_begin, p->st_scan));          // after the state reset
@@ -751,10 +847,12 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
         CK(cudaEventRecord(c.fft.b, p->st_fft));
         CK(cudaStreamWaitEvent(p->st_scan, c.fft.b, 0));
         CK(cudaEventRecord(c.scan.a, p->st_scan));
-        if (f1 > f0 && p->scan_mode != 0) {
+        if (f1 > f0 && p->scan_mode == 1) {
             CK(launch_detect_scan_auto(dc, p->d_state.p, p->d_base.p, p->d_hist.p, p->d_mag.p + f0 * N, f1 - f0,
                                        p->d_gone, p->gone_cap, p->st_scan));
             p->res.kernel_launches++;
+        } else if (f1 > f0 && p->scan_mode == 2) {
+            if (scan_seg_range(p, f0, f1, c.fft.b)) return -1;
         } else if (f1 > f0) {
             if (scan_stream_range(p, f0, f1, c.fft.b)) return -1;
         }
@@ -807,10 +905,19 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
         if (assemble_wave(p, p->waves[assembled])) return -1;
     if (host_iq) CK(cudaStreamSynchronize(p->st_copy));
     CK(cudaStreamSynchronize(p->st_burst));
+    memset(p->scan_stats, 0, sizeof(p->scan_stats));
     if (p->scan_mode == 0)
         CK(cudaMemcpy(p->scan_stats, p->d_ctl.p->stats, sizeof(p->scan_stats), cudaMemcpyDeviceToHost));
-    else
-        memset(p->scan_stats, 0, sizeof(p->scan_stats));
+    else if (p->scan_mode == 2) {
+        SegCtl hc;
+        CK(cudaMemcpy(&hc, p->seg.ctl, sizeof(SegCtl), cudaMemcpyDeviceToHost));
+        memcpy(p->scan_stats, hc.stats, sizeof(hc.stats));
+        p->scan_stats[6] = (uint64_t)hc.reason;
+        if (getenv("IR_SCAN_DEBUG"))
+            fprintf(stderr, "seg scan: chunks kept %llu bailed %llu (last reason %d) rounds %llu event frames (all rounds) %llu snapshots %llu quiet frames %llu\n",
+                    (unsigned long long)hc.stats[0], (unsigned long long)hc.stats[1], hc.reason, (unsigned long long)hc.stats[2],
+                    (unsigned long long)hc.stats[3], (unsigned long long)hc.stats[4], (unsigned long long)hc.stats[5]);
+    }
     if (p->scan_dbg && p->scan_mode == 0 && !p->scan_dbg_ev.empty()) {
         double t[4] = {0, 0, 0, 0};
         for (size_t i = 0; i + 4 < p->scan_dbg_ev.size() + 1; i += 5)
@@ -932,7 +1039,7 @@ extern "C" int ir_pipeline_set_start_time(ir_pipeline_t *p, uint64_t start_time_
 extern "C" int ir_pipeline_scan_stats(ir_pipeline_t *p, uint64_t *out, int n) {
     if (!p || !out) return -1;
     for (int i = 0; i < n && i < 8; i++) out[i] = p->scan_stats[i];
-    return p->scan_mode == 0 ? 1 : 0;
+    return p->scan_mode == 0 ? 1 : (p->scan_mode == 2 ? 2 : 0);
 }
 
 extern "C" int ir_pipeline_copy_mag(ir_pipeline_t *p, size_t frame0, size_t n_frames, float *dst) {

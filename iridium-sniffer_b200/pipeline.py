@@ -566,7 +566,8 @@ class Pipeline:
             raise RuntimeError("ir_pipeline_scan_stats failed")
         keys = ("launches_kept", "launches_bailed", "commands", "event_frames", "exact_words", "waits", "last_bail_frame")
         d = {k: int(a[i]) for i, k in enumerate(keys)}
-        d["streaming"] = bool(rc)
+        d["streaming"] = rc == 1
+        d["segmented"] = rc == 2          # launches_* count chunks, "commands" counts rounds
         return d
 
     def stats(self) -> dict:

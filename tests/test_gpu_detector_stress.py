@@ -1,5 +1,7 @@
 """Detector edge cases on the GPU against the CPU oracle, for every state-machine variant
-(the streaming state machine -- bitmaps against a guard-banded reference baseline, one-warp leader,
+(the segmented state machine -- the default: the chunk cut into 128-frame segments walked by a warp each,
+speculative burst lists and baseline versions, exact by fixed point, unusual chunks handed to the cluster
+kernel; the streaming state machine, IR_SCAN=stream -- bitmaps against a guard-banded reference baseline, one-warp leader,
 baseline workers -- which is the default and hands unusual launches to the cluster kernel; the
 8-CTA cluster with speculative batches, IR_SCAN=cluster; the same with the block-wide dense
 leader, IR_SCAN=cluster_dense; the single-CTA implementation, IR_SCAN=single): dense traffic (BASELINE config 4), squelch (> max_bursts simultaneous
@@ -19,7 +21,14 @@ def pl():
     return importlib.import_module("iridium-sniffer_b200.pipeline")
 
 
-MODES = ["stream", "cluster", "cluster_dense", "single"]
+MODES = ["seg", "stream", "cluster", "cluster_dense", "single"]
+
+
+def _set_mode(mode):
+    if mode == "seg":
+        os.environ.pop("IR_SCAN", None)            # the default
+    else:
+        os.environ["IR_SCAN"] = mode
 
 
 def _burst_key(b):
@@ -37,20 +46,19 @@ def _check(pl, port, iq, mode, expect_squelch=None, min_bursts=1, expect_bail=No
     assert len(want) >= min_bursts
     old = os.environ.get("IR_SCAN")
     try:
-        if mode != "stream":
-            os.environ["IR_SCAN"] = mode
-        else:
-            os.environ.pop("IR_SCAN", None)
+        _set_mode(mode)
         p = pl.Pipeline(sample_rate=10_000_000, start_time_ns=77)
         res = p.run_host(iq, "cf32")
         got = [_burst_key(b) for b in res.bursts]
         ss = p.scan_stats()
-        assert ss["streaming"] == (mode == "stream")
+        assert ss["streaming"] == (mode == "stream") and ss["segmented"] == (mode == "seg")
         assert got == want, ss
         if mode == "stream":
             assert ss["launches_kept"] >= 1, ss            # at least the priming launch ran on the fast path
-            if expect_bail is not None:
-                assert (ss["launches_bailed"] > 0) == expect_bail, ss
+        if mode in ("stream", "seg") and expect_bail is not None:
+            assert (ss["launches_bailed"] > 0) == expect_bail, ss
+            if not expect_bail:
+                assert ss["launches_kept"] >= 1, ss
         # frames: bits identical to the oracle's
         ores, _ = port.run(iq, start_time_ns=77)
         assert [(f["id"], f["bits"].tobytes()) for f in res.frames] == [(o["id"], o["bits"].tobytes()) for o in ores]
@@ -104,8 +112,8 @@ def test_ragged_length_and_leading_bursts(pl, port, synth, mode):
     _check(pl, port, iq, mode, min_bursts=1)      # (the polluted baseline may leave the guard band: either path)
 
 
-@pytest.mark.parametrize("mode", ["stream", "cluster"])
-def test_many_launches_bursts_across_launch_boundaries(pl, port, synth, mode):
+@pytest.mark.parametrize("mode,chunk", [("seg", 1 << 20), ("seg", 3 << 20), ("stream", 1 << 20), ("cluster", 1 << 20)])
+def test_many_launches_bursts_across_launch_boundaries(pl, port, synth, mode, chunk):
     """1 Mi-sample chunks = 128-frame launches of the state machine: priming spread over four launches,
     bursts alive across launch boundaries (their latest hit must survive the hand-over of the state)."""
     rec = synth.make_recording(33, duration_s=1.1, n_bursts=24)
@@ -115,11 +123,8 @@ def test_many_launches_bursts_across_launch_boundaries(pl, port, synth, mode):
     assert len(want) >= 15
     old = os.environ.get("IR_SCAN")
     try:
-        if mode != "stream":
-            os.environ["IR_SCAN"] = mode
-        else:
-            os.environ.pop("IR_SCAN", None)
-        p = pl.Pipeline(sample_rate=10_000_000, start_time_ns=77, h2d_chunk=1 << 20)
+        _set_mode(mode)
+        p = pl.Pipeline(sample_rate=10_000_000, start_time_ns=77, h2d_chunk=chunk)
         res = p.run_host(rec.iq, "cf32")
         got = [(b["id"], b["start"], b["stop"], b["last_active"], b["center_bin"], b["magnitude"], b["noise"])
                for b in res.bursts]
@@ -128,6 +133,8 @@ def test_many_launches_bursts_across_launch_boundaries(pl, port, synth, mode):
         assert got == want, ss
         if mode == "stream":
             assert ss["launches_kept"] >= 8 and ss["launches_bailed"] == 0, ss
+        if mode == "seg":       # (the priming launches are not counted) every chunk reached its fixed point
+            assert ss["launches_kept"] >= (8 if chunk == 1 << 20 else 2) and ss["launches_bailed"] == 0, ss
     finally:
         if old is None:
             os.environ.pop("IR_SCAN", None)
@@ -135,13 +142,14 @@ def test_many_launches_bursts_across_launch_boundaries(pl, port, synth, mode):
             os.environ["IR_SCAN"] = old
 
 
-def test_full_size_recording_stream_equals_cluster_and_truth(pl, synth):
+def test_full_size_recording_seg_equals_cluster_oracle_and_truth(pl, port, synth):
     """BASELINE config 2 at full size (60 s, 600 M samples, ~6500 bursts; generated on the GPU like
-    bench.py does): too long for the CPU oracle, so the checks are size-independent properties --
-    the streaming state machine and the cluster kernel (itself pinned to the oracle above) must emit
-    the same burst list field for field, no launch may bail, burst ids must be distinct multiples of 10
-    with (almost) none missing, and >= 99 % of the demodulated frames must carry exactly the
-    bits that were planted."""
+    bench.py does).  The first 8 s are held against the CPU oracle field by field (ids, bits, float fields
+    within SURVEY 8c); the whole recording is too long for the oracle, so there the checks are
+    size-independent properties -- the segmented state machine, the streaming one and the cluster kernel
+    (itself pinned to the oracle above) must emit the same burst list field for field, no chunk may bail,
+    burst ids must be distinct multiples of 10 with (almost) none missing, and >= 99 % of the demodulated
+    frames must carry exactly the bits that were planted."""
     import sys
     import torch
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -155,11 +163,27 @@ def test_full_size_recording_stream_equals_cluster_and_truth(pl, synth):
     out = {}
     old = os.environ.get("IR_SCAN")
     try:
-        for mode in ("stream", "cluster"):
-            if mode == "stream":
-                os.environ.pop("IR_SCAN", None)
-            else:
-                os.environ["IR_SCAN"] = mode
+        # ---- first 8 s against the oracle
+        m = 80_000_000
+        _set_mode("seg")
+        p = pl.Pipeline(sample_rate=10_000_000, start_time_ns=10**18)
+        res8 = p.run_device_ptr(iq.data_ptr(), m, "cf32")
+        ss8 = p.scan_stats()
+        p.close()
+        host8 = iq[:m].cpu().numpy().view(np.complex64).reshape(-1)
+        ores, ost = port.run(host8, start_time_ns=10**18)
+        assert ss8["segmented"] and ss8["launches_bailed"] == 0, ss8
+        assert len(res8.bursts) == ost["n_bursts"] and len(ores) > 700
+        assert [(f["id"], f["timestamp"], f["bits"].tobytes()) for f in res8.frames] == \
+               [(o["id"], o["timestamp"], o["bits"].tobytes()) for o in ores]
+        for g, o in zip(res8.frames, ores):
+            assert abs(g["center_frequency"] - o["center_frequency"]) < 2.0 and abs(g["level"] - o["level"]) < 2e-4
+            assert abs(g["magnitude"] - o["magnitude"]) < 0.05 and abs(g["noise"] - o["noise"]) < 0.05
+            assert abs(g["confidence"] - o["confidence"]) <= 1
+        del host8
+        # ---- the whole recording: every variant the same
+        for mode in ("seg", "stream", "cluster"):
+            _set_mode(mode)
             p = pl.Pipeline(sample_rate=10_000_000, start_time_ns=10**18)
             res = p.run_device_ptr(iq.data_ptr(), n, "cf32")
             out[mode] = ([tuple(b[k] for k in keys) for b in res.bursts],
@@ -170,12 +194,14 @@ def test_full_size_recording_stream_equals_cluster_and_truth(pl, synth):
             os.environ.pop("IR_SCAN", None)
         else:
             os.environ["IR_SCAN"] = old
-    sb, sf, ss, res = out["stream"]
+    gb, gf, gs, res = out["seg"]
+    sb, sf, ss, _ = out["stream"]
     cb, cf, _, _ = out["cluster"]
+    assert gs["segmented"] and gs["launches_bailed"] == 0 and gs["launches_kept"] >= 4, gs
     assert ss["streaming"] and ss["launches_bailed"] == 0 and ss["launches_kept"] >= 20, ss
-    assert len(sb) > 6000 and sb == cb
-    assert sf == cf
-    ids = sorted(b[0] for b in sb)
+    assert len(gb) > 6000 and gb == cb and sb == cb
+    assert gf == cf and sf == cf
+    ids = sorted(b[0] for b in gb)
     assert all(i % 10 == 0 for i in ids) and len(set(ids)) == len(ids) and ids[-1] < 10 * (len(ids) + 64)
     tset = set(truth)
     good = sum("".join(map(str, f["bits"])) in tset for f in res.frames)

@@ -1,0 +1,73 @@
+"""The segmented state machine's ALGORITHM (tests/model_seg_scan.py: fixed cuts, speculative burst lists at
+the cuts, baseline versions from the previous round's quiet flags, fixed point = exact) reproduces the CPU
+oracle's burst list field for field for every segment length, and gives up exactly where the kernels hand the
+chunk to the cluster kernel.  No GPU."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+_spec = importlib.util.spec_from_file_location("model_seg_scan", os.path.join(os.path.dirname(__file__), "model_seg_scan.py"))
+msm = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(msm)
+
+
+def _model(P, seg):
+    return msm.SegScanModel(P.fft_size, P.threshold_lin, P.burst_width_bins // 2, P.burst_pre_len, P.burst_post_len,
+                            P.max_burst_len, P.max_bursts, P.history_size, seg=seg)
+
+
+def _oracle(port, iq):
+    P = port.det_params()
+    pb, mag, nsq = port.detect(P, iq, dump_mag=True)
+    want = [(b.id, b.start, b.stop, b.last_active, b.center_bin, b.peak_rel, b.base_at_create) for b in pb]
+    return P, mag, want, nsq
+
+
+def _same(got, want):
+    assert [tuple(g[:5]) for g in got] == [w[:5] for w in want]
+    assert all(np.float32(g[5]) == np.float32(w[5]) and np.float32(g[6]) == np.float32(w[6]) for g, w in zip(got, want))
+
+
+@pytest.mark.parametrize("seg,chunk", [(64, 4096), (16, 4096), (7, 300), (256, 700), (4096, 4096)])
+def test_model_equals_oracle_config1(port, rec_small, seg, chunk):
+    P, mag, want, nsq = _oracle(port, rec_small.iq)
+    m = _model(P, seg)
+    got = m.run(mag, chunk_frames=chunk)
+    assert nsq == 0 and len(want) == 13
+    _same(got, want)
+    # the speculation settles fast: a handful of rounds per chunk whatever the cut spacing
+    assert m.stats["max_rounds_seen"] <= 8, m.stats
+
+
+@pytest.mark.parametrize("seed", [101, 102])
+def test_model_equals_oracle_random(port, synth, seed):
+    rec = synth.make_recording(seed, duration_s=0.75, n_bursts=8)
+    P, mag, want, _ = _oracle(port, rec.iq)
+    m = _model(P, 32)
+    got = m.run(mag, chunk_frames=100)            # bursts alive across many chunk boundaries
+    assert len(want) >= 3
+    _same(got, want)
+
+
+def test_model_gives_up_where_the_kernels_do(port, synth):
+    cases = [("squelch", synth.make_tone_recording(5, 236, 0.02, 0.5)),
+             ("too long", synth.make_tone_recording(6, 1, 0.13, 0.45, total_s=0.75))]
+    for reason, iq in cases:
+        P, mag, _, _ = _oracle(port, iq)
+        with pytest.raises(msm.Bail) as e:
+            _model(P, 64).run(mag)
+        assert e.value.reason in (reason, "a 33rd concurrent burst", "more bursts than lanes"), e.value.reason
+
+
+def test_model_guard_band_catches_a_moving_noise_floor(port, synth):
+    rec = synth.make_recording(21, duration_s=0.9, n_bursts=10, starts_s=np.linspace(0.05, 0.8, 10))
+    P, mag, want, _ = _oracle(port, rec.iq[:-12345])
+    m = _model(P, 64)
+    try:
+        got = m.run(mag, chunk_frames=4096)
+    except msm.Bail as e:
+        assert e.reason == "guard band"
+    else:
+        _same(got, want)
