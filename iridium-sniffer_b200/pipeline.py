@@ -568,6 +568,8 @@ class Pipeline:
         d = {k: int(a[i]) for i, k in enumerate(keys)}
         d["streaming"] = rc == 1
         d["segmented"] = rc == 2          # launches_* count chunks, "commands" counts rounds
+        if rc == 2:
+            d["last_bail_reason"] = d.pop("last_bail_frame")
         return d
 
     def stats(self) -> dict:

@@ -37,8 +37,9 @@ def test_model_equals_oracle_config1(port, rec_small, seg, chunk):
     got = m.run(mag, chunk_frames=chunk)
     assert nsq == 0 and len(want) == 13
     _same(got, want)
-    # the speculation settles fast: a handful of rounds per chunk whatever the cut spacing
-    assert m.stats["max_rounds_seen"] <= 8, m.stats
+    # the speculation settles in a handful of rounds once a segment is longer than a burst lives
+    # (burst + post_len ~ 30 frames); shorter segments need a round per segment a burst spans
+    assert m.stats["max_rounds_seen"] <= (12 if seg < 32 else 6), m.stats
 
 
 @pytest.mark.parametrize("seed", [101, 102])
