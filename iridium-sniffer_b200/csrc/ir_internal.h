@@ -13,7 +13,8 @@
 #define IR_STREAM_CL 8          // CTAs of the streaming state machine's cluster
 #define IR_STREAM_MAX_FRAMES 4096   // frames per launch of the streaming state machine
 #define IR_SEG_MAX_FRAMES 16384     // frames per chunk of the segmented state machine (k_detect_seg.cu)
-#define IR_SEG_LEN 128              // frames per segment (one warp each); multiple of 32
+#define IR_SEG_LEN 64              // frames per segment (one warp each); multiple of 32
+#define IR_SEG_GONE 256             // gone records a segment can hold (more: the chunk falls back)
 #define IR_SEG_ROUNDS 10            // rounds enqueued per chunk (a chunk without a fixed point by then falls back)
 // guard band of the bitmaps: valid while every baseline stays inside [LO, HI] x its reference value.
 // LO also sets how often pure noise lands in the uncertain band (e^(-23.1*LO) per bin and frame at 16 dB).
@@ -110,13 +111,13 @@ struct SegBurst {                  // an active burst at a segment cut; times in
     int dl, lah, tl;               // deletion deadline, frame of the latest hit (or NONE), last frame it cannot be too long
 };
 struct SegState { int n_act; int pad[3]; SegBurst b[32]; };
-struct SegGone { GoneBurst g; int seg, ord; };
 struct SegCtl {
-    int finished, converged, changed, round, cur, round_bail, hard_bail, F, S, nq, n_slots, sq0, hist_idx0;
+    int finished, converged, changed, round, cur, hard_bail, F, S, nq, n_slots, sq0, hist_idx0, skip_base, q_keep;
+    int qfc[2];                    // per round parity: first frame whose quiet flag changed in that round (INT_MAX: none)
     int bailed;                    // the chunk was not kept: the fallback must run
     int reason;                    // why (1 not primed, 2 guard band, 3 too-long burst, 4 peak list, 5/7 burst table, 6 squelch,
                                    //  9 missing snapshot, 10 gone pool, 11 snapshot slots, 12 no fixed point)
-    unsigned int guard_bad, pool_count, n_gone0;
+    unsigned int guard_bad, n_gone0;
     unsigned long long index0, next_id0;
     unsigned long long stats[8];   // 0 chunks kept, 1 chunks bailed, 2 rounds, 3 event frames (all rounds), 4 snapshots, 5 quiet frames
 };
@@ -125,9 +126,9 @@ struct SegBuffers {                // device memory of the segmented scan, owned
     SegState *stA = nullptr, *stB = nullptr;
     uint32_t *qw = nullptr, *valid = nullptr;
     int *wpre = nullptr, *qlist = nullptr, *slotv = nullptr, *fslot = nullptr, *ncreate = nullptr, *ngone = nullptr;
-    SegGone *pool = nullptr;
-    uint32_t pool_cap = 0;
-    float *snap = nullptr, *bfinal = nullptr;
+    int *segbail = nullptr, *stch = nullptr, *cpre = nullptr, *gpre = nullptr;
+    GoneBurst *glist = nullptr;
+    float *snap = nullptr, *bfinal = nullptr, *qmag = nullptr;
     int slot_cap = 0, frames_cap = 0;
 };
 

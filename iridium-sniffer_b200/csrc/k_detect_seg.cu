@@ -143,12 +143,13 @@ __device__ int block_excl_scan(int *arr, int n, int *sh /* >= 33 ints */) {
 // =========================================================================== chunk begin
 __global__ void __launch_bounds__(256)
 k_seg_begin(DetConfig c, const DetState *__restrict__ gs, SegCtl *ctl, SegState *stA, SegState *stB, uint32_t *qw,
-            int *ncreate, int *ngone, uint32_t *valid_g, int F, int S) {
+            int *ncreate, int *ngone, int *segbail, int *stch, uint32_t *valid_g, int F, int S) {
     const int t = threadIdx.x;
     const int N = c.N, W = N >> 5;
     if (t == 0) {
         ctl->finished = 0; ctl->converged = 0; ctl->changed = 1; ctl->round = 0; ctl->cur = 0;
-        ctl->round_bail = 0; ctl->hard_bail = 0; ctl->guard_bad = 0; ctl->pool_count = 0; ctl->bailed = 0;
+        ctl->hard_bail = 0; ctl->guard_bad = 0; ctl->bailed = 0;
+        ctl->qfc[0] = 0; ctl->qfc[1] = 0; ctl->skip_base = 0;
         ctl->F = F; ctl->S = S; ctl->nq = 0; ctl->n_slots = 0;
         ctl->index0 = gs->index; ctl->next_id0 = gs->next_id; ctl->sq0 = gs->squelch_count;
         ctl->n_gone0 = gs->n_gone; ctl->hist_idx0 = gs->hist_idx;
@@ -171,7 +172,9 @@ k_seg_begin(DetConfig c, const DetState *__restrict__ gs, SegCtl *ctl, SegState 
         stA[0].b[t] = sb; stB[0].b[t] = sb;
     }
     for (int s = 1 + t; s <= S; s += blockDim.x) { stA[s].n_act = 0; stB[s].n_act = 0; }
-    for (int s = t; s < S; s += blockDim.x) { ncreate[s] = 0; ngone[s] = 0; }
+    for (int s = t; s < S; s += blockDim.x) { ncreate[s] = 0; ngone[s] = 0; segbail[s] = 0; }
+    // [parity][s]: the list at segment s's first frame changed in the round of that parity (segment 0's never does)
+    for (int s = t; s < 2 * (S + 1); s += blockDim.x) stch[s] = (s == 0 || s == S + 1) ? 0 : 1;
     for (int w = t; w < (F + 31) / 32; w += blockDim.x) qw[w] = 0u;
     for (int w = t; w < W; w += blockDim.x) {
         uint32_t v = 0;
@@ -204,10 +207,19 @@ k_seg_index(SegCtl *ctl, const uint32_t *__restrict__ qw, const unsigned char *_
         return;
     }
     const int F = ctl->F, nW = (F + 31) / 32;
+    // no quiet flag changed in the previous round: list, versions, slots, snapshots, final baseline and the
+    // guard verdict of that round all stand
+    const bool keep = r > 0 && ctl->qfc[(r - 1) & 1] == 0x7fffffff;
+    __syncthreads();
     if (t == 0) {
-        ctl->round = r + 1; ctl->cur = r & 1; ctl->changed = 0; ctl->round_bail = 0; ctl->guard_bad = 0;
-        ctl->pool_count = 0;
+        ctl->round = r + 1; ctl->cur = r & 1; ctl->changed = 0;
+        ctl->qfc[r & 1] = 0x7fffffff;
+        ctl->skip_base = keep ? 1 : 0;
+        if (!keep) ctl->guard_bad = 0;
     }
+    if (keep) return;
+    // rows of the packed quiet frames that stand: the quiet frames before the first flag that changed last round
+    const int fc_prev = r > 0 ? ctl->qfc[(r - 1) & 1] : 0;
     for (int w = t; w < nW; w += blockDim.x) {
         uint32_t v = qw[w];
         if (w == nW - 1 && (F & 31)) v &= (1u << (F & 31)) - 1u;
@@ -244,6 +256,7 @@ k_seg_index(SegCtl *ctl, const uint32_t *__restrict__ qw, const unsigned char *_
     }
     if (t == 0) {
         ctl->nq = nq;
+        ctl->q_keep = (r > 0 && fc_prev < F) ? min(nq, wpre[fc_prev >> 5] + __popc(qw[fc_prev >> 5] & ((1u << (fc_prev & 31)) - 1u))) : 0;
         const int ns = slotv[nq + 1];
         ctl->n_slots = ns;
         if (ns > slot_cap) ctl->hard_bail = 11;
@@ -253,62 +266,125 @@ k_seg_index(SegCtl *ctl, const uint32_t *__restrict__ qw, const unsigned char *_
 // =========================================================================== round: baseline
 // One thread per bin.  slotp[v] (from k_seg_index) is the exclusive prefix of "version v needs a snapshot":
 // version v is stored at slot slotp[v] iff slotp[v+1] > slotp[v].
-constexpr int BU = 16;                 // quiet frames per register batch
-constexpr int BT = 128;                // bins per CTA
-constexpr int BQ = 512;                // quiet-list entries staged in shared memory at a time
+// The quiet frames' magnitude rows, packed in list order.  The baseline recurrence walks them one after the other,
+// all bins in step; read where they lie (rows 4*N bytes wide, a dozen frames apart) every step lands on a
+// new page for all CTAs at once and the pass runs at the pace of the page walks (measured: 155 us for 1300 quiet
+// frames whatever the prefetch depth).  Here every CTA takes different rows, so the misses overlap.
+// qbuf rows: [0, H) the carried-in history in replacement order (row j = history row (h0+j)%H, copied once per
+// chunk by k_seg_gather_hist), [H + q] the chunk's q-th quiet frame.  Quiet frame q then replaces row q: the
+// "old" row of the recurrence is always H rows before the "new" one.
+__global__ void __launch_bounds__(256)
+k_seg_gather(DetConfig c, const SegCtl *ctl, const float *__restrict__ mag, const int *__restrict__ qlist, float *__restrict__ qbuf) {
+    if (ctl->finished || ctl->hard_bail || ctl->skip_base) return;
+    const int n4 = c.N >> 2, nq = ctl->nq;
+    for (int q = ctl->q_keep + blockIdx.x; q < nq; q += gridDim.x) {
+        const float4 *src = reinterpret_cast<const float4 *>(mag + (size_t)qlist[q] * c.N);
+        float4 *dst = reinterpret_cast<float4 *>(qbuf + (size_t)(c.hist_size + q) * c.N);
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+}
+__global__ void __launch_bounds__(256)
+k_seg_gather_hist(DetConfig c, const DetState *__restrict__ gs, const float *__restrict__ hist, float *__restrict__ qbuf) {
+    const int n4 = c.N >> 2, H = c.hist_size, h0 = gs->hist_idx;
+    for (int j = blockIdx.x; j < H; j += gridDim.x) {
+        const float4 *src = reinterpret_cast<const float4 *>(hist + (size_t)((h0 + j) % H) * c.N);
+        float4 *dst = reinterpret_cast<float4 *>(qbuf + (size_t)j * c.N);
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+}
+
+// One warp per 128 bins, four adjacent bins per thread: four independent dependency chains per thread (the
+// recurrence is two dependent adds per bin and quiet frame -- with one or two warps per SM the pass runs at the
+// pace of a single warp's instruction stream, so it has to be short and carry its own parallelism).  Rows arrive
+// through a ring of 16-byte asynchronous copies; a thread reads back only what it copied: no barrier anywhere.
+constexpr int BU = 8;                  // quiet frames per batch (one cp.async group)
+constexpr int BD = 8;                  // batches in flight
+constexpr int BT = 32;                 // threads per CTA
+constexpr int BB = 4 * BT;             // bins per CTA
+constexpr int BQ = 1024;               // snapshot flags staged in shared memory at a time
+struct BaseShared {
+    float4 ring[BD][BU][2][BT];        // [stage][frame of the batch][new | old][thread]
+    int s_slot[BQ];
+};
 __global__ void __launch_bounds__(BT)
-k_seg_base(DetConfig c, SegCtl *ctl, const float *__restrict__ base_g, const float *__restrict__ hist,
-           const float *__restrict__ mag, const float *__restrict__ ref, const int *__restrict__ qlist,
+k_seg_base(DetConfig c, SegCtl *ctl, const float *__restrict__ base_g, const float *__restrict__ qbuf,
+           const float *__restrict__ ref,
            const int *__restrict__ slotp, float *__restrict__ snap, float *__restrict__ bfinal) {
-    __shared__ int s_new[BQ], s_old[BQ], s_slot[BQ + 1];
-    if (ctl->finished || ctl->hard_bail) return;
+    extern __shared__ __align__(16) unsigned char base_smem[];
+    BaseShared &S = *reinterpret_cast<BaseShared *>(base_smem);
+    if (ctl->finished || ctl->hard_bail || ctl->skip_base) return;
     const int N = c.N, H = c.hist_size;
-    const int bin = blockIdx.x * BT + threadIdx.x;
-    const int nq = ctl->nq, h0 = ctl->hist_idx0;
-    float base = base_g[bin];
-    const float r = ref[bin];
-    const float ga = r * IR_GUARD_LO, gb = r * IR_GUARD_HI;
-    const float glo = fminf(ga, gb), ghi = fmaxf(ga, gb);
-    int bad = !(base >= glo && base <= ghi);
+    const int t = threadIdx.x;
+    const int bin = blockIdx.x * BB + 4 * t;
+    const int nq = ctl->nq;
+    float base[4], glo[4], ghi[4], bmin[4], bmax[4];
     {
+        const float4 b4 = *reinterpret_cast<const float4 *>(base_g + bin), r4 = *reinterpret_cast<const float4 *>(ref + bin);
+        base[0] = b4.x; base[1] = b4.y; base[2] = b4.z; base[3] = b4.w;
+        const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float ga = rr[j] * IR_GUARD_LO, gb = rr[j] * IR_GUARD_HI;
+            glo[j] = fminf(ga, gb); ghi[j] = fmaxf(ga, gb);
+            bmin[j] = base[j]; bmax[j] = base[j];
+        }
         const int p0 = slotp[0], p1 = slotp[1];
-        if (p1 > p0) snap[(size_t)p0 * N + bin] = base;
+        if (p1 > p0) *reinterpret_cast<float4 *>(snap + (size_t)p0 * N + bin) = b4;
     }
-    for (int q0 = 0; q0 < nq; q0 += BQ) {
-        const int m = min(BQ, nq - q0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < m; i += BT) {
-            const int q = q0 + i;
-            s_new[i] = qlist[q];
-            // row the q-th quiet frame of the chunk replaces: history row (h0+q)%H for q < H (encoded < 0),
-            // else the chunk's own quiet frame q-H
-            s_old[i] = q < H ? -1 - ((h0 + q) % H) : qlist[q - H];
-            const int pa = slotp[q + 1], pb = slotp[q + 2];
-            s_slot[i] = pb > pa ? pa : -1;
+    // fetch cursor: the next quiet frame's row; the row it replaces lies H rows before (see k_seg_gather).  Past
+    // the end the copies read slack rows of the buffer that nobody applies.
+    const size_t back = (size_t)H * N;
+    const float *pn = qbuf + back + bin;
+    auto fetch = [&](int k) {                                  // batch k: quiet frames k*BU .. k*BU+BU
+        const uint32_t sa = smem_u32(&S.ring[k % BD][0][0][t]);
+#pragma unroll
+        for (int u = 0; u < BU; u++) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + (uint32_t)(u * 2 * BT * 16)), "l"(pn) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + (uint32_t)((u * 2 + 1) * BT * 16)), "l"(pn - back) : "memory");
+            pn += N;
         }
-        __syncthreads();
-        for (int i0 = 0; i0 < m; i0 += BU) {
-            float mv[BU], ov[BU];
+        cp_async_commit();
+    };
+    const int nb = (nq + BU - 1) / BU;
 #pragma unroll
-            for (int u = 0; u < BU; u++) {
-                const bool in = i0 + u < m;
-                const int fn = in ? s_new[i0 + u] : 0, fo = in ? s_old[i0 + u] : 0;
-                mv[u] = in ? __ldg(mag + (size_t)fn * N + bin) : 0.0f;
-                ov[u] = in ? (fo < 0 ? __ldg(hist + (size_t)(-1 - fo) * N + bin) : __ldg(mag + (size_t)fo * N + bin)) : 0.0f;
+    for (int d = 0; d < BD - 1; d++) fetch(d);
+    for (int k = 0; k < nb; k++) {
+        if ((k * BU) % BQ == 0) {                               // snapshot flags of the next BQ quiet frames
+            __syncwarp();
+            for (int i = t; i < BQ; i += BT) {
+                const int q = k * BU + i;
+                int sl = -1;
+                if (q < nq) { const int pa = slotp[q + 1], pb = slotp[q + 2]; sl = pb > pa ? pa : -1; }
+                S.s_slot[i] = sl;
             }
+            __syncwarp();
+        }
+        fetch(k + BD - 1);
+        cp_async_wait_group<BD - 1>();                          // batch k has landed (this thread's own copies)
+        const int stage = k % BD;
 #pragma unroll
-            for (int u = 0; u < BU; u++) {
-                if (i0 + u < m) {
-                    const float t = base - ov[u];              // simd_avx2.c:221-236: two roundings
-                    base = t + mv[u];
-                    bad |= !(base >= glo && base <= ghi);
-                    const int sl = s_slot[i0 + u];
-                    if (sl >= 0) snap[(size_t)sl * N + bin] = base;
+        for (int u = 0; u < BU; u++) {
+            const int q = k * BU + u;
+            if (q < nq) {
+                const float4 nv = S.ring[stage][u][0][t], ov = S.ring[stage][u][1][t];
+                const float nn[4] = {nv.x, nv.y, nv.z, nv.w}, oo[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float tt = base[j] - oo[j];              // simd_avx2.c:221-236: two roundings
+                    base[j] = tt + nn[j];
+                    bmin[j] = fminf(bmin[j], base[j]); bmax[j] = fmaxf(bmax[j], base[j]);
                 }
+                const int sl = S.s_slot[q % BQ];
+                if (sl >= 0) *reinterpret_cast<float4 *>(snap + (size_t)sl * N + bin) = make_float4(base[0], base[1], base[2], base[3]);
             }
         }
     }
-    bfinal[bin] = base;
+    cp_async_wait_all();
+    *reinterpret_cast<float4 *>(bfinal + bin) = make_float4(base[0], base[1], base[2], base[3]);
+    int bad = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)                                 // (a NaN is sticky under the adds: it reaches the final value)
+        bad |= !(bmin[j] >= glo[j] && bmax[j] <= ghi[j]) || !(base[j] == base[j]);
     if (bad) atomicOr(&ctl->guard_bad, 1u);
 }
 
@@ -317,7 +393,8 @@ template <int WPL>
 __global__ void __launch_bounds__(32, 1)
 k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint32_t *__restrict__ xu_c,
            const float *__restrict__ snap, const int *__restrict__ fslot_g, const uint32_t *__restrict__ valid_g,
-           SegState *stA, SegState *stB, uint32_t *qw_g, int *ncreate, int *ngone, SegGone *pool, uint32_t pool_cap) {
+           SegState *stA, SegState *stB, uint32_t *qw_g, int *ncreate, int *ngone, int *segbail, int *stch,
+           GoneBurst *glist) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     WkShared &S = *reinterpret_cast<WkShared *>(smem_raw);
     if (ctl->finished || ctl->hard_bail) return;
@@ -327,10 +404,23 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
     const int f0 = seg * IR_SEG_LEN;
     if (f0 >= F) return;
     const int n_frames = min(IR_SEG_LEN, F - f0);
-    const SegState *cur = ctl->cur ? stB : stA;
-    SegState *nxt = ctl->cur ? stA : stB;
-    const float *mag = mag_c + (size_t)f0 * N;
+    const int rnd = ctl->round - 1, par = rnd & 1;            // this round (k_seg_index counted it already)
+    const SegState *cur = par ? stB : stA;
+    SegState *nxt = par ? stA : stB;
+    const int Sp1 = ctl->S + 1;
+    const int *stch_prev = stch + (par ^ 1) * Sp1;            // [s]: the list at segment s's first frame changed last round
+    int *stch_now = stch + par * Sp1;
     const int lane = threadIdx.x & 31;
+    // Same inputs as last round -- the same burst list at the first frame, and no quiet flag changed before the
+    // last frame (so every baseline version this segment reads is the same) -- give the same outputs: keep them.
+    if (rnd > 0 && stch_prev[seg] == 0 && f0 + n_frames <= ctl->qfc[par ^ 1]) {
+        const SegState &old = cur[seg + 1];
+        if (lane < old.n_act) nxt[seg + 1].b[lane] = old.b[lane];
+        if (lane == 0) { nxt[seg + 1].n_act = old.n_act; stch_now[seg + 1] = 0; }
+        return;
+    }
+    const float *mag = mag_c + (size_t)f0 * N;
+    GoneBurst *gl = glist + (size_t)seg * IR_SEG_GONE;
     const float thr = c.thr;
     uint64_t *bars = reinterpret_cast<uint64_t *>(S.bar);
     uint32_t *ring = reinterpret_cast<uint32_t *>(smem_raw + ((sizeof(WkShared) + 127) / 128) * 128);
@@ -448,18 +538,14 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
                 rank_d += oid < r_id ? 1 : 0;
             }
         }
-        uint32_t slot0 = 0;
-        if (lane == 0) slot0 = atomicAdd(&ctl->pool_count, (unsigned)__popc(dmask));
-        slot0 = __shfl_sync(FULL, slot0, 0);
         if (done) {
-            const uint32_t slot_g = slot0 + (uint32_t)rank_d;
-            if (slot_g < pool_cap) {
-                SegGone sg;
-                sg.g.id = r_id; sg.g.start = r_start; sg.g.stop = (unsigned long long)(index0 + (long long)fr * N);
-                sg.g.last_active = b_lah == NONE ? r_last0 : (unsigned long long)(index0 + (long long)b_lah * N);
-                sg.g.center_bin = r_cb; sg.g.peak_rel = r_rel; sg.g.base_at_create = r_base; sg.g.pad = 0;
-                sg.seg = seg; sg.ord = (int)ng_local + rank_d;
-                pool[slot_g] = sg;
+            const uint32_t slot_g = ng_local + (uint32_t)rank_d;
+            if (slot_g < (uint32_t)IR_SEG_GONE) {
+                GoneBurst g;
+                g.id = r_id; g.start = r_start; g.stop = (unsigned long long)(index0 + (long long)fr * N);
+                g.last_active = b_lah == NONE ? r_last0 : (unsigned long long)(index0 + (long long)b_lah * N);
+                g.center_bin = r_cb; g.peak_rel = r_rel; g.base_at_create = r_base; g.pad = 0;
+                gl[slot_g] = g;
             } else {
                 bail = 10;
             }
@@ -735,13 +821,17 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
     // bulk copies still in flight must land before the shared memory is released
     for (; blk_landed < blk_issued; blk_landed++) mbar_wait_a(bars_a + 8u * (uint32_t)(blk_landed % RB), (uint32_t)((blk_landed / RB) & 1));
     // ---- outputs of this segment: quiet flags, burst list at its last frame, counts
-    int changed = 0;
+    int changed = 0, st_changed = 0;
     const int nqw = (n_frames + 31) / 32, qw0 = f0 >> 5;
     if (!bail) {
         flush_quiet();
+        int fc = 0x7fffffff;                                  // first frame whose quiet flag changed
         if (lane < nqw) {
-            if (qw_g[qw0 + lane] != qbits) { changed = 1; qw_g[qw0 + lane] = qbits; }
+            const uint32_t was = qw_g[qw0 + lane];
+            if (was != qbits) { changed = 1; qw_g[qw0 + lane] = qbits; fc = f0 + (lane << 5) + __ffs(was ^ qbits) - 1; }
         }
+        fc = __reduce_min_sync(FULL, fc);
+        if (lane == 0 && fc != 0x7fffffff) atomicMin(&ctl->qfc[par], fc);
         int rank_a = 0;
         for (uint32_t m = have_mask; m; m &= m - 1) {
             const int src = __ffs(m) - 1;
@@ -750,7 +840,7 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
             rank_a += (r_have && oid < r_id) ? 1 : 0;
         }
         const SegState &old = cur[seg + 1];
-        if (old.n_act != n_act) changed = 1;
+        if (old.n_act != n_act) st_changed = 1;
         if (r_have) {
             SegBurst b;
             b.id = r_id; b.start = r_start; b.last0 = r_last0; b.cb = r_cb; b.rel = r_rel; b.base = r_base;
@@ -760,19 +850,27 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
                 if (o.id != b.id || o.start != b.start || o.last0 != b.last0 || o.cb != b.cb ||
                     __float_as_uint(o.rel) != __float_as_uint(b.rel) || __float_as_uint(o.base) != __float_as_uint(b.base) ||
                     o.dl != b.dl || o.lah != b.lah || o.tl != b.tl)
-                    changed = 1;
+                    st_changed = 1;
             }
             nxt[seg + 1].b[rank_a] = b;
         }
-        if (lane == 0) { nxt[seg + 1].n_act = n_act; ncreate[seg] = (int)nc_local; ngone[seg] = (int)ng_local; }
+        if (lane == 0) {
+            nxt[seg + 1].n_act = n_act; ncreate[seg] = (int)nc_local; ngone[seg] = (int)ng_local;
+            if (segbail[seg]) { segbail[seg] = 0; changed = 1; }
+        }
     } else {
         // keep the previous round's view of this segment (a bail that only a wrong start produced goes away)
         const SegState &old = cur[seg + 1];
         if (lane < old.n_act) nxt[seg + 1].b[lane] = old.b[lane];
-        if (lane == 0) { nxt[seg + 1].n_act = old.n_act; ncreate[seg] = 0; ngone[seg] = 0; ctl->round_bail = bail; }
+        if (lane == 0) {
+            nxt[seg + 1].n_act = old.n_act; ncreate[seg] = 0; ngone[seg] = 0;
+            if (segbail[seg] != bail) { segbail[seg] = bail; changed = 1; }
+        }
     }
-    changed = __any_sync(FULL, changed);
+    st_changed = __any_sync(FULL, st_changed);
+    changed = __any_sync(FULL, changed) | st_changed;
     if (lane == 0) {
+        stch_now[seg + 1] = st_changed;
         if (changed) ctl->changed = 1;
         atomicAdd(&ctl->stats[3], st_events);
     }
@@ -781,42 +879,53 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
 // =========================================================================== commit
 // One CTA: ids, gone list, detector header + active list.  Sets ctl->bailed for the fallback.
 __global__ void __launch_bounds__(1024)
-k_seg_commit(DetConfig c, SegCtl *ctl, DetState *gs, const SegState *stA, const SegState *stB, int *ncreate, int *ngone,
-             const SegGone *__restrict__ pool, uint32_t pool_cap, GoneBurst *__restrict__ gone, uint32_t gone_cap) {
+k_seg_commit(DetConfig c, SegCtl *ctl, DetState *gs, const SegState *stA, const SegState *stB, const int *ncreate,
+             const int *ngone, const int *segbail, int *cpre, int *gpre, const GoneBurst *__restrict__ glist,
+             GoneBurst *__restrict__ gone, uint32_t gone_cap) {
     __shared__ int sh[40];
     const int t = threadIdx.x;
-    const bool ok = ctl->finished && ctl->converged && !ctl->round_bail && !ctl->guard_bad && !ctl->hard_bail &&
-                    ctl->pool_count <= pool_cap;
+    const int S = ctl->S, F = ctl->F;
+    int sb = 0;
+    for (int s = t; s < S; s += blockDim.x) sb = max(sb, segbail[s]);
+    sb = __syncthreads_or(sb);                                  // (which reason does not matter beyond != 0)
+    const bool ok = ctl->finished && ctl->converged && !sb && !ctl->guard_bad && !ctl->hard_bail;
     __syncthreads();
     if (!ok) {
         if (t == 0) {
+            int why = 12;
+            if (ctl->hard_bail) why = ctl->hard_bail;
+            else if (ctl->guard_bad) why = 2;
+            else if (sb) { for (int s = 0; s < S; s++) if (segbail[s]) { why = segbail[s]; break; } }
             ctl->bailed = 1;
-            ctl->reason = ctl->hard_bail ? ctl->hard_bail : (ctl->guard_bad ? 2 : (ctl->round_bail ? ctl->round_bail : 12));
+            ctl->reason = why;
             ctl->stats[1] += 1; ctl->stats[2] += (unsigned long long)ctl->round;
         }
         return;
     }
-    const int S = ctl->S, F = ctl->F;
-    const SegState *fin = ctl->cur ? stA : stB;               // written by the last executed round
-    const int n_created = block_excl_scan(ncreate, S, sh);
-    const int n_gone_new = block_excl_scan(ngone, S, sh);
+    const SegState *fin = (ctl->round - 1) & 1 ? stA : stB;    // written by the last executed round
+    for (int s = t; s < S; s += blockDim.x) { cpre[s] = ncreate[s]; gpre[s] = ngone[s]; }
+    __syncthreads();
+    const int n_created = block_excl_scan(cpre, S, sh);
+    const int n_gone_new = block_excl_scan(gpre, S, sh);
     const unsigned long long id0 = ctl->next_id0;
     auto real_id = [&](unsigned long long id) -> unsigned long long {
         if (!(id & CODE)) return id;
         const int sg = (int)((id >> 32) & 0x7fffffffu), ord = (int)(id & 0xffffffffu);
-        return id0 + 10ull * (unsigned long long)(ncreate[sg] + ord);
+        return id0 + 10ull * (unsigned long long)(cpre[sg] + ord);
     };
-    const uint32_t np = ctl->pool_count, g0 = ctl->n_gone0;
+    const uint32_t g0 = ctl->n_gone0;
     unsigned overflow = 0;
-    for (uint32_t i = t; i < np; i += blockDim.x) {
-        const SegGone sg = pool[i];
-        const uint32_t pos = g0 + (uint32_t)(ngone[sg.seg] + sg.ord);
-        if (pos < gone_cap) {
-            GoneBurst g = sg.g;
-            g.id = real_id(g.id);
-            gone[pos] = g;
-        } else {
-            overflow = 1;
+    for (int sg = t >> 5; sg < S; sg += (int)(blockDim.x >> 5)) {
+        const int cnt = ngone[sg];
+        for (int k = t & 31; k < cnt; k += 32) {
+            const uint32_t pos = g0 + (uint32_t)(gpre[sg] + k);
+            if (pos < gone_cap) {
+                GoneBurst g = glist[(size_t)sg * IR_SEG_GONE + k];
+                g.id = real_id(g.id);
+                gone[pos] = g;
+            } else {
+                overflow = 1;
+            }
         }
     }
     overflow = __syncthreads_or((int)overflow);
@@ -868,18 +977,19 @@ k_seg_commit_hist(DetConfig c, const SegCtl *ctl, float *base_g, float *hist, co
 // =========================================================================== priming
 // Frames before the detector is primed: nothing is detected (burst_detect.c:426-428), every frame is quiet
 // (:438-454) and the history rows it replaces still hold the zeros of calloc (:283-284).
-__global__ void __launch_bounds__(BT)
+constexpr int PT = 64, PU = 16;
+__global__ void __launch_bounds__(PT)
 k_seg_prime(DetConfig c, const DetState *__restrict__ gs, float *base_g, float *hist, const float *__restrict__ mag, int n_frames) {
     const int N = c.N, H = c.hist_size;
-    const int bin = blockIdx.x * BT + threadIdx.x;
+    const int bin = blockIdx.x * PT + threadIdx.x;
     const int h0 = gs->hist_idx;
     float base = base_g[bin];
-    for (int f0 = 0; f0 < n_frames; f0 += BU) {
-        float mv[BU];
+    for (int f0 = 0; f0 < n_frames; f0 += PU) {
+        float mv[PU];
 #pragma unroll
-        for (int u = 0; u < BU; u++) mv[u] = f0 + u < n_frames ? __ldg(mag + (size_t)(f0 + u) * N + bin) : 0.0f;
+        for (int u = 0; u < PU; u++) mv[u] = f0 + u < n_frames ? __ldg(mag + (size_t)(f0 + u) * N + bin) : 0.0f;
 #pragma unroll
-        for (int u = 0; u < BU; u++)
+        for (int u = 0; u < PU; u++)
             if (f0 + u < n_frames) {
                 const float t = base - 0.0f;
                 base = t + mv[u];
@@ -899,7 +1009,7 @@ __global__ void k_seg_prime_hdr(DetConfig c, DetState *gs, int n_frames) {
 cudaError_t launch_detect_seg_prime(const DetConfig &c, DetState *state, float *base, float *hist, const float *mag,
                                     int n_frames, cudaStream_t st) {
     if (n_frames <= 0) return cudaSuccess;
-    k_seg_prime<<<c.N / BT, BT, 0, st>>>(c, state, base, hist, mag, n_frames);
+    k_seg_prime<<<c.N / PT, PT, 0, st>>>(c, state, base, hist, mag, n_frames);
     k_seg_prime_hdr<<<1, 1, 0, st>>>(c, state, n_frames);
     return cudaGetLastError();
 }
@@ -929,7 +1039,7 @@ static cudaError_t launch_walk_t(const DetConfig &c, const SegBuffers &b, const 
         attr_set[dev] = true;
     }
     k_seg_walk<WPL><<<S, 32, smem, st>>>(c, b.ctl, mag, xu, b.snap, b.fslot, b.valid, b.stA, b.stB, b.qw, b.ncreate, b.ngone,
-                                         b.pool, b.pool_cap);
+                                         b.segbail, b.stch, b.glist);
     return cudaGetLastError();
 }
 
@@ -942,13 +1052,25 @@ cudaError_t launch_detect_scan_seg(const DetConfig &c, DetState *state, float *b
     if (n_frames <= 0) return cudaSuccess;
     if (n_frames > IR_SEG_MAX_FRAMES || n_frames > b.frames_cap) return cudaErrorInvalidValue;
     const int S = (n_frames + IR_SEG_LEN - 1) / IR_SEG_LEN;
-    k_seg_begin<<<1, 256, 0, st>>>(c, state, b.ctl, b.stA, b.stB, b.qw, b.ncreate, b.ngone, b.valid, n_frames, S);
+    {
+        static bool attr_set[64] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(k_seg_base, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BaseShared));
+            if (e != cudaSuccess) return e;
+            attr_set[dev] = true;
+        }
+    }
+    k_seg_gather_hist<<<256, 256, 0, st>>>(c, state, hist, b.qmag);
+    k_seg_begin<<<1, 256, 0, st>>>(c, state, b.ctl, b.stA, b.stB, b.qw, b.ncreate, b.ngone, b.segbail, b.stch, b.valid, n_frames, S);
     int rounds = IR_SEG_ROUNDS;
     if (const char *env = getenv("IR_SEG_ROUNDS")) { const int v = atoi(env); if (v >= 2 && v <= 64) rounds = v; }
     for (int r = 0; r <= rounds; r++) {
         k_seg_index<<<1, 1024, 0, st>>>(b.ctl, b.qw, rowany, b.wpre, b.qlist, b.slotv, b.fslot, b.slot_cap, rounds);
         if (r == rounds) break;                                 // the last index launch only tests for the fixed point
-        k_seg_base<<<c.N / BT, BT, 0, st>>>(c, b.ctl, base, hist, mag, ref, b.qlist, b.slotv, b.snap, b.bfinal);
+        k_seg_gather<<<592, 256, 0, st>>>(c, b.ctl, mag, b.qlist, b.qmag);
+        k_seg_base<<<c.N / BB, BT, sizeof(BaseShared), st>>>(c, b.ctl, base, b.qmag, ref, b.slotv, b.snap, b.bfinal);
         cudaError_t e;
         switch (c.N / 1024) {
         case 4: e = launch_walk_t<4>(c, b, mag, xu, S, st); break;
@@ -958,9 +1080,10 @@ cudaError_t launch_detect_scan_seg(const DetConfig &c, DetState *state, float *b
         }
         if (e != cudaSuccess) return e;
     }
-    k_seg_commit<<<1, 1024, 0, st>>>(c, b.ctl, state, b.stA, b.stB, b.ncreate, b.ngone, b.pool, b.pool_cap, gone, gone_cap);
+    k_seg_commit<<<1, 1024, 0, st>>>(c, b.ctl, state, b.stA, b.stB, b.ncreate, b.ngone, b.segbail, b.cpre, b.gpre, b.glist, gone,
+                                     gone_cap);
     k_seg_commit_hist<<<148, 256, 0, st>>>(c, b.ctl, base, hist, mag, b.qlist, b.bfinal);
-    if (n_launches) *n_launches += 1 + 3 * rounds + 1 + 2;
+    if (n_launches) *n_launches += 2 + 4 * rounds + 1 + 2;
     return cudaGetLastError();
 }
 

@@ -168,7 +168,7 @@ struct ir_pipeline {
     // segmented state machine (k_detect_seg.cu)
     SegBuffers seg;
     DevBuf<unsigned char> d_rowany[2], d_seg_raw;
-    DevBuf<float> d_seg_snap;
+    DevBuf<float> d_seg_snap, d_seg_qmag;
     size_t seg_frames_cap = 0;
     uint64_t scan_stats[24] = {0};
     // burst list: pinned host memory mapped into the device; the scan kernel stores the (few,
@@ -312,7 +312,7 @@ extern "C" void ir_pipeline_destroy(ir_pipeline_t *p) {
     p->d_base.release(); p->d_hist.release(); p->d_state.release();
     p->d_xu[0].release(); p->d_xu[1].release(); p->d_ref[0].release(); p->d_ref[1].release();
     p->d_undo.release(); p->d_base_snap.release();
-    p->d_rowany[0].release(); p->d_rowany[1].release(); p->d_seg_raw.release(); p->d_seg_snap.release();
+    p->d_rowany[0].release(); p->d_rowany[1].release(); p->d_seg_raw.release(); p->d_seg_snap.release(); p->d_seg_qmag.release();
     p->d_frame_src.release(); p->d_class.release();
     for (auto e : p->ev_cls) if (e) cudaEventDestroy(e);
     if (p->st_cls) cudaStreamDestroy(p->st_cls);
@@ -672,14 +672,14 @@ static int seg_ensure(ir_pipeline *p, size_t fc) {
     fc = (fc + IR_SEG_LEN - 1) / IR_SEG_LEN * IR_SEG_LEN;
     if (fc <= p->seg_frames_cap) return 0;
     const size_t N = (size_t)p->dc.N, S = fc / IR_SEG_LEN;
-    const uint32_t pool_cap = (uint32_t)std::max<size_t>(4096, fc * 4);
     size_t off = 0;
     auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_ctl = carve(sizeof(SegCtl)), o_a = carve((S + 1) * sizeof(SegState)), o_b = carve((S + 1) * sizeof(SegState)),
                  o_qw = carve((fc / 32 + 2) * 4), o_valid = carve(N / 32 * 4), o_wpre = carve((fc / 32 + 4) * 4),
                  o_ql = carve((fc + 2) * 4), o_sv = carve((fc + 4) * 4), o_fs = carve((fc + 2) * 4), o_nc = carve((S + 2) * 4),
-                 o_ng = carve((S + 2) * 4), o_pool = carve((size_t)pool_cap * sizeof(SegGone)), o_bf = carve(N * 4);
-    if (p->d_seg_raw.ensure(off) || p->d_seg_snap.ensure((fc + 1) * N) || p->d_rowany[0].ensure(fc) || p->d_rowany[1].ensure(fc) ||
+                 o_ng = carve((S + 2) * 4), o_sb = carve((S + 2) * 4), o_sc = carve(2 * (S + 2) * 4), o_cp = carve((S + 2) * 4),
+                 o_gp = carve((S + 2) * 4), o_gl = carve(S * (size_t)IR_SEG_GONE * sizeof(GoneBurst)), o_bf = carve(N * 4);
+    if (p->d_seg_raw.ensure(off) || p->d_seg_snap.ensure((fc + 1) * N) || p->d_seg_qmag.ensure((fc + (size_t)p->dc.hist_size + 128) * N) || p->d_rowany[0].ensure(fc) || p->d_rowany[1].ensure(fc) ||
         p->d_xu[0].ensure(fc * (N / 16)) || p->d_xu[1].ensure(fc * (N / 16)))
         return -1;
     CK(cudaMemset(p->d_seg_raw.p, 0, off));
@@ -688,8 +688,10 @@ static int seg_ensure(ir_pipeline *p, size_t fc) {
     g.ctl = (SegCtl *)(b + o_ctl); g.stA = (SegState *)(b + o_a); g.stB = (SegState *)(b + o_b);
     g.qw = (uint32_t *)(b + o_qw); g.valid = (uint32_t *)(b + o_valid); g.wpre = (int *)(b + o_wpre);
     g.qlist = (int *)(b + o_ql); g.slotv = (int *)(b + o_sv); g.fslot = (int *)(b + o_fs);
-    g.ncreate = (int *)(b + o_nc); g.ngone = (int *)(b + o_ng); g.pool = (SegGone *)(b + o_pool); g.pool_cap = pool_cap;
+    g.ncreate = (int *)(b + o_nc); g.ngone = (int *)(b + o_ng); g.segbail = (int *)(b + o_sb); g.stch = (int *)(b + o_sc);
+    g.cpre = (int *)(b + o_cp); g.gpre = (int *)(b + o_gp); g.glist = (GoneBurst *)(b + o_gl);
     g.bfinal = (float *)(b + o_bf);
+    g.qmag = p->d_seg_qmag.p;
     g.snap = p->d_seg_snap.p; g.slot_cap = (int)fc + 1; g.frames_cap = (int)fc;
     p->seg_frames_cap = fc;
     return 0;
@@ -792,7 +794,13 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     // chunk boundaries: full chunks, then the last stretch in halves (ir_plan_chunks)
     std::vector<size_t> bounds((n / std::max<size_t>(chunk, 1)) + 64);
     {
-        const long nb = ir_plan_chunks(n, chunk, (size_t)N, bounds.data(), bounds.size());
+        long nb = 0;
+        if (host_iq) {
+            nb = ir_plan_chunks(n, chunk, (size_t)N, bounds.data(), bounds.size());
+        } else {
+            // device-resident input: no copy to hide the tail behind -- equal chunks
+            for (size_t off = 0; off < n; off += chunk) bounds[(size_t)nb++] = std::min(n, off + chunk);
+        }
         if (nb < 0) { set_err("chunk plan does not fit"); return -1; }
         bounds.resize((size_t)nb);
         if (bounds.empty()) bounds.push_back(0);
