@@ -233,8 +233,9 @@ cudaError_t upload_input_taps(const float *taps, int ntaps);
 cudaError_t upload_chain_tables(const HostTables &t);
 cudaError_t launch_rot_tables(const float2 *incr, float2 *const *tables, const int *lens, int n,
                               cudaStream_t st);
+// tile_burst[tile] = index of the burst the tile belongs to (nullptr: the one-tile-per-CTA kernel with its search)
 cudaError_t launch_fir(int fmt, int dec, const void *iq, int64_t n_total, uint64_t ring,
-                       const BurstParam *bp, const int *tile_start, int n_bursts, int n_tiles,
+                       const BurstParam *bp, const int *tile_start, const int *tile_burst, int n_bursts, int n_tiles,
                        float2 *dec_out, cudaStream_t st);
 cudaError_t launch_chain(const BurstParam *bp, int n_bursts, const float2 *dec, float2 *scrA,
                          float2 *scrB, const float2 *tw4096, const float2 *tw2048,

@@ -11,6 +11,8 @@
 //                 from registers.  Summation order is the AVX2 kernel's (simd_avx2.c:62-110):
 //                 four interleaved chains k = j mod 4, combined (c0+c2)+(c1+c3), then tail taps.
 //  k_chain      : everything at 250 kHz (steps 2b-9), one CTA per burst.
+#include <stdlib.h>
+
 #include "ir_device.cuh"
 #include "ir_internal.h"
 
@@ -220,23 +222,187 @@ k_fir(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const BurstPa
     }
 }
 
+// ---- warp-specialised version: the default.  One CTA of 8 warps works through a strip of consecutive tiles
+// with two sample buffers.  Warps 4-7 ("producers") stage tile t+1 -- asynchronous copies, then the exact NCO
+// in place -- while warps 0-3 ("consumers", one per chain) run the FIR of tile t, so the FMA pipe never waits
+// for a copy or a rotate phase; hand-over by mbarriers (full / empty per buffer).  The arithmetic is k_fir's,
+// instruction for instruction (same fir_chains, same combine, same tail taps): results are bit-identical.
+#define IR_FIR_STRIP 16
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+constexpr int FWS_C = 128;             // consumer threads (one warp per chain)
+constexpr int FWS_P = 256;             // producer threads
+template <int DEC> __host__ __device__ constexpr int fws_pitch() { return (fir_pitch_elems<DEC>() + 8 + 1) & ~1; }
+template <int FMT, int DEC>
+__global__ void __launch_bounds__(FWS_C + FWS_P, 1)
+k_fir_ws(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const BurstParam *__restrict__ bp,
+         const int *__restrict__ tile_burst, int n_tiles, float2 *__restrict__ dec_out) {
+    static_assert(DEC % 4 == 0, "register-tiled FIR needs dec % 4 == 0");
+    static_assert((IR_FIR_TILE * DEC) % IR_ROT_G == 0, "tiles must start on a phase checkpoint");
+    static_assert((IR_FIR_R * DEC) % IR_ROT_G == 0 && IR_ROT_G == 16, "segment layout below");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int PITCH = fws_pitch<DEC>();
+    constexpr int NSEG_MAX = (fir_in_max<DEC>() + IR_ROT_G - 1) / IR_ROT_G;
+    constexpr int SPT = (NSEG_MAX + FWS_P - 1) / FWS_P;         // 16-sample segments per producer thread
+    constexpr int CPT = (fir_in_max<DEC>() + FWS_P - 1) / FWS_P; // copies per producer thread
+    constexpr int SEG_PER_ROW = IR_FIR_R * DEC / IR_ROT_G;       // segments between two "row" pads of fir_pi
+    float2 *sb0 = reinterpret_cast<float2 *>(smem_raw);
+    float2 *part0 = sb0 + 2 * PITCH;                           // [2][4][IR_FIR_TILE]
+    float *hp = reinterpret_cast<float *>(part0 + 2 * 4 * IR_FIR_TILE);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(hp + ((fir_hp_elems<DEC>() + 1) & ~1));   // full[2], empty[2]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = tid; k < fir_hp_elems<DEC>(); k += blockDim.x) {
+        const int kk = k - IR_FIR_HPAD;
+        hp[k] = (kk >= 0 && kk < (IR_INPUT_NTAPS / 4) * 4) ? c_in_taps[kk] : 0.0f;
+    }
+    if (tid == 0) {
+        mbar_init(&bars[0], FWS_P); mbar_init(&bars[1], FWS_P); mbar_init(&bars[2], FWS_C); mbar_init(&bars[3], FWS_C);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int t0 = blockIdx.x * IR_FIR_STRIP, t1 = min(n_tiles, t0 + IR_FIR_STRIP);
+    if (tid >= FWS_C) {
+        // ------------------------------------------------------------------ producers
+        const int ptid = tid - FWS_C;
+        for (int t = t0; t < t1; t++) {
+            const int b = (t - t0) & 1, use = (t - t0) >> 1;
+            float2 *s = sb0 + b * PITCH;
+            const BurstParam P = bp[tile_burst[t]];
+            const int o0 = (t - P.tile0) * IR_FIR_TILE;
+            const int n_out = min(IR_FIR_TILE, P.dec_len - o0);
+            const int e0 = o0 * DEC;
+            const int n_in = (n_out - 1) * DEC + IR_INPUT_NTAPS;
+            // the NCO checkpoints of this thread's segments: in flight while the samples are staged
+            const int nseg = (n_in + IR_ROT_G - 1) / IR_ROT_G;
+            const float2 *tab = P.rot_table + (e0 >> 4);
+            float2 ph[SPT];
+#pragma unroll
+            for (int j = 0; j < SPT; j++) {
+                const int seg = ptid + FWS_P * j;
+                ph[j] = seg < nseg ? __ldg(tab + seg) : make_float2(0.0f, 0.0f);
+            }
+            if (use > 0) mbar_wait(&bars[2 + b], (uint32_t)((use - 1) & 1));   // the consumers are done with this buffer
+            // A: stage the raw samples.  Positions the detector had not yet received when it emitted the burst
+            // read the ring slot's previous content: one lap earlier, or zero.
+            const int64_t q0 = P.start + e0;
+            const bool plain = FMT == IR_FMT_CF32 && q0 >= 0 && e0 + n_in <= P.n &&
+                               q0 + n_in <= (P.emit_count < n_total ? P.emit_count : n_total);
+            if (plain) {
+                const float2 *src = reinterpret_cast<const float2 *>(iq) + q0;
+#pragma unroll
+                for (int k = 0; k < CPT; k++) {
+                    const int e = ptid + FWS_P * k;
+                    if (e < n_in) cp_async_8(&s[fir_pi<DEC>(e)], src + e);
+                }
+            } else {
+#pragma unroll 4
+                for (int e = ptid; e < fir_in_max<DEC>(); e += FWS_P) {
+                    float2 *dst = &s[fir_pi<DEC>(e)];
+                    bool filled = false;
+                    if (e < n_in && e0 + e < P.n) {
+                        int64_t q = q0 + e;
+                        if (q >= P.emit_count) q -= (int64_t)ring;
+                        if (q >= 0 && q < n_total) {
+                            if (FMT == IR_FMT_CF32) cp_async_8(dst, reinterpret_cast<const float2 *>(iq) + q);
+                            else *dst = load_sample<FMT>(iq, q);
+                            filled = true;
+                        }
+                    }
+                    if (!filled) *dst = make_float2(0.0f, 0.0f);
+                }
+            }
+            if (FMT == IR_FMT_CF32) cp_async_wait_all();
+            asm volatile("bar.sync 2, %0;" ::"n"(FWS_P) : "memory");
+            // B: coarse frequency shift in place, 16 samples per checkpoint (rotator.h:36-42).  A thread's
+            // segments are independent recurrences: they advance together.  Inside a segment the padded index is
+            // the segment's base + i, and whatever lies past n_in in the last segment is nobody's input.
+            {
+                float2 *sp[SPT];
+#pragma unroll
+                for (int j = 0; j < SPT; j++) {
+                    const int seg = min(ptid + FWS_P * j, NSEG_MAX - 1);
+                    sp[j] = s + seg * (IR_ROT_G + 1) + seg / SEG_PER_ROW;
+                }
+                const float2 w = P.incr_coarse;
+#pragma unroll
+                for (int i = 0; i < IR_ROT_G; i++) {
+#pragma unroll
+                    for (int j = 0; j < SPT; j++) {
+                        if (ptid + FWS_P * j < nseg) sp[j][i] = cmul(sp[j][i], ph[j]);
+                        ph[j] = cmul(ph[j], w);
+                    }
+                }
+            }
+            mbar_arrive(&bars[b]);                              // full (release: the rotated samples are visible)
+        }
+    } else {
+        // ------------------------------------------------------------------ consumers: chain J = warp
+        for (int t = t0; t < t1; t++) {
+            const int b = (t - t0) & 1, use = (t - t0) >> 1;
+            float2 *s = sb0 + b * PITCH;
+            float2 *part = part0 + b * 4 * IR_FIR_TILE;
+            const BurstParam P = bp[tile_burst[t]];
+            const int o0 = (t - P.tile0) * IR_FIR_TILE;
+            const int n_out = min(IR_FIR_TILE, P.dec_len - o0);
+            mbar_wait(&bars[b], (uint32_t)(use & 1));
+            {
+                float2 acc[IR_FIR_R];
+#pragma unroll
+                for (int i = 0; i < IR_FIR_R; i++) acc[i] = make_float2(0.0f, 0.0f);
+                constexpr int ROW = IR_FIR_R * DEC + IR_FIR_R * DEC / 16 + 1;
+                fir_chains<DEC>(s + ROW * lane + warp, hp + IR_FIR_HPAD + warp, acc);
+#pragma unroll
+                for (int i = 0; i < IR_FIR_R; i++) part[warp * IR_FIR_TILE + IR_FIR_R * lane + i] = acc[i];
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(FWS_C) : "memory");
+            // D: (c0+c2)+(c1+c3), leftover taps, store (simd_avx2.c:88-109)
+            for (int o = tid; o < n_out; o += FWS_C) {
+                const float2 c0 = part[o], c1 = part[IR_FIR_TILE + o], c2 = part[2 * IR_FIR_TILE + o],
+                             c3 = part[3 * IR_FIR_TILE + o];
+                float ar = (c0.x + c2.x) + (c1.x + c3.x);
+                float ai = (c0.y + c2.y) + (c1.y + c3.y);
+#pragma unroll
+                for (int k = (IR_INPUT_NTAPS / 4) * 4; k < IR_INPUT_NTAPS; k++) {
+                    const float2 x = s[fir_pi<DEC>(o * DEC + k)];
+                    ar = fmaf(c_in_taps[k], x.x, ar);
+                    ai = fmaf(c_in_taps[k], x.y, ai);
+                }
+                dec_out[P.dec_off + o0 + o] = make_float2(ar, ai);
+            }
+            mbar_arrive(&bars[2 + b]);                          // empty
+        }
+    }
+}
+
 template <int FMT, int DEC>
 static cudaError_t launch_fir_t(const void *iq, int64_t n_total, uint64_t ring, const BurstParam *bp,
-                                const int *tile_start, int n_bursts, int n_tiles, float2 *dec_out,
+                                const int *tile_start, const int *tile_burst, int n_bursts, int n_tiles, float2 *dec_out,
                                 cudaStream_t st) {
-    const size_t smem = sizeof(float2) * (fir_pitch_elems<DEC>() + 4 * IR_FIR_TILE) + sizeof(float) * fir_hp_elems<DEC>();
-    cudaError_t e = cudaFuncSetAttribute(k_fir<FMT, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static const bool legacy = getenv("IR_FIR_LEGACY") != nullptr;
+    constexpr int PITCH = fws_pitch<DEC>();
+    const size_t smem_ws = sizeof(float2) * (2 * PITCH + 2 * 4 * IR_FIR_TILE) + sizeof(float) * ((fir_hp_elems<DEC>() + 1) & ~1) + 4 * sizeof(uint64_t);
+    // (two sample buffers of a 256-output tile do not fit 227 KB at DEC = 48: the one-tile kernel serves 12 MHz)
+    if (legacy || tile_burst == nullptr || smem_ws > (size_t)227 * 1024) {
+        const size_t smem = sizeof(float2) * (fir_pitch_elems<DEC>() + 4 * IR_FIR_TILE) + sizeof(float) * fir_hp_elems<DEC>();
+        cudaError_t e = cudaFuncSetAttribute(k_fir<FMT, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_fir<FMT, DEC><<<n_tiles, 128, smem, st>>>(iq, n_total, ring, bp, tile_start, n_bursts, dec_out);
+        return cudaGetLastError();
+    }
+    const size_t smem = smem_ws;
+    cudaError_t e = cudaFuncSetAttribute(k_fir_ws<FMT, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_fir<FMT, DEC><<<n_tiles, 128, smem, st>>>(iq, n_total, ring, bp, tile_start, n_bursts, dec_out);
+    k_fir_ws<FMT, DEC><<<(n_tiles + IR_FIR_STRIP - 1) / IR_FIR_STRIP, FWS_C + FWS_P, smem, st>>>(iq, n_total, ring, bp, tile_burst, n_tiles, dec_out);
     return cudaGetLastError();
 }
 
 cudaError_t launch_fir(int fmt, int dec, const void *iq, int64_t n_total, uint64_t ring,
-                       const BurstParam *bp, const int *tile_start, int n_bursts, int n_tiles,
+                       const BurstParam *bp, const int *tile_start, const int *tile_burst, int n_bursts, int n_tiles,
                        float2 *dec_out, cudaStream_t st) {
     if (n_tiles <= 0) return cudaSuccess;
 #define IR_FIR_CASE(F, D) \
-    if (fmt == F && dec == D) return launch_fir_t<F, D>(iq, n_total, ring, bp, tile_start, n_bursts, n_tiles, dec_out, st)
+    if (fmt == F && dec == D) return launch_fir_t<F, D>(iq, n_total, ring, bp, tile_start, tile_burst, n_bursts, n_tiles, dec_out, st)
     IR_FIR_CASE(IR_FMT_CF32, 40);
     IR_FIR_CASE(IR_FMT_CI16, 40);
     IR_FIR_CASE(IR_FMT_CI8, 40);

@@ -121,7 +121,7 @@ struct Wave {
     int n_tiles = 0;
     int64_t dec_total = 0;
     BurstParam *d_bp = nullptr, *h_bp = nullptr;
-    int *d_tile_start = nullptr, *h_tile_start = nullptr;
+    int *d_tile_start = nullptr, *h_tile_start = nullptr, *d_tile_burst = nullptr, *h_tile_burst = nullptr;
     float2 *d_dec = nullptr, *d_scrA = nullptr, *d_scrB = nullptr, *d_frames = nullptr;
     ChainOut *d_co = nullptr, *h_co = nullptr;
     DemodOut *d_do = nullptr, *h_do = nullptr;
@@ -497,6 +497,11 @@ static int launch_wave(ir_pipeline *p, size_t b0, size_t b1, const void *iq_dev,
     w.e0 = p->ev(); w.e1 = p->ev(); w.e1a = p->ev(); w.e1b = p->ev(); w.e2 = p->ev(); w.e3 = p->ev(); w.e_done = p->ev();
     w.d_bp = p->dev_arena.take<BurstParam>(nb);
     w.d_tile_start = p->dev_arena.take<int>(nb + 1);
+    w.h_tile_burst = p->pin_arena.take<int>((size_t)n_tiles + 1);
+    w.d_tile_burst = p->dev_arena.take<int>((size_t)n_tiles + 1);
+    if (!w.h_tile_burst || !w.d_tile_burst) return -1;
+    for (size_t i = b0; i < b1; i++)
+        for (int t = w.h_tile_start[i - b0]; t < w.h_tile_start[i - b0 + 1]; t++) w.h_tile_burst[t] = (int)(i - b0);
     w.d_dec = p->dev_arena.take<float2>((size_t)dec_total + 16);
     w.d_scrA = p->dev_arena.take<float2>((size_t)dec_total + 16);
     w.d_scrB = p->dev_arena.take<float2>((size_t)dec_total + 16);
@@ -514,9 +519,10 @@ static int launch_wave(ir_pipeline *p, size_t b0, size_t b1, const void *iq_dev,
     }
     CK(fetch_to_device(w.d_bp, w.h_bp, nb * sizeof(BurstParam), st));
     CK(fetch_to_device(w.d_tile_start, w.h_tile_start, (nb + 1) * sizeof(int), st));
+    if (n_tiles > 0) CK(fetch_to_device(w.d_tile_burst, w.h_tile_burst, (size_t)n_tiles * sizeof(int), st));
     p->res.h2d_bytes += nb * sizeof(BurstParam) + (nb + 1) * sizeof(int);
     CK(cudaEventRecord(w.e0, st));
-    CK(launch_fir(fmt, p->dec, iq_dev, (int64_t)n, R, w.d_bp, w.d_tile_start, (int)nb, n_tiles, w.d_dec, st));
+    CK(launch_fir(fmt, p->dec, iq_dev, (int64_t)n, R, w.d_bp, w.d_tile_start, w.d_tile_burst, (int)nb, n_tiles, w.d_dec, st));
     CK(cudaEventRecord(w.e1, st));
     // the 250 kHz chain of this wave overlaps the FIR of the next one
     CK(cudaStreamWaitEvent(p->st_chain, w.e1, 0));
@@ -529,7 +535,7 @@ static int launch_wave(ir_pipeline *p, size_t b0, size_t b1, const void *iq_dev,
     CK(cudaEventRecord(w.e2, sd));
     CK(launch_demod(w.d_co, (int)nb, w.d_frames, p->cfg.use_gardner, w.d_do, w.d_bits, w.d_llr, sd));
     CK(cudaEventRecord(w.e3, sd));
-    p->res.kernel_launches += (n_tiles > 0 ? 1 : 0) + 2 + 2;   // FIR, chain, demod + 2 parameter fetches
+    p->res.kernel_launches += (n_tiles > 0 ? 2 : 0) + 2 + 2;   // FIR, chain, demod + 3 parameter fetches
     CK(cudaMemcpyAsync(w.h_co, w.d_co, nb * sizeof(ChainOut), cudaMemcpyDeviceToHost, sd));
     CK(cudaMemcpyAsync(w.h_do, w.d_do, nb * sizeof(DemodOut), cudaMemcpyDeviceToHost, sd));
     CK(cudaMemcpyAsync(w.h_bits, w.d_bits, nb * nsym2, cudaMemcpyDeviceToHost, sd));

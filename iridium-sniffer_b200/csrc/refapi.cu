@@ -457,7 +457,7 @@ extern "C" int burst_downmix_process(_burst_downmix *dm, burst_data_t *burst, do
     RCK(cudaMemcpyAsync(dm->d_in, burst->samples, sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice, dm->st), 0);
     RCK(cudaMemcpyAsync(dm->d_bp, &bp, sizeof(bp), cudaMemcpyHostToDevice, dm->st), 0);
     RCK(cudaMemcpyAsync(dm->d_tiles, tiles, sizeof(tiles), cudaMemcpyHostToDevice, dm->st), 0);
-    RCK(launch_fir(IR_FMT_CF32, dec, dm->d_in, n, 1ull << 40, dm->d_bp, dm->d_tiles, 1, n_tiles, dm->d_dec, dm->st), 0);
+    RCK(launch_fir(IR_FMT_CF32, dec, dm->d_in, n, 1ull << 40, dm->d_bp, dm->d_tiles, nullptr, 1, n_tiles, dm->d_dec, dm->st), 0);
     RCK(launch_chain(dm->d_bp, 1, dm->d_dec, dm->d_a, dm->d_b, dm->d_tw12, dm->d_tw11, dm->d_sync_dl, dm->d_sync_ul,
                      dm->d_co, dm->d_frame, dm->st), 0);
     ChainOut co;
