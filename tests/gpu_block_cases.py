@@ -5,10 +5,10 @@ bar: same frames, same bits, time stamps on the stream's clock; (2) the merge of
 over the whole stream by the criteria tests/test_time_blocks.py states (bits exact for every matched burst, >= 99 %
 matched, each boundary burst exactly once).
 
-NOTE (round 1): written after the round's GPU minutes were spent.  The plan and the merge are host code and are
-pinned on the CPU against the oracle (tests/test_time_blocks.py); what this file adds -- the origin entering the
-device path's time stamps, blocks of different sizes through one pipeline -- had not run on a B200 when committed.
-Not collected by name; tests/test_zz_gpu_classify.py runs it in a child process, last."""
+The plan and the merge are host code and are pinned on the CPU against the oracle (tests/test_time_blocks.py); this
+file adds the device side -- the origin entering the device path's time stamps, blocks of different sizes through one
+pipeline, one process owning several GPUs (the last case needs two devices and skips only when the box has one).
+Not collected by name; tests/test_zz_gpu_classify.py runs it case by case in child processes, last."""
 import importlib
 import importlib.util
 import os
@@ -157,3 +157,41 @@ def test_one_process_driver_independent_streams_on_the_gpu():
         assert tb._bitstr(g) == tb._bitstr(w)
     assert len(m.raw_text("T").decode().splitlines()) == len(got)
     m.close()
+
+
+def test_two_devices_blocks_and_streams():
+    """ir_multi_* owning TWO GPUs (north_star: the stream shards by contiguous time blocks across the GPUs of one box,
+    independent per-GPU pipelines, results gathered on the host): the blocks dealt to devices 0 and 1 give the merge
+    a single device gives, line for line; two independent streams on two devices give what a pipeline of their own
+    gives.  Skips only on a one-GPU box."""
+    pl = importlib.import_module("iridium-sniffer_b200.pipeline")
+    synth = importlib.import_module("iridium-sniffer_b200.synth")
+    if pl.load_library().ir_device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    rec, cfg, blocks = tb._recording(synth)
+    one = pl.Multi([0], sample_rate=rec.sample_rate, start_time_ns=T0)
+    want = one.run_host(rec.iq, "cf32", n_blocks=4)
+    want_txt = one.raw_text("T")
+    one.close()
+    two = pl.Multi([0, 1], sample_rate=rec.sample_rate, start_time_ns=T0)
+    got = two.run_host(rec.iq, "cf32", n_blocks=4)
+    assert len(got) >= 120
+    assert [(d["id"], d["timestamp"], d["block"], tb._bitstr(d)) for d in got] == \
+        [(d["id"], d["timestamp"], d["block"], tb._bitstr(d)) for d in want]
+    assert two.raw_text("T") == want_txt
+    r = two.results()
+    assert r.n_blocks == 4 and r.samples_fed > rec.n_samples
+    # config 5 in one process on two devices
+    recs = [synth.make_recording(50 + s, duration_s=0.62 + 0.05 * s, n_bursts=4 + s, snr_db=(15.0, 22.0)) for s in range(4)]
+    ref = []
+    for q in recs:
+        p = pl.Pipeline(sample_rate=q.sample_rate, start_time_ns=T0)
+        ref.append(p.run_host(q.iq).frames)
+        p.close()
+    got = two.run_streams_host([q.iq for q in recs])
+    flat = [(s, d) for s, fl in enumerate(ref) for d in fl]
+    assert len(got) == len(flat) >= 12
+    for g, (s, w) in zip(got, flat):
+        assert g["block"] == s and g["id"] == s * pl.BLOCK_ID_STRIDE + w["id"] and g["timestamp"] == w["timestamp"]
+        assert tb._bitstr(g) == tb._bitstr(w)
+    two.close()
