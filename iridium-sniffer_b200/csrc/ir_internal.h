@@ -15,7 +15,7 @@
 #define IR_SEG_MAX_FRAMES 16384     // frames per chunk of the segmented state machine (k_detect_seg.cu)
 #define IR_SEG_LEN 64              // frames per segment (one warp each); multiple of 32
 #define IR_SEG_GONE 256             // gone records a segment can hold (more: the chunk falls back)
-#define IR_SEG_ROUNDS 10            // rounds enqueued per chunk (a chunk without a fixed point by then falls back)
+#define IR_SEG_ROUNDS 12            // rounds enqueued per chunk (a chunk without a fixed point by then falls back)
 // guard band of the bitmaps: valid while every baseline stays inside [LO, HI] x its reference value.
 // LO also sets how often pure noise lands in the uncertain band (e^(-23.1*LO) per bin and frame at 16 dB).
 #define IR_GUARD_LO 0.65f
@@ -117,9 +117,10 @@ struct SegCtl {
     int bailed;                    // the chunk was not kept: the fallback must run
     int reason;                    // why (1 not primed, 2 guard band, 3 too-long burst, 4 peak list, 5/7 burst table, 6 squelch,
                                    //  9 missing snapshot, 10 gone pool, 11 snapshot slots, 12 no fixed point)
-    unsigned int guard_bad, n_gone0;
+    unsigned int guard_bad, n_gone0, reclass, reclass_prev;
     unsigned long long index0, next_id0;
-    unsigned long long stats[8];   // 0 chunks kept, 1 chunks bailed, 2 rounds, 3 event frames (all rounds), 4 snapshots, 5 quiet frames
+    unsigned long long stats[8];   // 0 chunks kept, 1 chunks bailed, 2 rounds, 3 event frames (all rounds), 4 snapshots, 5 quiet frames,
+                                   // 7 bitmap rebuilds (a baseline left its band)
 };
 struct SegBuffers {                // device memory of the segmented scan, owned by the pipeline
     SegCtl *ctl = nullptr;
@@ -128,7 +129,7 @@ struct SegBuffers {                // device memory of the segmented scan, owned
     int *wpre = nullptr, *qlist = nullptr, *slotv = nullptr, *fslot = nullptr, *ncreate = nullptr, *ngone = nullptr;
     int *segbail = nullptr, *stch = nullptr, *cpre = nullptr, *gpre = nullptr;
     GoneBurst *glist = nullptr;
-    float *snap = nullptr, *bfinal = nullptr, *qmag = nullptr;
+    float *snap = nullptr, *bfinal = nullptr, *qmag = nullptr, *glo = nullptr, *ghi = nullptr;
     int slot_cap = 0, frames_cap = 0;
 };
 
@@ -218,7 +219,7 @@ cudaError_t launch_detect_seg_prime(const DetConfig &c, DetState *state, float *
                                     int n_frames, cudaStream_t st);
 size_t seg_walk_smem(const DetConfig &c);
 cudaError_t launch_detect_scan_seg(const DetConfig &c, DetState *state, float *base, float *hist, const float *mag,
-                                   const uint32_t *xu, const unsigned char *rowany, const float *ref, int n_frames,
+                                   uint32_t *xu, unsigned char *rowany, const float *ref, int n_frames,
                                    GoneBurst *gone, uint32_t gone_cap, const SegBuffers &b, int *n_launches, cudaStream_t st);
 cudaError_t launch_detect_scan_stream(const DetConfig &c, DetState *state, float *base, float *hist,
                                       const float *mag, const uint32_t *xu, const float *ref, int n_frames,

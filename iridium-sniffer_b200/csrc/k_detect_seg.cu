@@ -143,13 +143,14 @@ __device__ int block_excl_scan(int *arr, int n, int *sh /* >= 33 ints */) {
 // =========================================================================== chunk begin
 __global__ void __launch_bounds__(256)
 k_seg_begin(DetConfig c, const DetState *__restrict__ gs, SegCtl *ctl, SegState *stA, SegState *stB, uint32_t *qw,
-            int *ncreate, int *ngone, int *segbail, int *stch, uint32_t *valid_g, int F, int S) {
+            int *ncreate, int *ngone, int *segbail, int *stch, uint32_t *valid_g, const float *__restrict__ ref,
+            float *glo_g, float *ghi_g, int F, int S) {
     const int t = threadIdx.x;
     const int N = c.N, W = N >> 5;
     if (t == 0) {
         ctl->finished = 0; ctl->converged = 0; ctl->changed = 1; ctl->round = 0; ctl->cur = 0;
         ctl->hard_bail = 0; ctl->guard_bad = 0; ctl->bailed = 0;
-        ctl->qfc[0] = 0; ctl->qfc[1] = 0; ctl->skip_base = 0;
+        ctl->qfc[0] = 0; ctl->qfc[1] = 0; ctl->skip_base = 0; ctl->reclass = 0; ctl->reclass_prev = 0;
         ctl->F = F; ctl->S = S; ctl->nq = 0; ctl->n_slots = 0;
         ctl->index0 = gs->index; ctl->next_id0 = gs->next_id; ctl->sq0 = gs->squelch_count;
         ctl->n_gone0 = gs->n_gone; ctl->hist_idx0 = gs->hist_idx;
@@ -176,6 +177,12 @@ k_seg_begin(DetConfig c, const DetState *__restrict__ gs, SegCtl *ctl, SegState 
     // [parity][s]: the list at segment s's first frame changed in the round of that parity (segment 0's never does)
     for (int s = t; s < 2 * (S + 1); s += blockDim.x) stch[s] = (s == 0 || s == S + 1) ? 0 : 1;
     for (int w = t; w < (F + 31) / 32; w += blockDim.x) qw[w] = 0u;
+    // the band the chunk's bitmaps were made for (k_detect_classify: thresholds at LO and HI times the reference)
+    for (int bin = t; bin < N; bin += blockDim.x) {
+        const float r = ref[bin];
+        const float ga = r * IR_GUARD_LO, gb = r * IR_GUARD_HI;
+        glo_g[bin] = fminf(ga, gb); ghi_g[bin] = fmaxf(ga, gb);
+    }
     for (int w = t; w < W; w += blockDim.x) {
         uint32_t v = 0;
         for (int b = 0; b < 32; b++) {
@@ -209,10 +216,11 @@ k_seg_index(SegCtl *ctl, const uint32_t *__restrict__ qw, const unsigned char *_
     const int F = ctl->F, nW = (F + 31) / 32;
     // no quiet flag changed in the previous round: list, versions, slots, snapshots, final baseline and the
     // guard verdict of that round all stand
-    const bool keep = r > 0 && ctl->qfc[(r - 1) & 1] == 0x7fffffff;
+    const bool keep = r > 0 && ctl->qfc[(r - 1) & 1] == 0x7fffffff && !ctl->reclass;
     __syncthreads();
     if (t == 0) {
         ctl->round = r + 1; ctl->cur = r & 1; ctl->changed = 0;
+        ctl->reclass_prev = ctl->reclass; ctl->reclass = 0;
         ctl->qfc[r & 1] = 0x7fffffff;
         ctl->skip_base = keep ? 1 : 0;
         if (!keep) ctl->guard_bad = 0;
@@ -308,7 +316,7 @@ struct BaseShared {
 };
 __global__ void __launch_bounds__(BT)
 k_seg_base(DetConfig c, SegCtl *ctl, const float *__restrict__ base_g, const float *__restrict__ qbuf,
-           const float *__restrict__ ref,
+           float *__restrict__ glo_g, float *__restrict__ ghi_g,
            const int *__restrict__ slotp, float *__restrict__ snap, float *__restrict__ bfinal) {
     extern __shared__ __align__(16) unsigned char base_smem[];
     BaseShared &S = *reinterpret_cast<BaseShared *>(base_smem);
@@ -319,15 +327,13 @@ k_seg_base(DetConfig c, SegCtl *ctl, const float *__restrict__ base_g, const flo
     const int nq = ctl->nq;
     float base[4], glo[4], ghi[4], bmin[4], bmax[4];
     {
-        const float4 b4 = *reinterpret_cast<const float4 *>(base_g + bin), r4 = *reinterpret_cast<const float4 *>(ref + bin);
+        const float4 b4 = *reinterpret_cast<const float4 *>(base_g + bin);
+        const float4 l4 = *reinterpret_cast<const float4 *>(glo_g + bin), h4 = *reinterpret_cast<const float4 *>(ghi_g + bin);
         base[0] = b4.x; base[1] = b4.y; base[2] = b4.z; base[3] = b4.w;
-        const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+        glo[0] = l4.x; glo[1] = l4.y; glo[2] = l4.z; glo[3] = l4.w;
+        ghi[0] = h4.x; ghi[1] = h4.y; ghi[2] = h4.z; ghi[3] = h4.w;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float ga = rr[j] * IR_GUARD_LO, gb = rr[j] * IR_GUARD_HI;
-            glo[j] = fminf(ga, gb); ghi[j] = fmaxf(ga, gb);
-            bmin[j] = base[j]; bmax[j] = base[j];
-        }
+        for (int j = 0; j < 4; j++) { bmin[j] = base[j]; bmax[j] = base[j]; }
         const int p0 = slotp[0], p1 = slotp[1];
         if (p1 > p0) *reinterpret_cast<float4 *>(snap + (size_t)p0 * N + bin) = b4;
     }
@@ -381,11 +387,71 @@ k_seg_base(DetConfig c, SegCtl *ctl, const float *__restrict__ base_g, const flo
     }
     cp_async_wait_all();
     *reinterpret_cast<float4 *>(bfinal + bin) = make_float4(base[0], base[1], base[2], base[3]);
-    int bad = 0;
+    // The bitmaps hold for baselines inside [glo, ghi] (per bin).  A bin whose baseline left its band -- typically a
+    // channel that carried a burst while the detector was priming, whose inflated baseline collapses when those
+    // rows rotate out of the history -- gets a band that covers what it really did (with a margin, so that the
+    // small shifts of later rounds stay inside), and k_seg_reclass rebuilds the bitmaps before anybody walks them.
+    int bad = 0, widen = 0;
 #pragma unroll
-    for (int j = 0; j < 4; j++)                                 // (a NaN is sticky under the adds: it reaches the final value)
-        bad |= !(bmin[j] >= glo[j] && bmax[j] <= ghi[j]) || !(base[j] == base[j]);
+    for (int j = 0; j < 4; j++) {                               // (a NaN is sticky under the adds: it reaches the final value)
+        if (!(base[j] == base[j]) || !(bmin[j] > 0.0f) || !(bmax[j] < 3.0e38f)) {
+            if (!(bmin[j] >= glo[j] && bmax[j] <= ghi[j])) bad = 1;          // nothing a positive finite band can cover
+        } else if (!(bmin[j] >= glo[j] && bmax[j] <= ghi[j])) {
+            glo[j] = fminf(glo[j], bmin[j] * 0.9f); ghi[j] = fmaxf(ghi[j], bmax[j] * 1.1f);
+            widen = 1;
+        }
+    }
+    if (widen) {
+        *reinterpret_cast<float4 *>(glo_g + bin) = make_float4(glo[0], glo[1], glo[2], glo[3]);
+        *reinterpret_cast<float4 *>(ghi_g + bin) = make_float4(ghi[0], ghi[1], ghi[2], ghi[3]);
+        atomicOr(&ctl->reclass, 1u);
+    }
     if (bad) atomicOr(&ctl->guard_bad, 1u);
+}
+
+// Bitmaps of the whole chunk again, against the per-bin bands k_seg_base widened (a no-op unless it did, this
+// round).  The XU band only grows downwards, so "the row has a bit" flags are only ever added.
+__global__ void __launch_bounds__(128)
+k_seg_reclass(SegCtl *ctl, const float *__restrict__ mag, const float *__restrict__ glo_g, const float *__restrict__ ghi_g,
+              float thr, int N, int frames_per_warp, uint32_t *__restrict__ xu, unsigned char *__restrict__ rowany) {
+    if (ctl->finished || ctl->hard_bail || !ctl->reclass) return;
+    const int n_frames = ctl->F;
+    const int lane = threadIdx.x & 31;
+    const int gw = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int ncol = N >> 10;
+    const int col = gw % ncol, part = gw / ncol;
+    const int f0 = part * frames_per_warp;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->changed = 1; ctl->stats[7] += 1; }
+    if (f0 >= n_frames) return;
+    const int f1 = min(f0 + frames_per_warp, n_frames);
+    const int W = N >> 5;
+    float thi[32], tlo[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const int bin = (col << 10) + (j << 5) + lane;
+        // certainly above needs a positive baseline all along; possibly above needs one at some point
+        const float gl = glo_g[bin], gh = ghi_g[bin];
+        thi[j] = gl > 0.0f ? thr * gh * 1.0001f : __int_as_float(0x7f800000);
+        tlo[j] = gh > 0.0f ? thr * gl * 0.9999f : __int_as_float(0x7f800000);
+    }
+    for (int f = f0; f < f1; f++) {
+        const float *row = mag + (size_t)f * N + (col << 10) + lane;
+        float m[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) m[j] = __ldg(row + (j << 5));
+        uint32_t xw = 0, uw = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const bool hi = m[j] > thi[j];
+            const bool un = !(m[j] < tlo[j]);
+            const uint32_t bx = __ballot_sync(FULL, hi), bu = __ballot_sync(FULL, un);
+            if (lane == j) { xw = bx; uw = bu; }
+        }
+        uint32_t *o = xu + (size_t)f * (2 * W) + (col << 5) + lane;
+        o[0] = uw;
+        o[W] = xw;
+        if (__any_sync(FULL, uw != 0u) && lane == 0) rowany[f] = 1;
+    }
 }
 
 // =========================================================================== round: walk
@@ -413,7 +479,9 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
     const int lane = threadIdx.x & 31;
     // Same inputs as last round -- the same burst list at the first frame, and no quiet flag changed before the
     // last frame (so every baseline version this segment reads is the same) -- give the same outputs: keep them.
-    if (rnd > 0 && stch_prev[seg] == 0 && f0 + n_frames <= ctl->qfc[par ^ 1]) {
+    // (bitmaps rebuilt this round or the last: the snapshot slots moved too; a segment that gave up: its reason may be gone)
+    if (rnd > 0 && !ctl->reclass && !ctl->reclass_prev && segbail[seg] == 0 && stch_prev[seg] == 0 &&
+        f0 + n_frames <= ctl->qfc[par ^ 1]) {
         const SegState &old = cur[seg + 1];
         if (lane < old.n_act) nxt[seg + 1].b[lane] = old.b[lane];
         if (lane == 0) { nxt[seg + 1].n_act = old.n_act; stch_now[seg + 1] = 0; }
@@ -1047,7 +1115,7 @@ static cudaError_t launch_walk_t(const DetConfig &c, const SegBuffers &b, const 
 // from launch_detect_classify.  Enqueues begin + IR_SEG_ROUNDS x (index, base, walk) + commit; the caller
 // enqueues the gated fallback (cluster kernel on b.ctl->bailed) behind it.  Returns the number of kernels.
 cudaError_t launch_detect_scan_seg(const DetConfig &c, DetState *state, float *base, float *hist, const float *mag,
-                                   const uint32_t *xu, const unsigned char *rowany, const float *ref, int n_frames,
+                                   uint32_t *xu, unsigned char *rowany, const float *ref, int n_frames,
                                    GoneBurst *gone, uint32_t gone_cap, const SegBuffers &b, int *n_launches, cudaStream_t st) {
     if (n_frames <= 0) return cudaSuccess;
     if (n_frames > IR_SEG_MAX_FRAMES || n_frames > b.frames_cap) return cudaErrorInvalidValue;
@@ -1063,14 +1131,22 @@ cudaError_t launch_detect_scan_seg(const DetConfig &c, DetState *state, float *b
         }
     }
     k_seg_gather_hist<<<256, 256, 0, st>>>(c, state, hist, b.qmag);
-    k_seg_begin<<<1, 256, 0, st>>>(c, state, b.ctl, b.stA, b.stB, b.qw, b.ncreate, b.ngone, b.segbail, b.stch, b.valid, n_frames, S);
+    k_seg_begin<<<1, 256, 0, st>>>(c, state, b.ctl, b.stA, b.stB, b.qw, b.ncreate, b.ngone, b.segbail, b.stch, b.valid, ref, b.glo, b.ghi,
+                                   n_frames, S);
     int rounds = IR_SEG_ROUNDS;
     if (const char *env = getenv("IR_SEG_ROUNDS")) { const int v = atoi(env); if (v >= 2 && v <= 64) rounds = v; }
     for (int r = 0; r <= rounds; r++) {
         k_seg_index<<<1, 1024, 0, st>>>(b.ctl, b.qw, rowany, b.wpre, b.qlist, b.slotv, b.fslot, b.slot_cap, rounds);
         if (r == rounds) break;                                 // the last index launch only tests for the fixed point
         k_seg_gather<<<592, 256, 0, st>>>(c, b.ctl, mag, b.qlist, b.qmag);
-        k_seg_base<<<c.N / BB, BT, sizeof(BaseShared), st>>>(c, b.ctl, base, b.qmag, ref, b.slotv, b.snap, b.bfinal);
+        k_seg_base<<<c.N / BB, BT, sizeof(BaseShared), st>>>(c, b.ctl, base, b.qmag, b.glo, b.ghi, b.slotv, b.snap, b.bfinal);
+        {
+            const int ncol = c.N >> 10;
+            int parts = (148 * 16 + ncol - 1) / ncol;
+            int fpw = std::max((n_frames + parts - 1) / parts, 8);
+            parts = (n_frames + fpw - 1) / fpw;
+            k_seg_reclass<<<(parts * ncol + 3) / 4, 128, 0, st>>>(b.ctl, mag, b.glo, b.ghi, c.thr, c.N, fpw, xu, rowany);
+        }
         cudaError_t e;
         switch (c.N / 1024) {
         case 4: e = launch_walk_t<4>(c, b, mag, xu, S, st); break;
@@ -1083,7 +1159,7 @@ cudaError_t launch_detect_scan_seg(const DetConfig &c, DetState *state, float *b
     k_seg_commit<<<1, 1024, 0, st>>>(c, b.ctl, state, b.stA, b.stB, b.ncreate, b.ngone, b.segbail, b.cpre, b.gpre, b.glist, gone,
                                      gone_cap);
     k_seg_commit_hist<<<148, 256, 0, st>>>(c, b.ctl, base, hist, mag, b.qlist, b.bfinal);
-    if (n_launches) *n_launches += 2 + 4 * rounds + 1 + 2;
+    if (n_launches) *n_launches += 2 + 5 * rounds + 1 + 2;
     return cudaGetLastError();
 }
 

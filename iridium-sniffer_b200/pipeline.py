@@ -566,6 +566,7 @@ class Pipeline:
             raise RuntimeError("ir_pipeline_scan_stats failed")
         keys = ("launches_kept", "launches_bailed", "commands", "event_frames", "exact_words", "waits", "last_bail_frame")
         d = {k: int(a[i]) for i, k in enumerate(keys)}
+        d["bitmap_rebuilds"] = int(a[7])
         d["streaming"] = rc == 1
         d["segmented"] = rc == 2          # launches_* count chunks, "commands" counts rounds
         if rc == 2:

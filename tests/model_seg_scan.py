@@ -16,12 +16,14 @@ both by speculation and proves the result by a fixed point:
     burst list and the true baseline.  Ids are (segment, ordinal) codes until the end, when a prefix
     sum over the segments' creation counts gives the reference's running counter.
 
-Guard-banded bitmaps (X = certainly above, XU = above or uncertain for any baseline within
-[0.65, 1.5] x the chunk's first baseline) are used exactly as in the streaming kernel: they decide
-what they prove, everything else is an IEEE divide on B_v.  Squelch, a burst that may exceed
-max_burst_len, a baseline outside the guard band and a 33rd concurrent burst make the chunk "bail"
-(the cluster kernel redoes it); a bail that only a wrong speculative start produced disappears in
-the next round.
+Guard-banded bitmaps (X = certainly above, XU = above or uncertain for any baseline within the bin's
+band, at first [0.65, 1.5] x the chunk's first baseline) are used exactly as in the streaming kernel:
+they decide what they prove, everything else is an IEEE divide on B_v.  A baseline that leaves its
+band (a channel that carried a burst while the detector primed: its inflated baseline collapses when
+those rows rotate out of the history) gets a band that covers what it did, the bitmaps are rebuilt and
+the rounds go on.  Squelch, a burst that may exceed max_burst_len, a baseline that is not positive and
+finite and a 33rd concurrent burst make the chunk "bail" (the cluster kernel redoes it); a bail that
+only a wrong speculative start produced disappears in the next round.
 
 tests/test_seg_scan_model.py runs this on the CPU oracle's magnitude frames and demands the oracle's
 burst list field for field."""
@@ -70,7 +72,7 @@ class SegScanModel:
 
     # ------------------------------------------------------------------ baseline pass of one round
     def _base_pass(self, mag, Q, rowany, guard):
-        """B_v for the versions a frame with bitmap bits may ask for; final baseline; guard check."""
+        """B_v for the versions a frame with bitmap bits may ask for; final baseline; per-bin extremes of the baseline."""
         F = mag.shape[0]
         qlist = np.nonzero(Q)[0]
         ver = np.concatenate(([0], np.cumsum(Q)[:-1])).astype(np.int64) if F else np.zeros(0, np.int64)
@@ -78,8 +80,7 @@ class SegScanModel:
         vneed[ver[rowany]] = True
         snaps = {}
         base = self.base.copy()
-        lo, hi = guard
-        bad = not np.all((base >= lo) & (base <= hi))
+        bmin, bmax = base.copy(), base.copy()
         if vneed[0]:
             snaps[0] = base.copy()
         for q, f in enumerate(qlist):
@@ -88,11 +89,11 @@ class SegScanModel:
             old = self.hist[(self.hist_idx + q) % self.H] if q < self.H else mag[qlist[q - self.H]]
             t = base - old
             base = t + mag[f]
-            bad |= not np.all((base >= lo) & (base <= hi))
+            bmin, bmax = np.minimum(bmin, base), np.maximum(bmax, base)
             if vneed[q + 1]:
                 snaps[q + 1] = base.copy()
         self.stats["snapshots"] += len(snaps)
-        return ver, snaps, base, qlist, bad
+        return ver, snaps, base, qlist, (bmin, bmax)
 
     def _free_mask(self, act):
         free = np.ones(self.N, bool)
@@ -203,7 +204,7 @@ class SegScanModel:
         X = mag > thi
         XU = ~(mag < tlo)
         a, b = r * GUARD_LO, r * GUARD_HI
-        guard = (np.minimum(a, b), np.maximum(a, b))
+        glo, ghi = np.minimum(a, b).astype(np.float32), np.maximum(a, b).astype(np.float32)
         rowany = XU.any(axis=1)
         # carried-in bursts: deadlines in frames of this chunk, real ids as (0, id, 0)
         carried = []
@@ -220,7 +221,24 @@ class SegScanModel:
         prev_out = None
         for rnd in range(self.max_rounds):
             self.stats["rounds"] += 1
-            ver, snaps, base_final, qlist, bad = self._base_pass(mag, Q, rowany, guard)
+            ver, snaps, base_final, qlist, (bmin, bmax) = self._base_pass(mag, Q, rowany, None)
+            # a baseline outside the band its bin's bitmaps were made for: widen the band to what the baseline really
+            # did (with a margin) and rebuild the bitmaps before anybody walks them (k_seg_base + k_seg_reclass)
+            out_of_band = ~((bmin >= glo) & (bmax <= ghi))
+            hopeless = out_of_band & ~((bmin > 0) & np.isfinite(bmax) & np.isfinite(base_final))
+            bad = bool(hopeless.any())
+            fix = out_of_band & ~hopeless
+            reclass = bool(fix.any())
+            if reclass:
+                self.stats["rebuilds"] = self.stats.get("rebuilds", 0) + 1
+                glo = np.where(fix, np.minimum(glo, bmin * np.float32(0.9)), glo).astype(np.float32)
+                ghi = np.where(fix, np.maximum(ghi, bmax * np.float32(1.1)), ghi).astype(np.float32)
+                thi = np.where(glo > 0, (thr * ghi) * np.float32(1.0001), inf).astype(np.float32)
+                tlo = np.where(ghi > 0, (thr * glo) * np.float32(0.9999), inf).astype(np.float32)
+                X = mag > thi
+                XU = ~(mag < tlo)
+                rowany = rowany | XU.any(axis=1)
+                ver, snaps, base_final, qlist, _ = self._base_pass(mag, Q, rowany, None)   # (model only: slots for the new bits)
             ends, Qn, gones, ncs, bails = [], np.zeros(F, np.uint8), [], [], []
             for s in range(S):
                 e, q, g, nc, bl = self._walk(s, cuts[s], cuts[s + 1], starts[s], mag, X, XU, ver, snaps, index0, self.sq)
@@ -231,7 +249,7 @@ class SegScanModel:
                     ends.append(starts[s + 1] if s + 1 < S else []); gones.append([]); ncs.append(0)
                     Qn[cuts[s]:cuts[s + 1]] = Q[cuts[s]:cuts[s + 1]]
             out = (Qn.tobytes(), [self._state_key(e) for e in ends], ncs)
-            same = prev_out is not None and out == prev_out
+            same = prev_out is not None and out == prev_out and not reclass
             prev_out = out
             if same:
                 self.stats["max_rounds_seen"] = max(self.stats["max_rounds_seen"], rnd + 1)

@@ -112,6 +112,31 @@ def test_ragged_length_and_leading_bursts(pl, port, synth, mode):
     _check(pl, port, iq, mode, min_bursts=1)      # (the polluted baseline may leave the guard band: either path)
 
 
+def test_seg_follows_a_moving_noise_floor(pl, port, synth):
+    """Bursts inside the priming period inflate their channels' baselines; when those rows rotate out of the history
+    the baseline leaves the band the bitmaps were made for.  The segmented state machine widens the bin's band, rebuilds
+    the bitmaps and carries on: the oracle's burst list, no chunk handed to the cluster kernel.  (This is what every
+    time block of a sharded stream, and every real capture, looks like: detection starts in the middle of traffic.)"""
+    rec = synth.make_recording(21, duration_s=0.9, n_bursts=10, starts_s=np.linspace(0.05, 0.8, 10))
+    iq = rec.iq[:-12345]
+    P = port.det_params()
+    pb, _, _ = port.detect(P, iq)
+    want = [(o.id, o.start, o.stop, o.last_active, o.center_bin, o.magnitude, o.noise) for o in pb]
+    old = os.environ.get("IR_SCAN")
+    try:
+        _set_mode("seg")
+        p = pl.Pipeline(sample_rate=10_000_000, start_time_ns=77)
+        res = p.run_host(iq, "cf32")
+        ss = p.scan_stats()
+        p.close()
+    finally:
+        if old is not None:
+            os.environ["IR_SCAN"] = old
+    got = [(b["id"], b["start"], b["stop"], b["last_active"], b["center_bin"], b["magnitude"], b["noise"]) for b in res.bursts]
+    assert got == want and len(want) >= 1, ss
+    assert ss["segmented"] and ss["launches_bailed"] == 0 and ss["bitmap_rebuilds"] >= 1, ss
+
+
 @pytest.mark.parametrize("mode,chunk", [("seg", 1 << 20), ("seg", 3 << 20), ("stream", 1 << 20), ("cluster", 1 << 20)])
 def test_many_launches_bursts_across_launch_boundaries(pl, port, synth, mode, chunk):
     """1 Mi-sample chunks = 128-frame launches of the state machine: priming spread over four launches,

@@ -62,13 +62,13 @@ def test_model_gives_up_where_the_kernels_do(port, synth):
         assert e.value.reason in (reason, "a 33rd concurrent burst", "more bursts than lanes"), e.value.reason
 
 
-def test_model_guard_band_catches_a_moving_noise_floor(port, synth):
+def test_model_follows_a_moving_noise_floor(port, synth):
+    """bursts inside the priming period inflate the baseline; when they rotate out of the 512-frame history the
+    baseline leaves [0.65, 1.5] x reference: the bin's band is widened to what the baseline really did, the
+    bitmaps are rebuilt, and the result is still the oracle's, field for field"""
     rec = synth.make_recording(21, duration_s=0.9, n_bursts=10, starts_s=np.linspace(0.05, 0.8, 10))
     P, mag, want, _ = _oracle(port, rec.iq[:-12345])
     m = _model(P, 64)
-    try:
-        got = m.run(mag, chunk_frames=4096)
-    except msm.Bail as e:
-        assert e.reason == "guard band"
-    else:
-        _same(got, want)
+    got = m.run(mag, chunk_frames=4096)
+    _same(got, want)
+    assert m.stats.get("rebuilds", 0) >= 1, m.stats

@@ -1,0 +1,5 @@
+set -x
+cd $GRAFT_REPO_ROOT
+timeout 900 python -m pytest tests/test_gpu_detector_stress.py -x -q 2>&1 | tail -6
+timeout 300 python tools/dev_timeline.py 60 3 30 2>&1 | grep -v "^scan \|^stream scan\|^wave" | tail -12
+timeout 300 python tools/dev_timeline.py 60 3 2>&1 | grep -v "^scan \|^stream scan\|^wave\|^chunk" | tail -3
