@@ -243,8 +243,9 @@ cudaError_t launch_chain(const BurstParam *bp, int n_bursts, const float2 *dec, 
                          const float2 *sync_dl, const float2 *sync_ul, ChainOut *out,
                          float2 *frames, cudaStream_t st);
 // k_demod.cu
+// max_frame: an upper bound of the frame lengths of this launch (1910 unless a burst lies in the simplex band), 0 = 4440
 cudaError_t launch_demod(const ChainOut *co, int n_bursts, const float2 *frames, int use_gardner,
-                         DemodOut *out, uint8_t *bits, float *llr, cudaStream_t st);
+                         DemodOut *out, uint8_t *bits, float *llr, int max_frame, cudaStream_t st);
 // k_classify.cu: frame classification (frame_decode() + ida_decode() per frame), one warp per frame
 struct FrameSrc {
     const uint8_t *bits;     // one byte per bit, device memory

@@ -611,6 +611,16 @@ k_chain(const BurstParam *__restrict__ bp, int n_bursts, const float2 *__restric
     co.center_offset = coff;
     co.cfo_peak_bin = S.i0;
 
+    // What later steps read of the shifted, matched-filtered signal: the first IR_SYNC_SEARCH samples (correlation)
+    // and the frame, which starts at uw_start <= IR_SYNC_SEARCH - IR_SYNC_LEN + 1 + 320 and is at most 1910 / 4440
+    // samples long.  The burst's extract carries post_len (16 ms = 4000 samples here) of tail behind that: nobody
+    // reads it, so the shift and the matched filter stop where the frame can end (+ the filter's half width).
+    const double cfreq = P.cfreq_coarse + (double)(coff * (float)IR_OUT_RATE);
+    const bool simplex = cfreq > 1626000000.0;
+    const int maxl = simplex ? 4440 : 1910, minl = simplex ? 800 : 1310;
+    const int need = min(flen, IR_SYNC_SEARCH - IR_SYNC_LEN + 1 + 320 + maxl);
+    const int n_rrc_half = c_ntaps[3] / 2;
+    const int need_b = min(flen, need + n_rrc_half + 1);
     // 5: fine shift (:713-720): the phase recurrence is serial; one thread lays the phases down,
     // everybody applies them.
     {
@@ -619,14 +629,16 @@ k_chain(const BurstParam *__restrict__ bp, int n_bursts, const float2 *__restric
         co.incr_fine = w;
         if (tid == 0) {
             float2 p = make_float2(1.0f, 0.0f);
-            for (int i = 0; i < flen; i++) { B[i] = p; p = cmul(p, w); }
+            for (int i = 0; i < need_b; i++) { B[i] = p; p = cmul(p, w); }
         }
         __syncthreads();
-        for (int i = tid; i < flen; i += nth) B[i] = cmul(A[start + i], B[i]);
+        for (int i = tid; i < need_b; i += nth) B[i] = cmul(A[start + i], B[i]);
         __syncthreads();
     }
-    // 6: matched filter, centred (:723-734) -> A[0..flen)
-    for (int i = tid; i < flen; i += nth) A[i] = fir_same(c_rrc, n_rrc, B, flen, i);
+    // 6: matched filter, centred (:723-734) -> A[0..need).  The true length goes in (it decides which outputs are
+    // the SIMD body and which the scalar tail of the reference's kernel, and where its zero padding begins); the
+    // taps of output i < need reach B[i + half] < need_b at most, or past flen
+    for (int i = tid; i < need; i += nth) A[i] = fir_same(c_rrc, n_rrc, B, flen, i);
     __syncthreads();
 
     // 7: sync-word correlation (:539-639)
@@ -693,9 +705,6 @@ k_chain(const BurstParam *__restrict__ bp, int n_bursts, const float2 *__restric
     }
     // 9: extraction (:763-793)
     // center_frequency after both shifts decides the frame-length limits (:671,:719,:764-770)
-    const double cfreq = P.cfreq_coarse + (double)(coff * (float)IR_OUT_RATE);
-    const bool simplex = cfreq > 1626000000.0;
-    const int maxl = simplex ? 4440 : 1910, minl = simplex ? 800 : 1310;
     const int avail = flen - uw_start;
     if (avail < minl) {
         if (tid == 0) { co.status = 9; out[b] = co; }

@@ -533,7 +533,12 @@ static int launch_wave(ir_pipeline *p, size_t b0, size_t b1, const void *iq_dev,
     cudaStream_t sd = p->st_demod[p->waves.size() % ir_pipeline::kDemodStreams];
     CK(cudaStreamWaitEvent(sd, w.e1b, 0));
     CK(cudaEventRecord(w.e2, sd));
-    CK(launch_demod(w.d_co, (int)nb, w.d_frames, p->cfg.use_gardner, w.d_do, w.d_bits, w.d_llr, sd));
+    // frames are 191 symbols at most outside the simplex band (burst_downmix.c:764-770; the fine CFO moves the centre
+    // by less than 125 kHz): the slicer's shared-memory footprint follows
+    int max_frame = 1910;
+    for (size_t i = b0; i < b1; i++)
+        if (p->h_bp[i].cfreq_coarse > 1626000000.0 - 200000.0) max_frame = IR_MAX_FRAME;
+    CK(launch_demod(w.d_co, (int)nb, w.d_frames, p->cfg.use_gardner, w.d_do, w.d_bits, w.d_llr, max_frame, sd));
     CK(cudaEventRecord(w.e3, sd));
     p->res.kernel_launches += (n_tiles > 0 ? 2 : 0) + 2 + 2;   // FIR, chain, demod + 3 parameter fetches
     CK(cudaMemcpyAsync(w.h_co, w.d_co, nb * sizeof(ChainOut), cudaMemcpyDeviceToHost, sd));

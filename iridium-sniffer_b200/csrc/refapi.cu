@@ -524,7 +524,7 @@ extern "C" int qpsk_demod(downmix_frame_t *in, demod_frame_t **out) {
     co.status = 0; co.frame_len = (int)in->num_samples; co.direction = in->direction;
     RCK(cudaMemcpyAsync(c.d_frame, in->samples, sizeof(float2) * in->num_samples, cudaMemcpyHostToDevice, c.st), 0);
     RCK(cudaMemcpyAsync(c.d_co, &co, sizeof(co), cudaMemcpyHostToDevice, c.st), 0);
-    RCK(launch_demod(c.d_co, 1, c.d_frame, use_gardner, c.d_do, c.d_bits, c.d_llr, c.st), 0);
+    RCK(launch_demod(c.d_co, 1, c.d_frame, use_gardner, c.d_do, c.d_bits, c.d_llr, 0, c.st), 0);
     DemodOut d;
     RCK(cudaMemcpyAsync(&d, c.d_do, sizeof(d), cudaMemcpyDeviceToHost, c.st), 0);
     RCK(cudaStreamSynchronize(c.st), 0);
