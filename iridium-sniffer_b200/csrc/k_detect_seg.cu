@@ -43,11 +43,13 @@ namespace ir {
 
 namespace {
 
-constexpr int SGF = 8;                 // rows per ring block
-constexpr int RB = 4;                  // ring blocks
+// (small on purpose: a walker has to fit beside a resident FIR CTA -- 201 KB of an SM's shared memory -- or every
+// launch of a round waits for an SM to drain; measured, the wait was half of a chunk's scan time)
+constexpr int SGF = 4;                 // rows per ring block
+constexpr int RB = 2;                  // ring blocks
 constexpr int SPF = 4;                 // candidate words whose loads are in flight together
 constexpr int SMAXW = 512;             // bitmap words per frame (N <= 16384)
-constexpr int SMAXC = 256;             // candidate peaks of one frame
+constexpr int SMAXC = 128;             // candidate peaks of one frame
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr int NONE = -0x40000000;
 constexpr int BIGF = 0x3fffffff;
@@ -55,9 +57,8 @@ constexpr unsigned long long CODE = 1ull << 63;
 
 struct WkShared {
     unsigned long long bar[8];
-    uint32_t valid[SMAXW];
     uint32_t fvs[SMAXW];
-    int cw[SMAXW];
+    unsigned short cw[SMAXW];
     int cbin[SMAXC];
     float crel[SMAXC];
     float cbase[SMAXC];
@@ -197,7 +198,7 @@ k_seg_begin(DetConfig c, const DetState *__restrict__ gs, SegCtl *ctl, SegState 
 // =========================================================================== round: index
 // qw: quiet flags of the previous round (bit f%32 of word f/32).  Outputs: qlist[q] = frame of the q-th
 // quiet frame, slotv[v] = snapshot slot of baseline version v (or -1), fslot[f] = slot frame f reads.
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 k_seg_index(SegCtl *ctl, const uint32_t *__restrict__ qw, const unsigned char *__restrict__ rowany, int *wpre,
             int *qlist, int *slotv, int *fslot, int slot_cap, int max_rounds) {
     __shared__ int sh[40];
@@ -305,8 +306,8 @@ k_seg_gather_hist(DetConfig c, const DetState *__restrict__ gs, const float *__r
 // recurrence is two dependent adds per bin and quiet frame -- with one or two warps per SM the pass runs at the
 // pace of a single warp's instruction stream, so it has to be short and carry its own parallelism).  Rows arrive
 // through a ring of 16-byte asynchronous copies; a thread reads back only what it copied: no barrier anywhere.
-constexpr int BU = 8;                  // quiet frames per batch (one cp.async group)
-constexpr int BD = 8;                  // batches in flight
+constexpr int BU = 4;                  // quiet frames per batch (one cp.async group)
+constexpr int BD = 4;                  // batches in flight (ring: 16 KB, see the note on the walkers' ring)
 constexpr int BT = 32;                 // threads per CTA
 constexpr int BB = 4 * BT;             // bins per CTA
 constexpr int BQ = 1024;               // snapshot flags staged in shared memory at a time
@@ -526,7 +527,7 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
         set_window();
     }
     uint32_t have_mask = __ballot_sync(FULL, r_have);
-    for (int w = lane; w < W; w += 32) { const uint32_t v = valid_g[w]; S.valid[w] = v; S.fvs[w] = v; }
+    for (int w = lane; w < W; w += 32) S.fvs[w] = valid_g[w];
     for (int i = lane; i < n_frames; i += 32) S.fslot[i] = fslot_g[f0 + i];
     if (lane == 0) {
         for (int d = 0; d < RB; d++) mbar_init(&bars[d], 1);
@@ -537,7 +538,7 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
         const int w = (lo >> 5) + lane;
         if (lane < 3 && w <= (hi >> 5)) {
             const uint32_t m = range_bits(w, lo, hi);
-            S.fvs[w] = set ? (S.fvs[w] | (m & S.valid[w])) : (S.fvs[w] & ~m);
+            S.fvs[w] = set ? (S.fvs[w] | (m & __ldg(valid_g + w))) : (S.fvs[w] & ~m);
         }
         __syncwarp();
     };
@@ -737,13 +738,13 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
                         wm &= wm - 1;
 #pragma unroll
                         for (int j = 0; j < SPF; j++) if (j == n_cw) wj[j] = w;
-                        if (n_cw >= SPF && lane == 0) S.cw[n_cw] = w;
+                        if (n_cw >= SPF && lane == 0) S.cw[n_cw] = (unsigned short)w;
                         n_cw++;
                     }
                 }
                 if (n_cw > SPF && lane == 0) {
 #pragma unroll
-                    for (int j = 0; j < SPF; j++) S.cw[j] = wj[j];
+                    for (int j = 0; j < SPF; j++) S.cw[j] = (unsigned short)wj[j];
                 }
 #pragma unroll
                 for (int j = 0; j < SPF; j++)
@@ -776,7 +777,7 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
 #pragma unroll
                 for (int j = 0; j < SPF; j++) {
                     relj[j] = 0.0f; bsj[j] = 0.0f; exj[j] = false; mv[j] = 0.0f;
-                    if (j0 > 0) wj[j] = j0 + j < n_cw ? S.cw[j0 + j] : -1;
+                    if (j0 > 0) wj[j] = j0 + j < n_cw ? (int)S.cw[j0 + j] : -1;
                     if (wj[j] >= 0) {
                         const int bin = (wj[j] << 5) + lane;
                         mv[j] = j0 == 0 ? mvp[j] : __ldg(row + bin);
@@ -946,7 +947,7 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
 
 // =========================================================================== commit
 // One CTA: ids, gone list, detector header + active list.  Sets ctl->bailed for the fallback.
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 k_seg_commit(DetConfig c, SegCtl *ctl, DetState *gs, const SegState *stA, const SegState *stB, const int *ncreate,
              const int *ngone, const int *segbail, int *cpre, int *gpre, const GoneBurst *__restrict__ glist,
              GoneBurst *__restrict__ gone, uint32_t gone_cap) {
@@ -1136,7 +1137,7 @@ cudaError_t launch_detect_scan_seg(const DetConfig &c, DetState *state, float *b
     int rounds = IR_SEG_ROUNDS;
     if (const char *env = getenv("IR_SEG_ROUNDS")) { const int v = atoi(env); if (v >= 2 && v <= 64) rounds = v; }
     for (int r = 0; r <= rounds; r++) {
-        k_seg_index<<<1, 1024, 0, st>>>(b.ctl, b.qw, rowany, b.wpre, b.qlist, b.slotv, b.fslot, b.slot_cap, rounds);
+        k_seg_index<<<1, 256, 0, st>>>(b.ctl, b.qw, rowany, b.wpre, b.qlist, b.slotv, b.fslot, b.slot_cap, rounds);
         if (r == rounds) break;                                 // the last index launch only tests for the fixed point
         k_seg_gather<<<592, 256, 0, st>>>(c, b.ctl, mag, b.qlist, b.qmag);
         k_seg_base<<<c.N / BB, BT, sizeof(BaseShared), st>>>(c, b.ctl, base, b.qmag, b.glo, b.ghi, b.slotv, b.snap, b.bfinal);
@@ -1156,7 +1157,7 @@ cudaError_t launch_detect_scan_seg(const DetConfig &c, DetState *state, float *b
         }
         if (e != cudaSuccess) return e;
     }
-    k_seg_commit<<<1, 1024, 0, st>>>(c, b.ctl, state, b.stA, b.stB, b.ncreate, b.ngone, b.segbail, b.cpre, b.gpre, b.glist, gone,
+    k_seg_commit<<<1, 256, 0, st>>>(c, b.ctl, state, b.stA, b.stB, b.ncreate, b.ngone, b.segbail, b.cpre, b.gpre, b.glist, gone,
                                      gone_cap);
     k_seg_commit_hist<<<148, 256, 0, st>>>(c, b.ctl, base, hist, mag, b.qlist, b.bfinal);
     if (n_launches) *n_launches += 2 + 5 * rounds + 1 + 2;

@@ -248,8 +248,8 @@ k_fir_ws(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const Burs
     constexpr int CPT = (fir_in_max<DEC>() + FWS_P - 1) / FWS_P; // copies per producer thread
     constexpr int SEG_PER_ROW = IR_FIR_R * DEC / IR_ROT_G;       // segments between two "row" pads of fir_pi
     float2 *sb0 = reinterpret_cast<float2 *>(smem_raw);
-    float2 *part0 = sb0 + 2 * PITCH;                           // [2][4][IR_FIR_TILE]
-    float *hp = reinterpret_cast<float *>(part0 + 2 * 4 * IR_FIR_TILE);
+    float2 *part0 = sb0 + 2 * PITCH;                           // [4][IR_FIR_TILE]
+    float *hp = reinterpret_cast<float *>(part0 + 4 * IR_FIR_TILE);
     uint64_t *bars = reinterpret_cast<uint64_t *>(hp + ((fir_hp_elems<DEC>() + 1) & ~1));   // full[2], empty[2]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k = tid; k < fir_hp_elems<DEC>(); k += blockDim.x) {
@@ -341,7 +341,7 @@ k_fir_ws(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const Burs
         for (int t = t0; t < t1; t++) {
             const int b = (t - t0) & 1, use = (t - t0) >> 1;
             float2 *s = sb0 + b * PITCH;
-            float2 *part = part0 + b * 4 * IR_FIR_TILE;
+            float2 *part = part0;
             const BurstParam P = bp[tile_burst[t]];
             const int o0 = (t - P.tile0) * IR_FIR_TILE;
             const int n_out = min(IR_FIR_TILE, P.dec_len - o0);
@@ -352,6 +352,9 @@ k_fir_ws(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const Burs
                 for (int i = 0; i < IR_FIR_R; i++) acc[i] = make_float2(0.0f, 0.0f);
                 constexpr int ROW = IR_FIR_R * DEC + IR_FIR_R * DEC / 16 + 1;
                 fir_chains<DEC>(s + ROW * lane + warp, hp + IR_FIR_HPAD + warp, acc);
+                // (one partial-sum buffer: the previous tile's combine must be over before it is rewritten -- 8 KB
+                // less shared memory is what lets a state-machine walker sit beside this CTA)
+                if (t > t0) asm volatile("bar.sync 1, %0;" ::"n"(FWS_C) : "memory");
 #pragma unroll
                 for (int i = 0; i < IR_FIR_R; i++) part[warp * IR_FIR_TILE + IR_FIR_R * lane + i] = acc[i];
             }
@@ -381,7 +384,7 @@ static cudaError_t launch_fir_t(const void *iq, int64_t n_total, uint64_t ring, 
                                 cudaStream_t st) {
     static const bool legacy = getenv("IR_FIR_LEGACY") != nullptr;
     constexpr int PITCH = fws_pitch<DEC>();
-    const size_t smem_ws = sizeof(float2) * (2 * PITCH + 2 * 4 * IR_FIR_TILE) + sizeof(float) * ((fir_hp_elems<DEC>() + 1) & ~1) + 4 * sizeof(uint64_t);
+    const size_t smem_ws = sizeof(float2) * (2 * PITCH + 4 * IR_FIR_TILE) + sizeof(float) * ((fir_hp_elems<DEC>() + 1) & ~1) + 4 * sizeof(uint64_t);
     // (two sample buffers of a 256-output tile do not fit 227 KB at DEC = 48: the one-tile kernel serves 12 MHz)
     if (legacy || tile_burst == nullptr || smem_ws > (size_t)227 * 1024) {
         const size_t smem = sizeof(float2) * (fir_pitch_elems<DEC>() + 4 * IR_FIR_TILE) + sizeof(float) * fir_hp_elems<DEC>();

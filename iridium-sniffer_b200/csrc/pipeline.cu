@@ -17,7 +17,10 @@
 #include <time.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -204,7 +207,7 @@ struct ir_pipeline {
     std::string raw_rest;
     std::vector<size_t> raw_off;
     uint64_t raw_t0 = 0;
-    uint64_t alg = 0;
+    uint64_t alg = 0, alg_sink = 0;                             // (alg_sink: added by the thread that assembles the waves)
     ir_results_t res;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -582,7 +585,7 @@ static int assemble_wave(ir_pipeline *p, const Wave &w) {
         ob.center_offset = c.center_offset; ob.dm_start = c.start; ob.uw_start = c.uw_start;
         ob.frame_len = c.frame_len; ob.uw_start_frac = c.uw_corr; ob.dm_direction = c.direction;
         if (ob.downmix_status != 0) continue;
-        p->alg += 8ull * (uint64_t)c.frame_len;
+        p->alg_sink += 8ull * (uint64_t)c.frame_len;
         if (!d.ok) continue;
         ob.demod_ok = 1;
         ir_frame_t f;
@@ -609,7 +612,7 @@ static int assemble_wave(ir_pipeline *p, const Wave &w) {
         p->llr.insert(p->llr.end(), lr, lr + f.n_bits);
         p->frames.push_back(f);
         p->frame_src.push_back(FrameSrc{w.d_bits + (i - w.b0) * nsym2, w.d_llr + (i - w.b0) * nsym2, f.n_bits, f.direction});
-        p->alg += 8ull * (uint64_t)c.frame_len + (uint64_t)f.n_bits;
+        p->alg_sink += 8ull * (uint64_t)c.frame_len + (uint64_t)f.n_bits;
         {   // its RAW: line, while the GPU is busy with later waves
             if (p->frames.size() == 1) p->raw_t0 = (f.timestamp / 1000000000ULL) * 1000000000ULL;
             char line[160 + 2 * IR_MAX_SYMS];
@@ -772,6 +775,7 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     p->ev_used = 0;
     p->res.kernel_launches = 0; p->res.h2d_bytes = 0; p->res.d2h_bytes = 0;
     p->alg = (uint64_t)n * bps;
+    p->alg_sink = 0;
     if (p->cfg.start_time_ns) p->start_time_ns = p->cfg.start_time_ns;
     else {
         struct timespec ts;
@@ -825,7 +829,9 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     }
     if (p->dev_arena.begin((size_t)64 << 20) || p->pin_arena.begin((size_t)8 << 20)) return -1;
     p->waves.clear(); p->chunks.clear();
+    p->waves.reserve(n_chunks + 8);                          // (the sink thread reads earlier entries while later ones are pushed)
     p->bursts.clear(); p->h_bp.clear(); p->frame_ptr.clear(); p->dec_ptr.clear();
+    p->bursts.reserve(p->gone_cap); p->h_bp.reserve(p->gone_cap);
     p->frames.clear(); p->bits.clear(); p->llr.clear(); p->frame_src.clear();
     p->raw_rest.clear(); p->raw_off.clear(); p->raw_t0 = 0;
     p->scan_dbg = getenv("IR_SCAN_DEBUG") != nullptr;
@@ -884,13 +890,38 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     }
     // ---- follow the detector: one wave of bursts per chunk
     const uint64_t B = p->cfg.feed_block > 0 ? (uint64_t)p->cfg.feed_block : 32768;
-    size_t done = 0, assembled = 0;
+    size_t done = 0;
     DetState hs;
     memset(&hs, 0, kHdrBytes);
-    for (size_t ci = 0; ci < p->chunks.size(); ci++) {
-        CK(cudaEventSynchronize(p->chunks[ci].e_hdr));
+    // The sink: a second host thread turns every finished wave into demod_frame_t equivalents and RAW: text
+    // (snprintf per frame, ~1 us each) while this thread does nothing but follow the detector and launch the next
+    // wave -- with the formatting in line, the FIR of wave k+1 waited for the text of wave k-1.
+    std::atomic<size_t> n_waves_pub{0};
+    std::atomic<int> sink_stop{0}, sink_err{0};
+    std::string sink_msg;
+    std::thread sink([&]() {
+        cudaSetDevice(p->dev);
+        size_t wi = 0;
+        for (;;) {
+            while (wi >= n_waves_pub.load(std::memory_order_acquire)) {
+                if (sink_stop.load(std::memory_order_acquire) && wi >= n_waves_pub.load(std::memory_order_acquire)) return;
+                std::this_thread::yield();
+            }
+            if (assemble_wave(p, p->waves[wi])) { sink_msg = g_err; sink_err.store(1); return; }
+            wi++;
+        }
+    });
+    auto finish_sink = [&]() { sink_stop.store(1, std::memory_order_release); if (sink.joinable()) sink.join(); };
+    struct SinkGuard { decltype(finish_sink) &f; ~SinkGuard() { f(); } } sink_guard{finish_sink};   // (every early return joins)
+    int follow_rc = 0;
+    const bool host_dbg = getenv("IR_CHUNK_DEBUG") != nullptr;
+    const auto t_host0 = std::chrono::steady_clock::now();
+    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count(); };
+    for (size_t ci = 0; ci < p->chunks.size() && follow_rc == 0; ci++) {
+        if (cudaEventSynchronize(p->chunks[ci].e_hdr) != cudaSuccess) { set_err("cudaEventSynchronize(header) failed"); follow_rc = -1; break; }
+        const double t_seen = host_dbg ? host_ms() : 0.0;
         memcpy(&hs, p->h_hdr + ci * kHdrBytes, kHdrBytes);
-        if (hs.overflow || hs.n_gone > p->gone_cap) { set_err("detector capacity exceeded (IR_MAX_ACTIVE or burst list)"); return -1; }
+        if (hs.overflow || hs.n_gone > p->gone_cap) { set_err("detector capacity exceeded (IR_MAX_ACTIVE or burst list)"); follow_rc = -1; break; }
         const bool last = ci + 1 == p->chunks.size();
         // a burst can be processed once every sample its extract reads is resident: its emit point
         // (end of the emulated feed call) must lie inside what has been copied and scanned
@@ -903,16 +934,13 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
             hi++;
         }
         if (hi > done) {
-            if (launch_wave(p, done, hi, iq_dev, n, fmt)) return -1;
+            if (launch_wave(p, done, hi, iq_dev, n, fmt)) { follow_rc = -1; break; }
+            n_waves_pub.store(p->waves.size(), std::memory_order_release);
             done = hi;
         }
-        // assemble the earlier waves that have finished (never wait here: the slicer of a wave
-        // takes ~1 ms and the next chunk's bursts should be launched as soon as they are known)
-        while (assembled + 1 < p->waves.size() && cudaEventQuery(p->waves[assembled].e_done) == cudaSuccess) {
-            if (assemble_wave(p, p->waves[assembled])) return -1;
-            assembled++;
-        }
+        if (host_dbg) fprintf(stderr, "host: chunk %zu header seen at %.3f ms (after the follow loop began), wave enqueued by %.3f ms\n", ci, t_seen, host_ms());
     }
+    if (follow_rc != 0) { finish_sink(); return -1; }
     cudaEvent_t e_end = p->ev();
     if (!p->chunks.empty()) CK(cudaStreamWaitEvent(p->st_burst, p->chunks.back().e_hdr, 0));
     else CK(cudaStreamWaitEvent(p->st_burst, ev_begin, 0));
@@ -920,8 +948,8 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
          wi < p->waves.size(); wi++)
         CK(cudaStreamWaitEvent(p->st_burst, p->waves[wi].e_done, 0));     // the last wave of every demod stream
     CK(cudaEventRecord(e_end, p->st_burst));
-    for (; assembled < p->waves.size(); assembled++)
-        if (assemble_wave(p, p->waves[assembled])) return -1;
+    finish_sink();
+    if (sink_err.load()) { set_err(sink_msg); return -1; }
     if (host_iq) CK(cudaStreamSynchronize(p->st_copy));
     CK(cudaStreamSynchronize(p->st_burst));
     memset(p->scan_stats, 0, sizeof(p->scan_stats));
@@ -999,7 +1027,7 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     if (getenv("IR_SCAN_DEBUG") && ev_last_copy)
         fprintf(stderr, "run_host: first copy done at %.3f ms, last copy done at %.3f ms, end of device work at %.3f ms (%zu chunks)\n",
                 span(ev_begin, ev_first_copy), span(ev_begin, ev_last_copy), p->res.ms_total, p->chunks.size());
-    p->res.alg_bytes = p->alg;
+    p->res.alg_bytes = p->alg + p->alg_sink;
     p->res.n_bursts = p->bursts.size(); p->res.bursts = p->bursts.data();
     p->res.n_frames = p->frames.size(); p->res.frames = p->frames.data();
     p->res.bits = p->bits.data(); p->res.llr = p->llr.data(); p->res.n_bits_total = p->bits.size();
