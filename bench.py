@@ -22,6 +22,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")    # one hardware queue per stream (the library itself keeps to 8)
 
 METRIC = "IQ Msamples/s detect->RAW"
 UNIT = "Msamples/s"
@@ -360,12 +361,13 @@ def run_ours(args):
         sum_n = sum(b["num_samples"] for b in res.bursts if b["dec_len"] >= 100)
         sum_dec = sum(b["dec_len"] for b in res.bursts if b["dec_len"] >= 100)
         sum_fl = sum(b["frame_len"] for b in res.bursts if b["downmix_status"] == 0)
-        n_tiles = sum((b["dec_len"] + 255) // 256 for b in res.bursts if b["dec_len"] >= 100)
+        tile = 192 if fs // 250_000 == 48 else 256          # IR_FIR_TILE_OF(dec)
+        n_tiles = sum((b["dec_len"] + tile - 1) // tile for b in res.bursts if b["dec_len"] >= 100)
         n_det_frames = n // W["nfft"]
         kern = {   # name: (algorithmic bytes, ms of stream time per step, units one step launches, unit name)
             "k_detect_fft": ((bps + 4.0) * n, stage["ms_detect_fft"] / K, n_det_frames, "detector frames"),
             "k_detect_scan": (4.0 * n, stage["ms_detect_scan"] / K, n_det_frames, "detector frames"),   # bitmap pass + state machine
-            "k_fir": (bps * sum_n + 8.0 * sum_dec, stage["ms_downmix_fir"] / K, n_tiles, "256-output tiles"),
+            "k_fir": (bps * sum_n + 8.0 * sum_dec, stage["ms_downmix_fir"] / K, n_tiles, f"{tile}-output tiles"),
             "k_chain": (8.0 * (2 * sum_dec + sum_fl), stage["ms_downmix_chain"] / K, len(res.bursts), "bursts"),
             "k_demod": (8.0 * sum_fl + 5.0 * sum(f["n_bits"] for f in res.frames), stage["ms_demod"] / K, len(res.bursts), "bursts"),
         }
@@ -407,7 +409,8 @@ def run_ours(args):
                        "device_ms_per_step": round(dev_s / K * 1e3, 3), "gen_s": round(t_gen, 1),
                        "state_machine": {"mode": "segmented" if scan.get("segmented") else ("streaming" if scan.get("streaming") else "cluster"),
                                          "chunks_kept": scan["launches_kept"], "chunks_handed_over": scan["launches_bailed"],
-                                         "rounds": scan["commands"]}},
+                                         "rounds": scan["commands"], "bitmap_rebuilds": scan.get("bitmap_rebuilds", 0),
+                                         "last_hand_over_reason": scan.get("last_bail_reason", 0)}},
             "e2e": {"value": round(total / wall_e2e / 1e6, 2), "unit": UNIT,
                     "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
                     "ms_per_step": round(wall_e2e / K * 1e3, 3), "raw_lines_per_step": n_lines,

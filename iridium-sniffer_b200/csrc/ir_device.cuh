@@ -118,14 +118,16 @@ __device__ __forceinline__ void bfly_wq(float2 &a, float2 &b) {
 
 // One pass over one group: load 2^Q points, run Q stages, hand the results to `st`.
 // LD(pos) -> float2, ST(pos, m, value).  g = group index in [0, N>>Q).
-template <int L, int S0, int Q, bool INV, class LD, class ST>
-__device__ __forceinline__ void fft_group(const float2 *__restrict__ tw, int g, LD ld, ST st) {
+// twf: the full table (stages of the first pass), twc: the compact per-stage tables.  TWG: twf points to global
+// memory (read through the read-only path; the detector's FFT keeps only the 2 KB of compact tables in shared
+// memory so that three frames fit an SM) -- same values either way.
+template <int L, int S0, int Q, bool INV, bool TWG, class LD, class ST>
+__device__ __forceinline__ void fft_group(const float2 *__restrict__ twf, const float2 *__restrict__ twc, int g, LD ld, ST st) {
     constexpr int N = 1 << L;
     constexpr int B0 = N >> S0;
     constexpr int STRIDE = B0 >> Q;
     constexpr int M = 1 << Q;
     constexpr int Q0 = FftPlan<L>::Q0;
-    const float2 *twc = tw + fft_twfull_elems<L>();
     const int blk = g / STRIDE, r = g % STRIDE;
     const int base = blk * B0 + r;
     float2 v[M];
@@ -153,7 +155,7 @@ __device__ __forceinline__ void fft_group(const float2 *__restrict__ tw, int g, 
                     else bfly_wq<INV>(v[m], v[m + span]);
                 }
             } else {
-                float2 w = (s < Q0) ? tw[tw_pad(j << s)] : twc[twc_off<L>(s) + j];
+                float2 w = (s < Q0) ? (TWG ? __ldg(twf + tw_pad(j << s)) : twf[tw_pad(j << s)]) : twc[twc_off<L>(s) + j];
 #pragma unroll
                 for (int hi = 0; hi < M / (2 * span); hi++) {
                     int m = hi * 2 * span + mm;
@@ -180,45 +182,50 @@ __device__ __forceinline__ void fft_load_twiddles(float2 *tw_s, const float2 *__
 // pass hands (k = natural frequency index, value) to `out(k, value)` instead of storing when
 // FUSE_OUT is set.  The last pass maps thread t to group bitrev(t) so that, for fixed m,
 // consecutive threads own consecutive k.
-template <int L, bool INV, bool FUSE_OUT, class LD0, class OUT>
-__device__ __forceinline__ void fft_smem(float2 *data, const float2 *tw, LD0 ld0, OUT out) {
+template <int L, bool INV, bool FUSE_OUT, bool TWG, class LD0, class OUT>
+__device__ __forceinline__ void fft_smem2(float2 *data, const float2 *twf, const float2 *twc, LD0 ld0, OUT out) {
     using PL = FftPlan<L>;
     constexpr int N = 1 << L;
     auto lds = [&](int p) { return data[fft_pad<L>(p)]; };
     auto sts = [&](int p, int, float2 v) { data[fft_pad<L>(p)] = v; };
     // pass 0
     for (int g = threadIdx.x; g < (N >> PL::Q0); g += blockDim.x)
-        fft_group<L, 0, PL::Q0, INV>(tw, g, ld0, sts);
+        fft_group<L, 0, PL::Q0, INV, TWG>(twf, twc, g, ld0, sts);
     __syncthreads();
     if constexpr (PL::P == 2) {
         constexpr int Q = PL::Q1, S0 = PL::Q0;
         for (int t = threadIdx.x; t < (N >> Q); t += blockDim.x) {
             int g = bitrev_n(t, L - Q);
             if (FUSE_OUT) {
-                fft_group<L, S0, Q, INV>(tw, g, lds, [&](int, int m, float2 v) {
+                fft_group<L, S0, Q, INV, TWG>(twf, twc, g, lds, [&](int, int m, float2 v) {
                     out((bitrev_n(m, Q) << (L - Q)) | t, v);
                 });
             } else {
-                fft_group<L, S0, Q, INV>(tw, g, lds, sts);
+                fft_group<L, S0, Q, INV, TWG>(twf, twc, g, lds, sts);
             }
         }
     } else {
         for (int g = threadIdx.x; g < (N >> PL::Q1); g += blockDim.x)
-            fft_group<L, PL::Q0, PL::Q1, INV>(tw, g, lds, sts);
+            fft_group<L, PL::Q0, PL::Q1, INV, TWG>(twf, twc, g, lds, sts);
         __syncthreads();
         constexpr int Q = PL::Q2 > 0 ? PL::Q2 : 1, S0 = PL::Q0 + PL::Q1;
         for (int t = threadIdx.x; t < (N >> Q); t += blockDim.x) {
             int g = bitrev_n(t, L - Q);
             if (FUSE_OUT) {
-                fft_group<L, S0, Q, INV>(tw, g, lds, [&](int, int m, float2 v) {
+                fft_group<L, S0, Q, INV, TWG>(twf, twc, g, lds, [&](int, int m, float2 v) {
                     out((bitrev_n(m, Q) << (L - Q)) | t, v);
                 });
             } else {
-                fft_group<L, S0, Q, INV>(tw, g, lds, sts);
+                fft_group<L, S0, Q, INV, TWG>(twf, twc, g, lds, sts);
             }
         }
     }
     __syncthreads();
+}
+// the whole twiddle image (fft_load_twiddles) in shared memory
+template <int L, bool INV, bool FUSE_OUT, class LD0, class OUT>
+__device__ __forceinline__ void fft_smem(float2 *data, const float2 *tw, LD0 ld0, OUT out) {
+    fft_smem2<L, INV, FUSE_OUT, false>(data, tw, tw + fft_twfull_elems<L>(), ld0, out);
 }
 
 // Read X[k] after a non-fused fft_smem.

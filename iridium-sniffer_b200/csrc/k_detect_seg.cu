@@ -49,7 +49,7 @@ constexpr int SGF = 4;                 // rows per ring block
 constexpr int RB = 2;                  // ring blocks
 constexpr int SPF = 4;                 // candidate words whose loads are in flight together
 constexpr int SMAXW = 512;             // bitmap words per frame (N <= 16384)
-constexpr int SMAXC = 128;             // candidate peaks of one frame
+template <int WPL> __host__ __device__ constexpr int smaxc() { return WPL >= 16 ? 512 : 128; }   // candidate peaks of one frame
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr int NONE = -0x40000000;
 constexpr int BIGF = 0x3fffffff;
@@ -59,11 +59,9 @@ struct WkShared {
     unsigned long long bar[8];
     uint32_t fvs[SMAXW];
     unsigned short cw[SMAXW];
-    int cbin[SMAXC];
-    float crel[SMAXC];
-    float cbase[SMAXC];
     int fslot[IR_SEG_LEN];
 };
+// (after it in shared memory: cbin / crel / cbase [smaxc<WPL>()], then the ring)
 
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
     uint4 v;
@@ -492,7 +490,10 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
     GoneBurst *gl = glist + (size_t)seg * IR_SEG_GONE;
     const float thr = c.thr;
     uint64_t *bars = reinterpret_cast<uint64_t *>(S.bar);
-    uint32_t *ring = reinterpret_cast<uint32_t *>(smem_raw + ((sizeof(WkShared) + 127) / 128) * 128);
+    constexpr int SMAXC = smaxc<WPL>();
+    int *s_cbin = reinterpret_cast<int *>(smem_raw + ((sizeof(WkShared) + 15) / 16) * 16);
+    float *s_crel = reinterpret_cast<float *>(s_cbin + SMAXC), *s_cbase = s_crel + SMAXC;
+    uint32_t *ring = reinterpret_cast<uint32_t *>(smem_raw + (((sizeof(WkShared) + 15) / 16) * 16 + 3 * SMAXC * 4 + 127) / 128 * 128);
     const int RW = 2 * W;                                     // words per row: [XU][X]
     const uint32_t row_bytes = (uint32_t)RW * sizeof(uint32_t);
     const uint32_t *xu = xu_c + (size_t)f0 * RW;
@@ -792,7 +793,7 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
                         const uint32_t bal = __ballot_sync(FULL, exj[j]);
                         if (!fast && exj[j]) {
                             const int pos = n_cand + __popc(bal & ((1u << lane) - 1u));
-                            if (pos < SMAXC) { S.cbin[pos] = (wj[j] << 5) + lane; S.crel[pos] = relj[j]; S.cbase[pos] = bsj[j]; }
+                            if (pos < SMAXC) { s_cbin[pos] = (wj[j] << 5) + lane; s_crel[pos] = relj[j]; s_cbase[pos] = bsj[j]; }
                         }
                         n_cand += __popc(bal);
                     }
@@ -839,9 +840,9 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
                         ArgMax best{-1.0f, 0x7fffffff};
                         int bslot = -1;
                         for (int i = lane; i < nc; i += 32) {
-                            const int cbn = S.cbin[i];
+                            const int cbn = s_cbin[i];
                             if (cbn >= 0) {
-                                const ArgMax cur2{S.crel[i], cbn};
+                                const ArgMax cur2{s_crel[i], cbn};
                                 const ArgMax nb = argmax_pick(best, cur2);
                                 if (nb.i != best.i) bslot = i;
                                 best = nb;
@@ -852,10 +853,10 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
                         bin = wbest.i;
                         rel_w = wbest.v;
                         const unsigned owner = __ballot_sync(FULL, best.i == bin && bslot >= 0);
-                        bc = __shfl_sync(FULL, bslot >= 0 ? S.cbase[bslot] : 0.0f, __ffs(owner) - 1);
+                        bc = __shfl_sync(FULL, bslot >= 0 ? s_cbase[bslot] : 0.0f, __ffs(owner) - 1);
                         for (int i = lane; i < nc; i += 32) {
-                            const int bb = S.cbin[i];
-                            if (bb >= bin - c.half_bw && bb <= bin + c.half_bw) S.cbin[i] = -1;
+                            const int bb = s_cbin[i];
+                            if (bb >= bin - c.half_bw && bb <= bin + c.half_bw) s_cbin[i] = -1;
                         }
                         __syncwarp();
                     }
@@ -1092,7 +1093,9 @@ bool seg_scan_supported(const DetConfig &c) {
 }
 
 size_t seg_walk_smem(const DetConfig &c) {
-    return ((sizeof(WkShared) + 127) / 128) * 128 + (size_t)RB * SGF * (size_t)(c.N / 16) * sizeof(uint32_t);
+    const size_t smaxc_ = c.N / 1024 >= 16 ? 512 : 128;
+    return (((sizeof(WkShared) + 15) / 16) * 16 + 3 * smaxc_ * 4 + 127) / 128 * 128 +
+           (size_t)RB * SGF * (size_t)(c.N / 16) * sizeof(uint32_t);
 }
 
 template <int WPL>
@@ -1134,7 +1137,9 @@ cudaError_t launch_detect_scan_seg(const DetConfig &c, DetState *state, float *b
     k_seg_gather_hist<<<256, 256, 0, st>>>(c, state, hist, b.qmag);
     k_seg_begin<<<1, 256, 0, st>>>(c, state, b.ctl, b.stA, b.stB, b.qw, b.ncreate, b.ngone, b.segbail, b.stch, b.valid, ref, b.glo, b.ghi,
                                    n_frames, S);
-    int rounds = IR_SEG_ROUNDS;
+    // rounds enqueued: a chunk that has no fixed point by then goes to the cluster kernel -- cheap for a short chunk,
+    // so short chunks (the 4096-frame pieces of a host run) queue fewer no-op launches
+    int rounds = n_frames <= 4096 ? 8 : IR_SEG_ROUNDS;
     if (const char *env = getenv("IR_SEG_ROUNDS")) { const int v = atoi(env); if (v >= 2 && v <= 64) rounds = v; }
     for (int r = 0; r <= rounds; r++) {
         k_seg_index<<<1, 256, 0, st>>>(b.ctl, b.qw, rowany, b.wpre, b.qlist, b.slotv, b.fslot, b.slot_cap, rounds);

@@ -72,7 +72,10 @@ cudaError_t launch_rot_tables(const float2 *incr, float2 *const *tables, const i
 }
 
 // ============================================================== rotate + FIR + decimate
-template <int DEC> __host__ __device__ constexpr int fir_in_max() { return (IR_FIR_TILE - 1) * DEC + IR_INPUT_NTAPS; }
+// decimated outputs per tile: 256 (32 lanes x 8) at DEC = 40; 192 (24 lanes) at DEC = 48, where two 256-output sample
+// buffers (or two resident one-tile CTAs) would not fit an SM's shared memory
+template <int DEC> __host__ __device__ constexpr int fir_tile() { return IR_FIR_TILE_OF(DEC); }
+template <int DEC> __host__ __device__ constexpr int fir_in_max() { return (fir_tile<DEC>() - 1) * DEC + IR_INPUT_NTAPS; }
 // Shared-memory index of burst sample e.  Two access patterns must both be conflict-free for
 // 8-byte accesses: the rotate phase (lane stride 16 samples) and the FIR phase (lane stride
 // R*DEC samples).  e + e/16 + e/(R*DEC) gives lane strides of 17 and R*DEC*17/16+1 (341 for
@@ -132,11 +135,11 @@ __global__ void __launch_bounds__(128)
 k_fir(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const BurstParam *__restrict__ bp,
       const int *__restrict__ tile_start, int n_bursts, float2 *__restrict__ dec_out) {
     static_assert(DEC % 4 == 0, "register-tiled FIR needs dec % 4 == 0");
-    static_assert((IR_FIR_TILE * DEC) % IR_ROT_G == 0, "tiles must start on a phase checkpoint");
+    static_assert((fir_tile<DEC>() * DEC) % IR_ROT_G == 0, "tiles must start on a phase checkpoint");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *s = reinterpret_cast<float2 *>(smem_raw);
-    float2 *part = s + fir_pitch_elems<DEC>();            // [4][IR_FIR_TILE]
-    float *hp = reinterpret_cast<float *>(part + 4 * IR_FIR_TILE);   // zero-padded body taps
+    float2 *part = s + fir_pitch_elems<DEC>();            // [4][fir_tile<DEC>()]
+    float *hp = reinterpret_cast<float *>(part + 4 * fir_tile<DEC>());   // zero-padded body taps
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k = tid; k < fir_hp_elems<DEC>(); k += blockDim.x) {
         const int kk = k - IR_FIR_HPAD;
@@ -151,8 +154,8 @@ k_fir(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const BurstPa
         if (tile_start[mid] <= tile) lo = mid; else hi = mid;
     }
     const BurstParam P = bp[lo];
-    const int o0 = (tile - P.tile0) * IR_FIR_TILE;
-    const int n_out = min(IR_FIR_TILE, P.dec_len - o0);
+    const int o0 = (tile - P.tile0) * fir_tile<DEC>();
+    const int n_out = min(fir_tile<DEC>(), P.dec_len - o0);
     const int e0 = o0 * DEC;
     const int n_in = (n_out - 1) * DEC + IR_INPUT_NTAPS;
 
@@ -201,15 +204,17 @@ k_fir(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const BurstPa
 #pragma unroll
         for (int i = 0; i < IR_FIR_R; i++) acc[i] = make_float2(0.0f, 0.0f);
         constexpr int ROW = IR_FIR_R * DEC + IR_FIR_R * DEC / 16 + 1;
-        fir_chains<DEC>(s + ROW * lane + warp, hp + IR_FIR_HPAD + warp, acc);     // chain J = warp
+        if (IR_FIR_R * lane < fir_tile<DEC>()) {
+            fir_chains<DEC>(s + ROW * lane + warp, hp + IR_FIR_HPAD + warp, acc);     // chain J = warp
 #pragma unroll
-        for (int i = 0; i < IR_FIR_R; i++) part[warp * IR_FIR_TILE + IR_FIR_R * lane + i] = acc[i];
+            for (int i = 0; i < IR_FIR_R; i++) part[warp * fir_tile<DEC>() + IR_FIR_R * lane + i] = acc[i];
+        }
     }
     __syncthreads();
     // D: (c0+c2)+(c1+c3), leftover taps, store (simd_avx2.c:88-109)
     for (int o = tid; o < n_out; o += blockDim.x) {
-        const float2 c0 = part[o], c1 = part[IR_FIR_TILE + o], c2 = part[2 * IR_FIR_TILE + o],
-                     c3 = part[3 * IR_FIR_TILE + o];
+        const float2 c0 = part[o], c1 = part[fir_tile<DEC>() + o], c2 = part[2 * fir_tile<DEC>() + o],
+                     c3 = part[3 * fir_tile<DEC>() + o];
         float ar = (c0.x + c2.x) + (c1.x + c3.x);
         float ai = (c0.y + c2.y) + (c1.y + c3.y);
 #pragma unroll
@@ -239,7 +244,7 @@ __global__ void __launch_bounds__(FWS_C + FWS_P, 1)
 k_fir_ws(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const BurstParam *__restrict__ bp,
          const int *__restrict__ tile_burst, int n_tiles, float2 *__restrict__ dec_out) {
     static_assert(DEC % 4 == 0, "register-tiled FIR needs dec % 4 == 0");
-    static_assert((IR_FIR_TILE * DEC) % IR_ROT_G == 0, "tiles must start on a phase checkpoint");
+    static_assert((fir_tile<DEC>() * DEC) % IR_ROT_G == 0, "tiles must start on a phase checkpoint");
     static_assert((IR_FIR_R * DEC) % IR_ROT_G == 0 && IR_ROT_G == 16, "segment layout below");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int PITCH = fws_pitch<DEC>();
@@ -248,8 +253,8 @@ k_fir_ws(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const Burs
     constexpr int CPT = (fir_in_max<DEC>() + FWS_P - 1) / FWS_P; // copies per producer thread
     constexpr int SEG_PER_ROW = IR_FIR_R * DEC / IR_ROT_G;       // segments between two "row" pads of fir_pi
     float2 *sb0 = reinterpret_cast<float2 *>(smem_raw);
-    float2 *part0 = sb0 + 2 * PITCH;                           // [4][IR_FIR_TILE]
-    float *hp = reinterpret_cast<float *>(part0 + 4 * IR_FIR_TILE);
+    float2 *part0 = sb0 + 2 * PITCH;                           // [4][fir_tile<DEC>()]
+    float *hp = reinterpret_cast<float *>(part0 + 4 * fir_tile<DEC>());
     uint64_t *bars = reinterpret_cast<uint64_t *>(hp + ((fir_hp_elems<DEC>() + 1) & ~1));   // full[2], empty[2]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k = tid; k < fir_hp_elems<DEC>(); k += blockDim.x) {
@@ -269,8 +274,8 @@ k_fir_ws(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const Burs
             const int b = (t - t0) & 1, use = (t - t0) >> 1;
             float2 *s = sb0 + b * PITCH;
             const BurstParam P = bp[tile_burst[t]];
-            const int o0 = (t - P.tile0) * IR_FIR_TILE;
-            const int n_out = min(IR_FIR_TILE, P.dec_len - o0);
+            const int o0 = (t - P.tile0) * fir_tile<DEC>();
+            const int n_out = min(fir_tile<DEC>(), P.dec_len - o0);
             const int e0 = o0 * DEC;
             const int n_in = (n_out - 1) * DEC + IR_INPUT_NTAPS;
             // the NCO checkpoints of this thread's segments: in flight while the samples are staged
@@ -343,26 +348,28 @@ k_fir_ws(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const Burs
             float2 *s = sb0 + b * PITCH;
             float2 *part = part0;
             const BurstParam P = bp[tile_burst[t]];
-            const int o0 = (t - P.tile0) * IR_FIR_TILE;
-            const int n_out = min(IR_FIR_TILE, P.dec_len - o0);
+            const int o0 = (t - P.tile0) * fir_tile<DEC>();
+            const int n_out = min(fir_tile<DEC>(), P.dec_len - o0);
             mbar_wait(&bars[b], (uint32_t)(use & 1));
             {
                 float2 acc[IR_FIR_R];
 #pragma unroll
                 for (int i = 0; i < IR_FIR_R; i++) acc[i] = make_float2(0.0f, 0.0f);
                 constexpr int ROW = IR_FIR_R * DEC + IR_FIR_R * DEC / 16 + 1;
-                fir_chains<DEC>(s + ROW * lane + warp, hp + IR_FIR_HPAD + warp, acc);
+                if (IR_FIR_R * lane < fir_tile<DEC>()) fir_chains<DEC>(s + ROW * lane + warp, hp + IR_FIR_HPAD + warp, acc);
                 // (one partial-sum buffer: the previous tile's combine must be over before it is rewritten -- 8 KB
                 // less shared memory is what lets a state-machine walker sit beside this CTA)
                 if (t > t0) asm volatile("bar.sync 1, %0;" ::"n"(FWS_C) : "memory");
+                if (IR_FIR_R * lane < fir_tile<DEC>()) {
 #pragma unroll
-                for (int i = 0; i < IR_FIR_R; i++) part[warp * IR_FIR_TILE + IR_FIR_R * lane + i] = acc[i];
+                    for (int i = 0; i < IR_FIR_R; i++) part[warp * fir_tile<DEC>() + IR_FIR_R * lane + i] = acc[i];
+                }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(FWS_C) : "memory");
             // D: (c0+c2)+(c1+c3), leftover taps, store (simd_avx2.c:88-109)
             for (int o = tid; o < n_out; o += FWS_C) {
-                const float2 c0 = part[o], c1 = part[IR_FIR_TILE + o], c2 = part[2 * IR_FIR_TILE + o],
-                             c3 = part[3 * IR_FIR_TILE + o];
+                const float2 c0 = part[o], c1 = part[fir_tile<DEC>() + o], c2 = part[2 * fir_tile<DEC>() + o],
+                             c3 = part[3 * fir_tile<DEC>() + o];
                 float ar = (c0.x + c2.x) + (c1.x + c3.x);
                 float ai = (c0.y + c2.y) + (c1.y + c3.y);
 #pragma unroll
@@ -384,10 +391,10 @@ static cudaError_t launch_fir_t(const void *iq, int64_t n_total, uint64_t ring, 
                                 cudaStream_t st) {
     static const bool legacy = getenv("IR_FIR_LEGACY") != nullptr;
     constexpr int PITCH = fws_pitch<DEC>();
-    const size_t smem_ws = sizeof(float2) * (2 * PITCH + 4 * IR_FIR_TILE) + sizeof(float) * ((fir_hp_elems<DEC>() + 1) & ~1) + 4 * sizeof(uint64_t);
+    const size_t smem_ws = sizeof(float2) * (2 * PITCH + 4 * fir_tile<DEC>()) + sizeof(float) * ((fir_hp_elems<DEC>() + 1) & ~1) + 4 * sizeof(uint64_t);
     // (two sample buffers of a 256-output tile do not fit 227 KB at DEC = 48: the one-tile kernel serves 12 MHz)
     if (legacy || tile_burst == nullptr || smem_ws > (size_t)227 * 1024) {
-        const size_t smem = sizeof(float2) * (fir_pitch_elems<DEC>() + 4 * IR_FIR_TILE) + sizeof(float) * fir_hp_elems<DEC>();
+        const size_t smem = sizeof(float2) * (fir_pitch_elems<DEC>() + 4 * fir_tile<DEC>()) + sizeof(float) * fir_hp_elems<DEC>();
         cudaError_t e = cudaFuncSetAttribute(k_fir<FMT, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         k_fir<FMT, DEC><<<n_tiles, 128, smem, st>>>(iq, n_total, ring, bp, tile_start, n_bursts, dec_out);

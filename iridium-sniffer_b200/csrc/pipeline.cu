@@ -148,8 +148,10 @@ struct ir_pipeline {
     cudaStream_t st_copy = nullptr, st_fft = nullptr, st_scan = nullptr, st_burst = nullptr, st_chain = nullptr;
     // the symbol slicer is a serial recurrence per frame (long latency, few warps): its launches go
     // round-robin over a few streams of their own so that they overlap the FIR / chain of later waves
-    static constexpr int kDemodStreams = 4;
-    cudaStream_t st_demod[kDemodStreams] = {nullptr, nullptr, nullptr, nullptr};
+    static constexpr int kDemodStreams = 2;   // (8 streams in all: the default number of hardware queues -- a ninth
+                                              //  shares one with another stream, and sharing the copy stream's queue,
+                                              //  filled up front, kept every 4th wave's slicer waiting for the last copy)
+    cudaStream_t st_demod[kDemodStreams] = {nullptr, nullptr};
     // constants
     DevBuf<float> d_window;
     DevBuf<float2> d_tw_det, d_tw12, d_tw11, d_sync_dl, d_sync_ul;
@@ -447,7 +449,7 @@ static int launch_wave(ir_pipeline *p, size_t b0, size_t b1, const void *iq_dev,
         ob.dec_len = dlen;
         if (dlen >= 100) {
             dec_total += dlen;
-            n_tiles += (dlen + IR_FIR_TILE - 1) / IR_FIR_TILE;
+            n_tiles += (dlen + IR_FIR_TILE_OF(p->dec) - 1) / IR_FIR_TILE_OF(p->dec);
             auto it = p->rot.find(g.center_bin);
             if (it == p->rot.end() || it->second.len < nn + IR_ROT_G) need_bins.push_back(i);
             p->alg += 8ull * (uint64_t)nn + 8ull * (uint64_t)dlen;
@@ -818,6 +820,17 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
         }
         if (nb < 0) { set_err("chunk plan does not fit"); return -1; }
         bounds.resize((size_t)nb);
+        if (host_iq && p->scan_mode == 2 && bounds.size() > 1) {
+            // a chunk of the segmented state machine costs its rounds whatever its length (~0.4 ms): the tail of
+            // halves stops at 4 Mi samples
+            const size_t min_seg = std::max<size_t>(((size_t)4 << 20) / N, 1) * N;
+            std::vector<size_t> kept;
+            size_t prev = 0;
+            for (size_t i = 0; i + 1 < bounds.size(); i++)
+                if (bounds[i] - prev >= min_seg && bounds.back() - bounds[i] >= min_seg / 2) { kept.push_back(bounds[i]); prev = bounds[i]; }
+            kept.push_back(bounds.back());
+            bounds.swap(kept);
+        }
         if (bounds.empty()) bounds.push_back(0);
     }
     const size_t n_chunks = bounds.size();

@@ -452,7 +452,7 @@ extern "C" int burst_downmix_process(_burst_downmix *dm, burst_data_t *burst, do
     bp.rot_table = it->second.first;
     bp.tile0 = 0;
     bp.cfreq_coarse = burst->center_frequency + (double)(rel * fs);
-    const int n_tiles = (dlen + IR_FIR_TILE - 1) / IR_FIR_TILE;
+    const int n_tiles = (dlen + IR_FIR_TILE_OF(dec) - 1) / IR_FIR_TILE_OF(dec);
     int tiles[2] = {0, n_tiles};
     RCK(cudaMemcpyAsync(dm->d_in, burst->samples, sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice, dm->st), 0);
     RCK(cudaMemcpyAsync(dm->d_bp, &bp, sizeof(bp), cudaMemcpyHostToDevice, dm->st), 0);
