@@ -15,6 +15,8 @@
 
 namespace ir {
 
+#define IR_FFT_FPB 8             // frames per CTA of k_detect_fft
+
 // =========================================================================== FFT + |X|^2
 template <int L, int FMT>
 __global__ void __launch_bounds__(fft_threads<L>())
@@ -26,7 +28,11 @@ k_detect_fft(const void *__restrict__ iq, int64_t first_sample, const float *__r
     float2 *tw = data + fft_data_elems<L>();
     fft_load_twiddles<L>(tw, tw_g);
     __syncthreads();
-    for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x) {
+    // A CTA takes IR_FFT_FPB consecutive frames and retires (the twiddle load above is ~1 % of that): CTAs that
+    // lived for the whole launch kept every register of their SMs for 0.5 ms at a time, and the state machine's
+    // kernels -- high priority, but nothing preempts a resident CTA -- queued behind them.
+    const int64_t fa = (int64_t)blockIdx.x * IR_FFT_FPB, fb = fa + IR_FFT_FPB < n_frames ? fa + IR_FFT_FPB : n_frames;
+    for (int64_t f = fa; f < fb; f++) {
         const int64_t s0 = first_sample + f * N;
         float *out = mag + f * N;
         fft_smem<L, false, true>(
@@ -46,11 +52,8 @@ static cudaError_t launch_fft_L(int fmt, const void *iq, int64_t first_sample, c
                                 cudaStream_t st) {
     const size_t smem = sizeof(float2) * (fft_data_elems<L>() + fft_tw_elems<L>());
     const int threads = fft_threads<L>();
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
-    int64_t grid = (int64_t)sm_count * per_sm;
-    if (grid > n_frames) grid = n_frames;
+    (void)sm_count;
+    const int64_t grid = (n_frames + IR_FFT_FPB - 1) / IR_FFT_FPB;
     if (grid < 1) return cudaSuccess;
 #define IR_LAUNCH_FFT(F)                                                                          \
     do {                                                                                          \

@@ -815,8 +815,14 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
         if (host_iq) {
             nb = ir_plan_chunks(n, chunk, (size_t)N, bounds.data(), bounds.size());
         } else {
-            // device-resident input: no copy to hide the tail behind -- equal chunks
-            for (size_t off = 0; off < n; off += chunk) bounds[(size_t)nb++] = std::min(n, off + chunk);
+            // device-resident input: no copy to hide the tail behind -- equal chunks, after a short first one (the
+            // downmix of its bursts starts while the state machine is busy with the second)
+            size_t off = 0;
+            if (p->scan_mode == 2 && n > 2 * chunk) {
+                off = std::min(n, (size_t)(p->dc.hist_size + 4096) * N);
+                bounds[(size_t)nb++] = off;
+            }
+            for (; off < n; off += chunk) bounds[(size_t)nb++] = std::min(n, off + chunk);
         }
         if (nb < 0) { set_err("chunk plan does not fit"); return -1; }
         bounds.resize((size_t)nb);
