@@ -130,6 +130,41 @@ __device__ __forceinline__ void fir_chains(const float2 *__restrict__ sp, const 
     }
 }
 
+// The same chains with packed FMAs (sm_100 fma.rn.f32x2, SASS FFMA2): one instruction updates the real and the
+// imaginary accumulator of an output with the shared tap -- each lane of the pair is an IEEE fma with a single
+// rounding, so the sums are the ones above, bit for bit.  (FFMA2 takes the tap as a scalar operand broadcast to
+// both halves -- `FFMA2 Rd, Rh.F32, Rx.F32x2.HI_LO, Racc.F32x2.HI_LO` -- so the tap registers stay 80.)
+template <int DEC>
+__device__ __forceinline__ void fir_chains_f2(const float2 *__restrict__ sp, const float *__restrict__ hp,
+                                              float2 (&acc)[IR_FIR_R]) {
+    constexpr int D4 = DEC / 4;
+    constexpr int NIT = fir_nit<DEC>();
+    constexpr int ROW = IR_FIR_R * DEC + IR_FIR_R * DEC / 16 + 1;
+    float2 G[8][D4];
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int r = 0; r < D4; r++) G[a][r] = make_float2(0.0f, 0.0f);
+    for (int T = 0; T < (NIT + 7) / 8; T++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (8 * T + u < NIT) {                                     // warp-uniform
+#pragma unroll
+                for (int r = 0; r < D4; r++) { const float h = hp[DEC * u + 4 * r]; G[u][r] = make_float2(h, h); }
+#pragma unroll
+                for (int r = 0; r < D4; r++) {
+                    const int ql = D4 * u + r;
+                    const float2 x = sp[4 * ql + (ql >> 2)];
+#pragma unroll
+                    for (int i = 0; i < IR_FIR_R; i++) acc[i] = __ffma2_rn(G[(u - i + 8) & 7][r], x, acc[i]);
+                }
+            }
+        }
+        sp += ROW;
+        hp += 8 * DEC;
+    }
+}
+
 template <int FMT, int DEC>
 __global__ void __launch_bounds__(128)
 k_fir(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const BurstParam *__restrict__ bp,
@@ -237,9 +272,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 constexpr int FWS_C = 128;             // consumer threads (one warp per chain)
-constexpr int FWS_P = 256;             // producer threads
 template <int DEC> __host__ __device__ constexpr int fws_pitch() { return (fir_pitch_elems<DEC>() + 8 + 1) & ~1; }
-template <int FMT, int DEC>
+// FWS_P producer threads; F2: packed FMAs in the chains
+template <int FMT, int DEC, int FWS_P, bool F2>
 __global__ void __launch_bounds__(FWS_C + FWS_P, 1)
 k_fir_ws(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const BurstParam *__restrict__ bp,
          const int *__restrict__ tile_burst, int n_tiles, float2 *__restrict__ dec_out) {
@@ -356,7 +391,10 @@ k_fir_ws(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const Burs
 #pragma unroll
                 for (int i = 0; i < IR_FIR_R; i++) acc[i] = make_float2(0.0f, 0.0f);
                 constexpr int ROW = IR_FIR_R * DEC + IR_FIR_R * DEC / 16 + 1;
-                if (IR_FIR_R * lane < fir_tile<DEC>()) fir_chains<DEC>(s + ROW * lane + warp, hp + IR_FIR_HPAD + warp, acc);
+                if (IR_FIR_R * lane < fir_tile<DEC>()) {
+                    if (F2) fir_chains_f2<DEC>(s + ROW * lane + warp, hp + IR_FIR_HPAD + warp, acc);
+                    else fir_chains<DEC>(s + ROW * lane + warp, hp + IR_FIR_HPAD + warp, acc);
+                }
                 // (one partial-sum buffer: the previous tile's combine must be over before it is rewritten -- 8 KB
                 // less shared memory is what lets a state-machine walker sit beside this CTA)
                 if (t > t0) asm volatile("bar.sync 1, %0;" ::"n"(FWS_C) : "memory");
@@ -401,9 +439,21 @@ static cudaError_t launch_fir_t(const void *iq, int64_t n_total, uint64_t ring, 
         return cudaGetLastError();
     }
     const size_t smem = smem_ws;
-    cudaError_t e = cudaFuncSetAttribute(k_fir_ws<FMT, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    k_fir_ws<FMT, DEC><<<(n_tiles + IR_FIR_STRIP - 1) / IR_FIR_STRIP, FWS_C + FWS_P, smem, st>>>(iq, n_total, ring, bp, tile_burst, n_tiles, dec_out);
+    static const bool scalar = getenv("IR_FIR_SCALAR") != nullptr;    // the unpacked chains with eight producer warps
+    const unsigned grid = (unsigned)((n_tiles + IR_FIR_STRIP - 1) / IR_FIR_STRIP);
+    if (scalar) {
+        cudaError_t e = cudaFuncSetAttribute(k_fir_ws<FMT, DEC, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_fir_ws<FMT, DEC, 256, false><<<grid, FWS_C + 256, smem, st>>>(iq, n_total, ring, bp, tile_burst, n_tiles, dec_out);
+    } else if (getenv("IR_FIR_P128") != nullptr) {
+        cudaError_t e = cudaFuncSetAttribute(k_fir_ws<FMT, DEC, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_fir_ws<FMT, DEC, 128, true><<<grid, FWS_C + 128, smem, st>>>(iq, n_total, ring, bp, tile_burst, n_tiles, dec_out);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(k_fir_ws<FMT, DEC, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_fir_ws<FMT, DEC, 256, true><<<grid, FWS_C + 256, smem, st>>>(iq, n_total, ring, bp, tile_burst, n_tiles, dec_out);
+    }
     return cudaGetLastError();
 }
 
