@@ -110,6 +110,7 @@ extern "C" gpu_burst_fft *gpu_burst_fft_create(int fft_size, int batch_size, con
     if (cudaMalloc(&g->d_mag, sizeof(float) * (size_t)fft_size * batch_size) != cudaSuccess) return bail();
     if (cudaMemcpy(g->d_window, window, sizeof(float) * fft_size, cudaMemcpyHostToDevice) != cudaSuccess) return bail();
     if (cudaMemcpy(g->d_tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice) != cudaSuccess) return bail();
+    if (getenv("IR_PLUGIN_LOG")) fprintf(stderr, "iridium_b200: gpu_burst_fft_create(%d, %d): k_detect_fft on the GPU\n", fft_size, batch_size);
     return g;
 }
 

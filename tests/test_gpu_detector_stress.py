@@ -171,6 +171,60 @@ def test_many_launches_bursts_across_launch_boundaries(pl, port, synth, mode, ch
             os.environ["IR_SCAN"] = old
 
 
+FS12 = 12_000_000
+
+
+def _check12(pl, port, iq, mode, chunk=0, expect_squelch=None, min_bursts=0):
+    """the 12 MHz / 16384-pt geometry (k_detect_fft<14>, k_seg_walk<16>, k_detect_scan_stream<8>, k_fir<.,48>)"""
+    P = port.det_params(sample_rate=FS12)
+    pb, _, nsq = port.detect(P, iq)
+    want = [(o.id, o.start, o.stop, o.last_active, o.center_bin, o.magnitude, o.noise) for o in pb]
+    if expect_squelch is not None:
+        assert (nsq > 0) == expect_squelch
+    assert len(want) >= min_bursts
+    old = os.environ.get("IR_SCAN")
+    try:
+        _set_mode(mode)
+        p = pl.Pipeline(sample_rate=FS12, start_time_ns=77, h2d_chunk=chunk)
+        res = p.run_host(iq, "cf32")
+        ss = p.scan_stats()
+        p.close()
+    finally:
+        if old is None:
+            os.environ.pop("IR_SCAN", None)
+        else:
+            os.environ["IR_SCAN"] = old
+    got = [(b["id"], b["start"], b["stop"], b["last_active"], b["center_bin"], b["magnitude"], b["noise"]) for b in res.bursts]
+    assert got == want, ss
+    ores, _ = port.run(iq, sample_rate=FS12, start_time_ns=77)
+    assert [(f["id"], f["bits"].tobytes()) for f in res.frames] == [(o["id"], o["bits"].tobytes()) for o in ores]
+    return ss
+
+
+@pytest.mark.parametrize("mode", ["seg", "stream", "cluster"])
+def test_12mhz_squelch(pl, port, synth, mode):
+    iq = synth.make_tone_recording(5, 280, 0.02, 0.80, total_s=0.95, sample_rate=FS12)   # 280 carriers > max_bursts = 240
+    ss = _check12(pl, port, iq, mode, expect_squelch=True)
+    if mode in ("seg", "stream"):
+        assert ss["launches_bailed"] > 0, ss
+
+
+@pytest.mark.parametrize("mode", ["seg", "stream", "cluster"])
+def test_12mhz_too_long_burst(pl, port, synth, mode):
+    iq = synth.make_tone_recording(6, 1, 0.13, 0.78, total_s=1.08, sample_rate=FS12)      # 130 ms carrier > 90 ms
+    _check12(pl, port, iq, mode, expect_squelch=False, min_bursts=1)
+
+
+@pytest.mark.parametrize("mode", ["seg", "stream", "cluster"])
+def test_12mhz_many_launches(pl, port, synth, mode):
+    """2 Mi-sample chunks = 128-frame launches at N = 16384: priming spread over four launches, bursts alive across
+    launch boundaries"""
+    rec = synth.make_recording(34, sample_rate=FS12, duration_s=1.7, n_bursts=20)
+    ss = _check12(pl, port, rec.iq, mode, chunk=2 << 20, min_bursts=12)
+    if mode == "seg":
+        assert ss["launches_kept"] >= 4, ss
+
+
 def test_full_size_recording_seg_equals_cluster_oracle_and_truth(pl, port, synth):
     """BASELINE config 2 at full size (60 s, 600 M samples, ~6500 bursts; generated on the GPU like
     bench.py does).  The first 8 s are held against the CPU oracle field by field (ids, bits, float fields

@@ -19,6 +19,7 @@ CASES = ["gpu_classify_cases.py::" + c for c in (
     "test_generated_frames_one_launch", "test_pipeline_classifies_planted_frames_from_device_memory",
     "test_parsed_output_of_a_run", "test_reference_named_entry_points", "test_classify_refuses_bad_arguments")]
 CASES.append("gpu_dropin_cases.py::test_reference_main_linked_against_the_library")
+CASES.append("gpu_dropin_cases.py::test_reference_detector_on_the_fft_plugin")   # -DUSE_GPU reference on gpu_burst_fft_*
 CASES.append("gpu_block_cases.py::test_time_blocks_through_the_cuda_path")      # time blocks, merged
 CASES.append("gpu_block_cases.py::test_one_process_driver_on_the_gpu")           # ir_multi_*: the same in one C call
 CASES.append("gpu_block_cases.py::test_one_process_driver_parsed_on_the_gpu")    # ... with classification / --parsed text
