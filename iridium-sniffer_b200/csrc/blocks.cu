@@ -104,7 +104,9 @@ static long merge_impl(const ir_config_t *cfg, uint64_t start_time_ns, const ir_
         for (size_t i = 0; i < n_frames[k]; i++) {
             const ir_frame_t &f = frames[k][i];
             if (f.timestamp < t_first || (!last && f.timestamp >= t_end)) continue;
-            if (k > 0 && f.timestamp < t_first + kOverlapNs) {                            // the previous block's, if it has it
+            if (k > 0 && f.timestamp < t_first + 2 * kOverlapNs) {                        // the previous block's, if it has it
+                // (twice the overlap: two blocks stamp the same frame slightly differently -- each has its own
+                //  baseline -- and a copy just under the edge in one must still meet its twin just over it in the other)
                 bool dup = false;
                 for (size_t j = prev_begin; j < this_begin && !dup; j++) {
                     const ir_frame_t &o = frames[kept[j].block][kept[j].index];
@@ -149,6 +151,7 @@ struct ir_multi {
     std::vector<ir_frame_t> merged;
     std::vector<uint32_t> merged_block, merged_index;
     bool classify = false;                             // ir_multi_set_classify: frame_decode() + ida_decode() per frame too
+    bool classified_last = false;                      // ... and whether the LAST run was (what results / parsed text go by)
     std::vector<std::vector<ir_frame_class_t>> cls;    // per block, parallel to frames[k]
     std::vector<const ir_frame_class_t *> cls_ptr;
     uint64_t start_time_ns = 0, launches = 0, fed = 0;
@@ -191,6 +194,7 @@ extern "C" int ir_multi_run_host(ir_multi_t *m, const void *iq, size_t n, int fm
     const size_t bps = fmt == IR_FMT_CF32 ? 8 : fmt == IR_FMT_CI16 ? 4 : 2;
     const int nd = (int)m->pipes.size();
     if (n_blocks <= 0) n_blocks = nd;
+    m->classified_last = m->classify;
     m->start_time_ns = m->cfg.start_time_ns;
     if (!m->start_time_ns) {
         struct timespec ts;
@@ -265,7 +269,7 @@ extern "C" int ir_multi_results(ir_multi_t *m, ir_multi_results_t *out) {
     out->frames = m->merged.data();
     out->block = m->merged_block.data();
     out->index = m->merged_index.data();
-    out->classes = m->classify ? m->cls_ptr.data() : nullptr;
+    out->classes = m->classified_last ? m->cls_ptr.data() : nullptr;
     out->n_blocks = m->blocks.size();
     out->blocks = m->blocks.data();
     out->bits = m->bits_ptr.data();
@@ -298,7 +302,7 @@ extern "C" long ir_multi_format_raw_all(ir_multi_t *m, const char *file_info, ui
 // `--parsed` output of the merged run (main.c:328-331): the IDA line where ida_decode() accepted the frame, the RAW line otherwise
 extern "C" long ir_multi_format_parsed_all(ir_multi_t *m, const char *file_info, uint64_t t0, char *dst, size_t cap) {
     if (!m) return -1;
-    if (!m->classify) { set_err("ir_multi_format_parsed_all: the run was not classified (ir_multi_set_classify)"); return -1; }
+    if (!m->classified_last) { set_err("ir_multi_format_parsed_all: the last run was not classified (ir_multi_set_classify before the run)"); return -1; }
     const size_t head = 512 + (file_info ? strlen(file_info) : 0);
     size_t need = 64;
     for (const ir_frame_t &f : m->merged) need += head + (size_t)f.n_bits + 2;
@@ -309,6 +313,7 @@ extern "C" long ir_multi_format_parsed_all(ir_multi_t *m, const char *file_info,
     for (size_t i = 0; i < m->merged.size(); i++) {
         const ir_frame_t &f = m->merged[i];
         const uint32_t b = m->merged_block[i];
+        if (b >= m->cls.size() || m->merged_index[i] >= m->cls[b].size()) { set_err("ir_multi_format_parsed_all: no class record for a frame"); return -1; }
         const ir_frame_class_t &c = m->cls[b][m->merged_index[i]];
         if (pos + head + (size_t)f.n_bits + 2 > cap) { set_err("ir_multi_format_parsed_all: buffer too small"); return -1; }
         const int k = c.ida_ok ? ir_format_ida(dst + pos, cap - pos, t0, &f, &c)
@@ -327,6 +332,7 @@ extern "C" int ir_multi_run_streams_host(ir_multi_t *m, const void *const *iq, c
     if (fmt < 0 || fmt > 2) { set_err("bad sample format"); return -1; }
     const int nd = (int)m->pipes.size();
     const size_t ns = (size_t)n_streams;
+    m->classified_last = m->classify;
     m->start_time_ns = m->cfg.start_time_ns;
     if (!m->start_time_ns) {
         struct timespec ts;

@@ -787,7 +787,11 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     const int64_t n_frames = (int64_t)(n / (size_t)N);
     p->n_frames_last = n_frames;
     if (p->d_mag.ensure((size_t)std::max<int64_t>(n_frames, 1) * N)) return -1;
-    const uint32_t gone_cap = (uint32_t)std::max<size_t>(4096, n / 20000 + 1024);
+    // burst list: the reference limits the bursts that are ACTIVE (max_bursts), not how many it emits; the most a
+    // stream can emit is max_bursts per post_len samples (a burst lives at least that long)
+    const size_t per_post = (size_t)std::max(dc.max_bursts, 32);
+    const uint32_t gone_cap = (uint32_t)std::min<size_t>((size_t)1 << 24,
+        std::max<size_t>(4096, (n / (size_t)std::max(dc.post_len, 1) + 2) * per_post));
     if (gone_cap > p->gone_cap) {
         if (p->h_gone) cudaFreeHost(p->h_gone);
         p->h_gone = nullptr; p->gone_cap = 0;

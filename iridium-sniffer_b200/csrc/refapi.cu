@@ -4,6 +4,8 @@
 // reference's ownership rules.  No CPU arithmetic on the path; failures return NULL / 0 / -1.
 #include <math.h>
 #include <stdio.h>
+
+#include <algorithm>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -238,6 +240,17 @@ static void detector_feed(_burst_detector *d, const void *host, size_t n, bool i
         abort();                                                // no silent CPU fallback
     };
     cudaError_t e;
+    // burst list of this call: at most max_bursts bursts can end per post_len samples (the reference caps the ACTIVE
+    // bursts, not the emitted ones); grown before the call that could need more
+    {
+        const size_t need = ((size_t)n / (size_t)std::max(dc.post_len, 1) + 2) * (size_t)std::max(dc.max_bursts, 32);
+        if (need > d->gone_cap) {
+            cudaFree(d->d_gone);
+            d->d_gone = nullptr;
+            if ((e = cudaMalloc(&d->d_gone, sizeof(GoneBurst) * need)) != cudaSuccess) die("cudaMalloc(burst list)", e);
+            d->gone_cap = (uint32_t)need;
+        }
+    }
     // room: keep the last R + pre + 2N samples when the linear buffer would overflow
     uint64_t used = d->sample_count - d->buf_base;
     if (used + n > d->cap) {
