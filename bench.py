@@ -372,7 +372,14 @@ def run_ours(args):
             "k_demod": (8.0 * sum_fl + 5.0 * sum(f["n_bits"] for f in res.frames), stage["ms_demod"] / K, len(res.bursts), "bursts"),
         }
         traffic = kernel_traffic()
-        dom = max(kern, key=lambda k: kern[k][1])
+        # the kernel the roofline is reported for: the one with the largest share of the machine.  k_fir / k_chain /
+        # k_detect_fft launch enough CTAs to fill every SM; the state machine (a few hundred single warps) and the
+        # slicer (one thread per frame: ~45 warps per wave) are latency chains whose stream time overlaps everything
+        # else -- their ms figures are listed, but "dominant" is decided among the kernels that own the SMs
+        wide = [k for k in ("k_detect_fft", "k_fir", "k_chain") if kern[k][1] > 0] or list(kern)
+        dom = max(wide, key=lambda k: kern[k][1])
+        if kern["k_detect_scan"][1] > 2.0 * kern[dom][1]:
+            dom = "k_detect_scan"                    # (a chunk handed to the cluster kernel: the state machine IS the step)
         ach = kern[dom][0] / (kern[dom][1] * 1e-3) / 1e9 if kern[dom][1] > 0 else 0.0
         tr = traffic.get(dom)
         roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 2), "peak": peaks["hbm_gbs"],
@@ -382,6 +389,9 @@ def run_ours(args):
                 "traffic_note": (f"{tr['dram_bytes_per_unit']:.0f} DRAM bytes per {tr['unit']} (ncu --set full, {tr['source']}) x "
                                  f"{kern[dom][2]} {kern[dom][3]} of one step" if tr else "no ncu capture of this kernel committed"),
                 "ms_per_step": round(kern[dom][1], 4),
+                "how_chosen": "largest stream time among the kernels whose grids fill the machine (k_detect_fft, k_fir, k_chain); "
+                              "k_detect_scan only when it exceeds twice that (a chunk handed to the cluster kernel); k_demod is "
+                              "one thread per frame (~45 warps a wave), latency overlapped with later waves",
                 "whole_path": {"alg_bytes": res.stats["alg_bytes"],
                                "achieved": round(res.stats["alg_bytes"] / (dev_s / K) / 1e9, 2),
                                "frac": round(res.stats["alg_bytes"] / (dev_s / K) / 1e9 / peaks["hbm_gbs"], 5)},

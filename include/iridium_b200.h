@@ -164,6 +164,12 @@ int ir_pipeline_copy_burst_samples(ir_pipeline_t *p, size_t burst_index, float *
 int ir_format_raw(char *dst, size_t cap, const char *file_info, uint64_t t0,
                   const ir_frame_t *frame, const uint8_t *bits);
 
+/* printf's "%[+][0]<width>.<decimals>f" of x into dst (>= 400 bytes), computed exactly from the double's bits (integer
+ * part, 52-bit fraction * 10^decimals as a 128-bit integer, round to nearest, ties to even) -- the conversion the
+ * RAW: line formatter uses instead of printf (frame_output.c:176-190 prints four of them per line).  Returns the
+ * length.  Exposed for the tests that hold it against printf. */
+int ir_format_fixed(char *dst, double x, int decimals, int width, int zero_pad, int plus);
+
 /* All RAW: lines of the last run in one call, in frame order (the batched sink of SURVEY.md 8f
  * rank 2).  t0 = 0 selects frame_output.c:144-158's rule (first frame's timestamp floored to
  * 1 s).  Returns the number of bytes written (no trailing NUL counted); with dst == NULL the

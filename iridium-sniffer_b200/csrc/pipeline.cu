@@ -11,6 +11,7 @@
 // Bursts are (offset, length) pairs into iq -- the reference's ring-buffer copy
 // (burst_detect.c:401-422) does not exist here.
 #include <math.h>
+#include <cmath>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -556,20 +557,108 @@ static int launch_wave(ir_pipeline *p, size_t b0, size_t b1, const void *iq_dev,
     return 0;
 }
 
-// frame_output_print's line (frame_output.c:160-199) from the field after file_info on
+// ---- printf's %f, exactly, without printf: the RAW: line has four floating conversions and glibc's printf_fp costs
+// ~0.25 us each; at 10^5 frames/s of sink rate that is what the host spends its time on.  A double is m * 2^e: the
+// integer part and the 52-bit fraction are taken apart exactly, fraction * 10^decimals is an exact 128-bit integer,
+// and the division by 2^52 rounds to nearest, ties to even -- the rule printf applies to the exact binary value.
+// Falls back to snprintf outside the range this path needs (|x| >= 2^53, NaN, inf, decimals > 9).
+static inline int fmt_fixed(char *dst, double x, int decimals, int width, bool zero_pad, bool plus) {
+    const bool neg = std::signbit(x);
+    const double ax = neg ? -x : x;
+    if (!(ax < 9007199254740992.0) || decimals > 9) {
+        char f[16];
+        snprintf(f, sizeof f, "%%%s%s%d.%df", plus ? "+" : "", zero_pad ? "0" : "", width, decimals);
+        return snprintf(dst, 400, f, x);
+    }
+    static const uint64_t P10[10] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull, 1000000000ull};
+    uint64_t ip = (uint64_t)ax;                              // exact: ax < 2^53
+    const double fr = ax - (double)ip;                       // exact, in [0, 1)
+    const uint64_t f52 = (uint64_t)(fr * 4503599627370496.0);   // fraction * 2^52: exact (fr has at most 52 fraction bits... 
+    // ... when ax >= 1; below 1 the fraction can have more bits, handled by the remainder test below)
+    const double rem_lo = fr * 4503599627370496.0 - (double)f52;   // what f52 dropped (non-zero only for tiny ax), in [0, 1)
+    unsigned __int128 prod = (unsigned __int128)f52 * P10[decimals];
+    uint64_t q = (uint64_t)(prod >> 52);
+    const uint64_t r = (uint64_t)(prod & ((1ull << 52) - 1ull));
+    const uint64_t half = 1ull << 51;
+    // the dropped low bits add rem_lo * 10^decimals / 2^52 < 10^decimals * 2^-52 to the remainder: they can only matter at an exact tie
+    bool up = r > half || (r == half && ((q & 1ull) || rem_lo > 0.0));
+    if (r < half && rem_lo > 0.0) {                           // could the dropped bits lift r over the half?  (only for |x| < 1)
+        const double extra = rem_lo * (double)P10[decimals];  // in units of 2^-52 of the remainder... compared exactly enough:
+        if ((double)(half - r) <= extra) {                    // too close to call with this arithmetic: let printf decide
+            char f[16];
+            snprintf(f, sizeof f, "%%%s%s%d.%df", plus ? "+" : "", zero_pad ? "0" : "", width, decimals);
+            return snprintf(dst, 400, f, x);
+        }
+    }
+    if (up) { q++; if (q == P10[decimals]) { q = 0; ip++; } }
+    char tmp[48];
+    int n = 0;
+    for (int i = 0; i < decimals; i++) { tmp[n++] = (char)('0' + q % 10); q /= 10; }
+    if (decimals > 0) tmp[n++] = '.';
+    do { tmp[n++] = (char)('0' + ip % 10); ip /= 10; } while (ip);
+    const bool sign = neg || plus;
+    const int len = n + (sign ? 1 : 0);
+    int pos = 0;
+    if (!zero_pad) for (int i = len; i < width; i++) dst[pos++] = ' ';
+    if (sign) dst[pos++] = neg ? '-' : '+';
+    if (zero_pad) for (int i = len; i < width; i++) dst[pos++] = '0';
+    while (n > 0) dst[pos++] = tmp[--n];
+    dst[pos] = 0;
+    return pos;
+}
+static inline int fmt_uint(char *dst, unsigned long long v, int width, char pad) {
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    int pos = 0;
+    for (int i = n; i < width; i++) dst[pos++] = pad;
+    while (n > 0) dst[pos++] = tmp[--n];
+    return pos;
+}
+
+// frame_output_print's line (frame_output.c:160-199) from the field after file_info on:
+//   " %012.4f %010d N:%05.2f%+06.2f I:%011llu %3d%% %.5f %3d " + bits + newline
 static int format_raw_rest(char *dst, size_t cap, uint64_t t0, const ir_frame_t *f, const uint8_t *bits) {
     const double ts_ms = (double)(f->timestamp - t0) / 1000000.0;
     const int fhz = (int)(f->center_frequency + 0.5);
     int pay = f->n_payload_symbols;
     if (pay < 0) pay = 0;
-    int k = snprintf(dst, cap, " %012.4f %010d N:%05.2f%+06.2f I:%011llu %3d%% %.5f %3d ", ts_ms, fhz, f->magnitude,
-                     f->noise, (unsigned long long)f->id, f->confidence, f->level, pay);
-    if (k < 0) return -1;
-    size_t pos = (size_t)k < cap ? (size_t)k : cap - 1;
+    if (cap < 160 || fhz < 0 || f->confidence < 0) {         // (room for the fixed fields; odd values: printf's own rules)
+        int k = snprintf(dst, cap, " %012.4f %010d N:%05.2f%+06.2f I:%011llu %3d%% %.5f %3d ", ts_ms, fhz, f->magnitude,
+                         f->noise, (unsigned long long)f->id, f->confidence, f->level, pay);
+        if (k < 0) return -1;
+        size_t pos = (size_t)k < cap ? (size_t)k : cap - 1;
+        for (int i = 0; i < f->n_bits && pos + 2 < cap; i++) dst[pos++] = (char)('0' + bits[i]);
+        if (pos + 1 < cap) dst[pos++] = '\n';
+        dst[pos] = 0;
+        return (int)pos;
+    }
+    size_t pos = 0;
+    dst[pos++] = ' ';
+    pos += (size_t)fmt_fixed(dst + pos, ts_ms, 4, 12, true, false);
+    dst[pos++] = ' ';
+    pos += (size_t)fmt_uint(dst + pos, (unsigned long long)fhz, 10, '0');
+    dst[pos++] = ' '; dst[pos++] = 'N'; dst[pos++] = ':';
+    pos += (size_t)fmt_fixed(dst + pos, (double)f->magnitude, 2, 5, true, false);
+    pos += (size_t)fmt_fixed(dst + pos, (double)f->noise, 2, 6, true, true);
+    dst[pos++] = ' '; dst[pos++] = 'I'; dst[pos++] = ':';
+    pos += (size_t)fmt_uint(dst + pos, (unsigned long long)f->id, 11, '0');
+    dst[pos++] = ' ';
+    pos += (size_t)fmt_uint(dst + pos, (unsigned long long)f->confidence, 3, ' ');
+    dst[pos++] = '%'; dst[pos++] = ' ';
+    pos += (size_t)fmt_fixed(dst + pos, (double)f->level, 5, 0, false, false);
+    dst[pos++] = ' ';
+    pos += (size_t)fmt_uint(dst + pos, (unsigned long long)pay, 3, ' ');
+    dst[pos++] = ' ';
     for (int i = 0; i < f->n_bits && pos + 2 < cap; i++) dst[pos++] = (char)('0' + bits[i]);
     if (pos + 1 < cap) dst[pos++] = '\n';
     dst[pos] = 0;
     return (int)pos;
+}
+
+// test hook: printf's "%[+][0]<width>.<decimals>f" by the exact path above
+extern "C" int ir_format_fixed(char *dst, double x, int decimals, int width, int zero_pad, int plus) {
+    return fmt_fixed(dst, x, decimals, width, zero_pad != 0, plus != 0);
 }
 
 // demod_frame_t equivalents (qpsk_demod.c:505-527) of one finished wave, on the host, in double
@@ -771,6 +860,8 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     if (!p) { set_err("null pipeline"); return -1; }
     if (fmt < 0 || fmt > 2) { set_err("bad sample format"); return -1; }
     CK(cudaSetDevice(p->dev));
+    const auto t_run0 = std::chrono::steady_clock::now();
+    auto run_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_run0).count(); };
     const DetConfig &dc = p->dc;
     const int N = dc.N;
     const size_t bps = (size_t)fmt_bytes(fmt);
@@ -938,6 +1029,7 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
     struct SinkGuard { decltype(finish_sink) &f; ~SinkGuard() { f(); } } sink_guard{finish_sink};   // (every early return joins)
     int follow_rc = 0;
     const bool host_dbg = getenv("IR_CHUNK_DEBUG") != nullptr;
+    const double t_enqueued = run_ms();
     const auto t_host0 = std::chrono::steady_clock::now();
     auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count(); };
     for (size_t ci = 0; ci < p->chunks.size() && follow_rc == 0; ci++) {
@@ -971,10 +1063,15 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
          wi < p->waves.size(); wi++)
         CK(cudaStreamWaitEvent(p->st_burst, p->waves[wi].e_done, 0));     // the last wave of every demod stream
     CK(cudaEventRecord(e_end, p->st_burst));
+    const double t_followed = run_ms();
     finish_sink();
     if (sink_err.load()) { set_err(sink_msg); return -1; }
+    const double t_sunk = run_ms();
     if (host_iq) CK(cudaStreamSynchronize(p->st_copy));
     CK(cudaStreamSynchronize(p->st_burst));
+    if (host_dbg)
+        fprintf(stderr, "host: everything enqueued at %.3f ms after the call, last wave launched at %.3f, sink thread done at %.3f, "
+                        "device idle at %.3f\n", t_enqueued, t_followed, t_sunk, run_ms());
     memset(p->scan_stats, 0, sizeof(p->scan_stats));
     if (p->scan_mode == 0)
         CK(cudaMemcpy(p->scan_stats, p->d_ctl.p->stats, sizeof(p->scan_stats), cudaMemcpyDeviceToHost));

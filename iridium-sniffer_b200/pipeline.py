@@ -137,6 +137,8 @@ def load_library() -> C.CDLL:
     L.ir_host_free.argtypes = [C.c_void_p]
     L.ir_plan_chunks.restype = C.c_long
     L.ir_plan_chunks.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t), C.c_size_t]
+    L.ir_format_fixed.restype = C.c_int
+    L.ir_format_fixed.argtypes = [C.c_char_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]
     L.ir_pipeline_scan_stats.restype = C.c_int
     L.ir_pipeline_scan_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
     L.ir_classify_frames.restype = C.c_int
@@ -282,7 +284,7 @@ EXPORTED_SYMBOLS = [
     "ir_pipeline_reset", "ir_pipeline_run_host", "ir_pipeline_run_device", "ir_pipeline_results",
     "ir_pipeline_copy_mag", "ir_pipeline_copy_frame_samples", "ir_pipeline_copy_decimated",
     "ir_pipeline_copy_burst_samples", "ir_format_raw", "ir_pipeline_format_raw_all", "ir_host_alloc",
-    "ir_host_free", "ir_pipeline_scan_stats", "ir_plan_chunks", "ir_classify_frames", "ir_pipeline_classify",
+    "ir_host_free", "ir_format_fixed", "ir_pipeline_scan_stats", "ir_plan_chunks", "ir_classify_frames", "ir_pipeline_classify",
     "ir_format_lcw", "ir_format_ida", "ir_pipeline_format_parsed_all", "ir_pipeline_last_classify_ms",
     "ir_fill_decoded_frame", "ir_fill_ida_burst",
     "ir_block_halo", "ir_block_tail", "ir_plan_blocks", "ir_pipeline_set_origin", "ir_merge_blocks",

@@ -76,3 +76,34 @@ def test_chunk_plan_edges():
     assert e == [Mi, 2 * Mi, 3 * Mi, 3 * Mi + 12345]
     e = _plan(L, 40_000_000, 1000, 16384)                      # chunk below one frame is rounded up to one frame
     assert e[0] == 16384 and e[-1] == 40_000_000
+
+
+def test_fixed_point_formatter_is_printf():
+    """ir_format_fixed (what the RAW: line is built with) == printf's %f on the line's four conversions, over random
+    values, values next to rounding boundaries, exact ties (dyadic fractions: ties go to even) and the tiny / huge
+    ranges where it hands over to printf"""
+    _, L = _lib()
+    rng = np.random.default_rng(7)
+    buf = C.create_string_buffer(512)
+    cases = []
+    for dec, width, zp, plus, fmt in ((4, 12, 1, 0, "%012.4f"), (2, 5, 1, 0, "%05.2f"), (2, 6, 1, 1, "%+06.2f"), (5, 0, 0, 0, "%.5f")):
+        xs = list(rng.uniform(-200.0, 200.0, 4000)) + list(rng.uniform(0, 6.0e7, 4000)) + list(rng.uniform(-1e-4, 1e-4, 2000))
+        xs += list(np.float32(rng.uniform(-150, 60, 4000)).astype(np.float64))                     # float fields, promoted
+        xs += [k / 2.0 ** j for k in range(-40, 41) for j in range(0, 9)]                           # exact ties and friends
+        step = 10.0 ** -dec
+        for k in range(-300, 300, 7):
+            for e in (-1, 0, 1):
+                xs.append(np.nextafter(k * step + step / 2, np.inf if e > 0 else -np.inf) if e else k * step + step / 2)
+        xs += [0.0, -0.0, 1e15, -1e15, 9.007199254740991e15, 1e16, 1e300, 5e-324, 0.99999999, 9.999995, 99.995, 0.125, 0.375, 2.5, 3.5]
+        for x in xs:
+            cases.append((float(x), dec, width, zp, plus, fmt))
+    bad = 0
+    for x, dec, width, zp, plus, fmt in cases:
+        k = L.ir_format_fixed(buf, x, dec, width, zp, plus)
+        got = buf.value.decode()
+        want = fmt % x
+        assert k == len(got)
+        if got != want:
+            bad += 1
+            assert bad < 1, (x, fmt, got, want)
+    assert len(cases) > 50000

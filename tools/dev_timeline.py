@@ -21,4 +21,9 @@ for i in range(runs):
     p.run_device_raw(iq.data_ptr() + off * 8, n, "cf32")
     st = p.stats()
     print({k: round(v, 3) if isinstance(v, float) else v for k, v in st.items()})
+import json
+r = p.results()
+fs = 10_000_000
+print("RUNJSON " + json.dumps({"det_frames": n // 8192, "bursts": len(r.bursts),
+      "tiles": sum((b["dec_len"] + 255) // 256 for b in r.bursts if b["dec_len"] >= 100), "samples": n}))
 p.close()
