@@ -134,35 +134,57 @@ __device__ __forceinline__ void fir_chains(const float2 *__restrict__ sp, const 
 // imaginary accumulator of an output with the shared tap -- each lane of the pair is an IEEE fma with a single
 // rounding, so the sums are the ones above, bit for bit.  (FFMA2 takes the tap as a scalar operand broadcast to
 // both halves -- `FFMA2 Rd, Rh.F32, Rx.F32x2.HI_LO, Racc.F32x2.HI_LO` -- so the tap registers stay 80.)
+// The first and the last block of iterations are separate bodies that leave out the FMAs on zero taps (21 % of them).
+// One block of 8 iterations of the packed chains.  MODE 1: every (iteration, output) pair.  MODE 0 (the first block)
+// and MODE 2 (the last): the pairs whose tap block lies inside the filter -- output i lags output 0 by i iterations, so
+// in the first block it has not started before iteration i and in the last it has ended after iteration i + NB - 1;
+// outside that range the rotating registers hold zero taps and fma(0, x, acc) == acc: the FMA is dropped, not the sum.
+template <int DEC, int MODE, int T>
+__device__ __forceinline__ void fir_block_f2(const float2 *__restrict__ sp, const float *__restrict__ hp,
+                                             float (&G)[8][DEC / 4], float2 (&acc)[IR_FIR_R]) {
+    constexpr int D4 = DEC / 4;
+    constexpr int NIT = fir_nit<DEC>();
+    constexpr int NB = (IR_INPUT_NTAPS / 4 + D4 - 1) / D4;            // tap blocks of a chain
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const int it = 8 * T + u;
+        if (MODE != 1 && it >= NIT) break;
+        if (MODE == 1 && it >= NIT) break;
+#pragma unroll
+        for (int r = 0; r < D4; r++) G[u][r] = hp[DEC * u + 4 * r];
+#pragma unroll
+        for (int r = 0; r < D4; r++) {
+            const int ql = D4 * u + r;
+            const float2 x = sp[4 * ql + (ql >> 2)];
+#pragma unroll
+            for (int i = 0; i < IR_FIR_R; i++) {
+                const bool live = MODE == 1 || (it - i >= 0 && it - i < NB);
+                if (live) acc[i] = __ffma2_rn(make_float2(G[(u - i + 8) & 7][r], G[(u - i + 8) & 7][r]), x, acc[i]);
+            }
+        }
+    }
+}
 template <int DEC>
 __device__ __forceinline__ void fir_chains_f2(const float2 *__restrict__ sp, const float *__restrict__ hp,
                                               float2 (&acc)[IR_FIR_R]) {
     constexpr int D4 = DEC / 4;
     constexpr int NIT = fir_nit<DEC>();
+    constexpr int NT = (NIT + 7) / 8;
     constexpr int ROW = IR_FIR_R * DEC + IR_FIR_R * DEC / 16 + 1;
-    float2 G[8][D4];
+    static_assert(NT == 3 || NT == 4, "block structure below");
+    float G[8][D4];
 #pragma unroll
     for (int a = 0; a < 8; a++)
 #pragma unroll
-        for (int r = 0; r < D4; r++) G[a][r] = make_float2(0.0f, 0.0f);
-    for (int T = 0; T < (NIT + 7) / 8; T++) {
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            if (8 * T + u < NIT) {                                     // warp-uniform
-#pragma unroll
-                for (int r = 0; r < D4; r++) { const float h = hp[DEC * u + 4 * r]; G[u][r] = make_float2(h, h); }
-#pragma unroll
-                for (int r = 0; r < D4; r++) {
-                    const int ql = D4 * u + r;
-                    const float2 x = sp[4 * ql + (ql >> 2)];
-#pragma unroll
-                    for (int i = 0; i < IR_FIR_R; i++) acc[i] = __ffma2_rn(G[(u - i + 8) & 7][r], x, acc[i]);
-                }
-            }
-        }
-        sp += ROW;
-        hp += 8 * DEC;
+        for (int r = 0; r < D4; r++) G[a][r] = 0.0f;
+    fir_block_f2<DEC, 0, 0>(sp, hp, G, acc);
+    sp += ROW; hp += 8 * DEC;
+#pragma unroll 1
+    for (int T = 1; T < NT - 1; T++) {                                // (iterations 8..NIT-9+: every pair inside the filter,
+        fir_block_f2<DEC, 1, 1>(sp, hp, G, acc);                      //  or a handful of zero-tap FMAs not worth a third body)
+        sp += ROW; hp += 8 * DEC;
     }
+    fir_block_f2<DEC, 2, NT - 1>(sp, hp, G, acc);
 }
 
 template <int FMT, int DEC>

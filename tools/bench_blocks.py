@@ -5,8 +5,8 @@ pipeline (ir_pipeline_set_origin + ir_pipeline_run_device), frame lists gathered
 times and the final gather of the frames.  Rank 0 also runs the whole recording through its own pipeline once and says
 how the merge compares (frames matched, bits equal).  Every rank builds the same seeded recording on its own GPU.
 
-Prints one JSON line in bench.py's vocabulary with "scaling": "strong".  A developer aid for profiles/, not the
-driver's bench contract; written after round 1's GPU minutes were spent -- no measured line exists yet.
+Prints one JSON line in bench.py's vocabulary with "scaling": "strong".  A developer aid for profiles/ (measured lines:
+profiles/r2*_blocks_strong_n*.json, table in DESIGN.md section 7), not the driver's bench contract.
 
     python tools/bench_blocks.py [--seconds 60] [--steps 5] [--warmup 3]                         # one GPU, one block
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \\
