@@ -496,11 +496,11 @@ cudaError_t launch_demod(const ChainOut *co, int n_bursts, const float2 *frames,
                          DemodOut *out, uint8_t *bits, float *llr, int max_frame, cudaStream_t st) {
     if (n_bursts <= 0) return cudaSuccess;
     // Which slicer: IR_DEMOD=thread | group forces one; by default the frames-in-shared-memory kernel takes the small
-    // launches (a tail wave, a single frame through qpsk_demod(): latency is what counts, a few CTAs hold a few SMs)
+    // launches (<= 512 frames: a tail wave, a single frame through qpsk_demod(): latency is what counts, a few CTAs hold a few SMs)
     // and the one-thread-per-frame kernel the big waves (SIMT across 32 frames; no shared memory, so it never keeps
     // the FIR / chain CTAs of later waves off an SM -- measured in-run).
     static const char *mode = getenv("IR_DEMOD");
-    const bool legacy = mode ? strcmp(mode, "thread") == 0 : n_bursts > 256;
+    const bool legacy = mode ? strcmp(mode, "thread") == 0 : n_bursts > 512;
     if (legacy) {
         k_demod<<<(n_bursts + 31) / 32, 32, 0, st>>>(co, n_bursts, frames, use_gardner, out, bits, llr);
         return cudaGetLastError();

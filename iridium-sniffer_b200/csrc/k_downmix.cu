@@ -556,7 +556,8 @@ __device__ __forceinline__ float2 unit_phasor(float ph) {
 struct ChainShared {
     float2 data[3 * (IR_CORR_N + 16)];        // >= fft_data_elems<12>()
     float2 tw12[fft_tw_elems<12>()];
-    float2 tw11[fft_tw_elems<11>()];
+    float2 tw11c[fft_twc_elems<11>()];        // compact per-stage tables of the 2048-pt FFTs (the 8.7 KB full table of
+                                              // their first pass is read from global memory: 70 KB per CTA = 3 CTAs/SM)
     ArgMax red[32];
     float redf[32];
     int redi[32];
@@ -611,7 +612,7 @@ k_chain(const BurstParam *__restrict__ bp, int n_bursts, const float2 *__restric
         return;
     }
     for (int i = tid; i < fft_tw_elems<12>(); i += nth) S.tw12[i] = tw4096[i];
-    for (int i = tid; i < fft_tw_elems<11>(); i += nth) S.tw11[i] = tw2048[i];
+    for (int i = tid; i < fft_twc_elems<11>(); i += nth) S.tw11c[i] = tw2048[fft_twfull_elems<11>() + i];
     const int n_noise = c_ntaps[1], n_box = c_ntaps[2], n_rrc = c_ntaps[3];
 
     // 2b: noise-limiting low-pass, centred (burst_downmix.c:683-698)
@@ -729,15 +730,15 @@ k_chain(const BurstParam *__restrict__ bp, int n_bursts, const float2 *__restric
     for (int p = tid; p < IR_CORR_N; p += nth)
         F[fft_pad<11>(p)] = p < sl ? A[p] : make_float2(0.0f, 0.0f);
     __syncthreads();
-    fft_smem<11, false, false>(F, S.tw11, [&](int p) { return F[fft_pad<11>(p)]; }, [](int, float2) {});
+    fft_smem2<11, false, false, true>(F, tw2048, S.tw11c, [&](int p) { return F[fft_pad<11>(p)]; }, [](int, float2) {});
     for (int k = tid; k < IR_CORR_N; k += nth) {
         const float2 f = fft_result<11>(F, k);
         PD[fft_pad<11>(k)] = cmul(f, sync_dl[k]);
         PU[fft_pad<11>(k)] = cmul(f, sync_ul[k]);
     }
     __syncthreads();
-    fft_smem<11, true, false>(PD, S.tw11, [&](int p) { return PD[fft_pad<11>(p)]; }, [](int, float2) {});
-    fft_smem<11, true, false>(PU, S.tw11, [&](int p) { return PU[fft_pad<11>(p)]; }, [](int, float2) {});
+    fft_smem2<11, true, false, true>(PD, tw2048, S.tw11c, [&](int p) { return PD[fft_pad<11>(p)]; }, [](int, float2) {});
+    fft_smem2<11, true, false, true>(PU, tw2048, S.tw11c, [&](int p) { return PU[fft_pad<11>(p)]; }, [](int, float2) {});
     ArgMax bd{-1.0f, 0x7fffffff}, bu{-1.0f, 0x7fffffff};
     for (int i = tid; i < sl; i += nth) {
         bd = argmax_pick(bd, ArgMax{mag2_plain(fft_result<11>(PD, i)), i});
