@@ -14,7 +14,10 @@
 #define IR_STREAM_MAX_FRAMES 4096   // frames per launch of the streaming state machine
 #define IR_SEG_MAX_FRAMES 16384     // frames per chunk of the segmented state machine (k_detect_seg.cu)
 #define IR_SEG_LEN 64              // frames per segment (one warp each); multiple of 32
-#define IR_SEG_GONE 256             // gone records a segment can hold (more: the chunk falls back)
+#define IR_SEG_GONE 512             // gone records a segment can hold (more: the chunk falls back)
+#define IR_SEG_LIST 512             // bursts alive at a segment cut / inside a segment walked by the generic walker
+#define IR_SEG_OVF (IR_SEG_LIST - 32)   // ... of which 32 live in SegState, the rest in the overflow lists
+#define IR_SEG_PCAP 2048            // candidate peaks of one frame (generic walker)
 #define IR_SEG_ROUNDS 12            // rounds enqueued per chunk (a chunk without a fixed point by then falls back)
 // guard band of the bitmaps: valid while every baseline stays inside [LO, HI] x its reference value.
 // LO also sets how often pure noise lands in the uncertain band (e^(-23.1*LO) per bin and frame at 16 dB).
@@ -120,7 +123,7 @@ struct SegCtl {
     unsigned int guard_bad, n_gone0, reclass, reclass_prev;
     unsigned long long index0, next_id0;
     unsigned long long stats[8];   // 0 chunks kept, 1 chunks bailed, 2 rounds, 3 event frames (all rounds), 4 snapshots, 5 quiet frames,
-                                   // 7 bitmap rebuilds (a baseline left its band)
+                                   // 6 segments walked by the generic walker (all rounds), 7 bitmap rebuilds (a baseline left its band)
 };
 struct SegBuffers {                // device memory of the segmented scan, owned by the pipeline
     SegCtl *ctl = nullptr;
@@ -129,6 +132,10 @@ struct SegBuffers {                // device memory of the segmented scan, owned
     int *wpre = nullptr, *qlist = nullptr, *slotv = nullptr, *fslot = nullptr, *ncreate = nullptr, *ngone = nullptr;
     int *segbail = nullptr, *stch = nullptr, *cpre = nullptr, *gpre = nullptr;
     GoneBurst *glist = nullptr;
+    SegBurst *ovfA = nullptr, *ovfB = nullptr, *gwork = nullptr;      // lists longer than 32, the generic walker's work list
+    float *gprel = nullptr;
+    int *gpbin = nullptr;
+    uint32_t *seggen = nullptr;                                       // [s]: segment s went to the generic walker
     float *snap = nullptr, *bfinal = nullptr, *qmag = nullptr, *glo = nullptr, *ghi = nullptr;
     int slot_cap = 0, frames_cap = 0;
 };

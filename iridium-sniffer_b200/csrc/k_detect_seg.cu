@@ -38,6 +38,7 @@
 
 #include "ir_device.cuh"
 #include "ir_internal.h"
+#include "seg_generic.cuh"
 
 namespace ir {
 
@@ -60,6 +61,7 @@ struct WkShared {
     uint32_t fvs[SMAXW];
     unsigned short cw[SMAXW];
     int fslot[IR_SEG_LEN];
+    SegGenOut gout;                    // the generic walker's result and its shared candidate counter
 };
 // (after it in shared memory: cbin / crel / cbase [smaxc<WPL>()], then the ring)
 
@@ -143,7 +145,7 @@ __device__ int block_excl_scan(int *arr, int n, int *sh /* >= 33 ints */) {
 __global__ void __launch_bounds__(256)
 k_seg_begin(DetConfig c, const DetState *__restrict__ gs, SegCtl *ctl, SegState *stA, SegState *stB, uint32_t *qw,
             int *ncreate, int *ngone, int *segbail, int *stch, uint32_t *valid_g, const float *__restrict__ ref,
-            float *glo_g, float *ghi_g, int F, int S) {
+            float *glo_g, float *ghi_g, SegBurst *ovfA, SegBurst *ovfB, uint32_t *seggen, int F, int S) {
     const int t = threadIdx.x;
     const int N = c.N, W = N >> 5;
     if (t == 0) {
@@ -154,13 +156,13 @@ k_seg_begin(DetConfig c, const DetState *__restrict__ gs, SegCtl *ctl, SegState 
         ctl->index0 = gs->index; ctl->next_id0 = gs->next_id; ctl->sq0 = gs->squelch_count;
         ctl->n_gone0 = gs->n_gone; ctl->hist_idx0 = gs->hist_idx;
         if (!gs->primed) ctl->hard_bail = 1;
-        if (gs->n_act > 32) ctl->hard_bail = 7;
-        const int na = gs->n_act > 32 ? 0 : gs->n_act;
+        if (gs->n_act > IR_SEG_LIST) ctl->hard_bail = 7;
+        const int na = gs->n_act > IR_SEG_LIST ? 0 : gs->n_act;
         stA[0].n_act = na; stB[0].n_act = na;
     }
-    const int na = gs->n_act > 32 ? 0 : gs->n_act;
-    if (t < na) {
-        const ActBurst b = gs->act[t];
+    const int na = gs->n_act > IR_SEG_LIST ? 0 : gs->n_act;
+    for (int i = t; i < na; i += blockDim.x) {
+        const ActBurst b = gs->act[i];
         const unsigned long long index0 = gs->index;
         SegBurst sb;
         sb.id = b.id; sb.start = b.start; sb.last0 = b.last_active; sb.cb = b.center_bin; sb.rel = b.peak_rel; sb.base = b.base_at_create;
@@ -169,10 +171,11 @@ k_seg_begin(DetConfig c, const DetState *__restrict__ gs, SegCtl *ctl, SegState 
         sb.lah = NONE;
         const long long tl = (long long)(b.start + (unsigned long long)c.max_burst_len) - (long long)index0;
         sb.tl = c.max_burst_len <= 0 ? BIGF : (tl < 0 ? -1 : (int)min((long long)BIGF, tl / N));
-        stA[0].b[t] = sb; stB[0].b[t] = sb;
+        if (i < 32) { stA[0].b[i] = sb; stB[0].b[i] = sb; }
+        else { ovfA[i - 32] = sb; ovfB[i - 32] = sb; }
     }
     for (int s = 1 + t; s <= S; s += blockDim.x) { stA[s].n_act = 0; stB[s].n_act = 0; }
-    for (int s = t; s < S; s += blockDim.x) { ncreate[s] = 0; ngone[s] = 0; segbail[s] = 0; }
+    for (int s = t; s < S; s += blockDim.x) { ncreate[s] = 0; ngone[s] = 0; segbail[s] = 0; seggen[s] = 0u; }
     // [parity][s]: the list at segment s's first frame changed in the round of that parity (segment 0's never does)
     for (int s = t; s < 2 * (S + 1); s += blockDim.x) stch[s] = (s == 0 || s == S + 1) ? 0 : 1;
     for (int w = t; w < (F + 31) / 32; w += blockDim.x) qw[w] = 0u;
@@ -453,13 +456,33 @@ k_seg_reclass(SegCtl *ctl, const float *__restrict__ mag, const float *__restric
     }
 }
 
+// the 32 lanes of a segment's warp, for seg_generic.cuh
+struct SegLanesWarp {
+    static constexpr int L = 32;
+    __device__ int lane() const { return (int)(threadIdx.x & 31u); }
+    __device__ void sync() const { __syncwarp(); }
+    __device__ bool any(bool p) const { return __any_sync(FULL, p) != 0; }
+    __device__ int sum(int v) const { return __reduce_add_sync(FULL, v); }
+    __device__ int max(int v) const { return __reduce_max_sync(FULL, v); }
+    __device__ uint32_t ballot(bool p) const { return __ballot_sync(FULL, p); }
+    __device__ void and_word(uint32_t *p, uint32_t m) const { atomicAnd(p, m); }
+    __device__ int inc(int *p) const { return atomicAdd(p, 1); }
+    __device__ void best(float &r, int &b, int &i) const {
+        for (int off = 16; off; off >>= 1) {
+            const float o_r = __shfl_xor_sync(FULL, r, off);
+            const int o_b = __shfl_xor_sync(FULL, b, off), o_i = __shfl_xor_sync(FULL, i, off);
+            if (o_i >= 0 && (i < 0 || o_r > r || (o_r == r && o_b < b))) { r = o_r; b = o_b; i = o_i; }
+        }
+    }
+};
+
 // =========================================================================== round: walk
 template <int WPL>
 __global__ void __launch_bounds__(32, 1)
 k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint32_t *__restrict__ xu_c,
            const float *__restrict__ snap, const int *__restrict__ fslot_g, const uint32_t *__restrict__ valid_g,
            SegState *stA, SegState *stB, uint32_t *qw_g, int *ncreate, int *ngone, int *segbail, int *stch,
-           GoneBurst *glist) {
+           GoneBurst *glist, SegBurst *ovfA, SegBurst *ovfB, SegBurst *gwork, float *gprel, int *gpbin, uint32_t *seggen) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     WkShared &S = *reinterpret_cast<WkShared *>(smem_raw);
     if (ctl->finished || ctl->hard_bail) return;
@@ -472,6 +495,15 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
     const int rnd = ctl->round - 1, par = rnd & 1;            // this round (k_seg_index counted it already)
     const SegState *cur = par ? stB : stA;
     SegState *nxt = par ? stA : stB;
+    // bursts 32.. of a list (a segment cut with more than 32 alive: only the generic walker makes or reads those)
+    const SegBurst *ovf_cur = par ? ovfB : ovfA;
+    SegBurst *ovf_nxt = par ? ovfA : ovfB;
+    auto list_get = [&](const SegState *st, const SegBurst *ov, int sgi, int i) -> SegBurst {
+        return i < 32 ? st[sgi].b[i] : ov[(size_t)sgi * IR_SEG_OVF + (i - 32)];
+    };
+    auto list_put = [&](SegState *st, SegBurst *ov, int sgi, int i, const SegBurst &b) {
+        if (i < 32) st[sgi].b[i] = b; else ov[(size_t)sgi * IR_SEG_OVF + (i - 32)] = b;
+    };
     const int Sp1 = ctl->S + 1;
     const int *stch_prev = stch + (par ^ 1) * Sp1;            // [s]: the list at segment s's first frame changed last round
     int *stch_now = stch + par * Sp1;
@@ -481,9 +513,9 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
     // (bitmaps rebuilt this round or the last: the snapshot slots moved too; a segment that gave up: its reason may be gone)
     if (rnd > 0 && !ctl->reclass && !ctl->reclass_prev && segbail[seg] == 0 && stch_prev[seg] == 0 &&
         f0 + n_frames <= ctl->qfc[par ^ 1]) {
-        const SegState &old = cur[seg + 1];
-        if (lane < old.n_act) nxt[seg + 1].b[lane] = old.b[lane];
-        if (lane == 0) { nxt[seg + 1].n_act = old.n_act; stch_now[seg + 1] = 0; }
+        const int on = cur[seg + 1].n_act;
+        for (int i = lane; i < on; i += 32) list_put(nxt, ovf_nxt, seg + 1, i, list_get(cur, ovf_cur, seg + 1, i));
+        if (lane == 0) { nxt[seg + 1].n_act = on; stch_now[seg + 1] = 0; }
         return;
     }
     const float *mag = mag_c + (size_t)f0 * N;
@@ -520,6 +552,8 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
         const int w0 = (r_cb - 1) >> 5;
         b_o0 = (uint32_t)w0 * 4u; b_o1 = (uint32_t)min(w0 + 1, W - 1) * 4u; b_sh = (r_cb - 1) & 31; b_msk = 7u;
     };
+    const int n_start = n_act;
+    if (n_act > 32 || seggen[seg]) { bail = 7; n_act = 0; }   // more than the lanes hold (now, or inside the segment last round): the generic walker's
     if (lane < n_act) {
         const SegBurst b = cur[seg].b[lane];
         r_have = true;
@@ -890,10 +924,59 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
     }
     // bulk copies still in flight must land before the shared memory is released
     for (; blk_landed < blk_issued; blk_landed++) mbar_wait_a(bars_a + 8u * (uint32_t)(blk_landed % RB), (uint32_t)((blk_landed / RB) & 1));
+    // ---- more than 32 bursts alive somewhere in this segment: walk it again the plain way (seg_generic.cuh), from
+    // the same start list, on lane 0; the other lanes wait.  Its outputs replace the fast walker's.
+    bool generic = false;
+    if (bail == 4 || bail == 5 || bail == 7) {
+        generic = true;
+        if (lane == 0) seggen[seg] = 1u;                     // next round: straight here
+        SegBurst *work = gwork + (size_t)seg * IR_SEG_LIST;
+        for (int i = lane; i < n_start && i < IR_SEG_LIST; i += 32) work[i] = list_get(cur, ovf_cur, seg, i);
+        __syncwarp();
+        bail = 5;
+        if (n_start <= IR_SEG_LIST) {
+            SegGenArgs ga;
+            ga.N = N; ga.half_bw = c.half_bw; ga.max_bursts = c.max_bursts; ga.pre_len = c.pre_len; ga.post_len = c.post_len;
+            ga.max_burst_len = c.max_burst_len; ga.thr = c.thr; ga.seg = seg; ga.f0 = f0; ga.n_frames = n_frames;
+            ga.index0 = index0; ga.sq_start = max(ctl->sq0 - f0, 0);
+            ga.xu = xu_c; ga.mag = mag_c; ga.snap = snap; ga.fslot = fslot_g; ga.valid = valid_g;
+            ga.prel = gprel + (size_t)seg * IR_SEG_PCAP; ga.pbin = gpbin + (size_t)seg * IR_SEG_PCAP; ga.pcap = IR_SEG_PCAP;
+            bail = seg_walk_generic_t(SegLanesWarp{}, ga, work, n_start, IR_SEG_LIST, gl, IR_SEG_GONE, S.fvs, S.gout);
+        }
+        __syncwarp();
+    }
     // ---- outputs of this segment: quiet flags, burst list at its last frame, counts
     int changed = 0, st_changed = 0;
     const int nqw = (n_frames + 31) / 32, qw0 = f0 >> 5;
-    if (!bail) {
+    if (!bail && generic) {
+        const int n_end = S.gout.n_end;
+        int fc = 0x7fffffff;
+        if (lane < nqw) {
+            const uint32_t was = qw_g[qw0 + lane], now = S.gout.qbits[lane];
+            if (was != now) { changed = 1; qw_g[qw0 + lane] = now; fc = f0 + (lane << 5) + __ffs(was ^ now) - 1; }
+        }
+        fc = __reduce_min_sync(FULL, fc);
+        if (lane == 0 && fc != 0x7fffffff) atomicMin(&ctl->qfc[par], fc);
+        const int on = cur[seg + 1].n_act;
+        if (on != n_end) st_changed = 1;
+        const SegBurst *work = gwork + (size_t)seg * IR_SEG_LIST;
+        for (int i = lane; i < n_end; i += 32) {
+            const SegBurst b = work[i];
+            if (i < on) {
+                const SegBurst o = list_get(cur, ovf_cur, seg + 1, i);
+                if (o.id != b.id || o.start != b.start || o.last0 != b.last0 || o.cb != b.cb ||
+                    __float_as_uint(o.rel) != __float_as_uint(b.rel) || __float_as_uint(o.base) != __float_as_uint(b.base) ||
+                    o.dl != b.dl || o.lah != b.lah || o.tl != b.tl)
+                    st_changed = 1;
+            }
+            list_put(nxt, ovf_nxt, seg + 1, i, b);
+        }
+        if (lane == 0) {
+            nxt[seg + 1].n_act = n_end; ncreate[seg] = S.gout.n_create; ngone[seg] = S.gout.n_gone;
+            if (segbail[seg]) { segbail[seg] = 0; changed = 1; }
+            atomicAdd(&ctl->stats[6], 1ull);
+        }
+    } else if (!bail) {
         flush_quiet();
         int fc = 0x7fffffff;                                  // first frame whose quiet flag changed
         if (lane < nqw) {
@@ -930,10 +1013,10 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
         }
     } else {
         // keep the previous round's view of this segment (a bail that only a wrong start produced goes away)
-        const SegState &old = cur[seg + 1];
-        if (lane < old.n_act) nxt[seg + 1].b[lane] = old.b[lane];
+        const int on = cur[seg + 1].n_act;
+        for (int i = lane; i < on; i += 32) list_put(nxt, ovf_nxt, seg + 1, i, list_get(cur, ovf_cur, seg + 1, i));
         if (lane == 0) {
-            nxt[seg + 1].n_act = old.n_act; ncreate[seg] = 0; ngone[seg] = 0;
+            nxt[seg + 1].n_act = on; ncreate[seg] = 0; ngone[seg] = 0;
             if (segbail[seg] != bail) { segbail[seg] = bail; changed = 1; }
         }
     }
@@ -951,7 +1034,7 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
 __global__ void __launch_bounds__(256)
 k_seg_commit(DetConfig c, SegCtl *ctl, DetState *gs, const SegState *stA, const SegState *stB, const int *ncreate,
              const int *ngone, const int *segbail, int *cpre, int *gpre, const GoneBurst *__restrict__ glist,
-             GoneBurst *__restrict__ gone, uint32_t gone_cap) {
+             const SegBurst *ovfA, const SegBurst *ovfB, GoneBurst *__restrict__ gone, uint32_t gone_cap) {
     __shared__ int sh[40];
     const int t = threadIdx.x;
     const int S = ctl->S, F = ctl->F;
@@ -1000,13 +1083,14 @@ k_seg_commit(DetConfig c, SegCtl *ctl, DetState *gs, const SegState *stA, const 
     }
     overflow = __syncthreads_or((int)overflow);
     const SegState &e = fin[S];
-    if (t < e.n_act) {
-        const SegBurst b = e.b[t];
+    const SegBurst *ovf_fin = (ctl->round - 1) & 1 ? ovfA : ovfB;
+    for (int i = t; i < e.n_act; i += blockDim.x) {
+        const SegBurst b = i < 32 ? e.b[i] : ovf_fin[(size_t)S * IR_SEG_OVF + (i - 32)];
         ActBurst a;
         a.id = real_id(b.id); a.start = b.start;
         a.last_active = b.lah == NONE ? b.last0 : (unsigned long long)((long long)ctl->index0 + (long long)b.lah * c.N);
         a.center_bin = b.cb; a.peak_rel = b.rel; a.base_at_create = b.base; a.pad = 0;
-        gs->act[t] = a;
+        gs->act[i] = a;
     }
     if (t == 0) {
         gs->hist_idx = (ctl->hist_idx0 + ctl->nq) % c.hist_size;
@@ -1111,7 +1195,7 @@ static cudaError_t launch_walk_t(const DetConfig &c, const SegBuffers &b, const 
         attr_set[dev] = true;
     }
     k_seg_walk<WPL><<<S, 32, smem, st>>>(c, b.ctl, mag, xu, b.snap, b.fslot, b.valid, b.stA, b.stB, b.qw, b.ncreate, b.ngone,
-                                         b.segbail, b.stch, b.glist);
+                                         b.segbail, b.stch, b.glist, b.ovfA, b.ovfB, b.gwork, b.gprel, b.gpbin, b.seggen);
     return cudaGetLastError();
 }
 
@@ -1136,7 +1220,7 @@ cudaError_t launch_detect_scan_seg(const DetConfig &c, DetState *state, float *b
     }
     k_seg_gather_hist<<<256, 256, 0, st>>>(c, state, hist, b.qmag);
     k_seg_begin<<<1, 256, 0, st>>>(c, state, b.ctl, b.stA, b.stB, b.qw, b.ncreate, b.ngone, b.segbail, b.stch, b.valid, ref, b.glo, b.ghi,
-                                   n_frames, S);
+                                   b.ovfA, b.ovfB, b.seggen, n_frames, S);
     // rounds enqueued: a chunk that has no fixed point by then goes to the cluster kernel -- cheap for a short chunk,
     // so short chunks (the 4096-frame pieces of a host run) queue fewer no-op launches
     int rounds = n_frames <= 4096 ? 8 : IR_SEG_ROUNDS;
@@ -1162,8 +1246,8 @@ cudaError_t launch_detect_scan_seg(const DetConfig &c, DetState *state, float *b
         }
         if (e != cudaSuccess) return e;
     }
-    k_seg_commit<<<1, 256, 0, st>>>(c, b.ctl, state, b.stA, b.stB, b.ncreate, b.ngone, b.segbail, b.cpre, b.gpre, b.glist, gone,
-                                     gone_cap);
+    k_seg_commit<<<1, 256, 0, st>>>(c, b.ctl, state, b.stA, b.stB, b.ncreate, b.ngone, b.segbail, b.cpre, b.gpre, b.glist, b.ovfA, b.ovfB,
+                                     gone, gone_cap);
     k_seg_commit_hist<<<148, 256, 0, st>>>(c, b.ctl, base, hist, mag, b.qlist, b.bfinal);
     if (n_launches) *n_launches += 2 + 5 * rounds + 1 + 2;
     return cudaGetLastError();

@@ -572,7 +572,9 @@ class Pipeline:
         d["streaming"] = rc == 1
         d["segmented"] = rc == 2          # launches_* count chunks, "commands" counts rounds
         if rc == 2:
-            d["last_bail_reason"] = d.pop("last_bail_frame")
+            v = d.pop("last_bail_frame")
+            d["last_bail_reason"] = v & 0xFF
+            d["generic_segment_walks"] = v >> 8      # segments with more than 32 bursts alive (all rounds)
         return d
 
     def stats(self) -> dict:

@@ -43,7 +43,11 @@ class Bail(Exception):
 
 class SegScanModel:
     def __init__(self, N, thr, half_bw, pre_len, post_len, max_burst_len, max_bursts, hist_size=512, seg=64,
-                 max_rounds=12):
+                 max_rounds=12, c_walker=None, lanes=MAX_LANES):
+        """c_walker: ctypes handle of tests/seg_generic_host_shim.cpp -- the product's generic segment walker
+        (csrc/seg_generic.cuh) compiled for the host; when given, every segment is walked by IT instead of the numpy
+        walker below (segment length must be the library's IR_SEG_LEN), with `lanes` as the burst capacity."""
+        self.cw, self.lanes = c_walker, lanes
         self.N, self.thr, self.half_bw = N, np.float32(thr), half_bw
         self.pre, self.post, self.max_len, self.max_bursts, self.H = pre_len, post_len, max_burst_len, max_bursts, hist_size
         self.SEG, self.max_rounds = seg, max_rounds
@@ -104,6 +108,8 @@ class SegScanModel:
     # ------------------------------------------------------------------ one segment
     def _walk(self, s, f0, f1, start, mag, X, XU, ver, snaps, index0, sq0):
         """frames [f0, f1) from the burst list `start`; returns (end list, quiet flags, gone, n_create, bail)"""
+        if self.cw is not None:
+            return self._walk_c(s, f0, f1, start, mag, X, XU, ver, snaps, index0, sq0)
         N, thr = self.N, self.thr
         PF = -(-self.post // N)
         PF0 = max(1, -(-(self.post - self.pre) // N))
@@ -181,6 +187,66 @@ class SegScanModel:
         for bst in act:
             bst.pop("x3", None); bst.pop("u3", None); bst.pop("done", None)
         return act, q, gone, ncreate, None
+
+    # ------------------------------------------------------------------ one segment, by the product's C++ walker
+    def _walk_c(self, s, f0, f1, start, mag, X, XU, ver, snaps, index0, sq0):
+        import ctypes as C
+        N, W = self.N, self.N // 32
+        key = (id(X), id(XU))
+        if getattr(self, "_pack_key", None) != key:            # bitmaps of the chunk in the kernels' layout: [XU words][X words]
+            xu = np.empty((X.shape[0], 2 * W), np.uint32)
+            xu[:, :W] = np.packbits(XU, axis=1, bitorder="little").view(np.uint32)
+            xu[:, W:] = np.packbits(X, axis=1, bitorder="little").view(np.uint32)
+            self._xu, self._pack_key = np.ascontiguousarray(xu), key
+            self._valid_w = np.packbits(self.valid, bitorder="little").view(np.uint32).copy()
+        skey = id(snaps)
+        if getattr(self, "_snap_key", None) != skey:           # snapshots as [slots][N] + a slot per frame
+            vers = sorted(snaps)
+            self._snap = np.ascontiguousarray(np.stack([snaps[v] for v in vers]) if vers else np.zeros((1, N), np.float32), np.float32)
+            slot_of = {v: i for i, v in enumerate(vers)}
+            self._fslot = np.array([slot_of.get(int(v), -1) for v in ver], np.int32)
+            self._snap_key = skey
+        CODE = 1 << 63
+        cap = self.lanes
+        Burst = np.dtype([("id", "<u8"), ("start", "<u8"), ("last0", "<u8"), ("cb", "<i4"), ("rel", "<f4"), ("base", "<f4"),
+                          ("dl", "<i4"), ("lah", "<i4"), ("tl", "<i4")])
+        Gone = np.dtype([("id", "<u8"), ("start", "<u8"), ("stop", "<u8"), ("la", "<u8"), ("cb", "<i4"), ("rel", "<f4"),
+                         ("base", "<f4"), ("pad", "<i4")])
+        assert Burst.itemsize == self.cw.segg_sizeof_burst() and Gone.itemsize == self.cw.segg_sizeof_gone()
+        if len(start) > cap:
+            return None, None, None, 0, "more bursts than lanes"
+        work = np.zeros(cap + 1, Burst)
+        NONE = -0x40000000
+
+        def enc(code):
+            return code[1] if code[0] == 0 else CODE | (code[1] << 32) | code[2]
+
+        def dec(v):
+            v = int(v)
+            return (1, (v >> 32) & 0x7fffffff, v & 0xffffffff) if v & CODE else (0, v, 0)
+        for i, b in enumerate(start):
+            work[i] = (enc(b["id"]), b["start"], b["last_active"], b["cb"], b["rel"], b["basec"], b["dl"],
+                       NONE if b["lah"] is None else b["lah"], b["tl"])
+        gl = np.zeros(4096, Gone)
+        counts = (C.c_int * 3)()
+        qb = (C.c_uint32 * 8)()
+        rc = self.cw.segg_walk(N, self.half_bw, self.max_bursts, self.pre, self.post, self.max_len, C.c_float(float(self.thr)),
+                               s, f0, f1 - f0, C.c_longlong(index0 + f0 * N), max(sq0 - f0, 0),
+                               self._xu.ctypes.data_as(C.c_void_p), np.ascontiguousarray(mag, np.float32).ctypes.data_as(C.c_void_p),
+                               self._snap.ctypes.data_as(C.c_void_p), self._fslot.ctypes.data_as(C.c_void_p),
+                               self._valid_w.ctypes.data_as(C.c_void_p), work.ctypes.data_as(C.c_void_p), len(start), cap,
+                               gl.ctypes.data_as(C.c_void_p), len(gl), counts, qb)
+        if rc != 0:
+            return None, None, None, 0, {3: "too long", 4: "peak list", 5: "a 33rd concurrent burst", 6: "squelch",
+                                         9: "missing snapshot", 10: "gone list"}[rc]
+        n_end, n_gone, n_create = counts[0], counts[1], counts[2]
+        act = [dict(id=dec(w["id"]), start=int(w["start"]), last_active=int(w["last0"]), cb=int(w["cb"]), rel=np.float32(w["rel"]),
+                    basec=np.float32(w["base"]), dl=int(w["dl"]), lah=None if int(w["lah"]) == NONE else int(w["lah"]), tl=int(w["tl"]))
+               for w in work[:n_end]]
+        q = np.array([(qb[k >> 5] >> (k & 31)) & 1 for k in range(f1 - f0)], np.uint8)
+        gone = [(dec(g["id"]), int(g["start"]), int(g["stop"]), int(g["la"]), int(g["cb"]), np.float32(g["rel"]), np.float32(g["base"]))
+                for g in gl[:n_gone]]
+        return act, q, gone, n_create, None
 
     @staticmethod
     def _state_key(act):

@@ -13,9 +13,25 @@ msm = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(msm)
 
 
-def _model(P, seg):
+def _model(P, seg, **kw):
     return msm.SegScanModel(P.fft_size, P.threshold_lin, P.burst_width_bins // 2, P.burst_pre_len, P.burst_post_len,
-                            P.max_burst_len, P.max_bursts, P.history_size, seg=seg)
+                            P.max_burst_len, P.max_bursts, P.history_size, seg=seg, **kw)
+
+
+@pytest.fixture(scope="module")
+def c_walker(tmp_path_factory):
+    """the product's generic segment walker (csrc/seg_generic.cuh) compiled for the host"""
+    import ctypes as C
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = str(tmp_path_factory.mktemp("segg") / "libsegg_host.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I/usr/local/cuda/include", "-x", "c++",
+                    os.path.join(here, "seg_generic_host_shim.cpp"), "-o", out], check=True)
+    lib = C.CDLL(out)
+    lib.segg_walk.restype = C.c_int
+    lib.segg_walk.argtypes = [C.c_int] * 6 + [C.c_float] + [C.c_int] * 3 + [C.c_longlong, C.c_int] + [C.c_void_p] * 6 + \
+                             [C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
+    return lib
 
 
 def _oracle(port, iq):
@@ -72,3 +88,38 @@ def test_model_follows_a_moving_noise_floor(port, synth):
     got = m.run(mag, chunk_frames=4096)
     _same(got, want)
     assert m.stats.get("rebuilds", 0) >= 1, m.stats
+
+
+# ---------------------------------------------------------------- the generic walker of the kernels, on the CPU
+def test_generic_walker_equals_oracle(port, rec_small, synth, c_walker):
+    """csrc/seg_generic.cuh -- what k_seg_walk hands a segment with more than 32 bursts to -- walking EVERY segment
+    of the model's rounds: the oracle's burst list, field for field"""
+    seg = c_walker.segg_seg_len()
+    P, mag, want, _ = _oracle(port, rec_small.iq)
+    m = _model(P, seg, c_walker=c_walker, lanes=512)
+    _same(m.run(mag, chunk_frames=4096), want)
+    rec = synth.make_recording(102, duration_s=0.75, n_bursts=8)
+    P, mag, want, _ = _oracle(port, rec.iq)
+    _same(_model(P, seg, c_walker=c_walker, lanes=512).run(mag, chunk_frames=256), want)
+    rec = synth.make_recording(21, duration_s=0.9, n_bursts=10, starts_s=np.linspace(0.05, 0.8, 10))   # moving noise floor
+    P, mag, want, _ = _oracle(port, rec.iq[:-12345])
+    _same(_model(P, seg, c_walker=c_walker, lanes=512).run(mag, chunk_frames=4096), want)
+
+
+def test_generic_walker_on_dense_traffic(port, synth, c_walker):
+    """BASELINE config 4: ~170 bursts alive at once, far beyond the 32 a fast walker holds -- no bail, the oracle's list"""
+    rec = synth.make_dense_recording(1234)
+    P, mag, want, nsq = _oracle(port, rec.iq)
+    assert nsq == 0 and len(want) >= 600
+    m = _model(P, c_walker.segg_seg_len(), c_walker=c_walker, lanes=512)
+    _same(m.run(mag, chunk_frames=4096), want)
+    assert m.stats["max_rounds_seen"] <= 10, m.stats
+
+
+def test_generic_walker_gives_up_where_it_must(port, synth, c_walker):
+    for reason, iq in (("squelch", synth.make_tone_recording(5, 236, 0.02, 0.5)),
+                       ("too long", synth.make_tone_recording(6, 1, 0.13, 0.45, total_s=0.75))):
+        P, mag, _, _ = _oracle(port, iq)
+        with pytest.raises(msm.Bail) as e:
+            _model(P, c_walker.segg_seg_len(), c_walker=c_walker, lanes=512).run(mag)
+        assert e.value.reason == reason, e.value.reason
