@@ -15,7 +15,8 @@
 #define IR_SEG_MAX_FRAMES 16384     // frames per chunk of the segmented state machine (k_detect_seg.cu)
 #define IR_SEG_LEN 64              // frames per segment (one warp each); multiple of 32
 #define IR_SEG_GONE 512             // gone records a segment can hold (more: the chunk falls back)
-#define IR_SEG_LIST 512             // bursts alive at a segment cut / inside a segment walked by the generic walker
+#define IR_SEG_LIST 256             // bursts alive at a segment cut / inside a segment walked by the generic walker
+                                    // (its list lives in the walker's shared memory; max_bursts squelches at 200-240)
 #define IR_SEG_OVF (IR_SEG_LIST - 32)   // ... of which 32 live in SegState, the rest in the overflow lists
 #define IR_SEG_PCAP 2048            // candidate peaks of one frame (generic walker)
 #define IR_SEG_ROUNDS 12            // rounds enqueued per chunk (a chunk without a fixed point by then falls back)
@@ -132,9 +133,8 @@ struct SegBuffers {                // device memory of the segmented scan, owned
     int *wpre = nullptr, *qlist = nullptr, *slotv = nullptr, *fslot = nullptr, *ncreate = nullptr, *ngone = nullptr;
     int *segbail = nullptr, *stch = nullptr, *cpre = nullptr, *gpre = nullptr;
     GoneBurst *glist = nullptr;
-    SegBurst *ovfA = nullptr, *ovfB = nullptr, *gwork = nullptr;      // lists longer than 32, the generic walker's work list
-    float *gprel = nullptr;
-    int *gpbin = nullptr;
+    SegBurst *ovfA = nullptr, *ovfB = nullptr;                        // bursts 32.. of the lists at the segment cuts
+    unsigned long long *gkeys = nullptr;                              // [S][IR_SEG_PCAP] candidate peaks of the generic walker
     uint32_t *seggen = nullptr;                                       // [s]: segment s went to the generic walker
     float *snap = nullptr, *bfinal = nullptr, *qmag = nullptr, *glo = nullptr, *ghi = nullptr;
     int slot_cap = 0, frames_cap = 0;
@@ -224,6 +224,9 @@ cudaError_t launch_detect_classify(const float *mag, const float *base, float th
 bool seg_scan_supported(const DetConfig &c);
 cudaError_t launch_detect_seg_prime(const DetConfig &c, DetState *state, float *base, float *hist, const float *mag,
                                     int n_frames, cudaStream_t st);
+#ifdef IR_SEG_TIMING
+void seg_timing_dump();
+#endif
 size_t seg_walk_smem(const DetConfig &c);
 cudaError_t launch_detect_scan_seg(const DetConfig &c, DetState *state, float *base, float *hist, const float *mag,
                                    uint32_t *xu, unsigned char *rowany, const float *ref, int n_frames,

@@ -456,9 +456,37 @@ k_seg_reclass(SegCtl *ctl, const float *__restrict__ mag, const float *__restric
     }
 }
 
+#ifdef IR_SEG_TIMING
+// cycles (lane 0): generic walker phases 0 stage 1 scan 2 quiet update 3 hits 4 peaks 5 delete 6 create; 7 generic walks whole,
+// 8 the fast walker's attempt before them, 9 how many; 10 fast walks whole, 11 how many; 12 candidates, 13 creations, 14 event frames
+__device__ unsigned long long g_seg_prof[16];
+void seg_timing_dump() {
+    unsigned long long h[16], z[16] = {0};
+    cudaMemcpyFromSymbol(h, g_seg_prof, sizeof(h));
+    cudaMemcpyToSymbol(g_seg_prof, z, sizeof(z));
+    fprintf(stderr, "seg timing (Mcycles): generic walks %llu: stage %.2f scan %.2f quiet %.2f hits %.2f peaks %.2f delete %.2f create %.2f | whole %.2f "
+                    "fast attempt before %.2f | fast walks %llu whole %.2f | generic start lists %llu bursts\n",
+            h[9], h[0] * 1e-6, h[1] * 1e-6, h[2] * 1e-6, h[3] * 1e-6, h[4] * 1e-6, h[5] * 1e-6, h[6] * 1e-6, h[7] * 1e-6, h[8] * 1e-6,
+            h[11], h[10] * 1e-6, h[12]);
+}
+#endif
 // the 32 lanes of a segment's warp, for seg_generic.cuh
 struct SegLanesWarp {
     static constexpr int L = 32;
+    uint32_t *rowbuf;                                         // shared memory for one bitmap row
+#ifdef IR_SEG_TIMING
+    long long *tacc, *tlast;
+    __device__ void tick(int k) const { const long long t = clock64(); if (k >= 0) tacc[k] += t - *tlast; *tlast = t; }
+#else
+    __device__ void tick(int) const {}
+#endif
+    __device__ const uint32_t *stage(const uint32_t *row, int words) const {
+        __syncwarp();                                         // the previous row's readers are done
+        for (int w = (int)(threadIdx.x & 31u) * 4; w < words; w += 128)
+            *reinterpret_cast<uint4 *>(rowbuf + w) = __ldg(reinterpret_cast<const uint4 *>(row + w));
+        __syncwarp();
+        return rowbuf;
+    }
     __device__ int lane() const { return (int)(threadIdx.x & 31u); }
     __device__ void sync() const { __syncwarp(); }
     __device__ bool any(bool p) const { return __any_sync(FULL, p) != 0; }
@@ -466,13 +494,20 @@ struct SegLanesWarp {
     __device__ int max(int v) const { return __reduce_max_sync(FULL, v); }
     __device__ uint32_t ballot(bool p) const { return __ballot_sync(FULL, p); }
     __device__ void and_word(uint32_t *p, uint32_t m) const { atomicAnd(p, m); }
-    __device__ int inc(int *p) const { return atomicAdd(p, 1); }
-    __device__ void best(float &r, int &b, int &i) const {
-        for (int off = 16; off; off >>= 1) {
-            const float o_r = __shfl_xor_sync(FULL, r, off);
-            const int o_b = __shfl_xor_sync(FULL, b, off), o_i = __shfl_xor_sync(FULL, i, off);
-            if (o_i >= 0 && (i < 0 || o_r > r || (o_r == r && o_b < b))) { r = o_r; b = o_b; i = o_i; }
+    __device__ int excl_scan(int v, int &total) const {
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(FULL, x, o);
+            if ((int)(threadIdx.x & 31u) >= o) x += y;
         }
+        total = __shfl_sync(FULL, x, 31);
+        return x - v;
+    }
+    __device__ unsigned long long max64(unsigned long long v) const {
+        const uint32_t hi = __reduce_max_sync(FULL, (uint32_t)(v >> 32));
+        const uint32_t lo = __reduce_max_sync(FULL, (uint32_t)(v >> 32) == hi ? (uint32_t)v : 0u);
+        return ((unsigned long long)hi << 32) | lo;
     }
 };
 
@@ -482,7 +517,7 @@ __global__ void __launch_bounds__(32, 1)
 k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint32_t *__restrict__ xu_c,
            const float *__restrict__ snap, const int *__restrict__ fslot_g, const uint32_t *__restrict__ valid_g,
            SegState *stA, SegState *stB, uint32_t *qw_g, int *ncreate, int *ngone, int *segbail, int *stch,
-           GoneBurst *glist, SegBurst *ovfA, SegBurst *ovfB, SegBurst *gwork, float *gprel, int *gpbin, uint32_t *seggen) {
+           GoneBurst *glist, SegBurst *ovfA, SegBurst *ovfB, unsigned long long *gkeys, uint32_t *seggen) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     WkShared &S = *reinterpret_cast<WkShared *>(smem_raw);
     if (ctl->finished || ctl->hard_bail) return;
@@ -518,6 +553,10 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
         if (lane == 0) { nxt[seg + 1].n_act = on; stch_now[seg + 1] = 0; }
         return;
     }
+#ifdef IR_SEG_TIMING
+    const long long t_in = clock64();
+    long long t_fast = 0, t_gen = 0, tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+#endif
     const float *mag = mag_c + (size_t)f0 * N;
     GoneBurst *gl = glist + (size_t)seg * IR_SEG_GONE;
     const float thr = c.thr;
@@ -926,11 +965,14 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
     for (; blk_landed < blk_issued; blk_landed++) mbar_wait_a(bars_a + 8u * (uint32_t)(blk_landed % RB), (uint32_t)((blk_landed / RB) & 1));
     // ---- more than 32 bursts alive somewhere in this segment: walk it again the plain way (seg_generic.cuh), from
     // the same start list, on lane 0; the other lanes wait.  Its outputs replace the fast walker's.
+#ifdef IR_SEG_TIMING
+    t_fast = clock64() - t_in;
+#endif
     bool generic = false;
+    SegBurst *work = reinterpret_cast<SegBurst *>(ring);      // (the ring is drained: its shared memory holds the list and a bitmap row)
     if (bail == 4 || bail == 5 || bail == 7) {
         generic = true;
         if (lane == 0) seggen[seg] = 1u;                     // next round: straight here
-        SegBurst *work = gwork + (size_t)seg * IR_SEG_LIST;
         for (int i = lane; i < n_start && i < IR_SEG_LIST; i += 32) work[i] = list_get(cur, ovf_cur, seg, i);
         __syncwarp();
         bail = 5;
@@ -940,11 +982,30 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
             ga.max_burst_len = c.max_burst_len; ga.thr = c.thr; ga.seg = seg; ga.f0 = f0; ga.n_frames = n_frames;
             ga.index0 = index0; ga.sq_start = max(ctl->sq0 - f0, 0);
             ga.xu = xu_c; ga.mag = mag_c; ga.snap = snap; ga.fslot = fslot_g; ga.valid = valid_g;
-            ga.prel = gprel + (size_t)seg * IR_SEG_PCAP; ga.pbin = gpbin + (size_t)seg * IR_SEG_PCAP; ga.pcap = IR_SEG_PCAP;
-            bail = seg_walk_generic_t(SegLanesWarp{}, ga, work, n_start, IR_SEG_LIST, gl, IR_SEG_GONE, S.fvs, S.gout);
+            ga.keys = gkeys + (size_t)seg * IR_SEG_PCAP; ga.pcap = IR_SEG_PCAP;
+            #ifdef IR_SEG_TIMING
+            SegLanesWarp lw{ring + IR_SEG_LIST * (sizeof(SegBurst) / 4), tacc, &tlast};
+#else
+            SegLanesWarp lw{ring + IR_SEG_LIST * (sizeof(SegBurst) / 4)};
+#endif
+            bail = seg_walk_generic_t(lw, ga, work, n_start, IR_SEG_LIST, gl, IR_SEG_GONE, S.fvs, S.gout);
         }
         __syncwarp();
+#ifdef IR_SEG_TIMING
+        t_gen = clock64() - t_in - t_fast;
+#endif
     }
+#ifdef IR_SEG_TIMING
+    if (lane == 0) {
+        if (generic) {
+            for (int k = 0; k < 7; k++) atomicAdd(&g_seg_prof[k], (unsigned long long)tacc[k]);
+            atomicAdd(&g_seg_prof[7], (unsigned long long)t_gen); atomicAdd(&g_seg_prof[8], (unsigned long long)t_fast);
+            atomicAdd(&g_seg_prof[9], 1ull); atomicAdd(&g_seg_prof[12], (unsigned long long)n_start);
+        } else {
+            atomicAdd(&g_seg_prof[10], (unsigned long long)t_fast); atomicAdd(&g_seg_prof[11], 1ull);
+        }
+    }
+#endif
     // ---- outputs of this segment: quiet flags, burst list at its last frame, counts
     int changed = 0, st_changed = 0;
     const int nqw = (n_frames + 31) / 32, qw0 = f0 >> 5;
@@ -959,7 +1020,6 @@ k_seg_walk(DetConfig c, SegCtl *ctl, const float *__restrict__ mag_c, const uint
         if (lane == 0 && fc != 0x7fffffff) atomicMin(&ctl->qfc[par], fc);
         const int on = cur[seg + 1].n_act;
         if (on != n_end) st_changed = 1;
-        const SegBurst *work = gwork + (size_t)seg * IR_SEG_LIST;
         for (int i = lane; i < n_end; i += 32) {
             const SegBurst b = work[i];
             if (i < on) {
@@ -1178,8 +1238,9 @@ bool seg_scan_supported(const DetConfig &c) {
 
 size_t seg_walk_smem(const DetConfig &c) {
     const size_t smaxc_ = c.N / 1024 >= 16 ? 512 : 128;
-    return (((sizeof(WkShared) + 15) / 16) * 16 + 3 * smaxc_ * 4 + 127) / 128 * 128 +
-           (size_t)RB * SGF * (size_t)(c.N / 16) * sizeof(uint32_t);
+    const size_t row_bytes = (size_t)(c.N / 16) * sizeof(uint32_t);
+    const size_t ring = (size_t)RB * SGF * row_bytes, gen = (size_t)IR_SEG_LIST * sizeof(SegBurst) + row_bytes;   // (one or the other)
+    return (((sizeof(WkShared) + 15) / 16) * 16 + 3 * smaxc_ * 4 + 127) / 128 * 128 + (ring > gen ? ring : gen);
 }
 
 template <int WPL>
@@ -1195,7 +1256,7 @@ static cudaError_t launch_walk_t(const DetConfig &c, const SegBuffers &b, const 
         attr_set[dev] = true;
     }
     k_seg_walk<WPL><<<S, 32, smem, st>>>(c, b.ctl, mag, xu, b.snap, b.fslot, b.valid, b.stA, b.stB, b.qw, b.ncreate, b.ngone,
-                                         b.segbail, b.stch, b.glist, b.ovfA, b.ovfB, b.gwork, b.gprel, b.gpbin, b.seggen);
+                                         b.segbail, b.stch, b.glist, b.ovfA, b.ovfB, b.gkeys, b.seggen);
     return cudaGetLastError();
 }
 

@@ -785,8 +785,7 @@ static int seg_ensure(ir_pipeline *p, size_t fc) {
                  o_ng = carve((S + 2) * 4), o_sb = carve((S + 2) * 4), o_sc = carve(2 * (S + 2) * 4), o_cp = carve((S + 2) * 4),
                  o_gp = carve((S + 2) * 4), o_gl = carve(S * (size_t)IR_SEG_GONE * sizeof(GoneBurst)), o_bf = carve(N * 4), o_glo = carve(N * 4), o_ghi = carve(N * 4),
                  o_oa = carve((S + 1) * (size_t)IR_SEG_OVF * sizeof(SegBurst)), o_ob = carve((S + 1) * (size_t)IR_SEG_OVF * sizeof(SegBurst)),
-                 o_gw = carve(S * (size_t)IR_SEG_LIST * sizeof(SegBurst)), o_pr = carve(S * (size_t)IR_SEG_PCAP * 4),
-                 o_pb = carve(S * (size_t)IR_SEG_PCAP * 4), o_fv = carve((S + 2) * 4);
+                 o_pr = carve(S * (size_t)IR_SEG_PCAP * 8), o_fv = carve((S + 2) * 4);
     if (p->d_seg_raw.ensure(off) || p->d_seg_snap.ensure((fc + 1) * N) || p->d_seg_qmag.ensure((fc + (size_t)p->dc.hist_size + 128) * N) || p->d_rowany[0].ensure(fc) || p->d_rowany[1].ensure(fc) ||
         p->d_xu[0].ensure(fc * (N / 16)) || p->d_xu[1].ensure(fc * (N / 16)))
         return -1;
@@ -799,8 +798,8 @@ static int seg_ensure(ir_pipeline *p, size_t fc) {
     g.ncreate = (int *)(b + o_nc); g.ngone = (int *)(b + o_ng); g.segbail = (int *)(b + o_sb); g.stch = (int *)(b + o_sc);
     g.cpre = (int *)(b + o_cp); g.gpre = (int *)(b + o_gp); g.glist = (GoneBurst *)(b + o_gl);
     g.bfinal = (float *)(b + o_bf); g.glo = (float *)(b + o_glo); g.ghi = (float *)(b + o_ghi);
-    g.ovfA = (SegBurst *)(b + o_oa); g.ovfB = (SegBurst *)(b + o_ob); g.gwork = (SegBurst *)(b + o_gw);
-    g.gprel = (float *)(b + o_pr); g.gpbin = (int *)(b + o_pb); g.seggen = (uint32_t *)(b + o_fv);
+    g.ovfA = (SegBurst *)(b + o_oa); g.ovfB = (SegBurst *)(b + o_ob);
+    g.gkeys = (unsigned long long *)(b + o_pr); g.seggen = (uint32_t *)(b + o_fv);
     g.qmag = p->d_seg_qmag.p;
     g.snap = p->d_seg_snap.p; g.slot_cap = (int)fc + 1; g.frames_cap = (int)fc;
     p->seg_frames_cap = fc;
@@ -1090,6 +1089,9 @@ static int run_common(ir_pipeline *p, const void *host_iq, const void *dev_iq, s
                     (unsigned long long)hc.stats[0], (unsigned long long)hc.stats[1], hc.reason, (unsigned long long)hc.stats[2],
                     (unsigned long long)hc.stats[3], (unsigned long long)hc.stats[4], (unsigned long long)hc.stats[5],
                     (unsigned long long)hc.stats[7], (unsigned long long)hc.stats[6]);
+#ifdef IR_SEG_TIMING
+        if (getenv("IR_SCAN_DEBUG")) seg_timing_dump();
+#endif
     }
     if (p->scan_dbg && p->scan_mode == 0 && !p->scan_dbg_ev.empty()) {
         double t[4] = {0, 0, 0, 0};

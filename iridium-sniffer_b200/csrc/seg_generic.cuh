@@ -35,14 +35,12 @@ struct SegGenArgs {
     const float *snap;                  // baseline snapshots [slots][N]
     const int *fslot;                   // snapshot slot per chunk frame (-1: none)
     const uint32_t *valid;              // peak search range minus the DC notch, N/32 words
-    float *prel;                        // scratch: candidate peaks of one frame
-    int *pbin;
+    unsigned long long *keys;           // scratch: candidate peaks of one frame (pcap of them)
     int pcap;
 };
 
 struct SegGenOut {
     int n_end, n_gone, n_create;
-    int np;                             // scratch: candidate count of the frame at hand (shared by the lanes)
     uint32_t qbits[(IR_SEG_LEN + 31) / 32];
 };
 
@@ -59,9 +57,11 @@ struct SegLanesOne {
     IR_HD int max(int v) const { return v; }
     IR_HD uint32_t ballot(bool p) const { return p ? 1u : 0u; }
     IR_HD void and_word(uint32_t *p, uint32_t m) const { *p &= m; }
-    IR_HD int inc(int *p) const { return (*p)++; }
-    // strongest candidate over the lanes: larger rel, then smaller bin; idx < 0 = none
-    IR_HD void best(float &, int &, int &) const {}
+    IR_HD int excl_scan(int v, int &total) const { total = v; return 0; }     // over the lanes
+    IR_HD unsigned long long max64(unsigned long long v) const { return v; }
+    // the bitmap row of the frame at hand, somewhere close (the device copies it into shared memory)
+    IR_HD const uint32_t *stage(const uint32_t *row, int) const { return row; }
+    IR_HD void tick(int) const {}     // phase boundary (cycle counters of -DIR_SEG_TIMING builds)
 };
 
 IR_HD inline int segg_ctz(uint32_t m) {
@@ -69,6 +69,24 @@ IR_HD inline int segg_ctz(uint32_t m) {
     return __ffs((int)m) - 1;
 #else
     return __builtin_ctz(m);
+#endif
+}
+IR_HD inline uint32_t segg_f2u(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t u;
+    __builtin_memcpy(&u, &f, 4);
+    return u;
+#endif
+}
+IR_HD inline float segg_u2f(uint32_t u) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    __builtin_memcpy(&f, &u, 4);
+    return f;
 #endif
 }
 IR_HD inline int segg_popc(uint32_t m) {
@@ -127,7 +145,9 @@ IR_HD inline int seg_walk_generic_t(const LP lp, const SegGenArgs &a, SegBurst *
     // (burst i is lane i % L's between two compactions / creations: its fields need no hand-over in between)
     for (int fl = 0; fl < a.n_frames; fl++) {
         const int f = a.f0 + fl;                            // frame of the chunk
-        const uint32_t *XU = a.xu + (size_t)f * (2 * W), *X = XU + W;
+        lp.tick(-1);
+        const uint32_t *XU = lp.stage(a.xu + (size_t)f * (2 * W), 2 * W), *X = XU + W;
+        lp.tick(0);
         uint32_t acc = 0;
         for (int w = lane; w < W; w += L) acc |= XU[w] & fv[w];
         bool ev = acc != 0u, too_long = false;
@@ -139,11 +159,13 @@ IR_HD inline int seg_walk_generic_t(const LP lp, const SegGenArgs &a, SegBurst *
         }
         ev = lp.any(ev);
         too_long = lp.any(too_long);
+        lp.tick(1);
         if (!ev) {
             for (int i = lane; i < n; i += L)
                 if (bits3(X, work[i].cb)) { work[i].dl = f + PF; work[i].lah = f; }
             sq = sq > 0 ? sq - 1 : 0;
             if (n == 0) qb[fl >> 5] |= 1u << (fl & 31);
+            lp.tick(2);
             continue;
         }
         if (too_long) return 3;
@@ -170,30 +192,52 @@ IR_HD inline int seg_walk_generic_t(const LP lp, const SegGenArgs &a, SegBurst *
             if (hit) { b.dl = f + PF; b.lah = f; }
             if (!hit && f >= b.dl) n_done++;
         }
-        // peaks: exact crossings & mask of the previous frame & search range (:522-548); any order
-        if (lane == 0) out.np = 0;
-        lp.sync();
-        for (int w = lane; w < W; w += L) {
-            uint32_t m = XU[w] & fv[w];
+        lp.tick(3);
+        // peaks: exact crossings & mask of the previous frame & search range (:522-548).  First the bins the bitmaps
+        // cannot rule out, packed into the list 32 words at a time; then lane l takes entries l, l + L, ... (bins of
+        // one burst sit in one word: this spreads them over the lanes), divides, and keeps what crosses as a key
+        // (rel's bits, then the bin counted from the top: a larger key is a stronger peak, or the same at a lower bin)
+        unsigned long long *keys = a.keys;
+        int np = 0;
+        for (int w0 = 0; w0 < W; w0 += L) {
+            const int w = w0 + lane;
+            uint32_t m = w < W ? (XU[w] & fv[w]) : 0u;
+            int tot;
+            int pos = np + lp.excl_scan(segg_popc(m), tot);
+            if (np + tot > a.pcap) { err = 4; break; }
             while (m) {
-                const int bn = (w << 5) + segg_ctz(m);
+                keys[pos++] = (unsigned long long)((w << 5) + segg_ctz(m));
                 m &= m - 1;
-                if (!B) { err = 9; break; }
-                if (B[bn] > 0.0f) {
-                    const float rel = row[bn] / B[bn];
-                    if (rel > a.thr) {
-                        const int k = lp.inc(&out.np);
-                        if (k >= a.pcap) { err = 4; break; }
-                        a.prel[k] = rel; a.pbin[k] = bn;
-                    }
-                }
             }
+            np += tot;
         }
+        if (np && !B) err = 9;
         err = lp.max(err);
         n_done = lp.sum(n_done);
         if (err) return err;
         lp.sync();
-        const int np = out.np;
+        int cl = np > lane ? (np - lane + L - 1) / L : 0;   // this lane's entries: lane + L * k, k < cl
+        for (int k0 = cl - 1; k0 >= 0; k0 -= 4) {
+            int bnv[4];
+            float bv[4], rv[4];
+            for (int u = 0; u < 4; u++) bnv[u] = k0 - u >= 0 ? (int)keys[lane + L * (k0 - u)] : -1;
+            for (int u = 0; u < 4; u++)
+                if (bnv[u] >= 0) { bv[u] = B[bnv[u]]; rv[u] = row[bnv[u]]; }
+            for (int u = 0; u < 4; u++) {
+                if (bnv[u] < 0) continue;
+                const int k = k0 - u;
+                float rel = 0.0f;
+                bool keep = false;
+                if (bv[u] > 0.0f) { rel = rv[u] / bv[u]; keep = rel > a.thr; }
+                if (keep) {
+                    keys[lane + L * k] = ((unsigned long long)segg_f2u(rel) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)bnv[u]);
+                } else {                                    // the lane's last entry (examined already) takes the slot
+                    cl--;
+                    if (k != cl) keys[lane + L * k] = keys[lane + L * cl];
+                }
+            }
+        }
+        lp.tick(4);
         // delete_gone_bursts: list order = creation order = ascending id; compacted L entries at a time
         if (n_done) {
             int k = 0;
@@ -224,22 +268,28 @@ IR_HD inline int seg_walk_generic_t(const LP lp, const SegGenArgs &a, SegBurst *
             lp.sync();
             rebuild_fv();                                   // update_burst_mask (:482-486)
         }
-        // create_new_bursts (:556-591): strongest remaining peak first, ties by bin; a peak inside the range a
-        // new burst masks can never be taken later, so it is dropped at once
-        for (int i = lane; i < np; i += L)
-            if (!live(a.pbin[i])) a.pbin[i] = -1;
-        lp.sync();
+        lp.tick(5);
+        // create_new_bursts (:556-591): strongest remaining peak first, ties by bin.  Every candidate was outside
+        // every burst's range when it was listed; the only ranges that can cover it since are the ones created here,
+        // so each pass drops what the newest burst covers (the reference skips those when their turn comes) and
+        // finds the strongest of the rest.
+        int klo = 1, khi = 0;
         for (;;) {
-            float br = 0.0f;
-            int bb = 0x7fffffff, bi = -1;
-            for (int i = lane; i < np; i += L) {
-                const int pb = a.pbin[i];
-                if (pb < 0) continue;
-                const float pr = a.prel[i];
-                if (bi < 0 || pr > br || (pr == br && pb < bb)) { br = pr; bb = pb; bi = i; }
+            unsigned long long best = 0ull;
+            for (int k = cl - 1; k >= 0; k--) {
+                const unsigned long long key = keys[lane + L * k];
+                const int bn = (int)(0xffffffffu - (uint32_t)key);
+                if (bn >= klo && bn <= khi) {
+                    cl--;
+                    if (k != cl) keys[lane + L * k] = keys[lane + L * cl];
+                } else if (key > best) {
+                    best = key;
+                }
             }
-            lp.best(br, bb, bi);
-            if (bi < 0) break;
+            best = lp.max64(best);
+            if (best == 0ull) break;
+            const int bb = (int)(0xffffffffu - (uint32_t)best);
+            const float br = segg_u2f((uint32_t)(best >> 32));
             if (n >= cap) return 5;
             if (lane == 0) {
                 SegBurst nb;
@@ -253,13 +303,10 @@ IR_HD inline int seg_walk_generic_t(const LP lp, const SegGenArgs &a, SegBurst *
             }
             n++;
             n_create++;
-            lp.sync();
-            for (int i = lane; i < np; i += L) {
-                const int pb = a.pbin[i];
-                if (pb >= 0 && !live(pb)) a.pbin[i] = -1;
-            }
-            lp.sync();
+            klo = bb - a.half_bw; khi = bb + a.half_bw;
         }
+        lp.sync();
+        lp.tick(6);
         if (a.max_bursts > 0 && n > a.max_bursts) return 6;  // squelch (:593-631)
         if (sq > 0) sq--;
         if (n == 0) qb[fl >> 5] |= 1u << (fl & 31);

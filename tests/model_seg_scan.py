@@ -43,11 +43,12 @@ class Bail(Exception):
 
 class SegScanModel:
     def __init__(self, N, thr, half_bw, pre_len, post_len, max_burst_len, max_bursts, hist_size=512, seg=64,
-                 max_rounds=12, c_walker=None, lanes=MAX_LANES):
+                 max_rounds=12, c_walker=None, lanes=MAX_LANES, walker_lanes=1):
         """c_walker: ctypes handle of tests/seg_generic_host_shim.cpp -- the product's generic segment walker
         (csrc/seg_generic.cuh) compiled for the host; when given, every segment is walked by IT instead of the numpy
         walker below (segment length must be the library's IR_SEG_LEN), with `lanes` as the burst capacity."""
         self.cw, self.lanes = c_walker, lanes
+        self.walker_lanes = walker_lanes      # 1, or 3 / 4: that many threads play the warp's lanes
         self.N, self.thr, self.half_bw = N, np.float32(thr), half_bw
         self.pre, self.post, self.max_len, self.max_bursts, self.H = pre_len, post_len, max_burst_len, max_bursts, hist_size
         self.SEG, self.max_rounds = seg, max_rounds
@@ -235,8 +236,9 @@ class SegScanModel:
                                self._xu.ctypes.data_as(C.c_void_p), np.ascontiguousarray(mag, np.float32).ctypes.data_as(C.c_void_p),
                                self._snap.ctypes.data_as(C.c_void_p), self._fslot.ctypes.data_as(C.c_void_p),
                                self._valid_w.ctypes.data_as(C.c_void_p), work.ctypes.data_as(C.c_void_p), len(start), cap,
-                               gl.ctypes.data_as(C.c_void_p), len(gl), counts, qb)
+                               gl.ctypes.data_as(C.c_void_p), len(gl), counts, qb, self.walker_lanes)
         if rc != 0:
+            assert rc > 0, f"the walker's lanes disagree ({rc})"
             return None, None, None, 0, {3: "too long", 4: "peak list", 5: "a 33rd concurrent burst", 6: "squelch",
                                          9: "missing snapshot", 10: "gone list"}[rc]
         n_end, n_gone, n_create = counts[0], counts[1], counts[2]

@@ -25,12 +25,12 @@ def c_walker(tmp_path_factory):
     import subprocess
     here = os.path.dirname(os.path.abspath(__file__))
     out = str(tmp_path_factory.mktemp("segg") / "libsegg_host.so")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I/usr/local/cuda/include", "-x", "c++",
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-pthread", "-I/usr/local/cuda/include", "-x", "c++",
                     os.path.join(here, "seg_generic_host_shim.cpp"), "-o", out], check=True)
     lib = C.CDLL(out)
     lib.segg_walk.restype = C.c_int
     lib.segg_walk.argtypes = [C.c_int] * 6 + [C.c_float] + [C.c_int] * 3 + [C.c_longlong, C.c_int] + [C.c_void_p] * 6 + \
-                             [C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
+                             [C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.c_int]
     return lib
 
 
@@ -114,6 +114,24 @@ def test_generic_walker_on_dense_traffic(port, synth, c_walker):
     m = _model(P, c_walker.segg_seg_len(), c_walker=c_walker, lanes=512)
     _same(m.run(mag, chunk_frames=4096), want)
     assert m.stats["max_rounds_seen"] <= 10, m.stats
+
+
+@pytest.mark.parametrize("walker_lanes", [3, 4])
+def test_generic_walker_with_several_lanes(port, rec_small, synth, c_walker, walker_lanes):
+    """the same walker with its lane loops, ballots, scans and reductions really spread over several lanes (threads
+    meeting at barriers stand in for the warp): dense traffic and an ordinary recording, the oracle's list"""
+    rec = synth.make_dense_recording(1234)
+    P, mag, want, _ = _oracle(port, rec.iq)
+    m = _model(P, c_walker.segg_seg_len(), c_walker=c_walker, lanes=512, walker_lanes=walker_lanes)
+    _same(m.run(mag, chunk_frames=4096), want)
+    P, mag, want, _ = _oracle(port, rec_small.iq)
+    _same(_model(P, c_walker.segg_seg_len(), c_walker=c_walker, lanes=512, walker_lanes=walker_lanes).run(mag, chunk_frames=4096), want)
+    for reason, iq in (("squelch", synth.make_tone_recording(5, 236, 0.02, 0.5)),
+                       ("too long", synth.make_tone_recording(6, 1, 0.13, 0.45, total_s=0.75))):
+        P, mag, _, _ = _oracle(port, iq)
+        with pytest.raises(msm.Bail) as e:
+            _model(P, c_walker.segg_seg_len(), c_walker=c_walker, lanes=512, walker_lanes=walker_lanes).run(mag)
+        assert e.value.reason == reason, e.value.reason
 
 
 def test_generic_walker_gives_up_where_it_must(port, synth, c_walker):
