@@ -32,6 +32,23 @@ __device__ __forceinline__ float2 load_sample(const void *__restrict__ base, int
     }
 }
 
+// the same in two steps for the integer formats: the raw sample (4 or 2 bytes), so that many loads can be in flight
+// before the first conversion
+template <int FMT>
+__device__ __forceinline__ uint32_t load_raw(const void *__restrict__ base, int64_t i) {
+    if (FMT == IR_FMT_CI16) return __ldg(reinterpret_cast<const uint32_t *>(base) + i);
+    return (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(base) + i);
+}
+template <int FMT>
+__device__ __forceinline__ float2 conv_raw(uint32_t r) {
+    if (FMT == IR_FMT_CI16) {
+        const int a = (int)(signed char)(r >> 8), b = (int)(signed char)(r >> 24);
+        return make_float2((float)a / 128.0f, (float)b / 128.0f);
+    }
+    const int a = (int)(signed char)(r & 0xffu), b = (int)(signed char)((r >> 8) & 0xffu);
+    return make_float2((float)a / 128.0f, (float)b / 128.0f);
+}
+
 __host__ __device__ inline int fmt_bytes(int fmt) {
     return fmt == IR_FMT_CF32 ? 8 : (fmt == IR_FMT_CI16 ? 4 : 2);
 }

@@ -348,14 +348,27 @@ k_fir_ws(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const Burs
             // A: stage the raw samples.  Positions the detector had not yet received when it emitted the burst
             // read the ring slot's previous content: one lap earlier, or zero.
             const int64_t q0 = P.start + e0;
-            const bool plain = FMT == IR_FMT_CF32 && q0 >= 0 && e0 + n_in <= P.n &&
+            const bool plain = q0 >= 0 && e0 + n_in <= P.n &&
                                q0 + n_in <= (P.emit_count < n_total ? P.emit_count : n_total);
-            if (plain) {
+            if (plain && FMT == IR_FMT_CF32) {
                 const float2 *src = reinterpret_cast<const float2 *>(iq) + q0;
 #pragma unroll
                 for (int k = 0; k < CPT; k++) {
                     const int e = ptid + FWS_P * k;
                     if (e < n_in) cp_async_8(&s[fir_pi<DEC>(e)], src + e);
+                }
+            } else if (plain) {
+                // integer samples: every load of the thread in flight, then the conversions (simd_avx2.c:264-294)
+                uint32_t raw[CPT];
+#pragma unroll
+                for (int k = 0; k < CPT; k++) {
+                    const int e = ptid + FWS_P * k;
+                    raw[k] = e < n_in ? load_raw<FMT>(iq, q0 + e) : 0u;
+                }
+#pragma unroll
+                for (int k = 0; k < CPT; k++) {
+                    const int e = ptid + FWS_P * k;
+                    if (e < n_in) s[fir_pi<DEC>(e)] = conv_raw<FMT>(raw[k]);
                 }
             } else {
 #pragma unroll 4
