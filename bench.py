@@ -361,7 +361,7 @@ def run_ours(args):
         sum_n = sum(b["num_samples"] for b in res.bursts if b["dec_len"] >= 100)
         sum_dec = sum(b["dec_len"] for b in res.bursts if b["dec_len"] >= 100)
         sum_fl = sum(b["frame_len"] for b in res.bursts if b["downmix_status"] == 0)
-        tile = 192 if fs // 250_000 == 48 else 256          # IR_FIR_TILE_OF(dec)
+        tile = 240 if fs // 250_000 == 48 else 256          # IR_FIR_TILE_OF(dec)
         n_tiles = sum((b["dec_len"] + tile - 1) // tile for b in res.bursts if b["dec_len"] >= 100)
         n_det_frames = n // W["nfft"]
         kern = {   # name: (algorithmic bytes, ms of stream time per step, units one step launches, unit name)
@@ -420,7 +420,8 @@ def run_ours(args):
                        "state_machine": {"mode": "segmented" if scan.get("segmented") else ("streaming" if scan.get("streaming") else "cluster"),
                                          "chunks_kept": scan["launches_kept"], "chunks_handed_over": scan["launches_bailed"],
                                          "rounds": scan["commands"], "bitmap_rebuilds": scan.get("bitmap_rebuilds", 0),
-                                         "last_hand_over_reason": scan.get("last_bail_reason", 0)}},
+                                         "last_hand_over_reason": scan.get("last_bail_reason", 0),
+                                         "crowded_segment_walks": scan.get("generic_segment_walks", 0)}},
             "e2e": {"value": round(total / wall_e2e / 1e6, 2), "unit": UNIT,
                     "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
                     "ms_per_step": round(wall_e2e / K * 1e3, 3), "raw_lines_per_step": n_lines,

@@ -25,7 +25,7 @@
 #define IR_GUARD_LO 0.65f
 #define IR_GUARD_HI 1.5f
 #define IR_ROT_G 16             // samples between NCO phase checkpoints
-#define IR_FIR_TILE_OF(dec) ((dec) == 48 ? 192 : 256)   // decimated outputs per FIR tile (k_downmix.cu)
+#define IR_FIR_TILE_OF(dec) ((dec) == 48 ? 240 : 256)   // decimated outputs per FIR tile (k_downmix.cu)
 #define IR_FIR_R 8              // outputs per lane
 #define IR_INPUT_NTAPS 801      // burst_downmix.c:252-259 (always designed for 10 MHz)
 #define IR_DM_WORK (2 * 1024 * 1024)   // burst_downmix.c:366

@@ -19,7 +19,7 @@ namespace ir {
 
 // =========================================================================== FFT + |X|^2
 template <int L, int FMT>
-__global__ void __launch_bounds__(fft_threads<L>())
+__global__ void __launch_bounds__(fft_threads<L>(), (L == 12 || L == 13) ? 2 : 1)   // (two 101 KB CTAs an SM at N = 8192: 128 registers)
 k_detect_fft(const void *__restrict__ iq, int64_t first_sample, const float *__restrict__ window,
              const float2 *__restrict__ tw_g, float *__restrict__ mag, int64_t n_frames) {
     constexpr int N = 1 << L;

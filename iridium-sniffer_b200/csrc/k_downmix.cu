@@ -72,8 +72,8 @@ cudaError_t launch_rot_tables(const float2 *incr, float2 *const *tables, const i
 }
 
 // ============================================================== rotate + FIR + decimate
-// decimated outputs per tile: 256 (32 lanes x 8) at DEC = 40; 192 (24 lanes) at DEC = 48, where two 256-output sample
-// buffers (or two resident one-tile CTAs) would not fit an SM's shared memory
+// decimated outputs per tile: 256 (32 lanes x 8) at DEC = 40; 240 (30 lanes) at DEC = 48, where two 256-output sample
+// buffers would not fit an SM's shared memory (240: 216.5 KB of the 227)
 template <int DEC> __host__ __device__ constexpr int fir_tile() { return IR_FIR_TILE_OF(DEC); }
 template <int DEC> __host__ __device__ constexpr int fir_in_max() { return (fir_tile<DEC>() - 1) * DEC + IR_INPUT_NTAPS; }
 // Shared-memory index of burst sample e.  Two access patterns must both be conflict-free for
@@ -465,7 +465,7 @@ static cudaError_t launch_fir_t(const void *iq, int64_t n_total, uint64_t ring, 
     static const bool legacy = getenv("IR_FIR_LEGACY") != nullptr;
     constexpr int PITCH = fws_pitch<DEC>();
     const size_t smem_ws = sizeof(float2) * (2 * PITCH + 4 * fir_tile<DEC>()) + sizeof(float) * ((fir_hp_elems<DEC>() + 1) & ~1) + 4 * sizeof(uint64_t);
-    // (two sample buffers of a 256-output tile do not fit 227 KB at DEC = 48: the one-tile kernel serves 12 MHz)
+    // (the one-tile kernel: for comparison, and should a tile size ever not fit two sample buffers)
     if (legacy || tile_burst == nullptr || smem_ws > (size_t)227 * 1024) {
         const size_t smem = sizeof(float2) * (fir_pitch_elems<DEC>() + 4 * fir_tile<DEC>()) + sizeof(float) * fir_hp_elems<DEC>();
         cudaError_t e = cudaFuncSetAttribute(k_fir<FMT, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
