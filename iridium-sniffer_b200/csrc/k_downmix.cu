@@ -294,7 +294,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 constexpr int FWS_C = 128;             // consumer threads (one warp per chain)
-template <int DEC> __host__ __device__ constexpr int fws_pitch() { return (fir_pitch_elems<DEC>() + 8 + 1) & ~1; }
+// a sample buffer: the padded index of the last sample + 4, and -- the rotate phase turns whole 16-sample segments, so
+// the last segment's unused tail is written too -- the end of the last segment (at DEC = 48 that tail is 15 samples
+// and reached two elements past the old pitch, into the other buffer's first samples)
+template <int DEC> __host__ __device__ constexpr int fws_seg_end() {
+    constexpr int last = (fir_in_max<DEC>() + IR_ROT_G - 1) / IR_ROT_G - 1;
+    return last * (IR_ROT_G + 1) + last / (IR_FIR_R * DEC / IR_ROT_G) + IR_ROT_G;
+}
+template <int DEC> __host__ __device__ constexpr int fws_pitch() {
+    constexpr int a = fir_pitch_elems<DEC>() + 8, b = fws_seg_end<DEC>();
+    return ((a > b ? a : b) + 1) & ~1;
+}
+static_assert(fws_pitch<40>() >= fws_seg_end<40>() && fws_pitch<48>() >= fws_seg_end<48>(), "rotate phase stays inside its buffer");
 // FWS_P producer threads; F2: packed FMAs in the chains
 template <int FMT, int DEC, int FWS_P, bool F2>
 __global__ void __launch_bounds__(FWS_C + FWS_P, 1)
