@@ -82,7 +82,14 @@ template <int DEC> __host__ __device__ constexpr int fir_in_max() { return (fir_
 // DEC=40, 409 for DEC=48), both odd.
 template <int DEC> __host__ __device__ constexpr int fir_pi_c(int e) { return e + (e >> 4) + e / (IR_FIR_R * DEC); }
 template <int DEC> __device__ __forceinline__ int fir_pi(int e) { return e + (e >> 4) + e / (IR_FIR_R * DEC); }
-template <int DEC> __host__ __device__ constexpr int fir_pitch_elems() { return fir_pi_c<DEC>(fir_in_max<DEC>()) + 4; }
+// A chain walks whole blocks of DEC/4 taps: at DEC = 48 its last block holds taps 192..203 of which 200..203 are
+// zero padding, and the samples those meet lie up to 15 past the tile's last input.  0 * x must be 0: the staging
+// writes zeros there (stale shared memory can hold anything, NaN patterns included).
+template <int DEC> __host__ __device__ constexpr int fir_over() {
+    return 4 * ((IR_INPUT_NTAPS / 4 + DEC / 4 - 1) / (DEC / 4)) * (DEC / 4) - (IR_INPUT_NTAPS / 4) * 4;
+}
+template <int DEC> __host__ __device__ constexpr int fir_stage_max() { return fir_in_max<DEC>() + fir_over<DEC>(); }
+template <int DEC> __host__ __device__ constexpr int fir_pitch_elems() { return fir_pi_c<DEC>(fir_stage_max<DEC>()) + 4; }
 
 // Zero-padded tap table in shared memory: hp[IR_FIR_HPAD + k] = taps[k] for 0 <= k < 800, else 0.
 #define IR_FIR_HPAD 0
@@ -222,7 +229,7 @@ k_fir(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const BurstPa
     // guaranteed 8-byte aligned inside the pitched layout), so all ~86 copies of a thread are in
     // flight at once instead of one L2 round trip per element.
 #pragma unroll 4
-    for (int e = tid; e < fir_in_max<DEC>(); e += blockDim.x) {
+    for (int e = tid; e < fir_stage_max<DEC>(); e += blockDim.x) {
         float2 *dst = &s[fir_pi<DEC>(e)];
         bool filled = false;
         if (e < n_in && e0 + e < P.n) {
@@ -306,6 +313,7 @@ template <int DEC> __host__ __device__ constexpr int fws_pitch() {
     return ((a > b ? a : b) + 1) & ~1;
 }
 static_assert(fws_pitch<40>() >= fws_seg_end<40>() && fws_pitch<48>() >= fws_seg_end<48>(), "rotate phase stays inside its buffer");
+static_assert(fir_over<40>() == 0 && fir_over<48>() == 16, "zero-tap over-read of the last tap block");
 // FWS_P producer threads; F2: packed FMAs in the chains
 template <int FMT, int DEC, int FWS_P, bool F2>
 __global__ void __launch_bounds__(FWS_C + FWS_P, 1)
@@ -368,6 +376,7 @@ k_fir_ws(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const Burs
                     const int e = ptid + FWS_P * k;
                     if (e < n_in) cp_async_8(&s[fir_pi<DEC>(e)], src + e);
                 }
+                if (ptid < fir_over<DEC>()) s[fir_pi<DEC>(n_in + ptid)] = make_float2(0.0f, 0.0f);
             } else if (plain) {
                 // integer samples: every load of the thread in flight, then the conversions (simd_avx2.c:264-294)
                 uint32_t raw[CPT];
@@ -381,9 +390,10 @@ k_fir_ws(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const Burs
                     const int e = ptid + FWS_P * k;
                     if (e < n_in) s[fir_pi<DEC>(e)] = conv_raw<FMT>(raw[k]);
                 }
+                if (ptid < fir_over<DEC>()) s[fir_pi<DEC>(n_in + ptid)] = make_float2(0.0f, 0.0f);
             } else {
 #pragma unroll 4
-                for (int e = ptid; e < fir_in_max<DEC>(); e += FWS_P) {
+                for (int e = ptid; e < fir_stage_max<DEC>(); e += FWS_P) {
                     float2 *dst = &s[fir_pi<DEC>(e)];
                     bool filled = false;
                     if (e < n_in && e0 + e < P.n) {
