@@ -83,8 +83,11 @@ template <int DEC> __host__ __device__ constexpr int fir_in_max() { return (fir_
 template <int DEC> __host__ __device__ constexpr int fir_pi_c(int e) { return e + (e >> 4) + e / (IR_FIR_R * DEC); }
 template <int DEC> __device__ __forceinline__ int fir_pi(int e) { return e + (e >> 4) + e / (IR_FIR_R * DEC); }
 // A chain walks whole blocks of DEC/4 taps: at DEC = 48 its last block holds taps 192..203 of which 200..203 are
-// zero padding, and the samples those meet lie up to 15 past the tile's last input.  0 * x must be 0: the staging
-// writes zeros there (stale shared memory can hold anything, NaN patterns included).
+// zero padding, and the samples those meet lie up to 15 past the tile's last input; the unpeeled middle blocks
+// also run a handful of zero-tap FMAs on samples past an output's last input, which for the last outputs of a burst's
+// last (partial) tile lie past what was staged.  0 * x must be 0: the staging writes zeros from the tile's last input
+// to the end of the buffer (stale shared memory can hold anything, NaN patterns included; IR_FIR_POISON=1 fills the
+// shared memory with NaNs at kernel start so that tests/test_zzz_gpu_fir_poison.py sees any such read).
 template <int DEC> __host__ __device__ constexpr int fir_over() {
     return 4 * ((IR_INPUT_NTAPS / 4 + DEC / 4 - 1) / (DEC / 4)) * (DEC / 4) - (IR_INPUT_NTAPS / 4) * 4;
 }
@@ -300,6 +303,7 @@ k_fir(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const BurstPa
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ int g_fir_poison = 0;       // IR_FIR_POISON=1 (tests): start from shared memory full of NaNs
 constexpr int FWS_C = 128;             // consumer threads (one warp per chain)
 // a sample buffer: the padded index of the last sample + 4, and -- the rotate phase turns whole 16-sample segments, so
 // the last segment's unused tail is written too -- the end of the last segment (at DEC = 48 that tail is 15 samples
@@ -333,6 +337,10 @@ k_fir_ws(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const Burs
     float *hp = reinterpret_cast<float *>(part0 + 4 * fir_tile<DEC>());
     uint64_t *bars = reinterpret_cast<uint64_t *>(hp + ((fir_hp_elems<DEC>() + 1) & ~1));   // full[2], empty[2]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (g_fir_poison) {
+        for (int k = tid; k < 2 * (2 * PITCH + 4 * fir_tile<DEC>()); k += blockDim.x) reinterpret_cast<uint32_t *>(smem_raw)[k] = 0xffffffffu;
+        __syncthreads();
+    }
     for (int k = tid; k < fir_hp_elems<DEC>(); k += blockDim.x) {
         const int kk = k - IR_FIR_HPAD;
         hp[k] = (kk >= 0 && kk < (IR_INPUT_NTAPS / 4) * 4) ? c_in_taps[kk] : 0.0f;
@@ -376,7 +384,7 @@ k_fir_ws(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const Burs
                     const int e = ptid + FWS_P * k;
                     if (e < n_in) cp_async_8(&s[fir_pi<DEC>(e)], src + e);
                 }
-                if (ptid < fir_over<DEC>()) s[fir_pi<DEC>(n_in + ptid)] = make_float2(0.0f, 0.0f);
+                for (int e = n_in + ptid; e < fir_stage_max<DEC>(); e += FWS_P) s[fir_pi<DEC>(e)] = make_float2(0.0f, 0.0f);
             } else if (plain) {
                 // integer samples: every load of the thread in flight, then the conversions (simd_avx2.c:264-294)
                 uint32_t raw[CPT];
@@ -390,7 +398,7 @@ k_fir_ws(const void *__restrict__ iq, int64_t n_total, uint64_t ring, const Burs
                     const int e = ptid + FWS_P * k;
                     if (e < n_in) s[fir_pi<DEC>(e)] = conv_raw<FMT>(raw[k]);
                 }
-                if (ptid < fir_over<DEC>()) s[fir_pi<DEC>(n_in + ptid)] = make_float2(0.0f, 0.0f);
+                for (int e = n_in + ptid; e < fir_stage_max<DEC>(); e += FWS_P) s[fir_pi<DEC>(e)] = make_float2(0.0f, 0.0f);
             } else {
 #pragma unroll 4
                 for (int e = ptid; e < fir_stage_max<DEC>(); e += FWS_P) {
@@ -495,6 +503,13 @@ static cudaError_t launch_fir_t(const void *iq, int64_t n_total, uint64_t ring, 
         return cudaGetLastError();
     }
     const size_t smem = smem_ws;
+    static const bool poison = [] {
+        const bool on = getenv("IR_FIR_POISON") != nullptr;
+        const int v = on ? 1 : 0;
+        if (on) cudaMemcpyToSymbol(g_fir_poison, &v, sizeof(int));
+        return on;
+    }();
+    (void)poison;
     static const bool scalar = getenv("IR_FIR_SCALAR") != nullptr;    // the unpacked chains with eight producer warps
     const unsigned grid = (unsigned)((n_tiles + IR_FIR_STRIP - 1) / IR_FIR_STRIP);
     if (scalar) {
