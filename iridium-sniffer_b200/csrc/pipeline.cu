@@ -1354,12 +1354,30 @@ extern "C" int ir_classify_frames(int device, const ir_frame_t *frames, size_t n
     CK(cudaSetDevice(device));
     const void *d_tab = nullptr;
     CK(classify_tables(device, &d_tab));
-    DevBuf<uint8_t> d_bits;
-    DevBuf<float> d_llr;
-    DevBuf<FrameSrc> d_src;
-    DevBuf<ir_frame_class_t> d_out;
-    struct Guard { DevBuf<uint8_t> &a; DevBuf<float> &b; DevBuf<FrameSrc> &c; DevBuf<ir_frame_class_t> &d;
-                   ~Guard() { a.release(); b.release(); c.release(); d.release(); } } guard{d_bits, d_llr, d_src, d_out};
+    // the calling thread's buffers on this device, kept between calls (the reference-named frame_decode() /
+    // ida_decode() come here once per frame: four allocations and four frees each time cost more than the kernel);
+    // a call with more than a few MB of bits gives them back
+    struct ClassifyBufs {
+        DevBuf<uint8_t> bits;
+        DevBuf<float> llr;
+        DevBuf<FrameSrc> src;
+        DevBuf<ir_frame_class_t> out;
+        int device = -1;
+        void drop() { if (device >= 0 && cudaSetDevice(device) == cudaSuccess) { bits.release(); llr.release(); src.release(); out.release(); } device = -1; }
+        ~ClassifyBufs() { drop(); }
+    };
+    static thread_local ClassifyBufs t_bufs;
+    if (t_bufs.device != device) {
+        int cur = device;
+        t_bufs.drop();
+        CK(cudaSetDevice(cur));
+        t_bufs.device = cur;
+    }
+    DevBuf<uint8_t> &d_bits = t_bufs.bits;
+    DevBuf<float> &d_llr = t_bufs.llr;
+    DevBuf<FrameSrc> &d_src = t_bufs.src;
+    DevBuf<ir_frame_class_t> &d_out = t_bufs.out;
+    struct Guard { ClassifyBufs &b; bool big; ~Guard() { if (big) b.drop(); } } guard{t_bufs, n_bits_total > (size_t)(4u << 20)};
     std::vector<FrameSrc> src(n_frames);
     if (d_bits.ensure(n_bits_total + 1) || (llr && d_llr.ensure(n_bits_total + 1)) || d_src.ensure(n_frames) || d_out.ensure(n_frames))
         return -1;

@@ -102,7 +102,9 @@ extern "C" gpu_burst_fft *gpu_burst_fft_create(int fft_size, int batch_size, con
     gpu_burst_fft *g = new gpu_burst_fft();
     g->N = fft_size; g->L = L; g->batch = batch_size;
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, 0) == cudaSuccess) g->sm_count = prop.multiProcessorCount;
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);                                   // the caller's device, not device 0
+    if (cudaGetDeviceProperties(&prop, cur_dev) == cudaSuccess) g->sm_count = prop.multiProcessorCount;
     std::vector<float2> tw = build_twiddle_image(L);
     auto bail = [&]() -> gpu_burst_fft * { gpu_burst_fft_destroy(g); return nullptr; };
     if (cudaStreamCreate(&g->st) != cudaSuccess) return bail();
@@ -199,7 +201,9 @@ extern "C" _burst_detector *burst_detector_create(burst_config_t *cfg) {
         return nullptr;
     }
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, 0) == cudaSuccess) d->sm_count = prop.multiProcessorCount;
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (cudaGetDeviceProperties(&prop, cur_dev) == cudaSuccess) d->sm_count = prop.multiProcessorCount;
     HostTables tab;
     build_host_tables(tab, d->dc.N);
     std::vector<float2> tw = build_twiddle_image(d->dc.L);

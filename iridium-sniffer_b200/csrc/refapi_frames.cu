@@ -6,6 +6,7 @@
 // ida_decode.c from the build and link the library instead.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "frame_classify.cuh"
@@ -110,9 +111,10 @@ static int classify_one(const demod_frame_t *frame, ir_frame_t *f, ir_frame_clas
     cudaGetDevice(&dev);
     int rc = 0;
     if (ir_classify_frames(dev, f, 1, frame->bits, frame->llr, (size_t)frame->n_bits, c) != 0) {
+        // frame_decode() / ida_decode() have no way to say "failed": answering "not an IRA / IBC / IDA frame" would
+        // silently drop frames, so a CUDA failure ends the program like the detector's drop-in does (refapi.cu)
         fprintf(stderr, "iridium_b200: frame classification failed: %s\n", ir_last_error());
-        memset(c, 0, sizeof(*c));
-        rc = -1;
+        abort();
     }
     L.valid = true; L.id = frame->id; L.timestamp = frame->timestamp; L.bits = frame->bits; L.llr = frame->llr; L.n_bits = frame->n_bits;
     L.hash = h; L.rc = rc; L.c = *c;
