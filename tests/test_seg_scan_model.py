@@ -134,6 +134,28 @@ def test_generic_walker_with_several_lanes(port, rec_small, synth, c_walker, wal
         assert e.value.reason == reason, e.value.reason
 
 
+@pytest.mark.parametrize("walker_lanes", [1, 4])
+def test_generic_walker_12mhz_clipped_int16(port, synth, c_walker, walker_lanes):
+    """BASELINE config 3's geometry and its trouble in small: 12 MHz, 16384-pt frames, int16 samples of which the
+    reference keeps the upper byte; strong bursts clip and every one of them spawns dozens of spurious detections
+    (229 bursts from 14 planted, 76 alive at once) -- the segments the device hands to this walker"""
+    fs = 12_000_000
+    rec = synth.make_recording(3, sample_rate=fs, duration_s=1.6, n_bursts=14, fmt="ci16", snr_db=(26.0, 30.0))
+    iq = port.convert_ci16(rec.iq)
+    P = port.det_params(sample_rate=fs)
+    pb, mag, nsq = port.detect(P, iq, dump_mag=True)
+    want = [(b.id, b.start, b.stop, b.last_active, b.center_bin, b.peak_rel, b.base_at_create) for b in pb]
+    assert P.fft_size == 16384 and len(want) > 150 and nsq == 0
+    ev = sorted([(b.start, 1) for b in pb] + [(b.stop, -1) for b in pb])
+    alive = peak = 0
+    for _, d in ev:
+        alive += d
+        peak = max(peak, alive)
+    assert peak > 40
+    m = _model(P, c_walker.segg_seg_len(), c_walker=c_walker, lanes=256, walker_lanes=walker_lanes)
+    _same(m.run(mag, chunk_frames=2048), want)
+
+
 def test_generic_walker_gives_up_where_it_must(port, synth, c_walker):
     for reason, iq in (("squelch", synth.make_tone_recording(5, 236, 0.02, 0.5)),
                        ("too long", synth.make_tone_recording(6, 1, 0.13, 0.45, total_s=0.75))):
