@@ -232,6 +232,35 @@ def test_12mhz_many_launches(pl, port, synth, mode):
         assert ss["launches_kept"] >= 4, ss
 
 
+def test_12mhz_clipped_int16_crowded_segments(pl, port, synth):
+    """BASELINE config 3's trouble in small, through the device path in its own format: 12 MHz, 16384-pt frames, ci16
+    samples (upper byte kept), strong bursts that clip and spawn dozens of spurious detections each -- 229 bursts from
+    14 planted, 76 alive at once.  The segmented state machine keeps the chunk (crowded segments go to the plain walker),
+    the FIR stages integer samples on its fast path with 240-output tiles; bursts and frame bits are the oracle's."""
+    rec = synth.make_recording(3, sample_rate=FS12, duration_s=1.6, n_bursts=14, fmt="ci16", snr_db=(26.0, 30.0))
+    iq = port.convert_ci16(rec.iq)
+    P = port.det_params(sample_rate=FS12)
+    pb, _, nsq = port.detect(P, iq)
+    want = [(o.id, o.start, o.stop, o.last_active, o.center_bin, o.magnitude, o.noise) for o in pb]
+    assert len(want) > 150 and nsq == 0
+    old = os.environ.get("IR_SCAN")
+    try:
+        _set_mode("seg")
+        p = pl.Pipeline(sample_rate=FS12, start_time_ns=77)
+        res = p.run_host(rec.iq, "ci16")
+        ss = p.scan_stats()
+        p.close()
+    finally:
+        if old is not None:
+            os.environ["IR_SCAN"] = old
+    got = [(b["id"], b["start"], b["stop"], b["last_active"], b["center_bin"], b["magnitude"], b["noise"]) for b in res.bursts]
+    assert got == want, ss
+    assert ss["segmented"] and ss["launches_bailed"] == 0 and ss["generic_segment_walks"] > 0, ss
+    ores, _ = port.run(iq, sample_rate=FS12, start_time_ns=77)
+    assert len(ores) >= 10
+    assert [(f["id"], f["bits"].tobytes()) for f in res.frames] == [(o["id"], o["bits"].tobytes()) for o in ores]
+
+
 def test_full_size_recording_seg_equals_cluster_oracle_and_truth(pl, port, synth):
     """BASELINE config 2 at full size (60 s, 600 M samples, ~6500 bursts; generated on the GPU like
     bench.py does).  The first 8 s are held against the CPU oracle field by field (ids, bits, float fields
