@@ -92,6 +92,30 @@ def test_dense_672_bursts(pl, port, dense, mode):
     assert good >= 0.97 * len(res.frames) and len(res.frames) >= 600
 
 
+def test_dense_traffic_fed_in_pieces(pl, port, dense):
+    """The same recording copied in 2 Mi-sample pieces (the host joins them into chunks of >= 4 Mi samples: three
+    chunks here, the crowded stretch inside the second): the oracle's burst list, nothing handed to the cluster kernel.
+    (A chunk boundary INSIDE a crowded stretch -- lists longer than a warp through k_seg_begin, the overflow arrays and
+    k_seg_commit -- needs chunks shorter than the host makes from host memory; tests/test_seg_scan_model.py covers the
+    algorithm with 256-frame chunks, the 60 s 12 MHz bench recording crosses a few such boundaries.)"""
+    P = port.det_params()
+    pb, _, _ = port.detect(P, dense.iq)
+    want = [(o.id, o.start, o.stop, o.last_active, o.center_bin, o.magnitude, o.noise) for o in pb]
+    old = os.environ.get("IR_SCAN")
+    try:
+        _set_mode("seg")
+        p = pl.Pipeline(sample_rate=10_000_000, start_time_ns=77, h2d_chunk=2 << 20)
+        res = p.run_host(dense.iq, "cf32")
+        ss = p.scan_stats()
+        p.close()
+    finally:
+        if old is not None:
+            os.environ["IR_SCAN"] = old
+    got = [(b["id"], b["start"], b["stop"], b["last_active"], b["center_bin"], b["magnitude"], b["noise"]) for b in res.bursts]
+    assert got == want, ss
+    assert ss["segmented"] and ss["launches_bailed"] == 0 and ss["generic_segment_walks"] > 0 and ss["launches_kept"] >= 2, ss
+
+
 def _tones(seed, n_tones, dur_s, t0_s, total_s=0.62, snr_db=20.0):
     synth = importlib.import_module("iridium-sniffer_b200.synth")
     return synth.make_tone_recording(seed, n_tones, dur_s, t0_s, total_s=total_s, snr_db=snr_db)

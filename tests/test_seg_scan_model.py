@@ -156,6 +156,19 @@ def test_generic_walker_12mhz_clipped_int16(port, synth, c_walker, walker_lanes)
     _same(m.run(mag, chunk_frames=2048), want)
 
 
+def test_generic_walker_chunk_boundary_inside_a_crowded_stretch(port, synth, c_walker):
+    """112 bursts alive where one chunk ends and the next begins (the input of tests/gpu_crowded_boundary_cases.py):
+    the list a chunk leaves is the list the next starts from, whatever its length (up to the device's 256)"""
+    dense = synth.make_dense_recording(1234)
+    rng = np.random.default_rng(77)
+    lead = (rng.standard_normal(2_500_000) + 1j * rng.standard_normal(2_500_000)).astype(np.complex64) * np.float32(0.01)
+    P, mag, want, nsq = _oracle(port, np.concatenate([lead, dense.iq]))
+    assert nsq == 0 and len(want) > 600
+    for chunk_frames in (512, 256):
+        m = _model(P, c_walker.segg_seg_len(), c_walker=c_walker, lanes=256, walker_lanes=4)
+        _same(m.run(mag, chunk_frames=chunk_frames), want)
+
+
 def test_generic_walker_gives_up_where_it_must(port, synth, c_walker):
     for reason, iq in (("squelch", synth.make_tone_recording(5, 236, 0.02, 0.5)),
                        ("too long", synth.make_tone_recording(6, 1, 0.13, 0.45, total_s=0.75))):

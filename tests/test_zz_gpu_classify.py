@@ -26,6 +26,7 @@ CASES.append("gpu_block_cases.py::test_one_process_driver_parsed_on_the_gpu")   
 CASES.append("gpu_block_cases.py::test_one_process_driver_independent_streams_on_the_gpu")   # config 5 in one process
 CASES.append("gpu_block_cases.py::test_two_devices_blocks_and_streams")          # ir_multi_* owning two GPUs
 CASES.append("gpu_fir_poison_cases.py::test_fir_ignores_what_shared_memory_held")  # NaN-filled shared memory under the FIR
+CASES.append("gpu_crowded_boundary_cases.py::test_crowded_chunk_boundary")   # 112 bursts alive at a chunk boundary
 MAY_SKIP = {"gpu_block_cases.py::test_two_devices_blocks_and_streams"}           # ... on a one-GPU box
 
 
